@@ -1,0 +1,84 @@
+/* xhe.h -- C ABI of libxhe_cuda.so: the B200 (sm_100a) batch verifier for XELIS-HE confidential transactions.
+ *
+ * This is the drop-in boundary for the reference's batch-verification hot path.  The reference (pure Rust) has no
+ * FFI; each entry point below names the reference call site it replaces (paths relative to the reference repo).
+ * Conventions: int32 return, 0 = XHE_OK; >0 = verification verdicts mirroring ProofVerificationError /
+ * VerificationError (src/lib.rs:71-89, src/tx/verify.rs:16-21); <0 = infrastructure failure (bad argument, CUDA
+ * error; text via xhe_last_error).  No exceptions cross the ABI.  Points cross as 32-byte canonical ristretto255
+ * encodings, scalars as 32-byte canonical little-endian.  A ctx is bound to one device and one host thread at a time.
+ * There is NO CPU fallback: every compute entry point launches sm_100a kernels or fails with XHE_E_CUDA. */
+#ifndef XHE_H
+#define XHE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  XHE_OK = 0,
+  XHE_ERR_SIGNATURE = 1,            /* ProofVerificationError::Signature               src/lib.rs:73 */
+  XHE_ERR_DECOMPRESSION = 2,        /* ::Decompression                                 src/lib.rs:75 */
+  XHE_ERR_COMMITMENT_EQ_PROOF = 3,  /* ::CommitmentEqProof                             src/lib.rs:77 */
+  XHE_ERR_CT_VALIDITY_PROOF = 4,    /* ::CiphertextValidityProof                       src/lib.rs:79 */
+  XHE_ERR_GENERIC_PROOF = 5,        /* ::GenericProof (sigma MSM != identity)          src/lib.rs:81, src/tx/verify.rs:500-502 */
+  XHE_ERR_RANGE_PROOF = 6,          /* ::RangeProof(..)                                src/lib.rs:83, src/tx/verify.rs:504-514 */
+  XHE_ERR_TRANSCRIPT = 7,           /* ::Transcript(IdentityPoint)                     src/lib.rs:85, src/transcript.rs:73-84 */
+  XHE_ERR_FORMAT = 8,               /* ::Format                                        src/lib.rs:87 */
+  XHE_ERR_INVALID_NONCE = 9,        /* VerificationError::InvalidNonce                 src/tx/verify.rs:19 */
+  XHE_ERR_STATE = 10,               /* VerificationError::State(..)                    src/tx/verify.rs:18 */
+  XHE_ERR_PARSE = 11,               /* wire-format / serde-level rejection (before verify is reachable) */
+  XHE_E_ARG = -1, XHE_E_CUDA = -2, XHE_E_NOMEM = -3, XHE_E_NCCL = -4
+};
+
+typedef struct xhe_ctx xhe_ctx;
+
+/* Replaces the lazy_statics H, BP_GENS = BulletproofGens::new(64, 512), PC_GENS (src/elgamal.rs:16-24,
+ * src/proofs.rs:19-22): builds G/H tables and the 2*64*party_capacity generator table on `device`. */
+int32_t xhe_ctx_create(int device, uint32_t party_capacity, xhe_ctx** out);
+void xhe_ctx_destroy(xhe_ctx* ctx);
+const char* xhe_last_error(const xhe_ctx* ctx);
+/* stream all subsequent *_dev calls are launched on (a cudaStream_t passed as void*; NULL = default stream) */
+int32_t xhe_ctx_set_stream(xhe_ctx* ctx, void* cuda_stream);
+int32_t xhe_ctx_sync(xhe_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
+uint64_t xhe_ctx_launch_count(const xhe_ctx* ctx);
+
+/* ---- host-buffer entry points (copies inside) ------------------------------------------------------------ */
+/* CompressedRistretto::decompress, batched (src/compressed.rs:28-34,57-62,78-84,100-106; src/tx/verify.rs:85-92;
+ * src/proofs.rs:168-179,306-317).  ok[i] = 1/0 per point, never aborts.  xy (optional) = canonical affine x||y, 64 B. */
+int32_t xhe_ristretto_decompress(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy, uint8_t* ok);
+/* RistrettoPoint::compress, batched (src/compressed.rs:17-21,43-50,71-75,93-97; src/elgamal.rs:40,61) from affine x||y */
+int32_t xhe_ristretto_compress(xhe_ctx* ctx, const uint8_t* xy, size_t n, uint8_t* enc);
+/* ristretto255 one-way map RistrettoPoint::from_uniform_bytes (src/elgamal.rs:22; bulletproofs generator chains) */
+int32_t xhe_ristretto_from_uniform(xhe_ctx* ctx, const uint8_t* uniform64, size_t n, uint8_t* enc);
+/* RistrettoPoint::vartime_multiscalar_mul + is_identity (src/proofs.rs:49-67).  Accepts n = 0, identity and
+ * duplicate points; a non-canonical scalar or invalid point is XHE_E_ARG. */
+int32_t xhe_msm_vartime(xhe_ctx* ctx, const uint8_t* scalars, const uint8_t* enc_points, size_t n, uint8_t out_enc[32], int32_t* is_identity);
+/* ElGamalCiphertext Add/Sub on compressed balances (src/elgamal.rs:322-342; src/tx/verify.rs:561-609): out = bal +/- delta */
+int32_t xhe_ct_update(xhe_ctx* ctx, const uint8_t* bal, const uint8_t* delta, const uint8_t* sub, size_t n, uint8_t* out, uint8_t* ok);
+/* Signature::verify group part (src/elgamal.rs:38-42): r = s*H - e*P, compressed; the SHA3-512 stays with the caller */
+int32_t xhe_sig_r(xhe_ctx* ctx, const uint8_t* s, const uint8_t* e, const uint8_t* pk_enc, size_t n, uint8_t* r_enc, uint8_t* ok);
+
+/* ---- device-pointer entry points (asynchronous on the ctx stream; buffers are caller-owned device memory) -- */
+int32_t xhe_decompress_dev(xhe_ctx* ctx, const void* d_enc, size_t n, void* d_affine /* n*64 B, 8x32-bit limbs x,y */, void* d_niels /* n*96 B or NULL */, void* d_ok /* n bytes */);
+int32_t xhe_compress_dev(xhe_ctx* ctx, const void* d_ext /* n*128 B X,Y,Z,T */, size_t n, void* d_enc);
+int32_t xhe_from_uniform_dev(xhe_ctx* ctx, const void* d_uniform64, size_t n, void* d_enc);
+/* resident balance update (config 4): bal (extended, 2 points per account, in place) +/- delta (affine Niels, 2 per account) */
+int32_t xhe_ct_update_resident_dev(xhe_ctx* ctx, void* d_bal_ext, const void* d_delta_niels, const void* d_sub, size_t n);
+int32_t xhe_ct_update_dev(xhe_ctx* ctx, const void* d_bal, const void* d_delta, const void* d_sub, size_t n, void* d_out, void* d_ok);
+/* MSM over resident points: scalars n*32 B (canonical), points as affine Niels n*96 B; out = 32-byte encoding + flag word */
+size_t  xhe_msm_workspace_bytes(const xhe_ctx* ctx, size_t n);
+int32_t xhe_msm_dev(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_workspace, size_t workspace_bytes, void* d_out_enc32, void* d_is_identity_u32);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------------- */
+/* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns
+ * achieved instructions/s summed over the device in *rate. */
+int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate);
+/* self-test of the arithmetic layer: runs op (tests/hostemu op codes) on n operand pairs on the device */
+int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

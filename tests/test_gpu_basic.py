@@ -1,0 +1,120 @@
+"""GPU parity tests (through the C ABI) for the arithmetic layer and the per-point kernels, against the CPU oracle and
+Python big integers.  Bit-exact: every comparison is on bytes."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 2**255 - 19
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import xelis_he_b200 as xhe
+    c = xhe.Ctx(0, party_capacity=8)
+    yield c
+    c.close()
+
+
+def _words(vals):
+    return np.array([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for v in vals], dtype=np.uint32)
+
+
+def _ints(arr):
+    return [sum(int(arr[r, i]) << (32 * i) for i in range(8)) for r in range(arr.shape[0])]
+
+
+def test_field_ops_vs_bigint(ctx):
+    rng = random.Random(7)
+    edge = [0, 1, 2, 19, 38, P - 1, P, P + 1, 2 * P, 2 * P + 37, 2**256 - 1, 2**256 - 38, 2**255, 2**255 - 1, 2**32 - 1, (2**256 - 1) ^ (2**128)]
+    a = edge * len(edge) + [rng.getrandbits(256) for _ in range(4096)]
+    b = [y for y in edge for _ in edge] + [rng.getrandbits(256) for _ in range(4096)]
+    A, B = _words(a), _words(b)
+    for op, f in ((0, lambda x, y: x + y), (1, lambda x, y: x - y), (2, lambda x, y: x * y), (3, lambda x, y: x * x), (7, lambda x, y: -x)):
+        got = _ints(ctx.selftest_fe(op, A, B))
+        for x, y, g in zip(a, b, got):
+            assert g < 2**256 and g % P == f(x, y) % P, (op, hex(x), hex(y))
+    got = _ints(ctx.selftest_fe(4, A, B))
+    assert got == [x % P for x in a]
+    sub = [x for x in a[:512] if x % P]
+    got = _ints(ctx.selftest_fe(5, _words(sub), _words(sub)))
+    assert all(g * x % P == 1 for g, x in zip(got, sub))
+    got = _ints(ctx.selftest_fe(6, _words(sub), _words(sub)))
+    assert all(g % P == pow(x, (P - 5) // 8, P) for g, x in zip(got, sub))
+
+
+def test_scalar_ops_vs_bigint(ctx):
+    rng = random.Random(11)
+    edge = [0, 1, L - 1, L, L + 1, 2**256 - 1, 2**252]
+    a = edge * len(edge) + [rng.getrandbits(256) for _ in range(2048)]
+    b = [y for y in edge for _ in edge] + [rng.getrandbits(256) for _ in range(2048)]
+    A, B = _words(a), _words(b)
+    assert _ints(ctx.selftest_fe(8, A, B)) == [x * y % L for x, y in zip(a, b)]
+    assert _ints(ctx.selftest_fe(9, A, B)) == [(x + (y << 256)) % L for x, y in zip(a, b)]
+    nz = [x for x in a if x % L]
+    got = _ints(ctx.selftest_fe(10, _words(nz), _words(nz)))
+    assert all(g * x % L == 1 for g, x in zip(got, nz))
+
+
+def _sample_encodings(n_valid=600, n_random=600):
+    import oracle
+    rnd = hashlib.shake_256(b"gpu-basic").digest(64 * n_valid)
+    valid = [oracle.from_uniform(rnd[64 * i:64 * i + 64]) for i in range(n_valid)]
+    random_enc = hashlib.shake_256(b"random-encodings-gpu").digest(32 * n_random)
+    special = [bytes(32), (P).to_bytes(32, "little"), (1).to_bytes(32, "little"), b"\xff" * 32, (2).to_bytes(32, "little"),
+               (P - 1).to_bytes(32, "little"), bytes(31) + b"\x80"]
+    return b"".join(valid) + random_enc + b"".join(special)
+
+
+def test_decompress_compress_parity(ctx):
+    import oracle
+    enc = _sample_encodings()
+    n = len(enc) // 32
+    ok_ref, xy_ref = oracle.decode_batch(enc, want_xy=True)
+    ok, xy = ctx.decompress(enc, want_xy=True)
+    assert ok == ok_ref
+    for i in range(n):
+        if ok[i]:
+            assert xy[64 * i:64 * i + 64] == xy_ref[64 * i:64 * i + 64], i
+    good = [i for i in range(n) if ok[i]]
+    assert 600 < len(good) < n
+    xy_good = b"".join(xy[64 * i:64 * i + 64] for i in good)
+    assert ctx.compress(xy_good) == b"".join(enc[32 * i:32 * i + 32] for i in good)
+    assert ctx.decompress(b"") == b""
+
+
+def test_from_uniform_parity(ctx):
+    import oracle
+    u = hashlib.shake_256(b"uniform-gpu").digest(64 * 500) + bytes(64) + b"\xff" * 64
+    got = ctx.from_uniform(u)
+    for i in range(len(u) // 64):
+        assert got[32 * i:32 * i + 32] == oracle.from_uniform(u[64 * i:64 * i + 64]), i
+
+
+def test_ct_update_parity(ctx):
+    import oracle
+    rnd = hashlib.shake_256(b"ct-gpu").digest(64 * 1200)
+    pts = [oracle.from_uniform(rnd[64 * i:64 * i + 64]) for i in range(1200)]
+    n = 300
+    bal = b"".join(pts[0:2 * n]); delta = b"".join(pts[2 * n:4 * n])
+    # edge cases: identity balance, delta == balance (sub -> identity), invalid encodings
+    bal = bytes(64) + pts[5] + pts[6] + bal[128:]
+    delta = pts[1] + pts[2] + pts[5] + pts[6] + delta[128:]
+    bal = bal[:64 * 10] + b"\x01" + bal[64 * 10 + 1:]        # negative s: invalid
+    sub = bytes([i & 1 for i in range(n)])
+    sub = bytes([0, 1]) + sub[2:]
+    want, ok_ref = oracle.ct_update(bal, delta, sub)
+    got, ok = ctx.ct_update(bal, delta, sub)
+    assert ok == ok_ref and ok[10] == 0 and sum(ok) == n - 1
+    assert got == want
+    assert got[64:128] == bytes(64)   # P - P = identity encoding
+
+
+def test_int_peak_reports(ctx):
+    rates = [ctx.int_peak(w) for w in range(3)]
+    print("int peak (inst/s): IMAD.lo %.3e IMAD.HI %.3e IMAD.WIDE %.3e" % tuple(rates))
+    assert all(r > 1e11 for r in rates)

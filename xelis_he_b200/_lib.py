@@ -1,0 +1,149 @@
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libxhe_cuda.so")
+_lib = None
+
+ERR_NAMES = {0: "Ok", 1: "Signature", 2: "Decompression", 3: "CommitmentEqProof", 4: "CiphertextValidityProof", 5: "GenericProof",
+             6: "RangeProof", 7: "Transcript", 8: "Format", 9: "InvalidNonce", 10: "State", 11: "Parse",
+             -1: "E_ARG", -2: "E_CUDA", -3: "E_NOMEM", -4: "E_NCCL"}
+
+
+class XheError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"xhe error {code} ({ERR_NAMES.get(code, '?')}) {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libxhe_cuda.so; raises loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise XheError(-2, f"{_LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(_LIB_PATH)
+    vp, sz, i32, u8p = C.c_void_p, C.c_size_t, C.c_int32, C.c_char_p
+    sigs = {
+        "xhe_ctx_create": (i32, [C.c_int, C.c_uint32, C.POINTER(vp)]),
+        "xhe_ctx_destroy": (None, [vp]),
+        "xhe_last_error": (C.c_char_p, [vp]),
+        "xhe_ctx_set_stream": (i32, [vp, vp]),
+        "xhe_ctx_sync": (i32, [vp]),
+        "xhe_ctx_launch_count": (C.c_uint64, [vp]),
+        "xhe_ristretto_decompress": (i32, [vp, u8p, sz, vp, vp]),
+        "xhe_ristretto_compress": (i32, [vp, u8p, sz, vp]),
+        "xhe_ristretto_from_uniform": (i32, [vp, u8p, sz, vp]),
+        "xhe_ct_update": (i32, [vp, u8p, u8p, u8p, sz, vp, vp]),
+        "xhe_decompress_dev": (i32, [vp, vp, sz, vp, vp, vp]),
+        "xhe_compress_dev": (i32, [vp, vp, sz, vp]),
+        "xhe_from_uniform_dev": (i32, [vp, vp, sz, vp]),
+        "xhe_ct_update_resident_dev": (i32, [vp, vp, vp, vp, sz]),
+        "xhe_ct_update_dev": (i32, [vp, vp, vp, vp, sz, vp, vp]),
+        "xhe_msm_workspace_bytes": (sz, [vp, sz]),
+        "xhe_msm_dev": (i32, [vp, vp, vp, sz, vp, sz, vp, vp]),
+        "xhe_msm_vartime": (i32, [vp, u8p, u8p, sz, vp, C.POINTER(C.c_int32)]),
+        "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
+        "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class Ctx:
+    """One verifier context per device (xhe_ctx)."""
+
+    def __init__(self, device=0, party_capacity=8):
+        self.lib = load_library()
+        p = C.c_void_p()
+        rc = self.lib.xhe_ctx_create(device, party_capacity, C.byref(p))
+        if rc != 0:
+            raise XheError(rc, "xhe_ctx_create failed (a CUDA device is required; there is no CPU fallback)")
+        self.p = p
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.lib.xhe_ctx_destroy(self.p)
+            self.p = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise XheError(rc, self.lib.xhe_last_error(self.p).decode())
+        return rc
+
+    def set_stream(self, stream_ptr):
+        self._chk(self.lib.xhe_ctx_set_stream(self.p, C.c_void_p(stream_ptr)))
+
+    def sync(self):
+        self._chk(self.lib.xhe_ctx_sync(self.p))
+
+    @property
+    def launches(self):
+        return int(self.lib.xhe_ctx_launch_count(self.p))
+
+    # ---- host-buffer API
+    def decompress(self, enc: bytes, want_xy=False):
+        n = len(enc) // 32
+        ok = C.create_string_buffer(max(n, 1))
+        xy = C.create_string_buffer(64 * max(n, 1)) if want_xy else None
+        self._chk(self.lib.xhe_ristretto_decompress(self.p, enc, n, xy, ok))
+        return (ok.raw[:n], xy.raw[:64 * n]) if want_xy else ok.raw[:n]
+
+    def compress(self, xy: bytes):
+        n = len(xy) // 64
+        enc = C.create_string_buffer(32 * max(n, 1))
+        self._chk(self.lib.xhe_ristretto_compress(self.p, xy, n, enc))
+        return enc.raw[:32 * n]
+
+    def from_uniform(self, u: bytes):
+        n = len(u) // 64
+        enc = C.create_string_buffer(32 * max(n, 1))
+        self._chk(self.lib.xhe_ristretto_from_uniform(self.p, u, n, enc))
+        return enc.raw[:32 * n]
+
+    def ct_update(self, bal: bytes, delta: bytes, sub: bytes):
+        n = len(sub)
+        out = C.create_string_buffer(64 * max(n, 1))
+        ok = C.create_string_buffer(max(n, 1))
+        self._chk(self.lib.xhe_ct_update(self.p, bal, delta, sub, n, out, ok))
+        return out.raw[:64 * n], ok.raw[:n]
+
+    def msm(self, scalars: bytes, points: bytes):
+        """RistrettoPoint::vartime_multiscalar_mul + is_identity (src/proofs.rs:49-67): returns (encoding, is_identity)."""
+        n = len(scalars) // 32
+        out = C.create_string_buffer(32)
+        ident = C.c_int32(0)
+        rc = self.lib.xhe_msm_vartime(self.p, scalars, points, n, out, C.byref(ident))
+        if rc != 0:
+            raise XheError(rc, self.lib.xhe_last_error(self.p).decode())
+        return out.raw, bool(ident.value)
+
+    def msm_plan(self, n):
+        c, w = C.c_int(), C.c_int()
+        self.lib.xhe_msm_plan(n, C.byref(c), C.byref(w))
+        return c.value, w.value
+
+    def int_peak(self, which):
+        r = C.c_double()
+        self._chk(self.lib.xhe_measure_int_peak(self.p, which, C.byref(r)))
+        return r.value
+
+    def selftest_fe(self, op, a_words, b_words):
+        import numpy as np
+        a = np.ascontiguousarray(a_words, dtype=np.uint32)
+        b = np.ascontiguousarray(b_words, dtype=np.uint32)
+        n = a.size // 8
+        out = np.zeros_like(a)
+        self._chk(self.lib.xhe_selftest_fe(self.p, op, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
+        return out

@@ -1,0 +1,54 @@
+"""Build libxhe_cuda.so (sm_100a only) in-tree with nvcc.  Called by __graft_entry__.build()."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libxhe_cuda.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-pthread",
+         "-Xptxas", "-v", "--threads", "0"]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(r, f) for d in (CSRC, os.path.join(HERE, "host"), os.path.join(HERE, "..", "include"))
+            for r, _, fs in os.walk(d) for f in fs if f.endswith((".cu", ".cuh", ".hpp", ".h", ".cpp"))]
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
+                os.path.getmtime(p) for p in [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] +
+                [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))] + [os.path.join(HERE, "..", "include", "xhe.h")]):
+            continue
+        log = open(obj + ".log", "w")
+        procs.append((src, subprocess.Popen([NVCC, *FLAGS, "-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT), log))
+    for src, p, log in procs:
+        rc = p.wait()
+        log.close()
+        if rc != 0 or verbose:
+            sys.stderr.write(open(log.name).read())
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,83 @@
+// xhe_internal.cuh -- context, error plumbing and device memory layouts shared by the .cu files of libxhe_cuda.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/xhe.h"
+#include "ge25519.cuh"
+#include "sc25519.cuh"
+
+struct xhe_ctx {
+  int device = 0;
+  int sm_count = 148;
+  uint32_t party_capacity = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+  // generator tables (device): affine Niels, index 0 = G, 1 = H, then G_vec[party][64], H_vec[party][64]
+  void* d_gens_niels = nullptr;   // (2 + 128 * party_capacity) * 96 B
+  size_t n_gens = 0;
+  void* d_scratch = nullptr; size_t scratch_bytes = 0;       // grow-only device scratch for host-buffer entry points
+  void* h_pinned = nullptr; size_t pinned_bytes = 0;         // grow-only pinned staging
+};
+
+#define XHE_CUDA_OK(ctx, call)                                                                       \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+      return XHE_E_CUDA;                                                                             \
+    }                                                                                                \
+  } while (0)
+
+#define XHE_LAUNCHED(ctx) do { (ctx)->launches++; } while (0)
+
+namespace xhe {
+
+// 128-bit vector load/store of limb arrays (all device point arrays are 32-byte aligned)
+__device__ __forceinline__ void ld_fe(fe& r, const uint32_t* p) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void ld_fe_rw(fe& r, const uint32_t* p) {   // plain (non-nc) load for buffers written in the same kernel
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *(reinterpret_cast<const uint4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st_fe(uint32_t* p, const fe& r) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void ld_bytes32(uint8_t* dst, const uint8_t* src) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) { dst[4 * i] = (uint8_t)w[i]; dst[4 * i + 1] = (uint8_t)(w[i] >> 8); dst[4 * i + 2] = (uint8_t)(w[i] >> 16); dst[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+}
+// ristretto decode straight from global memory words (no byte shuffling): returns ok
+__device__ __forceinline__ bool decode_words(ge_aff& out, const uint8_t* enc32) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(enc32)), b = __ldg(reinterpret_cast<const uint4*>(enc32) + 1);
+  uint8_t bytes[32];
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) { bytes[4 * i] = (uint8_t)w[i]; bytes[4 * i + 1] = (uint8_t)(w[i] >> 8); bytes[4 * i + 2] = (uint8_t)(w[i] >> 16); bytes[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+  return ristretto_decode(out, bytes);
+}
+__device__ __forceinline__ void encode_words(uint8_t* enc32, const ge& p, ge_aff* aff = nullptr) {
+  uint8_t bytes[32];
+  ristretto_encode(bytes, p, aff);
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = (uint32_t)bytes[4 * i] | ((uint32_t)bytes[4 * i + 1] << 8) | ((uint32_t)bytes[4 * i + 2] << 16) | ((uint32_t)bytes[4 * i + 3] << 24);
+  reinterpret_cast<uint4*>(enc32)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(enc32)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void ld_niels(ge_niels& n, const uint32_t* p) { ld_fe(n.ypx, p); ld_fe(n.ymx, p + 8); ld_fe(n.t2d, p + 16); }
+__device__ __forceinline__ void st_niels(uint32_t* p, const ge_niels& n) { st_fe(p, n.ypx); st_fe(p + 8, n.ymx); st_fe(p + 16, n.t2d); }
+__device__ __forceinline__ void ld_ge(ge& g, const uint32_t* p) { ld_fe_rw(g.X, p); ld_fe_rw(g.Y, p + 8); ld_fe_rw(g.Z, p + 16); ld_fe_rw(g.T, p + 24); }
+__device__ __forceinline__ void st_ge(uint32_t* p, const ge& g) { st_fe(p, g.X); st_fe(p + 8, g.Y); st_fe(p + 16, g.Z); st_fe(p + 24, g.T); }
+
+}  // namespace xhe
+
+// kernel launchers implemented across the .cu files
+int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id);
