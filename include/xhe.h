@@ -71,6 +71,50 @@ int32_t xhe_ct_update_dev(xhe_ctx* ctx, const void* d_bal, const void* d_delta, 
 size_t  xhe_msm_workspace_bytes(const xhe_ctx* ctx, size_t n);
 int32_t xhe_msm_dev(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_workspace, size_t workspace_bytes, void* d_out_enc32, void* d_is_identity_u32);
 
+/* ---- Transaction::verify_batch, device part (src/tx/verify.rs:487-517 and everything it calls in src/proofs.rs,
+ * src/elgamal.rs, src/compressed.rs and the bulletproofs/dalek crates).  The caller (the Rust host in north_star; the
+ * C++ host layer xelis_he_b200/host here) parses transactions, resolves state lookups, replays the Merlin transcripts
+ * and hands over a struct-of-arrays batch with the Fiat-Shamir challenges and the per-proof random batch factors.
+ * All pointers are HOST memory; indices refer to the point table.  Point index 0 MUST be the identity encoding (used
+ * for the dud commitments of src/tx/verify.rs:466-475).  Indices >= n_points address balance-chain outputs
+ * (n_points + j = output of op j). ----------------------------------------------------------------------------------- */
+typedef struct xhe_batch {
+  uint32_t n_tx;
+  uint32_t n_points; const uint8_t* points;              /* n_points x 32 compressed ristretto255 */
+  /* Signature::verify (src/elgamal.rs:38-42): r_i = s_i*H - e_i*P[sig_pk_i]; the SHA3-512 compare stays with the caller */
+  uint32_t n_sigs; const uint8_t* sig_s; const uint8_t* sig_e; const uint32_t* sig_pk;
+  /* balance chains (src/tx/verify.rs:301-336,354-374; src/elgamal.rs:322-377): op j yields point n_points+j =
+   * prev_j + sum(+-P[term]) - amount_j*G, where prev_j >= 0 is an earlier op of the same (account, asset, half) chain
+   * and prev_j < 0 encodes the initial balance point -(1+index).  One op per ciphertext half (commitment / handle). */
+  uint32_t n_ops; const int64_t* op_prev; const uint32_t* op_term_off /* n_ops+1 */; const uint32_t* op_terms /* bit 31 = subtract */;
+  const uint64_t* op_amount; uint32_t max_chain /* longest chain length (>= 1) */;
+  /* CommitmentEqProof::pre_verify (src/proofs.rs:134-211): points P_src,Y0,D_src,C_src,Y1,C_dst,Y2; scalars z_s,z_x,z_r,c,w,bf */
+  uint32_t n_eq; const uint32_t* eq_points; const uint8_t* eq_scalars;
+  /* CiphertextValidityProof::pre_verify (src/proofs.rs:281-361): points C,Y0,P_dest,D_dest,Y1,P_src,D_src,Y2; scalars z_r,z_x,c,w,bf */
+  uint32_t n_val; const uint32_t* val_points; const uint8_t* val_scalars;
+  /* RangeProof::verify_batch views (src/tx/verify.rs:504-514): per proof m (parties, power of two), points
+   * A,S,T1,T2,L[lg],R[lg],V[m] (lg = 6 + log2 m), scalars t_x,t_x_blinding,e_blinding,a,b,c,rho (c = intra-proof random
+   * weight, rho = cross-proof batch factor), challenges y,z,x,w,u[lg] */
+  uint32_t n_rp; const uint32_t* rp_m; const uint32_t* rp_point_off /* n_rp+1 */; const uint32_t* rp_points;
+  const uint8_t* rp_scalars /* n_rp x 7 x 32 */; const uint32_t* rp_chal_off /* n_rp+1, in scalars */; const uint8_t* rp_challenges;
+} xhe_batch;
+
+typedef struct xhe_verdict {
+  int32_t sigma_is_identity;     /* BatchCollector::verify (src/proofs.rs:49-67) */
+  int32_t range_is_identity;     /* RangeProof::verify_batch mega-check */
+  uint8_t sigma_enc[32], range_enc[32];
+  uint8_t sigma_ext[128], range_ext[128];   /* un-normalised partial sums (X,Y,Z,T packed) for multi-GPU combination */
+  uint8_t* point_ok;             /* n_points: decompression flags (caller-allocated) */
+  uint8_t* sig_r;                /* n_sigs x 32: compressed r_i (caller-allocated) */
+  uint8_t* op_out;               /* n_ops x 32: compressed chain outputs = updated balance halves (caller-allocated) */
+} xhe_verdict;
+
+/* returns XHE_OK when the device work completed (verdict fields filled) -- the accept/reject decision and its error
+ * precedence belong to the caller, which knows the transaction structure. */
+int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* batch, xhe_verdict* verdict);
+/* K7: add n partial sums (n x 128 B as produced in *_ext) and test the Ristretto identity; out_enc optional */
+int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t out_enc[32], int32_t* is_identity);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns
  * achieved instructions/s summed over the device in *rate. */

@@ -211,3 +211,121 @@ def verify_batch(blobs, ledger: Ledger, rng_seed=1):
 
 def apply_without_verify(blob, ledger: Ledger):
     return lib.xo_apply_without_verify(_buf(blob), C.c_size_t(len(blob)), ledger.ptr)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# general transaction builder binding (xo_tx_build) -- used to replay the reference's test scenarios (src/lib.rs:254-1093)
+# ---------------------------------------------------------------------------------------------------------------------
+class _TransferSpec(C.Structure):
+    _fields_ = [("asset", C.c_uint8 * 32), ("dest", C.c_uint8 * 32), ("amount", C.c_uint64), ("extra", C.c_char_p), ("extra_len", C.c_uint32), ("has_extra", C.c_int)]
+
+
+class _TxSpec(C.Structure):
+    _fields_ = [("version", C.c_uint8), ("type", C.c_uint8), ("source", C.c_uint8 * 32), ("fee", C.c_uint64), ("nonce", C.c_uint64),
+                ("transfers", C.POINTER(_TransferSpec)), ("n_transfers", C.c_uint32),
+                ("burn_asset", C.c_uint8 * 32), ("burn_amount", C.c_uint64),
+                ("contract", C.c_uint8 * 32), ("call_assets", C.c_char_p), ("call_amounts", C.POINTER(C.c_uint64)), ("n_call_assets", C.c_uint32),
+                ("raw_tail", C.c_char_p), ("raw_tail_len", C.c_uint32), ("n_params", C.c_uint32),
+                ("signers", C.c_char_p), ("n_signers", C.c_uint32), ("threshold", C.c_uint8),
+                ("assets", C.c_char_p), ("balances", C.POINTER(C.c_uint64)), ("n_assets", C.c_uint32)]
+
+
+NATIVE = bytes(32)
+TRANSFERS, BURN, CALL, DEPLOY, MULTISIG = 0, 1, 2, 3, 4
+
+
+class Rng:
+    def __init__(self, seed: bytes):
+        self.buf = (C.c_uint8 * 512)()
+        lib.xo_rng_init(self.buf, seed, C.c_size_t(len(seed)))
+
+    def scalar(self):
+        out = (C.c_uint8 * 32)()
+        lib.xo_rng_scalar(self.buf, out)
+        return bytes(out)
+
+
+class Keypair:
+    """ElGamalKeypair (src/elgamal.rs:155-215): sk scalar bytes, pk compressed."""
+
+    def __init__(self, sk: bytes):
+        self.sk = sk
+        pk = (C.c_uint8 * 32)()
+        lib.xo_pubkey_from_secret(_buf(sk), pk, None)
+        self.pk = bytes(pk)
+
+    @staticmethod
+    def derive(tag: bytes):
+        import hashlib
+        return Keypair(sc_reduce_wide(hashlib.shake_256(b"xhe-test-key" + tag).digest(64)))
+
+    def encrypt(self, amount: int, rng: "Rng"):
+        """pubkey.encrypt(amount) -> compressed ciphertext (src/elgamal.rs:109-114)."""
+        ge = (C.c_uint8 * 160)()   # struct ge: 4 x fe (5 x u64)
+        pk = (C.c_uint8 * 32)()
+        lib.xo_pubkey_from_secret(_buf(self.sk), pk, ge)
+        ct = (C.c_uint8 * 64)()
+        lib.xo_encrypt(ct, ge, C.c_uint64(amount), _buf(rng.scalar()))
+        return bytes(ct)
+
+
+def build_tx(kp: Keypair, ledger: "Ledger", rng: Rng, *, fee=0, nonce=0, version=1, transfers=None, burn=None, call=None, deploy=None,
+             multisig_setup=None, balances, cosigners=None):
+    """TransactionBuilder::build (src/tx/builder.rs:547-554).  `balances` = [(asset, plaintext balance)] in commitment order
+    (native first).  transfers = [(asset, dest_pk, amount[, extra bytes])]; burn = (asset, amount); call = (contract, [(asset, amount)],
+    [(key, value)]); deploy = code bytes; multisig_setup = ([signer pks], threshold); cosigners = [(index, Keypair)]."""
+    sp = _TxSpec()
+    sp.version, sp.fee, sp.nonce = version, fee, nonce
+    keep = []
+    if transfers is not None:
+        sp.type = TRANSFERS
+        arr = (_TransferSpec * max(len(transfers), 1))()
+        for i, t in enumerate(transfers):
+            arr[i].asset[:] = t[0]; arr[i].dest[:] = t[1]; arr[i].amount = t[2]
+            if len(t) > 3 and t[3] is not None:
+                arr[i].extra = t[3]; arr[i].extra_len = len(t[3]); arr[i].has_extra = 1
+        sp.transfers = arr; sp.n_transfers = len(transfers); keep.append(arr)
+    elif burn is not None:
+        sp.type = BURN; sp.burn_asset[:] = burn[0]; sp.burn_amount = burn[1]
+    elif call is not None:
+        sp.type = CALL; sp.contract[:] = call[0]
+        assets = b"".join(a for a, _ in call[1]); amts = (C.c_uint64 * max(len(call[1]), 1))(*[v for _, v in call[1]])
+        tail = b"".join(len(k).to_bytes(4, "little") + k + len(v).to_bytes(4, "little") + v for k, v in call[2])
+        sp.call_assets = assets; sp.call_amounts = amts; sp.n_call_assets = len(call[1]); sp.raw_tail = tail; sp.raw_tail_len = len(tail); sp.n_params = len(call[2])
+        keep += [assets, amts, tail]
+    elif deploy is not None:
+        sp.type = DEPLOY; sp.raw_tail = deploy; sp.raw_tail_len = len(deploy)
+    elif multisig_setup is not None:
+        sp.type = MULTISIG; s = b"".join(multisig_setup[0]); sp.signers = s; sp.n_signers = len(multisig_setup[0]); sp.threshold = multisig_setup[1]; keep.append(s)
+    a = b"".join(x for x, _ in balances); bal = (C.c_uint64 * len(balances))(*[v for _, v in balances])
+    sp.assets = a; sp.balances = bal; sp.n_assets = len(balances)
+    out = C.POINTER(C.c_uint8)()
+    n_ms = len(cosigners) if cosigners else 0
+    ms_idx = bytes(i for i, _ in cosigners) if cosigners else None
+    ms_sk = b"".join(k.sk for _, k in cosigners) if cosigners else None
+    n = lib.xo_tx_build(C.byref(out), C.byref(sp), _buf(kp.sk), ledger.ptr, rng.buf, ms_idx, ms_sk, n_ms)
+    if n == 0:
+        raise RuntimeError("xo_tx_build failed (insufficient funds / bad input)")
+    return C.string_at(out, n)
+
+
+def tx_to_bytes(blob: bytes):
+    """Transaction::to_bytes (src/tx/verify.rs:623-688) -> (bytes, multisig_index)."""
+    view = (C.c_uint8 * 256)()
+    keep = _buf(blob)   # the parsed view points into this buffer
+    if lib.xo_tx_parse(view, keep, C.c_size_t(len(blob))) != 0:
+        return None
+    out = C.POINTER(C.c_uint8)()
+    msi = C.c_size_t(0)
+    lib.xo_tx_to_bytes.restype = C.c_size_t
+    n = lib.xo_tx_to_bytes(view, C.byref(out), C.byref(msi))
+    lib.xo_tx_free(view)
+    return C.string_at(out, n), msi.value
+
+
+def resign(blob: bytes, kp: Keypair, rng: Rng):
+    """Sign again after a mutation, so the tampering survives the signature check and reaches the proof checks."""
+    b = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+    if not lib.xo_resign(b, C.c_size_t(len(blob)), _buf(kp.sk), rng.buf):
+        return None
+    return bytes(b)

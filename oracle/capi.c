@@ -117,3 +117,10 @@ double xo_msm_timed(const uint8_t *scalars, const uint8_t *points, size_t n, uin
   struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0); ge r; ge_msm_vartime(&r, s, p, n); clock_gettime(CLOCK_MONOTONIC, &t1);
   ristretto_encode(out, &r); free(s); free(p); return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+/* re-sign a (possibly mutated) transaction in place: recompute to_bytes and the trailing 64-byte signature */
+int xo_resign(uint8_t *blob, size_t len, const sc *sk, xo_rng *rng) {
+  xo_tx tx; if (xo_tx_parse(&tx, blob, len)) return 0;
+  uint8_t *bytes; size_t msi; size_t nb = xo_tx_to_bytes(&tx, &bytes, &msi); xo_tx_free(&tx);
+  uint8_t pk[32]; xo_pubkey_from_secret(sk, pk, NULL);
+  xo_sign(blob + len - 64, sk, pk, bytes, nb, rng); free(bytes); return 1;
+}

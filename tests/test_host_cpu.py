@@ -1,0 +1,92 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/xhe.h declares, fails loudly without
+a device, and its host-side building blocks (Merlin, SHA3, BLAKE3, wide reduction, to_bytes) agree with public known
+answers and with the oracle."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import xelis_he_b200 as xhe
+    return xhe.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "xhe.h")).read()
+    names = sorted(set(re.findall(r"\b(xhe_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    import xelis_he_b200 as xhe
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(xhe.XheError):
+        xhe.Ctx(0, party_capacity=2)
+
+
+def test_product_does_not_import_oracle():
+    """the oracle is test infrastructure: nothing under xelis_he_b200/ may import, include, link or dlopen it"""
+    bad = re.compile(r"^\s*(import|from)\s+oracle\b|#include\s+\"[^\"]*oracle|liboracle|dlopen[^\n]*oracle", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "xelis_he_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not bad.search(src), os.path.join(dirpath, f)
+
+
+def test_host_merlin_and_hashes(lib):
+    out = C.create_string_buffer(32)
+    lib.xheh_merlin_test(b"test protocol", b"some label", b"some data", C.c_size_t(9), b"challenge", out, C.c_size_t(32))
+    assert out.raw.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    blake3 = pytest.importorskip("blake3")
+    for n in (0, 1, 71, 72, 73, 135, 136, 137, 1023, 1024, 1025, 1500, 3073, 5000):
+        msg = bytes((i * 7 + 3) & 0xFF for i in range(n))
+        o64 = C.create_string_buffer(64); lib.xheh_sha3_512(msg, C.c_size_t(n), o64)
+        assert o64.raw == hashlib.sha3_512(msg).digest()
+        o200 = C.create_string_buffer(200); lib.xheh_shake256(msg, C.c_size_t(n), o200, C.c_size_t(200))
+        assert o200.raw == hashlib.shake_256(msg).digest(200)
+        o32 = C.create_string_buffer(32); lib.xheh_blake3(msg, C.c_size_t(n), o32)
+        assert o32.raw == blake3.blake3(msg).digest()
+
+
+def test_host_wide_reduction(lib):
+    L = 2**252 + 27742317777372353535851937790883648493
+    stream = hashlib.shake_256(b"wide").digest(64 * 500)
+    cases = [stream[64 * i:64 * i + 64] for i in range(500)] + [bytes(64), b"\xff" * 64, (L - 1).to_bytes(64, "little"), L.to_bytes(64, "little"), ((L << 256) + L - 1).to_bytes(64, "little")]
+    for x in cases:
+        o = C.create_string_buffer(32); lib.xheh_reduce_wide(x, o)
+        assert int.from_bytes(o.raw, "little") == int.from_bytes(x, "little") % L
+        assert o.raw == oracle.sc_reduce_wide(x)
+
+
+def test_host_to_bytes_matches_oracle(lib):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import scenarios
+    blobs = []
+    for f in (scenarios.burn_world, scenarios.realistic_world, scenarios.transfer_with_extra_data_world):
+        blobs += f()[1]
+    blobs += list(scenarios.multisig_world()[1].values()) + scenarios.mixed_types_world(6)[1]
+    lib.xheh_tx_to_bytes.restype = C.c_int32
+    for b in blobs:
+        want, msi = oracle.tx_to_bytes(b)
+        out = C.create_string_buffer(len(b) + 64); n = C.c_size_t(0); m = C.c_size_t(0)
+        assert lib.xheh_tx_to_bytes(b, C.c_size_t(len(b)), out, C.c_size_t(len(out)), C.byref(n), C.byref(m)) == 0
+        assert out.raw[:n.value] == want and m.value == msi
+    # framing errors are rejected by both parsers
+    for bad in (blobs[0][:-1], blobs[0] + b"\x00", b"\x00" * 100):
+        out = C.create_string_buffer(4096); n = C.c_size_t(0); m = C.c_size_t(0)
+        assert lib.xheh_tx_to_bytes(bad, C.c_size_t(len(bad)), out, C.c_size_t(4096), C.byref(n), C.byref(m)) == 11
+        assert oracle.tx_to_bytes(bad) is None

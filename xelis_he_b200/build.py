@@ -12,7 +12,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    host = os.path.join(HERE, "host")
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")) + sorted(os.path.join(host, f) for f in os.listdir(host) if f.endswith(".cpp"))
 
 
 def needs_build():

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, 
         asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.u32 %3, %8, %9, %3;"
                      "mad.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
                      : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(b), "r"(a));
+      } else if (WHICH == 3) {
+        // carry-chained wide mads (what the radix-2^32 field multiply issues): 4 chains of 2 slots
+        asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.u32 %3, %8, %9, %3;"
+                     "mad.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
+                     : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(b), "r"(a));
       } else {
         asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
                      "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
@@ -221,6 +226,7 @@ extern "C" int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate) {
     if (which == 0) k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else if (which == 1) k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else if (which == 3) k_int_peak<3><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
+    else if (which == 3) k_int_peak<3><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else k_int_peak<2><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     XHE_LAUNCHED(ctx);
     cudaEventRecord(e1, ctx->stream); XHE_CUDA_OK(ctx, cudaEventSynchronize(e1));
@@ -253,12 +259,16 @@ __global__ void k_bench_op(uint32_t* out, const uint32_t* in, int iters, unsigne
   if (r == 0x12345u) out[0] = r;
 }
 extern "C" int32_t xhe_bench_op(xhe_ctx* ctx, int op, int threads_per_block, int blocks, int iters, double* cycles_per_op) {
+  // cycles_per_op[0]: latency seen by warp 0 (clock64); cycles_per_op[1]: whole-kernel ns per (iteration x warp per SMSP)
   uint32_t *d_in, *d_out; unsigned long long* d_c;
   XHE_CUDA_OK(ctx, cudaMalloc(&d_in, 32 * 32)); XHE_CUDA_OK(ctx, cudaMalloc(&d_out, 64)); XHE_CUDA_OK(ctx, cudaMalloc(&d_c, 8));
   uint32_t h[256]; for (int i = 0; i < 256; i++) h[i] = 0x9e3779b9u * (i + 1) + 12345u;
   for (int i = 0; i < 32; i++) h[8 * i + 7] &= 0x7fffffffu;
   cudaMemcpy(d_in, h, sizeof h, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0;
   for (int rep = 0; rep < 2; rep++) {
+    cudaEventRecord(e0, ctx->stream);
     switch (op) {
       case 0: k_bench_op<0><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
       case 1: k_bench_op<1><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
@@ -267,10 +277,15 @@ extern "C" int32_t xhe_bench_op(xhe_ctx* ctx, int op, int threads_per_block, int
       case 4: k_bench_op<4><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
       default: k_bench_op<5><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
     }
+    cudaEventRecord(e1, ctx->stream);
     XHE_LAUNCHED(ctx);
-    XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    XHE_CUDA_OK(ctx, cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
   }
   unsigned long long c; cudaMemcpy(&c, d_c, 8, cudaMemcpyDeviceToHost);
-  *cycles_per_op = (double)c / iters;
+  cycles_per_op[0] = (double)c / iters;
+  double warp_ops_per_smsp = (double)blocks * (threads_per_block / 32) * iters / (ctx->sm_count * 4.0);
+  cycles_per_op[1] = ms * 1e6 / warp_ops_per_smsp;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_c); return XHE_OK;
 }

@@ -33,7 +33,7 @@ struct MsmPlan {
   int seg_log;          // log2 of buckets per level-1 segment
   // workspace offsets (bytes)
   size_t n_tiles, max_runs;
-  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_glist, off_runs, off_runoff, off_part, off_partg, off_pstart, off_pcount, off_nodes_a, off_nodes_b, off_flag, total;
+  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_glist, off_runs, off_runoff, off_part, off_partg, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_flag, total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -65,6 +65,7 @@ MsmPlan make_plan(size_t n) {
   p.off_partg = o; o = align_up(o + 4 * p.max_runs, 256);
   p.off_pstart = o; o = align_up(o + 4 * p.total_buckets, 256);
   p.off_pcount = o; o = align_up(o + 4 * p.total_buckets, 256);
+  p.off_heavy = o; o = align_up(o + 4 * (p.total_buckets + 4), 256);
   size_t nodes1 = p.total_buckets >> p.seg_log;
   p.off_nodes_a = o; o = align_up(o + 256 * nodes1, 256);
   p.off_nodes_b = o; o = align_up(o + 256 * ((nodes1 + 31) / 32 + (size_t)p.W), 256);
@@ -222,6 +223,34 @@ __global__ void __launch_bounds__(256) k_msm_bucket_index(const uint32_t* __rest
   if (s == 0 || part_g[s - 1] != g) pstart[g] = (uint32_t)s;
 }
 
+// buckets whose partial list is long (under-filled top window, skewed scalars) are folded by a whole block first
+#define HEAVY_PARTIALS 6
+__global__ void __launch_bounds__(256) k_msm_find_heavy(const uint32_t* __restrict__ pcount, size_t m, uint32_t* __restrict__ heavy /* [0] = count, [1..] = bucket ids */) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < m && pcount[g] > HEAVY_PARTIALS) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)g;
+}
+#define FOLD_THREADS 128
+__global__ void __launch_bounds__(FOLD_THREADS) k_msm_fold_heavy(uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount, const uint32_t* __restrict__ heavy) {
+  __shared__ uint32_t sm[FOLD_THREADS * 32];
+  uint32_t nh = heavy[0];
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    uint32_t g = heavy[1 + h], ps = pstart[g], pc = pcount[g];
+    ge acc = ge_identity(), s;
+    for (uint32_t j = threadIdx.x; j < pc; j += FOLD_THREADS) { ld_ge(s, part + 32 * (size_t)(ps + j)); acc = ge_add(acc, s); }
+    st_ge(sm + 32 * threadIdx.x, acc);
+    __syncthreads();
+    for (int stride = FOLD_THREADS / 2; stride >= 1; stride >>= 1) {
+      if ((int)threadIdx.x < stride && threadIdx.x + stride < min(pc, (uint32_t)FOLD_THREADS)) {
+        ge a, b; ld_ge(a, sm + 32 * threadIdx.x); ld_ge(b, sm + 32 * (threadIdx.x + stride));
+        st_ge(sm + 32 * threadIdx.x, ge_add(a, b));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { ge r; ld_ge(r, sm); st_ge(part + 32 * (size_t)ps, r); pcount[g] = 1; }
+    __syncthreads();
+  }
+}
+
 // ---- bucket reduction -----------------------------------------------------------------------------------------------
 // node = (run, wsum): run = sum of the bucket sums in its range, wsum = sum (b - lo) * S_b (weights relative to the range)
 __global__ void __launch_bounds__(128) k_msm_seg(const uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
@@ -319,11 +348,12 @@ int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_nie
   uint32_t *counts = (uint32_t*)(ws + p.off_counts), *offsets = (uint32_t*)(ws + p.off_offsets), *cursor = (uint32_t*)(ws + p.off_cursor),
            *blocksums = (uint32_t*)(ws + p.off_blocksums), *list = (uint32_t*)(ws + p.off_list), *glist = (uint32_t*)(ws + p.off_glist),
            *runs = (uint32_t*)(ws + p.off_runs), *run_off = (uint32_t*)(ws + p.off_runoff), *part = (uint32_t*)(ws + p.off_part), *part_g = (uint32_t*)(ws + p.off_partg),
-           *pstart = (uint32_t*)(ws + p.off_pstart), *pcount = (uint32_t*)(ws + p.off_pcount), *nodes_a = (uint32_t*)(ws + p.off_nodes_a),
+           *pstart = (uint32_t*)(ws + p.off_pstart), *pcount = (uint32_t*)(ws + p.off_pcount), *heavy = (uint32_t*)(ws + p.off_heavy), *nodes_a = (uint32_t*)(ws + p.off_nodes_a),
            *nodes_b = (uint32_t*)(ws + p.off_nodes_b), *flag = d_bad_flag ? (uint32_t*)d_bad_flag : (uint32_t*)(ws + p.off_flag);
   const size_t m = p.total_buckets;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, 4 * (m + 1), st));
   XHE_CUDA_OK(ctx, cudaMemsetAsync(pcount, 0, 4 * m, st));
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(heavy, 0, 4, st));
   if (!d_bad_flag) XHE_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, 4, st));
   k_msm_count<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, counts, flag); XHE_LAUNCHED(ctx);
   unsigned nb = nblk(m, SCAN_THREADS * SCAN_ITEMS);
@@ -346,6 +376,8 @@ int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_nie
   }
   XHE_LAUNCHED(ctx);
   k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(part_g, run_off + p.n_tiles, p.max_runs, pstart, pcount); XHE_LAUNCHED(ctx);
+  k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(pcount, m, heavy); XHE_LAUNCHED(ctx);
+  k_msm_fold_heavy<<<std::min<size_t>(m, 2048), FOLD_THREADS, 0, st>>>(part, pstart, pcount, heavy); XHE_LAUNCHED(ctx);
   size_t n_nodes = m >> p.seg_log;
   k_msm_seg<<<nblk(n_nodes, 128), 128, 0, st>>>(part, pstart, pcount, n_nodes, p.seg_log, nodes_a); XHE_LAUNCHED(ctx);
   uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;

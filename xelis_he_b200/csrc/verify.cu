@@ -1,0 +1,524 @@
+// verify.cu -- device part of Transaction::verify_batch (reference src/tx/verify.rs:487-517): everything between the
+// host-derived Fiat-Shamir challenges and the two identity checks.
+//
+//   k_decompress         all referenced points                      (kernels_point.cu)
+//   k_sig_r              r = s*H - e*P per signature                (src/elgamal.rs:38-42)
+//   k_op_delta           per balance-chain op: sum(+-P) - amount*G  (src/tx/verify.rs:107-144, src/elgamal.rs:322-377)
+//   k_op_jump            pointer-jumping prefix sums along each (account, asset) chain   [log2(max_chain) rounds]
+//   k_op_finish          prev + delta -> compressed balance half + affine-Niels MSM input (src/tx/verify.rs:314,329-336,365-374)
+//   k_sigma_weights      7 / 8 weighted scalars per sigma proof + g/h contributions       (src/proofs.rs:181-208,326-358)
+//   k_rp_prep            per range proof: batch inversion, delta(y,z), dynamic scalars     (bulletproofs verify)
+//   k_rp_gens            per range proof block: s-vector DP, g_i / h_i, accumulate static  (idem)
+//   k_reduce_scalars     sum mod l of per-proof / per-block partial scalars
+//   k_gather_niels       MSM operand assembly
+//   msm x 2              sigma MSM and range MSM (msm.cu), partial sums returned un-normalised for multi-GPU combination
+#include "xhe_internal.cuh"
+#include <vector>
+#include <string.h>
+using namespace xhe;
+
+int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag);
+extern "C" size_t xhe_msm_workspace_bytes(const xhe_ctx*, size_t n);
+
+namespace {
+
+__device__ __forceinline__ void ld_sc(sc& r, const uint32_t* p) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void ld_sc_rw(sc& r, const uint32_t* p) {
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *(reinterpret_cast<const uint4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st_sc(uint32_t* p, const sc& r) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ sc mmul(const sc& a, const sc& b) { return sc_montmul(a, b); }
+__device__ __forceinline__ sc mont_one() { return sc_load_const(SC_R1); }
+
+// ---- fixed-base tables (built once per ctx) -------------------------------------------------------------------------
+// tab8[w][j-1] = j * 2^(8w) * base as affine Niels, w < nwin, j = 1..255
+__global__ void k_build_tab8(const uint32_t* __restrict__ base_niels, int nwin, uint32_t* __restrict__ tab) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwin) return;
+  ge_niels bn; ld_niels(bn, base_niels);
+  ge b = ge_from_niels(bn);
+  for (int k = 0; k < 8 * w; k++) b = ge_double(b);
+  ge acc = b;
+  for (int j = 1; j <= 255; j++) {
+    fe zi = fe_invert(acc.Z);
+    ge_aff a; a.x = fe_mul(acc.X, zi); a.y = fe_mul(acc.Y, zi);
+    st_niels(tab + 24 * ((size_t)w * 255 + (j - 1)), niels_from_affine(a));
+    acc = ge_add(acc, b);
+  }
+}
+// acc += s * base using the 8-bit fixed-base table (s given as nbytes little-endian bytes); optionally negated
+__device__ __forceinline__ ge fixed_base_mul(const uint32_t* __restrict__ tab, const uint8_t* bytes, int nbytes) {
+  ge acc = ge_identity();
+  for (int w = 0; w < nbytes; w++) {
+    uint32_t d = bytes[w];
+    if (d) { ge_niels q; ld_niels(q, tab + 24 * ((size_t)w * 255 + (d - 1))); acc = ge_madd(acc, q); }
+  }
+  return acc;
+}
+
+// ---- K8: signature group part ----------------------------------------------------------------------------------------
+// r = s*H - e*P.  s*H from the 32-window fixed-base table of H; (-e)*P by 4-bit fixed-window double-and-add.
+__global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in, const uint32_t* __restrict__ e_in, const uint32_t* __restrict__ pk_idx,
+                                              const uint32_t* __restrict__ pt_aff, const uint8_t* __restrict__ pt_ok, const uint32_t* __restrict__ tabH,
+                                              uint32_t n, uint8_t* __restrict__ r_enc, uint32_t* __restrict__ scratch /* n x 16 x 32 words */) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc s, e; ld_sc(s, s_in + 8 * i); ld_sc(e, e_in + 8 * i);
+  sc ne = sc_neg(e);
+  uint8_t sb[32]; sc_tobytes(sb, s);
+  ge acc_h = fixed_base_mul(tabH, sb, 32);
+  // table of 0..15 multiples of P in global scratch (extended coordinates)
+  uint32_t pi = pk_idx[i];
+  ge_aff pa; ld_fe(pa.x, pt_aff + 16 * (size_t)pi); ld_fe(pa.y, pt_aff + 16 * (size_t)pi + 8);
+  ge P = ge_from_affine(pa);
+  uint32_t* tab = scratch + (size_t)i * 16 * 32;
+  ge cur = ge_identity();
+  for (int j = 0; j < 16; j++) { st_ge(tab + 32 * j, cur); cur = ge_add(cur, P); }
+  ge acc = ge_identity();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) { acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); }
+    uint32_t d = (ne.v[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (d) { ge t; ld_ge(t, tab + 32 * d); acc = ge_add(acc, t); }
+  }
+  acc = ge_add(acc, acc_h);
+  (void)pt_ok;
+  encode_words(r_enc + 32 * (size_t)i, acc);
+}
+
+// ---- balance chains -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_op_delta(const uint32_t* __restrict__ term_off, const uint32_t* __restrict__ terms, const uint64_t* __restrict__ amount,
+                                                  const uint32_t* __restrict__ pt_niels, const uint32_t* __restrict__ tabG, uint32_t n_ops, uint32_t* __restrict__ delta) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_ops) return;
+  ge acc = ge_identity();
+  for (uint32_t k = term_off[j]; k < term_off[j + 1]; k++) {
+    uint32_t t = terms[k];
+    ge_niels q; ld_niels(q, pt_niels + 24 * (size_t)(t & 0x7fffffffu));
+    acc = ge_madd(acc, niels_cneg(q, (t >> 31) != 0));
+  }
+  uint64_t a = amount[j];
+  if (a) {
+    uint8_t b[8];
+    for (int k = 0; k < 8; k++) b[k] = (uint8_t)(a >> (8 * k));
+    ge ag = fixed_base_mul(tabG, b, 8);
+    acc = ge_add(acc, ge_neg(ag));      // balance - amount*G
+  }
+  st_ge(delta + 32 * (size_t)j, acc);
+}
+// one pointer-jumping round: acc'[j] = acc[j] + acc[ptr[j]], ptr'[j] = ptr[ptr[j]]   (ptr < 0: reached the chain head)
+__global__ void __launch_bounds__(128) k_op_jump(const uint32_t* __restrict__ acc_in, const long long* __restrict__ ptr_in, uint32_t n_ops,
+                                                 uint32_t* __restrict__ acc_out, long long* __restrict__ ptr_out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_ops) return;
+  long long p = ptr_in[j];
+  ge a; ld_ge(a, acc_in + 32 * (size_t)j);
+  if (p >= 0) { ge b; ld_ge(b, acc_in + 32 * (size_t)p); a = ge_add(a, b); p = ptr_in[p]; }
+  st_ge(acc_out + 32 * (size_t)j, a); ptr_out[j] = p;
+}
+// out_j = initial balance half + accumulated deltas; emit encoding, affine and affine-Niels (MSM operand) forms
+__global__ void __launch_bounds__(128) k_op_finish(const uint32_t* __restrict__ acc, const long long* __restrict__ ptr, uint32_t n_ops, uint32_t n_points,
+                                                   uint32_t* __restrict__ pt_aff, uint32_t* __restrict__ pt_niels, uint8_t* __restrict__ out_enc) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_ops) return;
+  long long p = ptr[j];          // always < 0 after enough rounds: -(1 + initial point index)
+  uint32_t init = (uint32_t)(-(p + 1));
+  ge_aff ia; ld_fe(ia.x, pt_aff + 16 * (size_t)init); ld_fe(ia.y, pt_aff + 16 * (size_t)init + 8);
+  ge a; ld_ge(a, acc + 32 * (size_t)j);
+  ge r = ge_add(ge_from_affine(ia), a);
+  encode_words(out_enc + 32 * (size_t)j, r);
+  fe zi = fe_invert(r.Z);
+  ge_aff ra; ra.x = fe_mul(r.X, zi); ra.y = fe_mul(r.Y, zi);
+  size_t slot = (size_t)n_points + j;
+  st_fe(pt_aff + 16 * slot, ra.x); st_fe(pt_aff + 16 * slot + 8, ra.y);
+  st_niels(pt_niels + 24 * slot, niels_from_affine(ra));
+}
+
+// ---- sigma proof weights ----------------------------------------------------------------------------------------------
+// eq proof (src/proofs.rs:181-208): scalars [z_s, -1, w z_s, -w c, -w, -w^2 c, -w^2] * bf ; g += (w + w^2) z_x bf ; h += (w^2 z_r - c) bf
+// validity proof (src/proofs.rs:326-358): [-c, -1, w z_r, -w c, -w, w^2 z_r, -w^2 c, -w^2] * bf ; g += z_x bf ; h += z_r bf
+__global__ void __launch_bounds__(128) k_sigma_weights(const uint32_t* __restrict__ eq_sc, uint32_t n_eq, const uint32_t* __restrict__ val_sc, uint32_t n_val,
+                                                       uint32_t* __restrict__ out_sc /* 7 n_eq + 8 n_val */, uint32_t* __restrict__ gh /* 2 per proof */) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_eq + n_val) return;
+  const sc RR = sc_load_const(SC_RR);
+  sc one; one = sc_zero(); one.v[0] = 1;
+  if (i < n_eq) {
+    sc z_s, z_x, z_r, c, w, bf; const uint32_t* p = eq_sc + 48 * (size_t)i;
+    ld_sc(z_s, p); ld_sc(z_x, p + 8); ld_sc(z_r, p + 16); ld_sc(c, p + 24); ld_sc(w, p + 32); ld_sc(bf, p + 40);
+    sc bfm = mmul(bf, RR);                          // bf * R : multiplying a plain value by it yields the plain product
+    sc wm = mmul(w, RR);
+    sc wbf = mmul(w, bfm);                          // w bf
+    sc wwbf = mmul(wm, wbf);                        // w^2 bf
+    sc cm = mmul(c, RR);
+    uint32_t* o = out_sc + 8 * (size_t)(7 * i);
+    sc zs_bf = mmul(z_s, bfm);
+    st_sc(o, zs_bf);                                // z_s bf
+    st_sc(o + 8, sc_neg(bf));                       // -bf
+    st_sc(o + 16, mmul(wm, zs_bf));                 // w z_s bf
+    sc wcbf = mmul(cm, wbf);
+    st_sc(o + 24, sc_neg(wcbf));                    // -w c bf
+    st_sc(o + 32, sc_neg(wbf));                     // -w bf
+    st_sc(o + 40, sc_neg(mmul(cm, wwbf)));          // -w^2 c bf
+    st_sc(o + 48, sc_neg(wwbf));                    // -w^2 bf
+    sc zxm = mmul(z_x, RR);
+    st_sc(gh + 16 * (size_t)i, mmul(zxm, sc_add(wbf, wwbf)));                            // (w + w^2) z_x bf
+    sc zrm = mmul(z_r, RR);
+    st_sc(gh + 16 * (size_t)i + 8, sc_sub(mmul(zrm, wwbf), mmul(c, bfm)));               // (w^2 z_r - c) bf
+  } else {
+    uint32_t k = i - n_eq;
+    sc z_r, z_x, c, w, bf; const uint32_t* p = val_sc + 40 * (size_t)k;
+    ld_sc(z_r, p); ld_sc(z_x, p + 8); ld_sc(c, p + 16); ld_sc(w, p + 24); ld_sc(bf, p + 32);
+    sc bfm = mmul(bf, RR), wm = mmul(w, RR), cm = mmul(c, RR), zrm = mmul(z_r, RR);
+    sc wbf = mmul(w, bfm), wwbf = mmul(wm, wbf);
+    uint32_t* o = out_sc + 8 * (size_t)(7 * n_eq + 8 * k);
+    st_sc(o, sc_neg(mmul(c, bfm)));                 // -c bf
+    st_sc(o + 8, sc_neg(bf));                       // -bf
+    st_sc(o + 16, mmul(zrm, wbf));                  // w z_r bf
+    st_sc(o + 24, sc_neg(mmul(cm, wbf)));           // -w c bf
+    st_sc(o + 32, sc_neg(wbf));                     // -w bf
+    st_sc(o + 40, mmul(zrm, wwbf));                 // w^2 z_r bf
+    st_sc(o + 48, sc_neg(mmul(cm, wwbf)));          // -w^2 c bf
+    st_sc(o + 56, sc_neg(wwbf));                    // -w^2 bf
+    st_sc(gh + 16 * (size_t)i, mmul(z_x, bfm));     // z_x bf
+    st_sc(gh + 16 * (size_t)i + 8, mmul(z_r, bfm)); // z_r bf
+  }
+}
+
+// sum mod l of `count` scalars with stride (in scalars) -> one scalar per (blockIdx.y) column; two-stage by repeated launch
+__global__ void __launch_bounds__(256) k_reduce_scalars(const uint32_t* __restrict__ in, uint32_t count, uint32_t stride, uint32_t col_stride, uint32_t* __restrict__ out, uint32_t out_stride) {
+  __shared__ uint32_t sm[256 * 8];
+  uint32_t col = blockIdx.y;
+  sc acc = sc_zero();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    sc v; ld_sc_rw(v, in + 8 * ((size_t)k * stride + (size_t)col * col_stride));
+    acc = sc_add(acc, v);
+  }
+  for (int q = 0; q < 8; q++) sm[threadIdx.x * 8 + q] = acc.v[q];
+  __syncthreads();
+  for (int s = 128; s >= 1; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      sc a, b;
+      for (int q = 0; q < 8; q++) { a.v[q] = sm[threadIdx.x * 8 + q]; b.v[q] = sm[(threadIdx.x + s) * 8 + q]; }
+      a = sc_add(a, b);
+      for (int q = 0; q < 8; q++) sm[threadIdx.x * 8 + q] = a.v[q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sc r; for (int q = 0; q < 8; q++) r.v[q] = sm[q]; st_sc(out + 8 * ((size_t)blockIdx.x * out_stride + col), r); }
+}
+
+// ---- range proofs ----------------------------------------------------------------------------------------------------
+// per-proof derived scalars written by k_rp_prep (all in MONTGOMERY form unless noted), RP_DER scalars per proof:
+enum { D_ALLINV = 0, D_YINV, D_RZ /* rho z */, D_RA /* rho a */, D_RB /* rho b */, D_RZZ /* rho z^2 */, D_Z, D_USQ /* lg entries */ };
+#define RP_MAX_LG 16
+#define RP_DER (7 + 2 * RP_MAX_LG)   // + u_j^2 [lg], y_inv^(2^j) [lg]
+
+__global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ sc_in /* 7 per proof */, const uint32_t* __restrict__ chal_off,
+                                                const uint32_t* __restrict__ chal, const uint32_t* __restrict__ dyn_off /* term offset per proof */, uint32_t n_rp,
+                                                uint32_t* __restrict__ der, uint32_t* __restrict__ dyn_sc, uint32_t* __restrict__ gh /* 2 per proof: G (B) and H (B_blinding) */) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_rp) return;
+  const sc RR = sc_load_const(SC_RR);
+  uint32_t m = m_arr[p]; int lgm = 31 - __clz(m); int lg = 6 + lgm; uint32_t N = 64u * m;
+  sc t_x, t_x_bl, e_bl, a, b, c, rho; const uint32_t* s7 = sc_in + 56 * (size_t)p;
+  ld_sc(t_x, s7); ld_sc(t_x_bl, s7 + 8); ld_sc(e_bl, s7 + 16); ld_sc(a, s7 + 24); ld_sc(b, s7 + 32); ld_sc(c, s7 + 40); ld_sc(rho, s7 + 48);
+  const uint32_t* ch = chal + 8 * (size_t)chal_off[p];
+  sc y, z, x, w; ld_sc(y, ch); ld_sc(z, ch + 8); ld_sc(x, ch + 16); ld_sc(w, ch + 24);
+  // to Montgomery form
+  sc ym = mmul(y, RR), zm = mmul(z, RR), xm = mmul(x, RR), wm = mmul(w, RR), am = mmul(a, RR), bm = mmul(b, RR), cm = mmul(c, RR), rm = mmul(rho, RR);
+  sc onem = mont_one();
+  // batch inversion of u_0..u_{lg-1}, y, (y - 1)
+  sc um[RP_MAX_LG + 2], pre[RP_MAX_LG + 2];
+  for (int j = 0; j < lg; j++) { sc u; ld_sc(u, ch + 32 + 8 * j); um[j] = mmul(u, RR); }
+  um[lg] = ym; um[lg + 1] = sc_sub(ym, onem);
+  bool y_is_one = sc_iszero(um[lg + 1]);
+  if (y_is_one) um[lg + 1] = onem;
+  sc accp = onem;
+  for (int j = 0; j < lg + 2; j++) { pre[j] = accp; accp = mmul(accp, um[j]); }
+  sc inv = sc_mont_invert(accp);
+  sc uinv[RP_MAX_LG + 2];
+  for (int j = lg + 1; j >= 0; j--) { uinv[j] = mmul(inv, pre[j]); inv = mmul(inv, um[j]); }
+  // allinv = prod u_j^-1
+  sc allinv = onem;
+  for (int j = 0; j < lg; j++) allinv = mmul(allinv, uinv[j]);
+  sc yinv = uinv[lg], ym1inv = uinv[lg + 1];
+  uint32_t* d = der + 8 * (size_t)RP_DER * p;
+  sc zzm = mmul(zm, zm);
+  st_sc(d + 8 * D_ALLINV, allinv); st_sc(d + 8 * D_YINV, yinv);
+  st_sc(d + 8 * D_RZ, mmul(rm, zm)); st_sc(d + 8 * D_RA, mmul(rm, am)); st_sc(d + 8 * D_RB, mmul(rm, bm)); st_sc(d + 8 * D_RZZ, mmul(rm, zzm)); st_sc(d + 8 * D_Z, zm);
+  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), mmul(um[j], um[j])); st_sc(d + 8 * (D_USQ + RP_MAX_LG + j), yp); yp = mmul(yp, yp); } }
+  // dynamic scalars (plain form): A: rho ; S: rho x ; T1: rho c x ; T2: rho c x^2 ; L_j: rho u_j^2 ; R_j: rho u_j^-2 ; V_j: rho c z^2 z^j
+  uint32_t* o = dyn_sc + 8 * (size_t)dyn_off[p];
+  sc rx = mmul(rm, xm), rcx = mmul(rx, cm), rcxx = mmul(rcx, xm);
+  st_sc(o, rho); st_sc(o + 8, sc_from_mont(rx)); st_sc(o + 16, sc_from_mont(rcx)); st_sc(o + 24, sc_from_mont(rcxx));
+  for (int j = 0; j < lg; j++) { st_sc(o + 8 * (4 + j), sc_from_mont(mmul(rm, mmul(um[j], um[j])))); st_sc(o + 8 * (4 + lg + j), sc_from_mont(mmul(rm, mmul(uinv[j], uinv[j])))); }
+  sc rczz = mmul(mmul(rm, cm), zzm), zj = onem, sum_z = sc_zero();
+  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), sc_from_mont(mmul(rczz, zj))); sum_z = sc_add(sum_z, zj); zj = mmul(zj, zm); }
+  // delta(y,z) = (z - z^2) * sum_{i<N} y^i - z^3 * (2^64 - 1) * sum_{j<m} z^j
+  sc yN = ym; for (int j = 0; j < lg; j++) yN = mmul(yN, yN);
+  sc sum_y = y_is_one ? mmul(sc_from_u64(N), RR) : mmul(sc_sub(yN, onem), ym1inv);
+  sc two64m1 = mmul(sc_from_u64(0xffffffffffffffffull), RR);
+  sc delta = sc_sub(mmul(sc_sub(zm, zzm), sum_y), mmul(mmul(mmul(zzm, zm), two64m1), sum_z));
+  // B (G): rho (w (t_x - a b) + c (delta - t_x)) ; B_blinding (H): rho (-e_bl - c t_x_bl)
+  sc txm = mmul(t_x, RR);
+  sc gB = mmul(rm, sc_add(mmul(wm, sc_sub(txm, mmul(am, bm))), mmul(cm, sc_sub(delta, txm))));
+  sc hB = mmul(rm, sc_neg(sc_add(mmul(e_bl, RR), mmul(cm, mmul(t_x_bl, RR)))));
+  st_sc(gh + 16 * (size_t)p, sc_from_mont(gB)); st_sc(gh + 16 * (size_t)p + 8, sc_from_mont(hB));
+}
+
+// 2^k in Montgomery form for k < 64 (filled once per ctx)
+__global__ void k_pow2_table(uint32_t* __restrict__ tab) {
+  int k = threadIdx.x; if (k >= 64) return;
+  sc v = sc_from_u64(1ull << k);
+  st_sc(tab + 8 * k, sc_montmul(v, sc_load_const(SC_RR)));
+}
+
+// persistent blocks: block b handles proofs b, b+grid, ...; accumulates rho*(-z - a s_i) and rho*(z + y^-i (z^2 z^j 2^k - b s_{N-1-i}))
+// into its private partial buffer part[b][2*Nmax] (plain form).  s-vector and y^-i by doubling DP in shared memory.
+#define RPG_THREADS 256
+__global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
+                                                         uint32_t Nmax, uint32_t* __restrict__ part) {
+  extern __shared__ uint32_t sm[];           // s[N] then ypow[N], 8 words each (Montgomery form)
+  uint32_t* my = part + 8 * (size_t)blockIdx.x * 2 * Nmax;
+  for (uint32_t i = threadIdx.x; i < 2 * Nmax; i += RPG_THREADS) st_sc(my + 8 * i, sc_zero());
+  for (uint32_t p = blockIdx.x; p < n_rp; p += gridDim.x) {
+    uint32_t m = m_arr[p]; int lg = 6 + (31 - __clz(m)); uint32_t N = 64u * m;
+    const uint32_t* d = der + 8 * (size_t)RP_DER * p;
+    uint32_t *s = sm, *yp = sm + 8 * (size_t)N;
+    __syncthreads();
+    if (threadIdx.x == 0) { sc a0; ld_sc(a0, d + 8 * D_ALLINV); st_sc(s, a0); st_sc(yp, mont_one()); }
+    __syncthreads();
+    for (int r = 0; r < lg; r++) {
+      sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - r))); ld_sc(ypw, d + 8 * (D_USQ + RP_MAX_LG + r));
+      uint32_t half = 1u << r;
+      for (uint32_t i = half + threadIdx.x; i < 2 * half; i += RPG_THREADS) {
+        sc a, b; ld_sc_rw(a, s + 8 * (i - half)); ld_sc_rw(b, yp + 8 * (i - half));
+        st_sc(s + 8 * i, mmul(a, usq)); st_sc(yp + 8 * i, mmul(b, ypw));
+      }
+      __syncthreads();
+    }
+    sc rz, ra, rb, rzz, zm; ld_sc(rz, d + 8 * D_RZ); ld_sc(ra, d + 8 * D_RA); ld_sc(rb, d + 8 * D_RB); ld_sc(rzz, d + 8 * D_RZZ); ld_sc(zm, d + 8 * D_Z);
+    for (uint32_t i = threadIdx.x; i < N; i += RPG_THREADS) {
+      uint32_t j = i >> 6, k = i & 63;
+      sc zj = mont_one(); for (uint32_t q = 0; q < j; q++) zj = mmul(zj, zm);      // z^j (j < m, small)
+      sc si, sr, ypi, p2; ld_sc_rw(si, s + 8 * i); ld_sc_rw(sr, s + 8 * (N - 1 - i)); ld_sc_rw(ypi, yp + 8 * i); ld_sc(p2, pow2m + 8 * k);
+      sc gi = sc_neg(sc_add(rz, mmul(ra, si)));
+      sc hi = sc_add(rz, mmul(ypi, sc_sub(mmul(mmul(rzz, zj), p2), mmul(rb, sr))));
+      sc g0, h0; ld_sc_rw(g0, my + 8 * i); ld_sc_rw(h0, my + 8 * (Nmax + i));
+      st_sc(my + 8 * i, sc_add(g0, sc_from_mont(gi))); st_sc(my + 8 * (Nmax + i), sc_add(h0, sc_from_mont(hi)));
+    }
+  }
+}
+
+// gather affine-Niels operands for an MSM: dst[i] = src[idx[i]]
+__global__ void __launch_bounds__(256) k_gather_niels(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ dst) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;     // 6 threads (uint4 lanes) per point
+  uint32_t i = t / 6, q = t % 6;
+  if (i >= n) return;
+  reinterpret_cast<uint4*>(dst + 24 * (size_t)i)[q] = __ldg(reinterpret_cast<const uint4*>(src + 24 * (size_t)idx[i]) + q);
+}
+__global__ void k_copy_words(const uint32_t* __restrict__ src, uint32_t n_words, uint32_t* __restrict__ dst) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_words) dst[t] = src[t];
+}
+// K7: sum n partial extended points, identity test, optional encoding
+__global__ void k_combine(const uint32_t* __restrict__ ext, uint32_t n, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_id) {
+  if (threadIdx.x || blockIdx.x) return;
+  ge acc = ge_identity();
+  for (uint32_t i = 0; i < n; i++) { ge p; ld_ge(p, ext + 32 * (size_t)i); acc = ge_add(acc, p); }
+  if (out_enc) encode_words(out_enc, acc);
+  *is_id = ge_ristretto_is_identity(acc) ? 1u : 0u;
+}
+
+inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+struct Arena {   // bump allocator over one cudaMalloc'd block (grow-only, owned by the ctx)
+  uint8_t* base; size_t cap, off;
+  void* take(size_t bytes) { size_t o = (off + 255) & ~(size_t)255; off = o + bytes; return off <= cap ? base + o : nullptr; }
+};
+
+}  // namespace
+
+// tables live in the ctx (created lazily on first use)
+struct xhe_tables { uint32_t *tabG = nullptr, *tabH = nullptr, *pow2m = nullptr; };
+static xhe_tables* g_tables[64] = {nullptr};
+
+static int32_t ensure_tables(xhe_ctx* ctx) {
+  if (ctx->device < 0 || ctx->device >= 64) return XHE_E_ARG;
+  if (g_tables[ctx->device]) return XHE_OK;
+  xhe_tables* t = new xhe_tables();
+  XHE_CUDA_OK(ctx, cudaMalloc(&t->tabG, 96 * 255 * 8)); XHE_CUDA_OK(ctx, cudaMalloc(&t->tabH, 96 * 255 * 32)); XHE_CUDA_OK(ctx, cudaMalloc(&t->pow2m, 32 * 64));
+  k_build_tab8<<<1, 8, 0, ctx->stream>>>((const uint32_t*)ctx->d_gens_niels, 8, t->tabG); XHE_LAUNCHED(ctx);
+  k_build_tab8<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->d_gens_niels + 24, 32, t->tabH); XHE_LAUNCHED(ctx);
+  k_pow2_table<<<1, 64, 0, ctx->stream>>>(t->pow2m); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  g_tables[ctx->device] = t;
+  return XHE_OK;
+}
+
+extern "C" int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t out_enc[32], int32_t* is_identity) {
+  if (!ctx || !is_identity || (n && !ext)) return XHE_E_ARG;
+  void* d = nullptr; XHE_CUDA_OK(ctx, cudaMalloc(&d, 128 * n + 64));
+  uint8_t* dout = (uint8_t*)d + 128 * n;
+  if (n) XHE_CUDA_OK(ctx, cudaMemcpyAsync(d, ext, 128 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_combine<<<1, 32, 0, ctx->stream>>>((const uint32_t*)d, (uint32_t)n, dout, (uint32_t*)(dout + 32)); XHE_LAUNCHED(ctx);
+  uint8_t h[36];
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h, dout, 36, cudaMemcpyDeviceToHost, ctx->stream));
+  XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  if (out_enc) memcpy(out_enc, h, 32);
+  uint32_t f; memcpy(&f, h + 32, 4); *is_identity = (int32_t)f;
+  return XHE_OK;
+}
+
+extern "C" int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* b, xhe_verdict* v) {
+  if (!ctx || !b || !v) return XHE_E_ARG;
+  if (b->n_points == 0 || !b->points) { ctx->err = "verify_batch: point table must contain the identity at index 0"; return XHE_E_ARG; }
+  int32_t rc = ensure_tables(ctx); if (rc) return rc;
+  xhe_tables* T = g_tables[ctx->device];
+  cudaStream_t st = ctx->stream;
+  // ---- sizes
+  uint32_t m_max = 1;
+  for (uint32_t p = 0; p < b->n_rp; p++) {
+    uint32_t m = b->rp_m[p];
+    if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity || 64u * m > 2048u) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs power of two <= min(party_capacity, 32))"; return XHE_E_ARG; }
+    if (m > m_max) m_max = m;
+  }
+  const uint32_t Nmax = 64 * m_max;
+  const size_t n_pts_total = (size_t)b->n_points + b->n_ops;
+  const size_t n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val, n_sigma = n_sigma_terms + 2;
+  const size_t n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0, n_range = n_dyn + (b->n_rp ? 2 * (size_t)Nmax + 2 : 0);
+  const size_t n_chal = b->n_rp ? b->rp_chal_off[b->n_rp] : 0;
+  const uint32_t rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * 4) : 0;
+  const size_t ws_sigma = xhe_msm_workspace_bytes(ctx, n_sigma), ws_range = xhe_msm_workspace_bytes(ctx, n_range);
+  const size_t n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
+  // ---- arena
+  size_t need = 32 * (size_t)b->n_points + 64 * n_pts_total + 96 * n_pts_total + b->n_points
+              + b->n_sigs * (32 + 32 + 4 + 32 + 16 * 128)
+              + (size_t)b->n_ops * (8 + 8 + 8 + 128 * 2 + 32) + 4 * (b->n_ops + 1) + 4 * n_terms
+              + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
+              + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
+              + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * RP_DER + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
+              + 64 * (size_t)rp_grid * Nmax + 64 * 64 * (size_t)Nmax / 64 + ws_sigma + ws_range + 4096 + 256 * 64;
+  if (ctx->scratch_bytes < need) {
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_scratch, need + need / 4));
+    ctx->scratch_bytes = need + need / 4;
+  }
+  Arena A{(uint8_t*)ctx->d_scratch, ctx->scratch_bytes, 0};
+#define TAKE(T_, name, count) T_* name = (T_*)A.take(sizeof(T_) * (size_t)(count) + 16); if (!name) { ctx->err = "verify_batch: arena overflow at " #name; return XHE_E_NOMEM; }
+#define UP(dst, src, bytes) do { if ((bytes) > 0) XHE_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st)); } while (0)
+  TAKE(uint8_t, d_enc, 32 * (size_t)b->n_points); TAKE(uint32_t, d_aff, 16 * n_pts_total); TAKE(uint32_t, d_niels, 24 * n_pts_total); TAKE(uint8_t, d_ok, b->n_points);
+  UP(d_enc, b->points, 32 * (size_t)b->n_points);
+  rc = xhe_decompress_dev(ctx, d_enc, b->n_points, d_aff, d_niels, d_ok); if (rc) return rc;
+  // ---- signatures
+  TAKE(uint32_t, d_sig_s, 8 * (size_t)b->n_sigs); TAKE(uint32_t, d_sig_e, 8 * (size_t)b->n_sigs); TAKE(uint32_t, d_sig_pk, b->n_sigs); TAKE(uint8_t, d_sig_r, 32 * (size_t)b->n_sigs);
+  TAKE(uint32_t, d_sig_tab, 16 * 32 * (size_t)b->n_sigs);
+  if (b->n_sigs) {
+    UP(d_sig_s, b->sig_s, 32 * (size_t)b->n_sigs); UP(d_sig_e, b->sig_e, 32 * (size_t)b->n_sigs); UP(d_sig_pk, b->sig_pk, 4 * (size_t)b->n_sigs);
+    k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, st>>>(d_sig_s, d_sig_e, d_sig_pk, d_aff, d_ok, T->tabH, b->n_sigs, d_sig_r, d_sig_tab); XHE_LAUNCHED(ctx);
+  }
+  // ---- balance chains
+  TAKE(long long, d_ptr_a, b->n_ops); TAKE(long long, d_ptr_b, b->n_ops); TAKE(uint64_t, d_amount, b->n_ops); TAKE(uint32_t, d_term_off, b->n_ops + 1); TAKE(uint32_t, d_terms, n_terms);
+  TAKE(uint32_t, d_acc_a, 32 * (size_t)b->n_ops); TAKE(uint32_t, d_acc_b, 32 * (size_t)b->n_ops); TAKE(uint8_t, d_op_out, 32 * (size_t)b->n_ops);
+  if (b->n_ops) {
+    UP(d_ptr_a, b->op_prev, 8 * (size_t)b->n_ops); UP(d_amount, b->op_amount, 8 * (size_t)b->n_ops); UP(d_term_off, b->op_term_off, 4 * ((size_t)b->n_ops + 1)); UP(d_terms, b->op_terms, 4 * n_terms);
+    k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(d_term_off, d_terms, d_amount, d_niels, T->tabG, b->n_ops, d_acc_a); XHE_LAUNCHED(ctx);
+    uint32_t *acc_cur = d_acc_a, *acc_nxt = d_acc_b; long long *ptr_cur = d_ptr_a, *ptr_nxt = d_ptr_b;
+    for (uint32_t span = 1; span < b->max_chain; span <<= 1) {
+      k_op_jump<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, acc_nxt, ptr_nxt); XHE_LAUNCHED(ctx);
+      std::swap(acc_cur, acc_nxt); std::swap(ptr_cur, ptr_nxt);
+    }
+    k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, d_aff, d_niels, d_op_out); XHE_LAUNCHED(ctx);
+  }
+  // ---- sigma proofs -> MSM operands
+  TAKE(uint32_t, d_eq_sc, 48 * (size_t)b->n_eq); TAKE(uint32_t, d_val_sc, 40 * (size_t)b->n_val); TAKE(uint32_t, d_sig_idx, n_sigma);
+  TAKE(uint32_t, d_sigma_sc, 8 * n_sigma); TAKE(uint32_t, d_sigma_niels, 24 * n_sigma); TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
+  TAKE(uint32_t, d_results, 128);   // [0..7] sigma enc, [8] sigma id, [16..47] sigma ext, [48..55] range enc, [56] range id, [64..95] range ext, [96] bad flag
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(d_results, 0, 512, st));
+  {
+    UP(d_eq_sc, b->eq_scalars, 192 * (size_t)b->n_eq); UP(d_val_sc, b->val_scalars, 160 * (size_t)b->n_val);
+    UP(d_sig_idx, b->eq_points, 28 * (size_t)b->n_eq); UP(d_sig_idx + 7 * (size_t)b->n_eq, b->val_points, 32 * (size_t)b->n_val);
+    uint32_t np = b->n_eq + b->n_val;
+    if (np) {
+      k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(d_eq_sc, b->n_eq, d_val_sc, b->n_val, d_sigma_sc, d_gh); XHE_LAUNCHED(ctx);
+      k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(d_niels, d_sig_idx, (uint32_t)n_sigma_terms, d_sigma_niels); XHE_LAUNCHED(ctx);
+      // g/h totals: two-stage reduction of the per-proof contributions (column 0 = g, column 1 = h)
+      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(d_gh, np, 2, 1, d_gh_part, 2); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(d_gh_part, 32, 2, 1, d_sigma_sc + 8 * n_sigma_terms, 2); XHE_LAUNCHED(ctx);
+    } else {
+      XHE_CUDA_OK(ctx, cudaMemsetAsync(d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
+    }
+    k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
+    TAKE(uint8_t, d_ws1, ws_sigma);
+    rc = xhe_launch_msm_ex(ctx, d_sigma_sc, d_sigma_niels, n_sigma, d_ws1, ws_sigma, d_results, d_results + 8, d_results + 16, d_results + 96); if (rc) return rc;
+  }
+  // ---- range proofs -> MSM operands
+  if (b->n_rp) {
+    TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
+    TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
+    TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)rp_grid * Nmax);
+    UP(d_m, b->rp_m, 4 * (size_t)b->n_rp); UP(d_pt_off, b->rp_point_off, 4 * ((size_t)b->n_rp + 1)); UP(d_ch_off, b->rp_chal_off, 4 * ((size_t)b->n_rp + 1));
+    UP(d_rp_sc, b->rp_scalars, 224 * (size_t)b->n_rp); UP(d_chal, b->rp_challenges, 32 * n_chal); UP(d_range_idx, b->rp_points, 4 * n_dyn);
+    k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(d_m, d_rp_sc, d_ch_off, d_chal, d_pt_off, b->n_rp, d_der, d_range_sc, d_rgh); XHE_LAUNCHED(ctx);
+    size_t smem = 64 * (size_t)Nmax;
+    if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rp_gens<<<rp_grid, RPG_THREADS, smem, st>>>(d_m, d_der, T->pow2m, b->n_rp, Nmax, d_part); XHE_LAUNCHED(ctx);
+    // static scalars: sum the per-block partials, G_vec[0..Nmax) then H_vec[0..Nmax)
+    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(d_part, rp_grid, 2 * Nmax, 1, d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(d_rgh, b->n_rp, 2, 1, d_rgh_part, 2); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(d_rgh_part, 32, 2, 1, d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(d_niels, d_range_idx, (uint32_t)n_dyn, d_range_niels); XHE_LAUNCHED(ctx);
+    const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
+    k_copy_words<<<1, 64, 0, st>>>(gens, 48, d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
+    TAKE(uint8_t, d_ws2, ws_range);
+    rc = xhe_launch_msm_ex(ctx, d_range_sc, d_range_niels, n_range, d_ws2, ws_range, d_results + 48, d_results + 56, d_results + 64, d_results + 96); if (rc) return rc;
+  }
+  // ---- results
+  uint32_t h_res[128];
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, d_results, 512, cudaMemcpyDeviceToHost, st));
+  if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, d_ok, b->n_points, cudaMemcpyDeviceToHost, st));
+  if (v->sig_r && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_r, d_sig_r, 32 * (size_t)b->n_sigs, cudaMemcpyDeviceToHost, st));
+  if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
+  XHE_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (h_res[96]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
+  memcpy(v->sigma_enc, h_res, 32); v->sigma_is_identity = (int32_t)h_res[8]; memcpy(v->sigma_ext, h_res + 16, 128);
+  if (b->n_rp) { memcpy(v->range_enc, h_res + 48, 32); v->range_is_identity = (int32_t)h_res[56]; memcpy(v->range_ext, h_res + 64, 128); }
+  else { memset(v->range_enc, 0, 32); v->range_is_identity = 1; memset(v->range_ext, 0, 128); ((uint32_t*)v->range_ext)[8] = 1; ((uint32_t*)v->range_ext)[16] = 1; }
+  return XHE_OK;
+#undef TAKE
+#undef UP
+}
+
+// Signature::verify group part, host-buffer entry point (src/elgamal.rs:38-42): r_i = s_i*H - e_i*P_i, compressed
+extern "C" int32_t xhe_sig_r(xhe_ctx* ctx, const uint8_t* s, const uint8_t* e, const uint8_t* pk_enc, size_t n, uint8_t* r_enc, uint8_t* ok) {
+  if (!ctx || (n && (!s || !e || !pk_enc || !r_enc || !ok))) return XHE_E_ARG;
+  if (!n) return XHE_OK;
+  int32_t rc = ensure_tables(ctx); if (rc) return rc;
+  void *d_enc = nullptr, *d_aff = nullptr, *d_ok = nullptr, *d_s = nullptr, *d_e = nullptr, *d_idx = nullptr, *d_r = nullptr, *d_tab = nullptr;
+  auto cleanup = [&]() { cudaFree(d_enc); cudaFree(d_aff); cudaFree(d_ok); cudaFree(d_s); cudaFree(d_e); cudaFree(d_idx); cudaFree(d_r); cudaFree(d_tab); };
+#define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return XHE_E_CUDA; } } while (0)
+  TRY(cudaMalloc(&d_enc, 32 * n)); TRY(cudaMalloc(&d_aff, 64 * n)); TRY(cudaMalloc(&d_ok, n)); TRY(cudaMalloc(&d_s, 32 * n)); TRY(cudaMalloc(&d_e, 32 * n));
+  TRY(cudaMalloc(&d_idx, 4 * n)); TRY(cudaMalloc(&d_r, 32 * n)); TRY(cudaMalloc(&d_tab, 16 * 128 * n));
+  std::vector<uint32_t> idx(n); for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+  for (size_t i = 0; i < n; i++) if (!xhe::sc_is_canonical(xhe::sc_frombytes(s + 32 * i)) || !xhe::sc_is_canonical(xhe::sc_frombytes(e + 32 * i))) { cleanup(); ctx->err = "sig_r: non-canonical scalar"; return XHE_E_ARG; }
+  TRY(cudaMemcpyAsync(d_enc, pk_enc, 32 * n, cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_s, s, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_idx, idx.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = xhe_decompress_dev(ctx, d_enc, n, d_aff, nullptr, d_ok); if (rc) { cleanup(); return rc; }
+  k_sig_r<<<nblk(n, 64), 64, 0, ctx->stream>>>((const uint32_t*)d_s, (const uint32_t*)d_e, (const uint32_t*)d_idx, (const uint32_t*)d_aff, (const uint8_t*)d_ok, g_tables[ctx->device]->tabH, (uint32_t)n, (uint8_t*)d_r, (uint32_t*)d_tab); XHE_LAUNCHED(ctx);
+  TRY(cudaMemcpyAsync(r_enc, d_r, 32 * n, cudaMemcpyDeviceToHost, ctx->stream)); TRY(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(cudaStreamSynchronize(ctx->stream));
+#undef TRY
+  cleanup();
+  return XHE_OK;
+}

@@ -1,0 +1,554 @@
+// host/verifier.cpp -- see verifier.hpp.  HOST side of Transaction::verify_batch / apply_without_verify.
+#include "verifier.hpp"
+#include "blake3.hpp"
+#include "keccak.hpp"
+#include "scalar_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <functional>
+#include <thread>
+#include <stdio.h>
+#include <string.h>
+
+namespace xhe_host {
+
+static inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+static inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | (uint64_t)rd32(p + 4) << 32; }
+static inline void put_be64(std::vector<uint8_t>& o, uint64_t v) { for (int i = 7; i >= 0; i--) o.push_back((uint8_t)(v >> (8 * i))); }
+static inline void put(std::vector<uint8_t>& o, const uint8_t* p, size_t n) { o.insert(o.end(), p, p + n); }
+static const uint8_t ZERO32[32] = {0};
+static inline bool is_zero32(const uint8_t* p) { return memcmp(p, ZERO32, 32) == 0; }
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// wire format (spec: oracle/tx.h header comment -- shared as a format, not as code)
+// ------------------------------------------------------------------------------------------------------------------
+int TxView::parse(const uint8_t* b, size_t n) {
+  blob = b; len = n; transfers.clear();
+  if (n < 128) return XHE_ERR_PARSE;
+  version = b[0]; type = b[1]; n_sc = b[2]; n_ms = b[3] == 0xFF ? -1 : b[3];
+  count = rd32(b + 4); aux = rd32(b + 8); rp_len = rd32(b + 12); source = b + 16; fee = rd64(b + 48); nonce = rd64(b + 56);
+  if (type > 4) return XHE_ERR_PARSE;
+  size_t off = 64;
+  auto need = [&](size_t k) { return n - off >= k; };
+  body = b + off;
+  switch (type) {
+    case 0:
+      if (count > 65535) return XHE_ERR_PARSE;
+      transfers.resize(count);
+      for (uint32_t i = 0; i < count; i++) {
+        if (!need(324)) return XHE_ERR_PARSE;
+        TransferView& t = transfers[i]; const uint8_t* p = b + off;
+        t.asset = p; t.dest = p + 32; t.commitment = p + 64; t.sender_handle = p + 96; t.receiver_handle = p + 128; t.proof = p + 160; off += 320;
+        uint32_t el = rd32(b + off); off += 4; t.has_extra = el != 0xFFFFFFFFu; t.extra_len = t.has_extra ? el : 0;
+        if (!need(t.extra_len)) return XHE_ERR_PARSE;
+        t.extra = b + off; off += t.extra_len;
+        if (!ScalarL::is_canonical(t.proof + 96) || !ScalarL::is_canonical(t.proof + 128)) return XHE_ERR_PARSE;
+      }
+      break;
+    case 1: if (!need(40)) return XHE_ERR_PARSE; off += 40; break;
+    case 2:
+      if (!need(32) || count > 65535 || aux > 65535) return XHE_ERR_PARSE; off += 32;
+      if (!need((size_t)count * 40)) return XHE_ERR_PARSE; off += (size_t)count * 40;
+      for (uint32_t i = 0; i < aux * 2; i++) { if (!need(4)) return XHE_ERR_PARSE; uint32_t l = rd32(b + off); off += 4; if (!need(l)) return XHE_ERR_PARSE; off += l; }
+      break;
+    case 3: if (!need(aux)) return XHE_ERR_PARSE; off += aux; break;
+    case 4: if (count > 255 || aux > 255 || !need((size_t)count * 32)) return XHE_ERR_PARSE; off += (size_t)count * 32; break;
+  }
+  body_len = off - 64;
+  if (!need(rp_len)) return XHE_ERR_PARSE; rp = b + off; off += rp_len;
+  if (!need((size_t)n_sc * 256)) return XHE_ERR_PARSE; sc = b + off; off += (size_t)n_sc * 256;
+  for (int i = 0; i < n_sc; i++) for (int k = 0; k < 3; k++) if (!ScalarL::is_canonical(sc + 256 * i + 160 + 32 * k)) return XHE_ERR_PARSE;
+  if (n_ms > 0) { if (!need((size_t)n_ms * 65)) return XHE_ERR_PARSE; ms = b + off; off += (size_t)n_ms * 65; }
+  if (!need(64)) return XHE_ERR_PARSE; sig = b + off; off += 64;
+  if (off != n) return XHE_ERR_PARSE;
+  // RangeProof::from_bytes structure + canonical scalars (FormatError at deserialisation time in the reference)
+  if (rp_len % 32 || rp_len < 9 * 32 || ((rp_len / 32 - 9) & 1) || (rp_len / 32 - 9) / 2 >= 32) return XHE_ERR_PARSE;
+  if (!ScalarL::is_canonical(rp + 128) || !ScalarL::is_canonical(rp + 160) || !ScalarL::is_canonical(rp + 192) || !ScalarL::is_canonical(rp + rp_len - 64) || !ScalarL::is_canonical(rp + rp_len - 32)) return XHE_ERR_PARSE;
+  if (!ScalarL::is_canonical(sig) || !ScalarL::is_canonical(sig + 32)) return XHE_ERR_PARSE;
+  for (int i = 0; i < n_ms; i++) if (!ScalarL::is_canonical(ms + 65 * i + 1) || !ScalarL::is_canonical(ms + 65 * i + 33)) return XHE_ERR_PARSE;
+  return XHE_OK;
+}
+
+void TxView::to_bytes(std::vector<uint8_t>& o, size_t* multisig_index) const {
+  o.clear(); o.reserve(len);
+  o.push_back(version); put(o, source, 32); put_be64(o, fee); put_be64(o, nonce);
+  const uint8_t* p = body;
+  switch (type) {
+    case 0: for (const TransferView& t : transfers) { put(o, t.asset, 160); if (t.has_extra) put(o, t.extra, t.extra_len); put(o, t.proof, 160); } break;
+    case 1: put(o, p, 32); put_be64(o, rd64(p + 32)); break;
+    case 2: put(o, p, 32); p += 32; for (uint32_t i = 0; i < count; i++) { put(o, p, 32); put_be64(o, rd64(p + 32)); p += 40; }
+      for (uint32_t i = 0; i < aux * 2; i++) { uint32_t l = rd32(p); put(o, p + 4, l); p += 4 + l; } break;
+    case 3: put(o, p, aux); break;
+    case 4: o.push_back((uint8_t)aux); put(o, p, (size_t)count * 32); break;
+  }
+  put(o, rp, rp_len);
+  put(o, sc, (size_t)n_sc * 256);
+  if (multisig_index) *multisig_index = o.size();
+  if (n_ms > 0) put(o, ms, (size_t)n_ms * 65);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batch assembly
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+const uint32_t OPREF = 0x80000000u;   // point reference to the output of a balance-chain op (fixed up once n_points is known)
+
+enum CheckKind : uint8_t { CK_HOST = 0, CK_POINT = 1, CK_SIG = 2 };
+struct Check { CheckKind kind; int32_t err; uint32_t a; };
+
+struct SigEntry { uint32_t tx; bool is_multisig; const uint8_t* sig; uint32_t pk; const uint8_t* pk_enc; };
+struct StateUpdate { Bytes32 account, asset; Role role; uint32_t op_c, op_d; };
+struct Chain { long last_c = -1, last_d = -1; uint32_t length = 0; };
+
+struct TxPlan {
+  uint32_t check_begin = 0, check_end = 0;
+  bool proofs = false;                  // true when the tx reached the sigma / range collection stage
+  uint32_t eq_begin = 0, val_begin = 0; // first eq / validity proof slot
+  int32_t rp_slot = -1;                 // range-proof slot or -1
+  uint32_t rp_chal_begin = 0;
+  uint32_t sig_begin = 0, sig_end = 0;
+  bool rp_structural_fail = false;
+};
+
+struct Builder {
+  std::vector<uint8_t> points;          // 32 B each; index 0 = identity
+  std::vector<Check> checks;
+  std::vector<SigEntry> sigs;
+  std::vector<long long> op_prev; std::vector<uint32_t> op_term_off, op_terms; std::vector<uint64_t> op_amount;
+  std::vector<uint32_t> eq_points, val_points; std::vector<uint8_t> eq_scalars, val_scalars;
+  std::vector<uint32_t> rp_m, rp_point_off, rp_points, rp_chal_off; std::vector<uint8_t> rp_scalars, rp_challenges;
+  std::vector<StateUpdate> updates;
+  std::unordered_map<Ct64, Chain, KeyHash> chains;
+  uint32_t max_chain = 1;
+  Builder() { points.assign(32, 0); op_term_off.push_back(0); rp_point_off.push_back(0); rp_chal_off.push_back(0); }
+  uint32_t add_point(const uint8_t* enc) { uint32_t i = (uint32_t)(points.size() / 32); points.insert(points.end(), enc, enc + 32); return i; }
+  uint32_t add_op(long long prev, uint64_t amount) { op_prev.push_back(prev); op_amount.push_back(amount); op_term_off.push_back((uint32_t)op_terms.size()); return (uint32_t)op_prev.size() - 1; }
+  void close_op() { op_term_off.back() = (uint32_t)op_terms.size(); }
+};
+
+struct Rng {   // SHAKE256(seed || tx index) stream for the per-proof random batch factors (reference: Scalar::random)
+  Sponge sp;
+  Rng(const uint8_t* seed, size_t n, uint64_t idx) : sp(136) { sp.absorb("xhe-batch-factors", 17); sp.absorb(seed, n); sp.absorb(&idx, 8); sp.finish(0x1f); }
+  void scalar(uint8_t out[32]) { sp.squeeze(out, 32); out[31] &= 0x0f; }   // uniform in [0, 2^252) -- canonical
+};
+
+void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& fn) {
+  if (threads <= 1 || n < 2) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) { size_t lo = n * t / threads, hi = n * (t + 1) / threads; if (lo < hi) th.emplace_back(fn, lo, hi, t); }
+  for (auto& x : th) x.join();
+}
+
+bool has_commitment_for(const TxView& tx, const uint8_t* asset) { for (int i = 0; i < tx.n_sc; i++) if (!memcmp(tx.sc + 256 * i, asset, 32)) return true; return false; }
+bool verify_commitment_assets(const TxView& tx) {   // src/tx/verify.rs:161-199
+  if (!has_commitment_for(tx, ZERO32)) return false;
+  for (int i = 0; i < tx.n_sc; i++) for (int j = 0; j < tx.n_sc; j++) if (i != j && !memcmp(tx.sc + 256 * i, tx.sc + 256 * j, 32)) return false;
+  if (tx.type == 0) { for (const TransferView& t : tx.transfers) if (!has_commitment_for(tx, t.asset)) return false; }
+  else if (tx.type == 1) return has_commitment_for(tx, tx.body);
+  else if (tx.type == 2) { for (uint32_t i = 0; i < tx.count; i++) if (!has_commitment_for(tx, tx.body + 32 + 40 * i)) return false; }
+  return true;
+}
+uint64_t plain_output_amount(const TxView& tx, const uint8_t* asset) {   // the `Scalar::from(..)` parts of get_sender_output_ct, src/tx/verify.rs:107-144
+  uint64_t a = 0;
+  if (is_zero32(asset)) a += tx.fee;
+  if (tx.type == 1) { if (!memcmp(asset, tx.body, 32)) a += rd64(tx.body + 32); }
+  else if (tx.type == 2) { const uint8_t* hit = nullptr; for (uint32_t i = 0; i < tx.count; i++) if (!memcmp(asset, tx.body + 32 + 40 * i, 32)) hit = tx.body + 32 + 40 * i; if (hit) a += rd64(hit + 32); }
+  return a;   // u64 wrap-around cannot occur for honest inputs; the reference adds Scalars (mod l) -- see DESIGN.md
+}
+
+// resolve the (account, asset) balance chain: returns prev references for the commitment / handle ops, registering the
+// initial balance points on first touch.  *loaded = point index of the first half if it was read from state now.
+bool resolve_chain(Builder& B, VerificationState& st, const uint8_t* account, const uint8_t* asset, Role role, long long* prev_c, long long* prev_d, int64_t* loaded) {
+  Ct64 key = MockLedger::key(account, asset);
+  auto it = B.chains.find(key);
+  *loaded = -1;
+  if (it == B.chains.end()) {
+    uint8_t ct[64];
+    if (!st.get_account_balance(account, asset, role, ct)) return false;
+    uint32_t ic = B.add_point(ct), id = B.add_point(ct + 32);
+    Chain c; c.last_c = -(1 + (long long)ic); c.last_d = -(1 + (long long)id); c.length = 0;
+    it = B.chains.emplace(key, c).first;
+    *loaded = ic;
+  }
+  *prev_c = it->second.last_c; *prev_d = it->second.last_d;
+  return true;
+}
+void advance_chain(Builder& B, const uint8_t* account, const uint8_t* asset, uint32_t op_c, uint32_t op_d) {
+  Chain& c = B.chains[MockLedger::key(account, asset)];
+  c.last_c = op_c; c.last_d = op_d; c.length++;
+  if (c.length > B.max_chain) B.max_chain = c.length;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// Transaction::verify_batch
+// ------------------------------------------------------------------------------------------------------------------
+int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
+  double t0 = now_ms();
+  if (fail_index) *fail_index = -1;
+  int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  uint8_t seed[32];
+  if (opt.rng_seed && opt.rng_seed_len) { uint8_t h[64]; sha3_512(opt.rng_seed, opt.rng_seed_len, h); memcpy(seed, h, 32); }
+  else { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(seed, 1, 32, f) != 32) { if (f) fclose(f); return XHE_E_ARG; } fclose(f); }
+
+  // ---- parse (parallel)
+  std::vector<TxView> txs(n); std::vector<int> parse_rc(n, 0);
+  parallel_for(n, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
+  size_t n_live = n; int parse_err = XHE_OK;
+  for (size_t i = 0; i < n; i++) if (parse_rc[i]) { n_live = i; parse_err = parse_rc[i]; break; }
+  double t1 = now_ms();
+
+  // ---- phase A: sequential state resolution and batch layout (mirrors pre_verify's order, src/tx/verify.rs:203-485)
+  Builder B; std::vector<TxPlan> plan(n_live);
+  size_t n_reached = n_live;    // txs after the first host-side hard error are never reached by the reference
+  for (size_t i = 0; i < n_live; i++) {
+    const TxView& tx = txs[i]; TxPlan& P = plan[i];
+    P.check_begin = (uint32_t)B.checks.size(); P.sig_begin = (uint32_t)B.sigs.size();
+    auto host_fail = [&](int err) { B.checks.push_back({CK_HOST, err, 0}); };
+    auto finish = [&]() { P.check_end = (uint32_t)B.checks.size(); P.sig_end = (uint32_t)B.sigs.size(); };
+    bool stop = false;
+    do {
+      uint64_t nonce;
+      if (!state.get_account_nonce(tx.source, &nonce)) { host_fail(XHE_ERR_STATE); stop = true; break; }
+      if (nonce != tx.nonce) { host_fail(XHE_ERR_INVALID_NONCE); stop = true; break; }
+      state.update_account_nonce(tx.source, tx.nonce);
+      if (!verify_commitment_assets(tx)) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+      const uint32_t k = tx.n_transfers(), a = tx.n_sc;
+      std::vector<uint32_t> iC(k), iDs(k), iDr(k), iN(a);
+      for (uint32_t t = 0; t < k; t++) {
+        iC[t] = B.add_point(tx.transfers[t].commitment); iDs[t] = B.add_point(tx.transfers[t].sender_handle); iDr[t] = B.add_point(tx.transfers[t].receiver_handle);
+        B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iC[t]}); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iDs[t]}); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iDr[t]});
+      }
+      for (uint32_t q = 0; q < a; q++) { iN[q] = B.add_point(tx.sc + 256 * q + 32); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iN[q]}); }
+      uint32_t iSrc = B.add_point(tx.source); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iSrc});
+      // 0. signature (src/tx/verify.rs:253-256)
+      B.checks.push_back({CK_SIG, XHE_ERR_SIGNATURE, (uint32_t)B.sigs.size()});
+      B.sigs.push_back({(uint32_t)i, false, tx.sig, iSrc, tx.source});
+      // multisig rules (259-292)
+      {
+        std::vector<Bytes32> signers; uint8_t threshold = 0; bool present = false;
+        if (!state.get_multisig_for_account(tx.source, &signers, &threshold, &present)) { host_fail(XHE_ERR_STATE); stop = true; break; }
+        if (present) {
+          if (tx.n_ms < 0) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+          if (tx.n_ms == 0 || tx.n_ms != (int)threshold) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+          for (int s = 0; s < tx.n_ms && !stop; s++) {
+            for (int s2 = 0; s2 < tx.n_ms; s2++) if (s != s2 && tx.ms[65 * s] == tx.ms[65 * s2]) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+            if (stop) break;
+            uint32_t idx = tx.ms[65 * s];
+            if (idx < signers.size()) {
+              // the signer key must outlive this call: copy it into the point table and point at that copy
+              uint32_t ip = B.add_point(signers[idx].data());
+              B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, ip});
+              B.checks.push_back({CK_SIG, XHE_ERR_SIGNATURE, (uint32_t)B.sigs.size()});
+              B.sigs.push_back({(uint32_t)i, true, tx.ms + 65 * s + 1, ip, nullptr});
+            }
+          }
+          if (stop) break;
+        } else if (tx.n_ms >= 0) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+      }
+      // 1. commitment equality proofs + sender balance updates (296-341)
+      P.eq_begin = (uint32_t)(B.eq_points.size() / 7); P.val_begin = (uint32_t)(B.val_points.size() / 8);
+      for (uint32_t q = 0; q < a && !stop; q++) {
+        const uint8_t* asset = tx.sc + 256 * q; const uint8_t* proof = asset + 64;
+        long long pc, pd; int64_t loaded;
+        if (!resolve_chain(B, state, tx.source, asset, Sender, &pc, &pd, &loaded)) { host_fail(XHE_ERR_STATE); stop = true; break; }
+        if (loaded >= 0) { B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded}); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded + 1}); }
+        uint32_t oc = B.add_op(pc, plain_output_amount(tx, asset));
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t] | 0x80000000u);
+        B.close_op();
+        uint32_t od = B.add_op(pd, 0);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t] | 0x80000000u);
+        B.close_op();
+        advance_chain(B, tx.source, asset, oc, od);
+        StateUpdate u; memcpy(u.account.data(), tx.source, 32); memcpy(u.asset.data(), asset, 32); u.role = Sender; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+        // eq proof: Y identity check (src/transcript.rs:73-84) then Y decompression (src/proofs.rs:168-179)
+        if (is_zero32(proof) || is_zero32(proof + 32) || is_zero32(proof + 64)) { host_fail(XHE_ERR_TRANSCRIPT); stop = true; break; }
+        uint32_t y0 = B.add_point(proof), y1 = B.add_point(proof + 32), y2 = B.add_point(proof + 64);
+        for (uint32_t y : {y0, y1, y2}) B.checks.push_back({CK_POINT, XHE_ERR_COMMITMENT_EQ_PROOF, y});
+        // P_src, Y0, D_src, C_src, Y1, C_dst, Y2
+        for (uint32_t p : {iSrc, y0, OPREF | od, OPREF | oc, y1, iN[q], y2}) B.eq_points.push_back(p);
+        size_t so = B.eq_scalars.size(); B.eq_scalars.resize(so + 192);
+        memcpy(&B.eq_scalars[so], proof + 96, 96);    // z_s, z_x, z_r ; c, w, bf are filled by the transcript phase
+      }
+      if (stop) break;
+      // 2. transfers: receiver balance updates + ciphertext validity proofs (344-394)
+      if (tx.type == 0) {
+        for (uint32_t t = 0; t < k && !stop; t++) {
+          const TransferView& tr = tx.transfers[t];
+          uint32_t iDest = B.add_point(tr.dest); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, iDest});
+          long long pc, pd; int64_t loaded;
+          if (!resolve_chain(B, state, tr.dest, tr.asset, Receiver, &pc, &pd, &loaded)) { host_fail(XHE_ERR_STATE); stop = true; break; }
+          if (loaded >= 0) { B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded}); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded + 1}); }
+          uint32_t oc = B.add_op(pc, 0); B.op_terms.push_back(iC[t]); B.close_op();
+          uint32_t od = B.add_op(pd, 0); B.op_terms.push_back(iDr[t]); B.close_op();
+          advance_chain(B, tr.dest, tr.asset, oc, od);
+          StateUpdate u; memcpy(u.account.data(), tr.dest, 32); memcpy(u.asset.data(), tr.asset, 32); u.role = Receiver; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+          const uint8_t* proof = tr.proof;
+          if (is_zero32(proof) || is_zero32(proof + 32) || is_zero32(proof + 64)) { host_fail(XHE_ERR_TRANSCRIPT); stop = true; break; }
+          uint32_t y0 = B.add_point(proof), y1 = B.add_point(proof + 32), y2 = B.add_point(proof + 64);
+          for (uint32_t y : {y0, y1, y2}) B.checks.push_back({CK_POINT, XHE_ERR_CT_VALIDITY_PROOF, y});
+          // C, Y0, P_dest, D_dest, Y1, P_src, D_src, Y2
+          for (uint32_t p : {iC[t], y0, iDest, iDr[t], y1, iSrc, iDs[t], y2}) B.val_points.push_back(p);
+          size_t so = B.val_scalars.size(); B.val_scalars.resize(so + 160);
+          memcpy(&B.val_scalars[so], proof + 96, 64);   // z_r, z_x
+        }
+        if (stop) break;
+      } else if (tx.type == 4) {   // MultiSig setup (401-428)
+        uint32_t ns = tx.count, th = tx.aux; bool bad = th > ns || (ns != 0 && th == 0);
+        for (uint32_t x = 0; x < ns && !bad; x++) for (uint32_t y = 0; y < ns; y++) if (x != y && !memcmp(tx.body + 32 * x, tx.body + 32 * y, 32)) { bad = true; break; }
+        for (uint32_t x = 0; x < ns && !bad; x++) if (!memcmp(tx.body + 32 * x, tx.source, 32)) bad = true;
+        if (bad) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+        state.set_multisig_for_account(tx.source, tx.body, ns, (uint8_t)th);
+      }
+      // 3. range proof view (434-478, 504-510): commitments = new source commitments ++ transfer commitments ++ identity duds
+      {
+        uint32_t nc = a + k, m = 1; while (m < nc) m <<= 1;
+        uint32_t lg = (tx.rp_len / 32 - 9) / 2, lg_need = 6; { uint32_t mm = m; while (mm > 1) { mm >>= 1; lg_need++; } }
+        bool structural = (lg != lg_need);
+        const uint8_t* rp = tx.rp;
+        for (int q = 0; q < 4 && !structural; q++) if (is_zero32(rp + 32 * q)) structural = true;
+        for (uint32_t q = 0; q < 2 * lg && !structural; q++) if (is_zero32(rp + 224 + 32 * q)) structural = true;
+        if (structural) { P.rp_structural_fail = true; }
+        else {
+          P.rp_slot = (int32_t)B.rp_m.size(); B.rp_m.push_back(m);
+          for (int q = 0; q < 4; q++) B.rp_points.push_back(B.add_point(rp + 32 * q));
+          std::vector<uint32_t> Ls(lg), Rs(lg);
+          for (uint32_t q = 0; q < lg; q++) { Ls[q] = B.add_point(rp + 224 + 64 * q); Rs[q] = B.add_point(rp + 224 + 64 * q + 32); }
+          for (uint32_t q = 0; q < lg; q++) B.rp_points.push_back(Ls[q]);
+          for (uint32_t q = 0; q < lg; q++) B.rp_points.push_back(Rs[q]);
+          for (uint32_t q = 0; q < a; q++) B.rp_points.push_back(iN[q]);
+          for (uint32_t q = 0; q < k; q++) B.rp_points.push_back(iC[q]);
+          for (uint32_t q = nc; q < m; q++) B.rp_points.push_back(0);
+          B.rp_point_off.push_back((uint32_t)B.rp_points.size());
+          size_t so = B.rp_scalars.size(); B.rp_scalars.resize(so + 224);
+          memcpy(&B.rp_scalars[so], rp + 128, 96);                        // t_x, t_x_blinding, e_blinding
+          memcpy(&B.rp_scalars[so + 96], rp + tx.rp_len - 64, 64);       // a, b
+          P.rp_chal_begin = B.rp_chal_off.back();
+          B.rp_chal_off.push_back(P.rp_chal_begin + 4 + lg);
+          B.rp_challenges.resize(32 * (size_t)B.rp_chal_off.back());
+        }
+      }
+      P.proofs = true;
+    } while (false);
+    finish();
+    if (stop) { n_reached = i + 1; plan.resize(n_reached); break; }
+  }
+  double t2 = now_ms();
+
+  // ---- phase B: Merlin transcripts / Fiat-Shamir challenges, message hashes, random batch factors (parallel over txs)
+  const size_t n_sigs = B.sigs.size();
+  std::vector<Sponge> sig_sponge(n_sigs, Sponge(72));
+  std::vector<uint64_t> perms(threads > 0 ? threads : 1, 0);
+  parallel_for(n_reached, threads, [&](size_t lo, size_t hi, int tid) {
+    std::vector<uint8_t> bytes; uint64_t kf = 0;
+    for (size_t i = lo; i < hi; i++) {
+      const TxView& tx = txs[i]; const TxPlan& P = plan[i];
+      // signature message hashes: SHA3-512(pk || message || r) -- absorb everything but r now (src/elgamal.rs:53-65)
+      if (P.sig_end > P.sig_begin) {
+        size_t msi; tx.to_bytes(bytes, &msi);
+        uint8_t h32[32]; bool have_hash = false;
+        for (uint32_t s = P.sig_begin; s < P.sig_end; s++) {
+          const SigEntry& e = B.sigs[s]; Sponge& sp = sig_sponge[s];
+          if (!e.is_multisig) { sp.absorb(tx.source, 32); sp.absorb(bytes.data(), bytes.size()); }
+          else { if (!have_hash) { blake3(bytes.data(), msi, h32); have_hash = true; } sp.absorb(&B.points[32 * (size_t)e.pk], 32); sp.absorb(h32, 32); }
+        }
+      }
+      if (!P.proofs) continue;
+      Rng rng(seed, 32, i);
+      Transcript T("transaction-proof");    // prepare_transcript, src/tx/verify.rs:146-158
+      T.append_u64("version", tx.version); T.append("source_pubkey", tx.source, 32); T.append_u64("fee", tx.fee); T.append_u64("nonce", tx.nonce);
+      auto challenge = [&](const char* label, uint8_t out[32]) { uint8_t b64[64]; T.challenge(label, b64, 64); ScalarL::reduce_wide(b64, out); };
+      for (uint32_t q = 0; q < tx.n_sc; q++) {   // src/tx/verify.rs:315-318 + src/proofs.rs:142-161
+        const uint8_t* asset = tx.sc + 256 * q; const uint8_t* proof = asset + 64;
+        T.append("dom-sep", "new-commitment-proof", 20); T.append("new_source_commitment_asset", asset, 32); T.append("new_source_commitment", asset + 32, 32);
+        T.append("dom-sep", "equality-proof", 14); T.append("Y_0", proof, 32); T.append("Y_1", proof + 32, 32); T.append("Y_2", proof + 64, 32);
+        uint8_t* sc = &B.eq_scalars[192 * (size_t)(P.eq_begin + q)];
+        challenge("c", sc + 96);
+        T.append("z_s", proof + 96, 32); T.append("z_x", proof + 128, 32); T.append("z_r", proof + 160, 32);
+        challenge("w", sc + 128); rng.scalar(sc + 160);
+      }
+      if (tx.type == 0) {
+        for (uint32_t t = 0; t < tx.count; t++) {   // src/tx/verify.rs:378-383 + src/proofs.rs:291-302
+          const TransferView& tr = tx.transfers[t];
+          T.append("dom-sep", "transfer-proof", 14); T.append("dest_pubkey", tr.dest, 32); T.append("amount_commitment", tr.commitment, 32);
+          T.append("amount_sender_handle", tr.sender_handle, 32); T.append("amount_receiver_handle", tr.receiver_handle, 32);
+          T.append("dom-sep", "validity-proof", 14); T.append("Y_0", tr.proof, 32); T.append("Y_1", tr.proof + 32, 32); T.append("Y_2", tr.proof + 64, 32);
+          uint8_t* sc = &B.val_scalars[160 * (size_t)(P.val_begin + t)];
+          challenge("c", sc + 64);
+          T.append("z_r", tr.proof + 96, 32); T.append("z_x", tr.proof + 128, 32);
+          challenge("w", sc + 96); rng.scalar(sc + 128);
+        }
+      } else if (tx.type == 1) {
+        T.append("dom-sep", "burn-proof", 10); T.append("asset", tx.body, 32); T.append_u64("amount", rd64(tx.body + 32));
+      } else if (tx.type == 4) {
+        T.append("dom-sep", "multisig-proof", 14); T.append_u64("threshold", tx.aux);
+        for (uint32_t s = 0; s < tx.count; s++) T.append("signer", tx.body + 32 * s, 32);
+      }
+      if (P.rp_slot >= 0) {   // bulletproofs verification transcript
+        uint32_t m = B.rp_m[P.rp_slot], lg = (tx.rp_len / 32 - 9) / 2; const uint8_t* rp = tx.rp;
+        T.append("dom-sep", "rangeproof v1", 13); T.append_u64("n", 64); T.append_u64("m", m);
+        for (uint32_t q = 0; q < tx.n_sc; q++) T.append("V", tx.sc + 256 * q + 32, 32);
+        for (uint32_t q = 0; q < tx.n_transfers(); q++) T.append("V", tx.transfers[q].commitment, 32);
+        for (uint32_t q = tx.n_sc + tx.n_transfers(); q < m; q++) T.append("V", ZERO32, 32);
+        uint8_t* ch = &B.rp_challenges[32 * (size_t)P.rp_chal_begin];
+        T.append("A", rp, 32); T.append("S", rp + 32, 32);
+        challenge("y", ch); challenge("z", ch + 32);
+        T.append("T_1", rp + 64, 32); T.append("T_2", rp + 96, 32);
+        challenge("x", ch + 64);
+        T.append("t_x", rp + 128, 32); T.append("t_x_blinding", rp + 160, 32); T.append("e_blinding", rp + 192, 32);
+        challenge("w", ch + 96);
+        T.append("dom-sep", "ipp v1", 6); T.append_u64("n", 64ull * m);
+        for (uint32_t q = 0; q < lg; q++) { T.append("L", rp + 224 + 64 * q, 32); T.append("R", rp + 224 + 64 * q + 32, 32); challenge("u", ch + 128 + 32 * q); }
+        uint8_t* sc = &B.rp_scalars[224 * (size_t)P.rp_slot];
+        rng.scalar(sc + 160); rng.scalar(sc + 192);     // c (intra-proof weight), rho (batch factor)
+      }
+      kf += T.permutations;
+    }
+    perms[tid] += kf;
+  });
+  double t3 = now_ms();
+
+  // ---- phase C: device
+  const uint32_t n_points = (uint32_t)(B.points.size() / 32);
+  for (uint32_t& p : B.eq_points) if (p & OPREF) p = n_points + (p & ~OPREF);
+  std::vector<uint8_t> sig_s(32 * n_sigs + 1), sig_e(32 * n_sigs + 1); std::vector<uint32_t> sig_pk(n_sigs + 1);
+  for (size_t s = 0; s < n_sigs; s++) { memcpy(&sig_s[32 * s], B.sigs[s].sig, 32); memcpy(&sig_e[32 * s], B.sigs[s].sig + 32, 32); sig_pk[s] = B.sigs[s].pk; }
+  xhe_batch xb; memset(&xb, 0, sizeof xb);
+  xb.n_tx = (uint32_t)n_reached; xb.n_points = n_points; xb.points = B.points.data();
+  xb.n_sigs = (uint32_t)n_sigs; xb.sig_s = sig_s.data(); xb.sig_e = sig_e.data(); xb.sig_pk = sig_pk.data();
+  xb.n_ops = (uint32_t)B.op_prev.size(); xb.op_prev = (const int64_t*)B.op_prev.data(); xb.op_term_off = B.op_term_off.data(); xb.op_terms = B.op_terms.data(); xb.op_amount = B.op_amount.data(); xb.max_chain = B.max_chain;
+  xb.n_eq = (uint32_t)(B.eq_points.size() / 7); xb.eq_points = B.eq_points.data(); xb.eq_scalars = B.eq_scalars.data();
+  xb.n_val = (uint32_t)(B.val_points.size() / 8); xb.val_points = B.val_points.data(); xb.val_scalars = B.val_scalars.data();
+  xb.n_rp = (uint32_t)B.rp_m.size(); xb.rp_m = B.rp_m.data(); xb.rp_point_off = B.rp_point_off.data(); xb.rp_points = B.rp_points.data();
+  xb.rp_scalars = B.rp_scalars.data(); xb.rp_chal_off = B.rp_chal_off.data(); xb.rp_challenges = B.rp_challenges.data();
+  std::vector<uint8_t> point_ok(n_points + 1), sig_r(32 * n_sigs + 1), op_out(32 * (size_t)xb.n_ops + 1);
+  xhe_verdict v; memset(&v, 0, sizeof v); v.point_ok = point_ok.data(); v.sig_r = sig_r.data(); v.op_out = op_out.data();
+  int32_t rc = xhe_verify_batch(ctx, &xb, &v);
+  double t4 = now_ms();
+  if (rc != XHE_OK) return rc;
+
+  // ---- phase D: verdict with the reference's precedence
+  std::vector<uint8_t> sig_ok(n_sigs + 1, 0);
+  parallel_for(n_sigs, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t s = lo; s < hi; s++) {
+      Sponge sp = sig_sponge[s]; sp.absorb(&sig_r[32 * s], 32); sp.finish(0x06);
+      uint8_t h[64], e2[32]; sp.squeeze(h, 64); ScalarL::reduce_wide(h, e2);
+      sig_ok[s] = memcmp(e2, B.sigs[s].sig + 32, 32) == 0;
+    }
+  });
+  int verdict = XHE_OK; long bad_tx = -1;
+  for (size_t i = 0; i < n_reached && verdict == XHE_OK; i++) {
+    for (uint32_t c = plan[i].check_begin; c < plan[i].check_end; c++) {
+      const Check& ck = B.checks[c]; bool fail = false;
+      if (ck.kind == CK_HOST) fail = true; else if (ck.kind == CK_POINT) fail = !point_ok[ck.a]; else fail = !sig_ok[ck.a];
+      if (fail) { verdict = ck.err; bad_tx = (long)i; break; }
+    }
+  }
+  if (verdict == XHE_OK && parse_err != XHE_OK) { verdict = parse_err; bad_tx = (long)n_live; }
+  if (verdict == XHE_OK && !v.sigma_is_identity) verdict = XHE_ERR_GENERIC_PROOF;                       // src/tx/verify.rs:500-502
+  if (verdict == XHE_OK) { for (size_t i = 0; i < n_reached; i++) if (plan[i].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
+  if (verdict == XHE_OK && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;                          // src/tx/verify.rs:504-514
+  if (verdict == XHE_OK && opt.apply_state) {
+    for (const StateUpdate& u : B.updates) {
+      uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
+      if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) { verdict = XHE_ERR_STATE; break; }
+    }
+  }
+  if (fail_index) *fail_index = bad_tx;
+  double t5 = now_ms();
+  if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->finish_ms = t5 - t4; tm->total_ms = t5 - t0; tm->keccak_f = 0; for (uint64_t p : perms) tm->keccak_f += p; }
+  return verdict;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Transaction::apply_without_verify over a list of txs (src/tx/verify.rs:545-619)
+// ------------------------------------------------------------------------------------------------------------------
+int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state) {
+  std::vector<TxView> txs(n);
+  for (size_t i = 0; i < n; i++) { int rc = txs[i].parse(blobs[i], lens[i]); if (rc) return rc; }
+  Builder B; std::vector<uint32_t> need_ok;
+  for (size_t i = 0; i < n; i++) {
+    const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
+    std::vector<uint32_t> iC(k), iDs(k), iDr(k);
+    for (uint32_t t = 0; t < k; t++) { iC[t] = B.add_point(tx.transfers[t].commitment); iDs[t] = B.add_point(tx.transfers[t].sender_handle); iDr[t] = B.add_point(tx.transfers[t].receiver_handle); need_ok.push_back(iC[t]); need_ok.push_back(iDs[t]); need_ok.push_back(iDr[t]); }
+    for (uint32_t q = 0; q < tx.n_sc; q++) {
+      const uint8_t* asset = tx.sc + 256 * q; long long pc, pd; int64_t loaded;
+      if (!resolve_chain(B, state, tx.source, asset, Sender, &pc, &pd, &loaded)) return XHE_ERR_STATE;
+      if (loaded >= 0) { need_ok.push_back((uint32_t)loaded); need_ok.push_back((uint32_t)loaded + 1); }
+      uint32_t oc = B.add_op(pc, plain_output_amount(tx, asset));
+      for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t] | 0x80000000u);
+      B.close_op();
+      uint32_t od = B.add_op(pd, 0);
+      for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t] | 0x80000000u);
+      B.close_op();
+      advance_chain(B, tx.source, asset, oc, od);
+      StateUpdate u; memcpy(u.account.data(), tx.source, 32); memcpy(u.asset.data(), asset, 32); u.role = Sender; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+    }
+    for (uint32_t t = 0; t < k; t++) {
+      const TransferView& tr = tx.transfers[t]; long long pc, pd; int64_t loaded;
+      if (!resolve_chain(B, state, tr.dest, tr.asset, Receiver, &pc, &pd, &loaded)) return XHE_ERR_STATE;
+      if (loaded >= 0) { need_ok.push_back((uint32_t)loaded); need_ok.push_back((uint32_t)loaded + 1); }
+      uint32_t oc = B.add_op(pc, 0); B.op_terms.push_back(iC[t]); B.close_op();
+      uint32_t od = B.add_op(pd, 0); B.op_terms.push_back(iDr[t]); B.close_op();
+      advance_chain(B, tr.dest, tr.asset, oc, od);
+      StateUpdate u; memcpy(u.account.data(), tr.dest, 32); memcpy(u.asset.data(), tr.asset, 32); u.role = Receiver; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+    }
+    if (tx.type == 4) state.set_multisig_for_account(tx.source, tx.body, tx.count, (uint8_t)tx.aux);
+  }
+  const uint32_t n_points = (uint32_t)(B.points.size() / 32);
+  xhe_batch xb; memset(&xb, 0, sizeof xb);
+  xb.n_tx = (uint32_t)n; xb.n_points = n_points; xb.points = B.points.data();
+  xb.n_ops = (uint32_t)B.op_prev.size(); xb.op_prev = (const int64_t*)B.op_prev.data(); xb.op_term_off = B.op_term_off.data(); xb.op_terms = B.op_terms.data(); xb.op_amount = B.op_amount.data(); xb.max_chain = B.max_chain;
+  uint32_t zero_off = 0; xb.rp_point_off = &zero_off; xb.rp_chal_off = &zero_off;
+  std::vector<uint8_t> point_ok(n_points + 1), op_out(32 * (size_t)xb.n_ops + 1);
+  xhe_verdict v; memset(&v, 0, sizeof v); v.point_ok = point_ok.data(); v.op_out = op_out.data();
+  int32_t rc = xhe_verify_batch(ctx, &xb, &v); if (rc) return rc;
+  for (uint32_t p : need_ok) if (!point_ok[p]) return XHE_ERR_DECOMPRESSION;   // "ill-formed ciphertext" (the reference panics)
+  for (const StateUpdate& u : B.updates) {
+    uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
+    if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
+  }
+  return XHE_OK;
+}
+
+}  // namespace xhe_host
+
+// ------------------------------------------------------------------------------------------------------------------
+// C exports for the Python binding / tests (the mock ledger plays the role of src/lib.rs::mock::Ledger)
+// ------------------------------------------------------------------------------------------------------------------
+using namespace xhe_host;
+extern "C" {
+void* xheh_ledger_new() { return new MockLedger(); }
+void* xheh_ledger_clone(const void* l) { return new MockLedger(*(const MockLedger*)l); }
+void xheh_ledger_free(void* l) { delete (MockLedger*)l; }
+void xheh_ledger_set_balance(void* l, const uint8_t* pk, const uint8_t* asset, const uint8_t* ct) { Ct64 v; memcpy(v.data(), ct, 64); ((MockLedger*)l)->balances[MockLedger::key(pk, asset)] = v; }
+int xheh_ledger_get_balance(void* l, const uint8_t* pk, const uint8_t* asset, uint8_t* ct) { return ((MockLedger*)l)->get_account_balance(pk, asset, Sender, ct) ? 1 : 0; }
+void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { Bytes32 k; memcpy(k.data(), pk, 32); ((MockLedger*)l)->nonces[k] = nonce; }
+void xheh_ledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { ((MockLedger*)l)->set_multisig_for_account(pk, signers, n, threshold); }
+int xheh_ledger_has_multisig(void* l, const uint8_t* pk) { std::vector<Bytes32> s; uint8_t t; bool p; ((MockLedger*)l)->get_multisig_for_account(pk, &s, &t, &p); return p ? 1 : 0; }
+size_t xheh_ledger_size(void* l) { return ((MockLedger*)l)->balances.size(); }
+// bulk import of records (pk[32] asset[32] ct[64]) and nonce-0 accounts
+void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; L->balances.reserve(L->balances.size() + n); for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; xheh_ledger_set_balance(l, r, r + 32, r + 64); Bytes32 k; memcpy(k.data(), r, 32); L->nonces.emplace(k, 0); } }
+size_t xheh_ledger_export(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; for (auto& kv : L->balances) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, kv.first.data(), 64); memcpy(out + 128 * i + 64, kv.second.data(), 64); } i++; } return i; }
+// timings: parse, resolve, transcript, device, finish, total (ms), keccak permutations
+int32_t xheh_verify_batch(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, long* fail_index, double* timings7) {
+  BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len;
+  BatchTimings tm;
+  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
+  return rc;
+}
+int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(MockLedger*)ledger); }
+// host-only helpers exposed for CPU tests of the host logic
+void xheh_merlin_test(const char* proto, const char* label, const uint8_t* msg, size_t n, const char* chal_label, uint8_t* out, size_t outlen) { Transcript t(proto); t.append(label, msg, n); t.challenge(chal_label, out, outlen); }
+void xheh_sha3_512(const uint8_t* m, size_t n, uint8_t* out) { sha3_512(m, n, out); }
+void xheh_shake256(const uint8_t* m, size_t n, uint8_t* out, size_t outlen) { shake256(m, n, out, outlen); }
+void xheh_blake3(const uint8_t* m, size_t n, uint8_t* out) { blake3(m, n, out); }
+void xheh_reduce_wide(const uint8_t* in, uint8_t* out) { ScalarL::reduce_wide(in, out); }
+int32_t xheh_tx_to_bytes(const uint8_t* blob, size_t len, uint8_t* out, size_t cap, size_t* out_len, size_t* ms_index) {
+  TxView tx; int rc = tx.parse(blob, len); if (rc) return rc; std::vector<uint8_t> b; tx.to_bytes(b, ms_index); *out_len = b.size(); if (b.size() <= cap) memcpy(out, b.data(), b.size()); return XHE_OK; }
+}

@@ -1,0 +1,84 @@
+// host/verifier.hpp -- HOST side of the drop-in: the C++ mirror of the reference's verification API.
+//
+//   reference (Rust)                                          here
+//   trait BlockchainVerificationState  src/tx/verify.rs:25-77   class xhe_host::VerificationState
+//   mock::Ledger                       src/lib.rs:106-201       class xhe_host::MockLedger
+//   Transaction (serde)                src/tx/mod.rs:102-119    xtx1 wire blobs (format: oracle/tx.h header comment) + TxView
+//   Transaction::to_bytes              src/tx/verify.rs:623-688 TxView::to_bytes
+//   Transaction::verify_batch          src/tx/verify.rs:487-517 xhe_host::verify_batch
+//   Transaction::apply_without_verify  src/tx/verify.rs:545-619 xhe_host::apply_without_verify
+//
+// The host keeps what north_star assigns to it: parsing, state lookups, Merlin transcripts / Fiat-Shamir challenges,
+// SHA3-512 / BLAKE3 message hashes and the verdict precedence; every group / field / scalar-expansion operation is
+// delegated to the device through the C ABI (include/xhe.h).  In a Rust deployment this file is the part that stays Rust.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+#include <array>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/xhe.h"
+
+namespace xhe_host {
+
+typedef std::array<uint8_t, 32> Bytes32;
+typedef std::array<uint8_t, 64> Ct64;   // CompressedCiphertext (src/compressed.rs:37-41): commitment || handle
+enum Role { Sender = 0, Receiver = 1 };
+
+struct VerificationState {               // src/tx/verify.rs:25-77; every call returns false for Self::Error
+  virtual ~VerificationState() {}
+  virtual bool get_account_balance(const uint8_t account[32], const uint8_t asset[32], Role role, uint8_t out_ct[64]) = 0;
+  virtual bool update_account_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t new_ct[64], Role role) = 0;
+  virtual bool get_account_nonce(const uint8_t account[32], uint64_t* nonce) = 0;
+  virtual bool update_account_nonce(const uint8_t account[32], uint64_t nonce) = 0;
+  virtual bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) = 0;
+  virtual bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) = 0;
+};
+
+struct KeyHash { size_t operator()(const Ct64& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); uint64_t g; memcpy(&g, k.data() + 37, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull ^ g); } };
+struct Key32Hash { size_t operator()(const Bytes32& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
+
+class MockLedger : public VerificationState {   // src/lib.rs:106-201
+ public:
+  std::unordered_map<Ct64, Ct64, KeyHash> balances;   // key = account || asset
+  std::unordered_map<Bytes32, uint64_t, Key32Hash> nonces;
+  std::unordered_map<Bytes32, std::pair<std::vector<Bytes32>, uint8_t>, Key32Hash> multisig;
+  static Ct64 key(const uint8_t a[32], const uint8_t b[32]) { Ct64 k; memcpy(k.data(), a, 32); memcpy(k.data() + 32, b, 32); return k; }
+  bool get_account_balance(const uint8_t account[32], const uint8_t asset[32], Role, uint8_t out_ct[64]) override {
+    auto it = balances.find(key(account, asset)); if (it == balances.end()) return false; memcpy(out_ct, it->second.data(), 64); return true; }
+  bool update_account_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t new_ct[64], Role) override {
+    auto it = balances.find(key(account, asset)); if (it == balances.end()) return false; memcpy(it->second.data(), new_ct, 64); return true; }
+  bool get_account_nonce(const uint8_t account[32], uint64_t* nonce) override { Bytes32 k; memcpy(k.data(), account, 32); auto it = nonces.find(k); if (it == nonces.end()) return false; *nonce = it->second; return true; }
+  bool update_account_nonce(const uint8_t account[32], uint64_t nonce) override { Bytes32 k; memcpy(k.data(), account, 32); auto it = nonces.find(k); if (it == nonces.end()) return false; it->second = nonce; return true; }
+  bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) override {
+    Bytes32 k; memcpy(k.data(), account, 32);
+    if (n == 0) { multisig.erase(k); return true; }
+    std::vector<Bytes32> v(n); for (size_t i = 0; i < n; i++) memcpy(v[i].data(), signers + 32 * i, 32);
+    multisig[k] = std::make_pair(v, threshold); return true; }
+  bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) override {
+    Bytes32 k; memcpy(k.data(), account, 32); auto it = multisig.find(k); *present = it != multisig.end();
+    if (*present) { *signers = it->second.first; *threshold = it->second.second; } return true; }
+};
+
+struct TransferView { const uint8_t *asset, *dest, *commitment, *sender_handle, *receiver_handle, *proof, *extra; uint32_t extra_len; bool has_extra; };
+struct TxView {   // parsed xtx1 blob (pointers into the caller's buffer)
+  const uint8_t* blob = nullptr; size_t len = 0;
+  uint8_t version = 0, type = 0, n_sc = 0; int n_ms = -1; uint32_t count = 0, aux = 0, rp_len = 0; const uint8_t* source = nullptr; uint64_t fee = 0, nonce = 0;
+  std::vector<TransferView> transfers; const uint8_t *body = nullptr, *rp = nullptr, *sc = nullptr, *ms = nullptr, *sig = nullptr; size_t body_len = 0;
+  int parse(const uint8_t* blob, size_t len);                     // XHE_OK / XHE_ERR_PARSE
+  void to_bytes(std::vector<uint8_t>& out, size_t* multisig_index) const;   // src/tx/verify.rs:623-688
+  uint32_t n_transfers() const { return type == 0 ? count : 0; }
+};
+
+struct BatchTimings { double parse_ms = 0, resolve_ms = 0, transcript_ms = 0, device_ms = 0, finish_ms = 0, total_ms = 0; uint64_t keccak_f = 0; };
+struct BatchOptions { int threads = 0; const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool apply_state = true; };
+
+// Transaction::verify_batch.  Returns XHE_OK or the verdict code; *fail_index = first failing tx (-1 for the two
+// batch-level MSM checks, as in the reference where those errors carry no tx).
+int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* timings);
+// Transaction::apply_without_verify for a list of txs applied in order (balance updates only; config 4 shape)
+int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state);
+
+}  // namespace xhe_host

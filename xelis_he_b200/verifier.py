@@ -1,0 +1,116 @@
+"""Python face of the host layer (xelis_he_b200/host/verifier.*): the reference's verification API over the C library.
+
+    reference                                     here
+    mock::Ledger              src/lib.rs:106-201     Ledger
+    Transaction::verify_batch src/tx/verify.rs:487   verify_batch(ctx, txs, ledger)
+    Transaction::verify       src/tx/verify.rs:520   verify(ctx, tx, ledger)   (same verdicts, appendix D.8)
+    apply_without_verify      src/tx/verify.rs:545   apply_without_verify(ctx, txs, ledger)
+"""
+import ctypes as C
+
+from ._lib import ERR_NAMES, XheError, load_library
+
+
+def _lib():
+    lib = load_library()
+    if getattr(lib, "_xheh_ready", False):
+        return lib
+    vp, sz = C.c_void_p, C.c_size_t
+    lib.xheh_ledger_new.restype = vp
+    lib.xheh_ledger_clone.restype = vp; lib.xheh_ledger_clone.argtypes = [vp]
+    lib.xheh_ledger_free.argtypes = [vp]
+    lib.xheh_ledger_set_balance.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.xheh_ledger_get_balance.argtypes = [vp, C.c_char_p, C.c_char_p, vp]
+    lib.xheh_ledger_set_nonce.argtypes = [vp, C.c_char_p, C.c_uint64]
+    lib.xheh_ledger_set_multisig.argtypes = [vp, C.c_char_p, C.c_char_p, sz, C.c_uint8]
+    lib.xheh_ledger_has_multisig.argtypes = [vp, C.c_char_p]
+    lib.xheh_ledger_size.restype = sz; lib.xheh_ledger_size.argtypes = [vp]
+    lib.xheh_ledger_import.argtypes = [vp, C.c_char_p, sz]
+    lib.xheh_ledger_export.restype = sz; lib.xheh_ledger_export.argtypes = [vp, vp, sz]
+    lib.xheh_verify_batch.restype = C.c_int32
+    lib.xheh_verify_batch.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    lib.xheh_apply_without_verify.restype = C.c_int32
+    lib.xheh_apply_without_verify.argtypes = [vp, vp, vp, vp, sz]
+    lib._xheh_ready = True
+    return lib
+
+
+class Ledger:
+    def __init__(self, ptr=None):
+        self.lib = _lib()
+        self.ptr = C.c_void_p(ptr if ptr is not None else self.lib.xheh_ledger_new())
+
+    def clone(self):
+        return Ledger(self.lib.xheh_ledger_clone(self.ptr))
+
+    def set_balance(self, pk, asset, ct):
+        self.lib.xheh_ledger_set_balance(self.ptr, pk, asset, ct)
+
+    def get_balance(self, pk, asset):
+        out = C.create_string_buffer(64)
+        return out.raw if self.lib.xheh_ledger_get_balance(self.ptr, pk, asset, out) else None
+
+    def set_nonce(self, pk, nonce):
+        self.lib.xheh_ledger_set_nonce(self.ptr, pk, nonce)
+
+    def set_multisig(self, pk, signers, threshold):
+        self.lib.xheh_ledger_set_multisig(self.ptr, pk, b"".join(signers), len(signers), threshold)
+
+    def has_multisig(self, pk):
+        return bool(self.lib.xheh_ledger_has_multisig(self.ptr, pk))
+
+    def import_records(self, records):
+        """records: iterable of (pk, asset, ct64); accounts get nonce 0."""
+        blob = b"".join(pk + asset + ct for pk, asset, ct in records)
+        self.lib.xheh_ledger_import(self.ptr, blob, len(blob) // 128)
+
+    def dump(self):
+        n = self.lib.xheh_ledger_size(self.ptr)
+        buf = C.create_string_buffer(128 * max(n, 1))
+        self.lib.xheh_ledger_export(self.ptr, buf, 128 * n)
+        raw = buf.raw[:128 * n]
+        return sorted((raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128))
+
+    def __del__(self):
+        try:
+            self.lib.xheh_ledger_free(self.ptr)
+        except Exception:
+            pass
+
+
+class _Blobs:
+    def __init__(self, blobs):
+        n = len(blobs)
+        self.keep = [C.create_string_buffer(b, len(b)) for b in blobs]
+        self.ptrs = (C.c_void_p * max(n, 1))(*[C.addressof(k) for k in self.keep])
+        self.lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+        self.n = n
+
+
+def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None):
+    """Transaction::verify_batch.  Returns (code, first_failing_tx, timings dict); code 0 = Ok, >0 = verdicts (ERR_NAMES)."""
+    lib = _lib()
+    bl = prepared or _Blobs(blobs)
+    fi = C.c_long(-1)
+    tm = (C.c_double * 7)()
+    rc = lib.xheh_verify_batch(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, C.byref(fi), tm)
+    if rc < 0:
+        raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
+    keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
+    return rc, fi.value, dict(zip(keys, tm))
+
+
+def verify(ctx, blob, ledger, seed=None):
+    return verify_batch(ctx, [blob], ledger, seed)[:2]
+
+
+def apply_without_verify(ctx, blobs, ledger):
+    lib = _lib()
+    bl = _Blobs(blobs)
+    rc = lib.xheh_apply_without_verify(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n)
+    if rc < 0:
+        raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
+    return rc
+
+
+prepare_blobs = _Blobs
