@@ -112,6 +112,13 @@ typedef struct xhe_verdict {
 /* returns XHE_OK when the device work completed (verdict fields filled) -- the accept/reject decision and its error
  * precedence belong to the caller, which knows the transaction structure. */
 int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* batch, xhe_verdict* verdict);
+/* The same call in three stages, so a batch can stay resident in HBM and be re-run (bench.py times xhe_batch_run alone
+ * for `value`): prepare = arena allocation + H2D, run = kernels only (asynchronous), fetch = D2H + stream sync. */
+int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* batch);
+int32_t xhe_batch_run(xhe_ctx* ctx);
+int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* verdict);
+size_t  xhe_batch_h2d_bytes(const xhe_ctx* ctx);
+size_t  xhe_batch_d2h_bytes(const xhe_ctx* ctx);
 /* K7: add n partial sums (n x 128 B as produced in *_ext) and test the Ristretto identity; out_enc optional */
 int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t out_enc[32], int32_t* is_identity);
 
@@ -119,6 +126,10 @@ int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t
 /* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns
  * achieved instructions/s summed over the device in *rate. */
 int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate);
+/* CUDA-event timing of the main kernels of xhe_batch_run / the MSM (roofline evidence): enable, run, then read.
+ * units[i] = algorithmic limb products (DESIGN.md work model) accumulated for kernel i. */
+int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable);
+int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap);
 /* self-test of the arithmetic layer: runs op (tests/hostemu op codes) on n operand pairs on the device */
 int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
 

@@ -28,6 +28,7 @@ def _load():
     lib.xo_msm_timed.restype = C.c_double
     lib.xo_mint_transfers.restype = C.c_void_p
     lib.xo_mint_chain.restype = C.c_void_p
+    lib.xo_batch_slice.restype = C.c_void_p
     lib.xo_ledger_new.restype = C.c_void_p
     lib.xo_ledger_clone.restype = C.c_void_p
     lib.xo_ledger_dump.restype = C.c_size_t
@@ -175,6 +176,9 @@ class Batch:
 
     def ledger(self):
         return Ledger(lib.xo_ledger_clone(C.c_void_p(self._ledger_ptr)))
+
+    def slice(self, count):
+        return Batch(lib.xo_batch_slice(self.ptr, C.c_size_t(count)))
 
     def verify_timed(self, threads=1):
         rc = C.c_int(0)

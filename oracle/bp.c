@@ -78,18 +78,19 @@ int xo_rp_prove(uint8_t *out, const uint64_t *values, const sc *blind, int m, xo
   sc *gc = sL, *hc = sR; sc yinv, e; sc_invert(&yinv, &y); sc_1(&e); for (int k = 0; k < N; k++) { sc_1(&gc[k]); hc[k] = e; sc_mul(&e, &e, &yinv); }
   ipp_domain_sep(t, N);
   ge Q; ge_scalarmult(&Q, &w, G);
-  sc *ms = malloc(sizeof(sc) * (2*N + 1)); ge *mp = malloc(sizeof(ge) * (2*N + 1));
+  sc *ms = malloc(sizeof(sc) * (2*N + 1)); ge *mp = malloc(sizeof(ge) * (2*N + 1)); ge *cp = malloc(sizeof(ge) * (N + 1));
   for (int k = 0; k < N; k++) { mp[k] = *xo_bp_G(k / n, k % n); mp[N + k] = *xo_bp_H(k / n, k % n); } mp[2*N] = Q;
   uint8_t *lr = o + 224; int np = N;
   while (np > 1) {
     int h = np / 2; sc cL, cR; sc_inner(&cL, a, b + h, h); sc_inner(&cR, a + h, b, h);
     for (int pass = 0; pass < 2; pass++) { /* pass 0: L, pass 1: R */
+      /* only the N + 1 non-zero terms are passed to the MSM (G_i or H_i per index, plus Q) */
       for (int i = 0; i < N; i++) {
-        int k = i % np; sc_0(&ms[i]); sc_0(&ms[N + i]);
-        if (pass == 0) { if (k >= h) sc_mul(&ms[i], &a[k - h], &gc[i]); else sc_mul(&ms[N + i], &b[k + h], &hc[i]); }
-        else           { if (k < h) sc_mul(&ms[i], &a[k + h], &gc[i]); else sc_mul(&ms[N + i], &b[k - h], &hc[i]); }
+        int k = i % np;
+        if (pass == 0) { if (k >= h) { sc_mul(&ms[i], &a[k - h], &gc[i]); cp[i] = mp[i]; } else { sc_mul(&ms[i], &b[k + h], &hc[i]); cp[i] = mp[N + i]; } }
+        else           { if (k < h) { sc_mul(&ms[i], &a[k + h], &gc[i]); cp[i] = mp[i]; } else { sc_mul(&ms[i], &b[k - h], &hc[i]); cp[i] = mp[N + i]; } }
       }
-      ms[2*N] = pass == 0 ? cL : cR; ge P; ge_msm_vartime(&P, ms, mp, 2*N + 1); ristretto_encode(lr, &P); xo_transcript_append(t, pass == 0 ? "L" : "R", lr, 32); lr += 32;
+      ms[N] = pass == 0 ? cL : cR; cp[N] = mp[2*N]; ge P; ge_msm_vartime(&P, ms, cp, N + 1); ristretto_encode(lr, &P); xo_transcript_append(t, pass == 0 ? "L" : "R", lr, 32); lr += 32;
     }
     sc u, uinv; xo_challenge_scalar(t, "u", &u); sc_invert(&uinv, &u);
     for (int k = 0; k < h; k++) { sc t1_, t2_; sc_mul(&t1_, &a[k], &u); sc_mul(&t2_, &a[k + h], &uinv); sc_add(&a[k], &t1_, &t2_); sc_mul(&t1_, &b[k], &uinv); sc_mul(&t2_, &b[k + h], &u); sc_add(&b[k], &t1_, &t2_); }
@@ -97,7 +98,7 @@ int xo_rp_prove(uint8_t *out, const uint64_t *values, const sc *blind, int m, xo
     np = h;
   }
   sc_tobytes(lr, &a[0]); sc_tobytes(lr + 32, &b[0]);
-  free(ms); free(mp); free(sL); free(sR); free(l0); free(r0); free(r1); free(a_bl); free(s_bl);
+  free(ms); free(mp); free(cp); free(sL); free(sR); free(l0); free(r0); free(r1); free(a_bl); free(s_bl);
   (void)lg; return 0;
 }
 

@@ -124,3 +124,9 @@ int xo_resign(uint8_t *blob, size_t len, const sc *sk, xo_rng *rng) {
   uint8_t pk[32]; xo_pubkey_from_secret(sk, pk, NULL);
   xo_sign(blob + len - 64, sk, pk, bytes, nb, rng); free(bytes); return 1;
 }
+/* first `count` transactions of a batch with a clone of its ledger (bounded CPU-baseline samples) */
+xo_batch *xo_batch_slice(const xo_batch *b, size_t count) {
+  if (count > b->n) count = b->n;
+  xo_batch *s = calloc(1, sizeof *s); s->n = count; s->offsets = calloc(count + 1, sizeof(size_t)); memcpy(s->offsets, b->offsets, (count + 1) * sizeof(size_t));
+  s->blobs = malloc(s->offsets[count] + 1); memcpy(s->blobs, b->blobs, s->offsets[count]); s->ledger = xo_ledger_clone(b->ledger); return s;
+}

@@ -69,6 +69,23 @@ extern "C" const char* xhe_last_error(const xhe_ctx* ctx) { return ctx ? ctx->er
 extern "C" int32_t xhe_ctx_set_stream(xhe_ctx* ctx, void* s) { if (!ctx) return XHE_E_ARG; ctx->stream = (cudaStream_t)s; return XHE_OK; }
 extern "C" int32_t xhe_ctx_sync(xhe_ctx* ctx) { if (!ctx) return XHE_E_ARG; XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); return XHE_OK; }
 extern "C" uint64_t xhe_ctx_launch_count(const xhe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable) {
+  if (!ctx) return XHE_E_ARG;
+  for (auto& p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  ctx->pending.clear(); ctx->n_timers = 0; ctx->timing = enable != 0;
+  for (auto& t : ctx->timers) t = xhe_ctx::KernelTimer();
+  return XHE_OK;
+}
+// collect: returns the number of timed kernels; fills names / total ms / launches / algorithmic units (limb products)
+extern "C" int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap) {
+  if (!ctx) return XHE_E_ARG;
+  XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) { float t = 0; cudaEventElapsedTime(&t, p.e0, p.e1); ctx->timers[p.timer].ms += t; cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  ctx->pending.clear();
+  int n = ctx->n_timers < cap ? ctx->n_timers : cap;
+  for (int i = 0; i < n; i++) { names[i] = ctx->timers[i].name; ms[i] = ctx->timers[i].ms; launches[i] = ctx->timers[i].launches; units[i] = ctx->timers[i].units; }
+  return n;
+}
 extern "C" const void* xhe_ctx_generators_dev(const xhe_ctx* ctx, size_t* n) { if (n) *n = ctx->n_gens; return ctx->d_gens_niels; }
 
 #define H2D(dst, src, n) XHE_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, ctx->stream))

@@ -369,11 +369,12 @@ int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_nie
   k_scan_blocks<<<nbt, SCAN_THREADS, 0, st>>>(runs, p.n_tiles + 1, run_off, blocksums); XHE_LAUNCHED(ctx);
   k_scan_totals<<<1, 1024, 0, st>>>(blocksums, (int)nbt, (uint32_t*)(ws + p.off_flag) + 2); XHE_LAUNCHED(ctx);
   k_scan_add<<<nbt, SCAN_THREADS, 0, st>>>(run_off, p.n_tiles + 1, blocksums, nullptr); XHE_LAUNCHED(ctx);
+  { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
   switch (g_accum_variant) {
     case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
     case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
     default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
-  }
+  } }
   XHE_LAUNCHED(ctx);
   k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(part_g, run_off + p.n_tiles, p.max_runs, pstart, pcount); XHE_LAUNCHED(ctx);
   k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(pcount, m, heavy); XHE_LAUNCHED(ctx);

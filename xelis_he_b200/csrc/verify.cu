@@ -378,35 +378,47 @@ extern "C" int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t
   return XHE_OK;
 }
 
-extern "C" int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* b, xhe_verdict* v) {
-  if (!ctx || !b || !v) return XHE_E_ARG;
+// device-side image of one batch: every pointer lives in the ctx arena
+struct DeviceBatch {
+  xhe_batch h;                       // scalar fields (counts) copied from the host description; pointers unused
+  uint32_t Nmax = 64, rp_grid = 0; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
+  uint8_t *d_enc, *d_ok, *d_sig_r, *d_op_out, *d_ws1, *d_ws2;
+  uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
+      *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
+  long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
+};
+
+// stage 1: allocate from the ctx arena and upload the host description
+extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
+  if (!ctx || !b) return XHE_E_ARG;
   if (b->n_points == 0 || !b->points) { ctx->err = "verify_batch: point table must contain the identity at index 0"; return XHE_E_ARG; }
   int32_t rc = ensure_tables(ctx); if (rc) return rc;
-  xhe_tables* T = g_tables[ctx->device];
   cudaStream_t st = ctx->stream;
-  // ---- sizes
+  if (!ctx->resident) ctx->resident = new DeviceBatch();
+  DeviceBatch& D = *(DeviceBatch*)ctx->resident;
+  D.h = *b;
   uint32_t m_max = 1;
   for (uint32_t p = 0; p < b->n_rp; p++) {
     uint32_t m = b->rp_m[p];
-    if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity || 64u * m > 2048u) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs power of two <= min(party_capacity, 32))"; return XHE_E_ARG; }
+    if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity || 64u * m > 2048u) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs a power of two <= min(party_capacity, 32))"; return XHE_E_ARG; }
     if (m > m_max) m_max = m;
   }
-  const uint32_t Nmax = 64 * m_max;
-  const size_t n_pts_total = (size_t)b->n_points + b->n_ops;
-  const size_t n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val, n_sigma = n_sigma_terms + 2;
-  const size_t n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0, n_range = n_dyn + (b->n_rp ? 2 * (size_t)Nmax + 2 : 0);
-  const size_t n_chal = b->n_rp ? b->rp_chal_off[b->n_rp] : 0;
-  const uint32_t rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * 4) : 0;
-  const size_t ws_sigma = xhe_msm_workspace_bytes(ctx, n_sigma), ws_range = xhe_msm_workspace_bytes(ctx, n_range);
-  const size_t n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
-  // ---- arena
+  D.Nmax = 64 * m_max;
+  D.n_pts_total = (size_t)b->n_points + b->n_ops;
+  D.n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val; D.n_sigma = D.n_sigma_terms + 2;
+  D.n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0; D.n_range = D.n_dyn + (b->n_rp ? 2 * (size_t)D.Nmax + 2 : 0);
+  D.n_chal = b->n_rp ? b->rp_chal_off[b->n_rp] : 0;
+  D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * 4) : 0;
+  D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_range);
+  D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
+  const size_t n_pts_total = D.n_pts_total, n_sigma = D.n_sigma, n_range = D.n_range, n_dyn = D.n_dyn, n_chal = D.n_chal, n_terms = D.n_terms; const uint32_t Nmax = D.Nmax;
   size_t need = 32 * (size_t)b->n_points + 64 * n_pts_total + 96 * n_pts_total + b->n_points
-              + b->n_sigs * (32 + 32 + 4 + 32 + 16 * 128)
-              + (size_t)b->n_ops * (8 + 8 + 8 + 128 * 2 + 32) + 4 * (b->n_ops + 1) + 4 * n_terms
+              + (size_t)b->n_sigs * (32 + 32 + 4 + 32 + 16 * 128)
+              + (size_t)b->n_ops * (8 + 8 + 8 + 8 + 128 * 2 + 32) + 4 * ((size_t)b->n_ops + 1) + 4 * n_terms
               + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
               + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * RP_DER + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
-              + 64 * (size_t)rp_grid * Nmax + 64 * 64 * (size_t)Nmax / 64 + ws_sigma + ws_range + 4096 + 256 * 64;
+              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + 4096 + 512 * 64;
   if (ctx->scratch_bytes < need) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
@@ -414,90 +426,126 @@ extern "C" int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* b, xhe_verdic
     ctx->scratch_bytes = need + need / 4;
   }
   Arena A{(uint8_t*)ctx->d_scratch, ctx->scratch_bytes, 0};
-#define TAKE(T_, name, count) T_* name = (T_*)A.take(sizeof(T_) * (size_t)(count) + 16); if (!name) { ctx->err = "verify_batch: arena overflow at " #name; return XHE_E_NOMEM; }
+#define TAKE(T_, name, count) D.name = (T_*)A.take(sizeof(T_) * (size_t)(count) + 16); if (!D.name) { ctx->err = "verify_batch: arena overflow at " #name; return XHE_E_NOMEM; }
 #define UP(dst, src, bytes) do { if ((bytes) > 0) XHE_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st)); } while (0)
   TAKE(uint8_t, d_enc, 32 * (size_t)b->n_points); TAKE(uint32_t, d_aff, 16 * n_pts_total); TAKE(uint32_t, d_niels, 24 * n_pts_total); TAKE(uint8_t, d_ok, b->n_points);
-  UP(d_enc, b->points, 32 * (size_t)b->n_points);
-  rc = xhe_decompress_dev(ctx, d_enc, b->n_points, d_aff, d_niels, d_ok); if (rc) return rc;
-  // ---- signatures
   TAKE(uint32_t, d_sig_s, 8 * (size_t)b->n_sigs); TAKE(uint32_t, d_sig_e, 8 * (size_t)b->n_sigs); TAKE(uint32_t, d_sig_pk, b->n_sigs); TAKE(uint8_t, d_sig_r, 32 * (size_t)b->n_sigs);
   TAKE(uint32_t, d_sig_tab, 16 * 32 * (size_t)b->n_sigs);
-  if (b->n_sigs) {
-    UP(d_sig_s, b->sig_s, 32 * (size_t)b->n_sigs); UP(d_sig_e, b->sig_e, 32 * (size_t)b->n_sigs); UP(d_sig_pk, b->sig_pk, 4 * (size_t)b->n_sigs);
-    k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, st>>>(d_sig_s, d_sig_e, d_sig_pk, d_aff, d_ok, T->tabH, b->n_sigs, d_sig_r, d_sig_tab); XHE_LAUNCHED(ctx);
-  }
-  // ---- balance chains
-  TAKE(long long, d_ptr_a, b->n_ops); TAKE(long long, d_ptr_b, b->n_ops); TAKE(uint64_t, d_amount, b->n_ops); TAKE(uint32_t, d_term_off, b->n_ops + 1); TAKE(uint32_t, d_terms, n_terms);
+  TAKE(long long, d_ptr_init, b->n_ops); TAKE(long long, d_ptr_a, b->n_ops); TAKE(long long, d_ptr_b, b->n_ops); TAKE(uint64_t, d_amount, b->n_ops); TAKE(uint32_t, d_term_off, b->n_ops + 1); TAKE(uint32_t, d_terms, n_terms);
   TAKE(uint32_t, d_acc_a, 32 * (size_t)b->n_ops); TAKE(uint32_t, d_acc_b, 32 * (size_t)b->n_ops); TAKE(uint8_t, d_op_out, 32 * (size_t)b->n_ops);
+  TAKE(uint32_t, d_eq_sc, 48 * (size_t)b->n_eq); TAKE(uint32_t, d_val_sc, 40 * (size_t)b->n_val); TAKE(uint32_t, d_sig_idx, n_sigma);
+  TAKE(uint32_t, d_sigma_sc, 8 * n_sigma); TAKE(uint32_t, d_sigma_niels, 24 * n_sigma); TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
+  TAKE(uint32_t, d_results, 128); TAKE(uint8_t, d_ws1, D.ws_sigma);
+  TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
+  TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
+  TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range);
+  UP(D.d_enc, b->points, 32 * (size_t)b->n_points);
+  UP(D.d_sig_s, b->sig_s, 32 * (size_t)b->n_sigs); UP(D.d_sig_e, b->sig_e, 32 * (size_t)b->n_sigs); UP(D.d_sig_pk, b->sig_pk, 4 * (size_t)b->n_sigs);
+  if (b->n_ops) { UP(D.d_ptr_init, b->op_prev, 8 * (size_t)b->n_ops); UP(D.d_amount, b->op_amount, 8 * (size_t)b->n_ops); UP(D.d_term_off, b->op_term_off, 4 * ((size_t)b->n_ops + 1)); UP(D.d_terms, b->op_terms, 4 * n_terms); }
+  UP(D.d_eq_sc, b->eq_scalars, 192 * (size_t)b->n_eq); UP(D.d_val_sc, b->val_scalars, 160 * (size_t)b->n_val);
+  UP(D.d_sig_idx, b->eq_points, 28 * (size_t)b->n_eq); UP(D.d_sig_idx + 7 * (size_t)b->n_eq, b->val_points, 32 * (size_t)b->n_val);
+  if (b->n_rp) {
+    UP(D.d_m, b->rp_m, 4 * (size_t)b->n_rp); UP(D.d_pt_off, b->rp_point_off, 4 * ((size_t)b->n_rp + 1)); UP(D.d_ch_off, b->rp_chal_off, 4 * ((size_t)b->n_rp + 1));
+    UP(D.d_rp_sc, b->rp_scalars, 224 * (size_t)b->n_rp); UP(D.d_chal, b->rp_challenges, 32 * n_chal); UP(D.d_range_idx, b->rp_points, 4 * n_dyn);
+  }
+#undef TAKE
+#undef UP
+  return XHE_OK;
+}
+extern "C" size_t xhe_batch_h2d_bytes(const xhe_ctx* ctx) {
+  if (!ctx || !ctx->resident) return 0;
+  const DeviceBatch& D = *(const DeviceBatch*)ctx->resident; const xhe_batch& b = D.h;
+  return 32 * (size_t)b.n_points + (size_t)b.n_sigs * 68 + (size_t)b.n_ops * 16 + 4 * ((size_t)b.n_ops + 1) + 4 * D.n_terms + 220 * (size_t)b.n_eq + 192 * (size_t)b.n_val
+       + (size_t)b.n_rp * (4 + 8 + 224) + 32 * D.n_chal + 4 * D.n_dyn;
+}
+extern "C" size_t xhe_batch_d2h_bytes(const xhe_ctx* ctx) {
+  if (!ctx || !ctx->resident) return 0;
+  const xhe_batch& b = ((const DeviceBatch*)ctx->resident)->h;
+  return 512 + b.n_points + 32 * (size_t)b.n_sigs + 32 * (size_t)b.n_ops;
+}
+
+// stage 2: kernels only, on the resident batch (re-runnable: inputs are never overwritten)
+extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
+  if (!ctx || !ctx->resident) return XHE_E_ARG;
+  DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h;
+  xhe_tables* T = g_tables[ctx->device];
+  cudaStream_t st = ctx->stream; int32_t rc;
+  const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_range = D.n_range; const uint32_t Nmax = D.Nmax;
+  { XheTimed t(ctx, "k_decompress", 12632.0 * b->n_points);
+    rc = xhe_decompress_dev(ctx, D.d_enc, b->n_points, D.d_aff, D.d_niels, D.d_ok); if (rc) return rc; }
+  if (b->n_sigs) { XheTimed t(ctx, "k_sig_r", 160000.0 * b->n_sigs);
+    k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, st>>>(D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_aff, D.d_ok, T->tabH, b->n_sigs, D.d_sig_r, D.d_sig_tab); XHE_LAUNCHED(ctx); }
   if (b->n_ops) {
-    UP(d_ptr_a, b->op_prev, 8 * (size_t)b->n_ops); UP(d_amount, b->op_amount, 8 * (size_t)b->n_ops); UP(d_term_off, b->op_term_off, 4 * ((size_t)b->n_ops + 1)); UP(d_terms, b->op_terms, 4 * n_terms);
-    k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(d_term_off, d_terms, d_amount, d_niels, T->tabG, b->n_ops, d_acc_a); XHE_LAUNCHED(ctx);
-    uint32_t *acc_cur = d_acc_a, *acc_nxt = d_acc_b; long long *ptr_cur = d_ptr_a, *ptr_nxt = d_ptr_b;
+    XheTimed t(ctx, "balance_chain", (504.0 * 2 + 2 * 12688.0) * b->n_ops);
+    XHE_CUDA_OK(ctx, cudaMemcpyAsync(D.d_ptr_a, D.d_ptr_init, 8 * (size_t)b->n_ops, cudaMemcpyDeviceToDevice, st));
+    k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(D.d_term_off, D.d_terms, D.d_amount, D.d_niels, T->tabG, b->n_ops, D.d_acc_a); XHE_LAUNCHED(ctx);
+    uint32_t *acc_cur = D.d_acc_a, *acc_nxt = D.d_acc_b; long long *ptr_cur = D.d_ptr_a, *ptr_nxt = D.d_ptr_b;
     for (uint32_t span = 1; span < b->max_chain; span <<= 1) {
       k_op_jump<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, acc_nxt, ptr_nxt); XHE_LAUNCHED(ctx);
       std::swap(acc_cur, acc_nxt); std::swap(ptr_cur, ptr_nxt);
     }
-    k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, d_aff, d_niels, d_op_out); XHE_LAUNCHED(ctx);
+    k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, D.d_aff, D.d_niels, D.d_op_out); XHE_LAUNCHED(ctx);
   }
-  // ---- sigma proofs -> MSM operands
-  TAKE(uint32_t, d_eq_sc, 48 * (size_t)b->n_eq); TAKE(uint32_t, d_val_sc, 40 * (size_t)b->n_val); TAKE(uint32_t, d_sig_idx, n_sigma);
-  TAKE(uint32_t, d_sigma_sc, 8 * n_sigma); TAKE(uint32_t, d_sigma_niels, 24 * n_sigma); TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
-  TAKE(uint32_t, d_results, 128);   // [0..7] sigma enc, [8] sigma id, [16..47] sigma ext, [48..55] range enc, [56] range id, [64..95] range ext, [96] bad flag
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(d_results, 0, 512, st));
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, st));
   {
-    UP(d_eq_sc, b->eq_scalars, 192 * (size_t)b->n_eq); UP(d_val_sc, b->val_scalars, 160 * (size_t)b->n_val);
-    UP(d_sig_idx, b->eq_points, 28 * (size_t)b->n_eq); UP(d_sig_idx + 7 * (size_t)b->n_eq, b->val_points, 32 * (size_t)b->n_val);
     uint32_t np = b->n_eq + b->n_val;
     if (np) {
-      k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(d_eq_sc, b->n_eq, d_val_sc, b->n_val, d_sigma_sc, d_gh); XHE_LAUNCHED(ctx);
-      k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(d_niels, d_sig_idx, (uint32_t)n_sigma_terms, d_sigma_niels); XHE_LAUNCHED(ctx);
-      // g/h totals: two-stage reduction of the per-proof contributions (column 0 = g, column 1 = h)
-      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(d_gh, np, 2, 1, d_gh_part, 2); XHE_LAUNCHED(ctx);
-      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(d_gh_part, 32, 2, 1, d_sigma_sc + 8 * n_sigma_terms, 2); XHE_LAUNCHED(ctx);
+      { XheTimed t(ctx, "k_sigma_weights", 136.0 * 14 * np);
+        k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(D.d_eq_sc, b->n_eq, D.d_val_sc, b->n_val, D.d_sigma_sc, D.d_gh); XHE_LAUNCHED(ctx); }
+      k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_gh, np, 2, 1, D.d_gh_part, 2); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_gh_part, 32, 2, 1, D.d_sigma_sc + 8 * n_sigma_terms, 2); XHE_LAUNCHED(ctx);
     } else {
-      XHE_CUDA_OK(ctx, cudaMemsetAsync(d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
+      XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
     }
-    k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
-    TAKE(uint8_t, d_ws1, ws_sigma);
-    rc = xhe_launch_msm_ex(ctx, d_sigma_sc, d_sigma_niels, n_sigma, d_ws1, ws_sigma, d_results, d_results + 8, d_results + 16, d_results + 96); if (rc) return rc;
+    k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, D.d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
+    XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
+    rc = xhe_launch_msm_ex(ctx, D.d_sigma_sc, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, D.d_results + 96); if (rc) return rc;
   }
-  // ---- range proofs -> MSM operands
   if (b->n_rp) {
-    TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
-    TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
-    TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)rp_grid * Nmax);
-    UP(d_m, b->rp_m, 4 * (size_t)b->n_rp); UP(d_pt_off, b->rp_point_off, 4 * ((size_t)b->n_rp + 1)); UP(d_ch_off, b->rp_chal_off, 4 * ((size_t)b->n_rp + 1));
-    UP(d_rp_sc, b->rp_scalars, 224 * (size_t)b->n_rp); UP(d_chal, b->rp_challenges, 32 * n_chal); UP(d_range_idx, b->rp_points, 4 * n_dyn);
-    k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(d_m, d_rp_sc, d_ch_off, d_chal, d_pt_off, b->n_rp, d_der, d_range_sc, d_rgh); XHE_LAUNCHED(ctx);
+    { XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
+      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
     size_t smem = 64 * (size_t)Nmax;
     if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rp_gens<<<rp_grid, RPG_THREADS, smem, st>>>(d_m, d_der, T->pow2m, b->n_rp, Nmax, d_part); XHE_LAUNCHED(ctx);
-    // static scalars: sum the per-block partials, G_vec[0..Nmax) then H_vec[0..Nmax)
-    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(d_part, rp_grid, 2 * Nmax, 1, d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(d_rgh, b->n_rp, 2, 1, d_rgh_part, 2); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(d_rgh_part, 32, 2, 1, d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
-    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(d_niels, d_range_idx, (uint32_t)n_dyn, d_range_niels); XHE_LAUNCHED(ctx);
+    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * (double)n_dyn /* ~6 products per generator index; refined in DESIGN.md */);
+      k_rp_gens<<<D.rp_grid, RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.d_part); XHE_LAUNCHED(ctx); }
+    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
     const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
-    k_copy_words<<<1, 64, 0, st>>>(gens, 48, d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
-    TAKE(uint8_t, d_ws2, ws_range);
-    rc = xhe_launch_msm_ex(ctx, d_range_sc, d_range_niels, n_range, d_ws2, ws_range, d_results + 48, d_results + 56, d_results + 64, d_results + 96); if (rc) return rc;
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
+    k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
+    XheTimed t(ctx, "msm_range", 8064.0 * n_range + 6.04e8);
+    rc = xhe_launch_msm_ex(ctx, D.d_range_sc, D.d_range_niels, n_range, D.d_ws2, D.ws_range, D.d_results + 48, D.d_results + 56, D.d_results + 64, D.d_results + 96); if (rc) return rc;
   }
-  // ---- results
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+
+// stage 3: read the results back (synchronises the stream)
+extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
+  if (!ctx || !ctx->resident || !v) return XHE_E_ARG;
+  DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h; cudaStream_t st = ctx->stream;
   uint32_t h_res[128];
-  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, d_results, 512, cudaMemcpyDeviceToHost, st));
-  if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, d_ok, b->n_points, cudaMemcpyDeviceToHost, st));
-  if (v->sig_r && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_r, d_sig_r, 32 * (size_t)b->n_sigs, cudaMemcpyDeviceToHost, st));
-  if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, D.d_results, 512, cudaMemcpyDeviceToHost, st));
+  if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, D.d_ok, b->n_points, cudaMemcpyDeviceToHost, st));
+  if (v->sig_r && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_r, D.d_sig_r, 32 * (size_t)b->n_sigs, cudaMemcpyDeviceToHost, st));
+  if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, D.d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
   XHE_CUDA_OK(ctx, cudaStreamSynchronize(st));
   if (h_res[96]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
   memcpy(v->sigma_enc, h_res, 32); v->sigma_is_identity = (int32_t)h_res[8]; memcpy(v->sigma_ext, h_res + 16, 128);
   if (b->n_rp) { memcpy(v->range_enc, h_res + 48, 32); v->range_is_identity = (int32_t)h_res[56]; memcpy(v->range_ext, h_res + 64, 128); }
   else { memset(v->range_enc, 0, 32); v->range_is_identity = 1; memset(v->range_ext, 0, 128); ((uint32_t*)v->range_ext)[8] = 1; ((uint32_t*)v->range_ext)[16] = 1; }
   return XHE_OK;
-#undef TAKE
-#undef UP
+}
+
+extern "C" int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* b, xhe_verdict* v) {
+  if (!ctx || !b || !v) return XHE_E_ARG;
+  int32_t rc = xhe_batch_prepare(ctx, b); if (rc) return rc;
+  rc = xhe_batch_run(ctx); if (rc) return rc;
+  return xhe_batch_fetch(ctx, v);
 }
 
 // Signature::verify group part, host-buffer entry point (src/elgamal.rs:38-42): r_i = s_i*H - e_i*P_i, compressed

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <vector>
 #include "../../include/xhe.h"
 #include "ge25519.cuh"
 #include "sc25519.cuh"
@@ -20,6 +22,28 @@ struct xhe_ctx {
   size_t n_gens = 0;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;       // grow-only device scratch for host-buffer entry points
   void* h_pinned = nullptr; size_t pinned_bytes = 0;         // grow-only pinned staging
+  // optional CUDA-event timing of the main kernels (bench.py roofline): accumulated since the last reset
+  bool timing = false;
+  struct KernelTimer { const char* name; double ms = 0; uint64_t launches = 0; double units = 0; };
+  KernelTimer timers[16];
+  int n_timers = 0;
+  struct Pending { int timer; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
+};
+
+// scoped timing of one kernel launch on ctx->stream (no-op unless ctx->timing)
+struct XheTimed {
+  xhe_ctx* ctx; int idx = -1; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  XheTimed(xhe_ctx* c, const char* name, double units) : ctx(c) {
+    if (!c->timing) return;
+    for (int i = 0; i < c->n_timers; i++) if (!strcmp(c->timers[i].name, name)) idx = i;
+    if (idx < 0 && c->n_timers < 16) { idx = c->n_timers++; c->timers[idx].name = name; }
+    if (idx < 0) return;
+    c->timers[idx].launches++; c->timers[idx].units += units;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream);
+  }
+  ~XheTimed() { if (idx >= 0) { cudaEventRecord(e1, ctx->stream); ctx->pending.push_back({idx, e0, e1}); } }
 };
 
 #define XHE_CUDA_OK(ctx, call)                                                                       \
