@@ -213,6 +213,20 @@ def verify_batch(blobs, ledger: Ledger, rng_seed=1):
     return rc, fi.value
 
 
+def verify_batch_partial(blobs, ledger: Ledger, rng_seed=1):
+    """one shard of a multi-GPU batch: local verdict plus the partial sigma / range MSM encodings (no identity decision)."""
+    n = len(blobs)
+    arr = (C.c_char_p * max(n, 1))(*blobs) if n else (C.c_char_p * 1)()
+    lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+    rng = (C.c_uint8 * 512)()
+    seed = (C.c_uint64 * 1)(rng_seed)
+    lib.xo_rng_init(rng, seed, C.c_size_t(8))
+    fi = C.c_long(-1)
+    part = (C.c_uint8 * 64)()
+    rc = lib.xo_verify_batch_ex(arr, lens, C.c_size_t(n), ledger.ptr, rng, C.byref(fi), part)
+    return rc, fi.value, bytes(part[:32]), bytes(part[32:])
+
+
 def apply_without_verify(blob, ledger: Ledger):
     return lib.xo_apply_without_verify(_buf(blob), C.c_size_t(len(blob)), ledger.ptr)
 

@@ -102,7 +102,7 @@ int xo_rp_prove(uint8_t *out, const uint64_t *values, const sc *blind, int m, xo
   (void)lg; return 0;
 }
 
-int xo_rp_verify_batch(const xo_rp_item *items, size_t n_items, xo_rng *rng, uint8_t out_enc[32]) {
+int xo_rp_verify_batch_ex(const xo_rp_item *items, size_t n_items, xo_rng *rng, uint8_t out_enc[32], int no_decision) {
   const int n = XO_BP_N; int m_max = 0;
   for (size_t q = 0; q < n_items; q++) { if (items[q].m > XO_BP_PARTY_CAP) return XO_ERR_RANGE_PROOF; if (items[q].m > m_max) m_max = items[q].m; }
   xo_bp_ensure(m_max);
@@ -166,7 +166,8 @@ int xo_rp_verify_batch(const xo_rp_item *items, size_t n_items, xo_rng *rng, uin
     for (int k = 0; k < Nmax; k++) { PUSH(gs[k], *xo_bp_G(k / n, k % n)); } for (int k = 0; k < Nmax; k++) { PUSH(hs[k], *xo_bp_H(k / n, k % n)); }
     PUSH(base_s, *xo_G()); PUSH(blind_s, *xo_H());
     ge r; ge_msm_vartime(&r, ds, dp, nd); if (out_enc) ristretto_encode(out_enc, &r);
-    if (!ge_ristretto_is_identity(&r)) rc = XO_ERR_RANGE_PROOF;
+    if (!no_decision && !ge_ristretto_is_identity(&r)) rc = XO_ERR_RANGE_PROOF;
   }
   free(gs); free(hs); free(ds); free(dp); return rc;
 }
+int xo_rp_verify_batch(const xo_rp_item *items, size_t n_items, xo_rng *rng, uint8_t out_enc[32]) { return xo_rp_verify_batch_ex(items, n_items, rng, out_enc, 0); }

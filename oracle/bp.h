@@ -19,4 +19,5 @@ int xo_rp_prove(uint8_t *out, const uint64_t *values, const sc *blindings, int m
 /* one proof to verify in a batch: transcript already advanced to the range-proof position, commitments compressed (+ decoded) */
 typedef struct { const uint8_t *proof; size_t len; xo_transcript *t; const uint8_t *commit_enc; const ge *commit_pts; int m; } xo_rp_item;
 int xo_rp_verify_batch(const xo_rp_item *items, size_t n_items, xo_rng *rng, uint8_t out_enc[32]); /* XO_OK / XO_ERR_RANGE_PROOF */
+int xo_rp_verify_batch_ex(const xo_rp_item *items, size_t n_items, xo_rng *rng, uint8_t out_enc[32], int no_decision);
 #endif

@@ -203,19 +203,22 @@ done:
   free(dt); free(nsc); free(bytes); return rc;
 }
 static void prepared_free(prepared *p) { free(p->commit_enc); free(p->commit_pts); }
-int xo_verify_batch(const uint8_t *const *blobs, const size_t *lens, size_t n, xo_ledger *state, xo_rng *rng, long *fail_index) {
+/* partial != NULL: multi-GPU shard mode -- skip the two identity decisions and return the partial sums' encodings (sigma || range) */
+int xo_verify_batch_ex(const uint8_t *const *blobs, const size_t *lens, size_t n, xo_ledger *state, xo_rng *rng, long *fail_index, uint8_t *partial) {
   xo_collector col; xo_collector_init(&col); prepared *prep = calloc(n ? n : 1, sizeof(prepared)); xo_tx *txs = calloc(n ? n : 1, sizeof(xo_tx)); int rc = XO_OK; size_t done = 0;
   if (fail_index) *fail_index = -1;
   for (size_t i = 0; i < n; i++) { rc = xo_tx_parse(&txs[i], blobs[i], lens[i]); if (rc) { if (fail_index) *fail_index = (long)i; n = i; goto out; } }
   for (size_t i = 0; i < n; i++) { rc = pre_verify(&txs[i], state, &col, rng, &prep[i]); done = i + 1; if (rc) { if (fail_index) *fail_index = (long)i; goto out; } }
-  if (!xo_collector_verify(&col, NULL)) { rc = XO_ERR_GENERIC_PROOF; goto out; }
+  if (partial) memset(partial, 0, 64);
+  if (!xo_collector_verify(&col, partial) && !partial) { rc = XO_ERR_GENERIC_PROOF; goto out; }
   { xo_rp_item *items = malloc(sizeof(xo_rp_item) * (n + 1));
     for (size_t i = 0; i < n; i++) { items[i].proof = txs[i].rp; items[i].len = txs[i].rp_len; items[i].t = &prep[i].t; items[i].commit_enc = prep[i].commit_enc; items[i].commit_pts = prep[i].commit_pts; items[i].m = prep[i].m; }
-    rc = n ? xo_rp_verify_batch(items, n, rng, NULL) : XO_OK; free(items); }
+    rc = n ? xo_rp_verify_batch_ex(items, n, rng, partial ? partial + 32 : NULL, partial != NULL) : XO_OK; free(items); }
 out:
   for (size_t i = 0; i < done; i++) prepared_free(&prep[i]); for (size_t i = 0; i < n; i++) xo_tx_free(&txs[i]);
   free(prep); free(txs); xo_collector_free(&col); return rc;
 }
+int xo_verify_batch(const uint8_t *const *blobs, const size_t *lens, size_t n, xo_ledger *state, xo_rng *rng, long *fail_index) { return xo_verify_batch_ex(blobs, lens, n, state, rng, fail_index, NULL); }
 int xo_verify(const uint8_t *blob, size_t len, xo_ledger *state, xo_rng *rng) { long fi; return xo_verify_batch(&blob, &len, 1, state, rng, &fi); }
 int xo_apply_without_verify(const uint8_t *blob, size_t len, xo_ledger *st) { /* src/tx/verify.rs:545-619 */
   xo_tx tx; int rc = xo_tx_parse(&tx, blob, len); if (rc) return rc;

@@ -39,6 +39,7 @@ int  xo_ledger_get_multisig(const xo_ledger *l, const uint8_t pk[32], const uint
 size_t xo_ledger_dump(const xo_ledger *l, uint8_t *out, size_t cap); /* sorted (pk,asset,ct) records, 128 B each */
 /* entry points; *fail_index = index of the first failing tx (or -1 for the batch-level MSM checks) */
 int xo_verify_batch(const uint8_t *const *blobs, const size_t *lens, size_t n, xo_ledger *state, xo_rng *rng, long *fail_index);
+int xo_verify_batch_ex(const uint8_t *const *blobs, const size_t *lens, size_t n, xo_ledger *state, xo_rng *rng, long *fail_index, uint8_t *partial64);
 int xo_verify(const uint8_t *blob, size_t len, xo_ledger *state, xo_rng *rng);
 int xo_apply_without_verify(const uint8_t *blob, size_t len, xo_ledger *state);
 /* builder (src/tx/builder.rs).  Spec for one transfer / the tx data; plaintext balances come from `balances` */

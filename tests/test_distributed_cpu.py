@@ -1,0 +1,80 @@
+"""world_size-2 `gloo` test of the multi-GPU host logic on CPU: sharding, the all-gather of per-rank records and the joint
+decision (xelis_he_b200/distributed.py).  The per-shard partial results come from the oracle here (no GPU); the decision
+must equal the oracle's verdict on the whole batch."""
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, blobs, records, q):
+    import torch.distributed as dist
+    import oracle
+    from xelis_he_b200 import distributed as xd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    led = oracle.Ledger()
+    for pk, asset, ct in records:
+        led.set_balance(pk, asset, ct); led.set_nonce(pk, 0)
+    n = len(blobs); lo, hi = n * rank // world, n * (rank + 1) // world
+    code, idx, s_enc, r_enc = oracle.verify_batch_partial(blobs[lo:hi], led, rng_seed=100 + rank)
+    recs = xd.all_gather_records(xd.pack_local(code, idx, lo, s_enc, r_enc))
+
+    def sum_is_identity(encs):
+        acc = bytes(32)
+        for e in encs:
+            acc = oracle.point_add(acc, e)
+        return acc == bytes(32)
+    q.put((rank, xd.decide(recs, sum_is_identity)))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def _run(blobs, records):
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue(); port = _free_port()
+    ps = [ctxm.Process(target=_worker, args=(r, 2, port, blobs, records, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=240) for _ in range(2))
+    for p in ps:
+        p.join(60)
+    assert out[0] == out[1]
+    return out[0]
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_sharded_verdicts_match_single_process_oracle():
+    import oracle
+    b = oracle.mint_transfers(21, 10, 1, 1, threads=4)
+    records = b.ledger().dump()
+    assert _run(b.blobs, records) == oracle.verify_batch(b.blobs, b.ledger()) == (0, -1)
+    # a per-tx failure in the second shard is reported with its global index
+    bad = list(b.blobs); x = bytearray(bad[7]); x[-40] ^= 1; bad[7] = bytes(x)
+    assert _run(bad, records) == oracle.verify_batch(bad, b.ledger()) == (1, 7)
+    # failures in both shards: the earliest transaction wins
+    x = bytearray(bad[2]); x[56] ^= 1; bad[2] = bytes(x)
+    assert _run(bad, records) == oracle.verify_batch(bad, b.ledger()) == (9, 2)
+
+
+def test_decide_orders_checks_like_the_reference():
+    from xelis_he_b200 import distributed as xd
+    z = bytes(32); nz = bytes([1]) + bytes(31)
+    ident = lambda encs: all(e == z for e in encs)   # stand-in group: only the all-zero encoding is the identity
+    ok = xd.pack_local(0, -1, 0, z, z)
+    assert xd.decide([ok, ok], ident) == (0, -1)
+    assert xd.decide([ok, xd.pack_local(0, -1, 5, nz, z)], ident) == (5, -1)                 # sigma sum != identity
+    assert xd.decide([ok, xd.pack_local(0, -1, 5, z, nz)], ident) == (6, -1)                 # range sum != identity
+    assert xd.decide([xd.pack_local(0, -1, 0, nz, nz), ok], ident) == (5, -1)                # sigma is checked before range
+    assert xd.decide([xd.pack_local(6, -1, 0, z, z), ok], ident) == (6, -1)                  # structural range failure in a shard
+    assert xd.decide([xd.pack_local(6, -1, 0, z, z), xd.pack_local(0, -1, 5, nz, z)], ident) == (5, -1)
+    assert xd.decide([ok, xd.pack_local(1, 3, 5, nz, nz)], ident) == (1, 8)                  # per-tx errors come first, global index
+    assert xd.decide([xd.pack_local(9, 4, 0, z, z), xd.pack_local(1, 0, 5, z, z)], ident) == (9, 4)

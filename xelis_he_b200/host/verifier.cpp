@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <stdio.h>
 #include <string.h>
@@ -183,6 +184,25 @@ void advance_chain(Builder& B, const uint8_t* account, const uint8_t* asset, uin
 }
 
 }  // namespace
+
+// shard-mode state updates waiting for the cross-rank decision (one slot per ctx)
+namespace {
+struct Pending { std::vector<StateUpdate> updates; std::vector<uint8_t> op_out; };
+std::mutex g_pending_mu;
+std::unordered_map<xhe_ctx*, Pending> g_pending;
+}  // namespace
+
+int commit_pending(xhe_ctx* ctx, VerificationState& state) {
+  std::lock_guard<std::mutex> g(g_pending_mu);
+  auto it = g_pending.find(ctx);
+  if (it == g_pending.end()) return XHE_E_ARG;
+  for (const StateUpdate& u : it->second.updates) {
+    uint8_t ct[64]; memcpy(ct, &it->second.op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &it->second.op_out[32 * (size_t)u.op_d], 32);
+    if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
+  }
+  g_pending.erase(it);
+  return XHE_OK;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Transaction::verify_batch
@@ -449,10 +469,15 @@ int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, 
     }
   }
   if (verdict == XHE_OK && parse_err != XHE_OK) { verdict = parse_err; bad_tx = (long)n_live; }
-  if (verdict == XHE_OK && !v.sigma_is_identity) verdict = XHE_ERR_GENERIC_PROOF;                       // src/tx/verify.rs:500-502
+  const bool shard = opt.partial_out != nullptr;
+  if (shard) { memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32); }
+  if (verdict == XHE_OK && !shard && !v.sigma_is_identity) verdict = XHE_ERR_GENERIC_PROOF;            // src/tx/verify.rs:500-502
   if (verdict == XHE_OK) { for (size_t i = 0; i < n_reached; i++) if (plan[i].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
-  if (verdict == XHE_OK && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;                          // src/tx/verify.rs:504-514
-  if (verdict == XHE_OK && opt.apply_state) {
+  if (verdict == XHE_OK && !shard && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;               // src/tx/verify.rs:504-514
+  if (shard) {
+    std::lock_guard<std::mutex> g(g_pending_mu);
+    Pending& P = g_pending[ctx]; P.updates = B.updates; P.op_out = op_out;
+  } else if (verdict == XHE_OK && opt.apply_state) {
     for (const StateUpdate& u : B.updates) {
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
       if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) { verdict = XHE_ERR_STATE; break; }
@@ -542,6 +567,14 @@ int32_t xheh_verify_batch(xhe_ctx* ctx, void* ledger, const uint8_t* const* blob
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
   return rc;
 }
+int32_t xheh_verify_batch_partial(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, long* fail_index, double* timings7, uint8_t* partial64) {
+  BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.partial_out = partial64;
+  BatchTimings tm;
+  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
+  return rc;
+}
+int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(ctx, *(MockLedger*)ledger); }
 int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(MockLedger*)ledger); }
 // host-only helpers exposed for CPU tests of the host logic
 void xheh_merlin_test(const char* proto, const char* label, const uint8_t* msg, size_t n, const char* chal_label, uint8_t* out, size_t outlen) { Transcript t(proto); t.append(label, msg, n); t.challenge(chal_label, out, outlen); }

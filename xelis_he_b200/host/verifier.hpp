@@ -73,11 +73,17 @@ struct TxView {   // parsed xtx1 blob (pointers into the caller's buffer)
 };
 
 struct BatchTimings { double parse_ms = 0, resolve_ms = 0, transcript_ms = 0, device_ms = 0, finish_ms = 0, total_ms = 0; uint64_t keccak_f = 0; };
-struct BatchOptions { int threads = 0; const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool apply_state = true; };
+struct BatchOptions { int threads = 0; const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool apply_state = true;
+                      uint8_t* partial_out = nullptr; /* 64 B: shard mode, see verify_batch */ };
 
 // Transaction::verify_batch.  Returns XHE_OK or the verdict code; *fail_index = first failing tx (-1 for the two
 // batch-level MSM checks, as in the reference where those errors carry no tx).
+// Shard mode (opt.partial_out != nullptr, multi-GPU): the two identity decisions are NOT taken here; the encodings of this
+// shard's partial sigma / range sums are returned (sigma || range) for the caller to combine across ranks, and the state
+// updates are held back until commit_pending().
 int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* timings);
+// apply the balance updates a shard-mode verify_batch held back (after the cross-rank decision accepted the batch)
+int commit_pending(xhe_ctx* ctx, VerificationState& state);
 // Transaction::apply_without_verify for a list of txs applied in order (balance updates only; config 4 shape)
 int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state);
 

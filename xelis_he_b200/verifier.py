@@ -29,6 +29,9 @@ def _lib():
     lib.xheh_ledger_export.restype = sz; lib.xheh_ledger_export.argtypes = [vp, vp, sz]
     lib.xheh_verify_batch.restype = C.c_int32
     lib.xheh_verify_batch.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    lib.xheh_verify_batch_partial.restype = C.c_int32
+    lib.xheh_verify_batch_partial.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
+    lib.xheh_commit_pending.restype = C.c_int32; lib.xheh_commit_pending.argtypes = [vp, vp]
     lib.xheh_apply_without_verify.restype = C.c_int32
     lib.xheh_apply_without_verify.argtypes = [vp, vp, vp, vp, sz]
     lib._xheh_ready = True
@@ -98,6 +101,26 @@ def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None):
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
     return rc, fi.value, dict(zip(keys, tm))
+
+
+def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None):
+    """Shard mode for multi-GPU batches: (local code, first failing local tx, sigma partial enc, range partial enc, timings).
+    The sigma / range identity decisions are left to the caller (xelis_he_b200.distributed); balance updates are held back
+    until commit_pending()."""
+    lib = _lib()
+    bl = prepared or _Blobs(blobs)
+    fi = C.c_long(-1)
+    tm = (C.c_double * 7)()
+    part = C.create_string_buffer(64)
+    rc = lib.xheh_verify_batch_partial(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, C.byref(fi), tm, part)
+    if rc < 0:
+        raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
+    keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
+    return rc, fi.value, part.raw[:32], part.raw[32:], dict(zip(keys, tm))
+
+
+def commit_pending(ctx, ledger):
+    return _lib().xheh_commit_pending(ctx.p, ledger.ptr)
 
 
 def verify(ctx, blob, ledger, seed=None):
