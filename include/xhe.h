@@ -97,6 +97,19 @@ typedef struct xhe_batch {
    * weight, rho = cross-proof batch factor), challenges y,z,x,w,u[lg] */
   uint32_t n_rp; const uint32_t* rp_m; const uint32_t* rp_point_off /* n_rp+1 */; const uint32_t* rp_points;
   const uint8_t* rp_scalars /* n_rp x 7 x 32 */; const uint32_t* rp_chal_off /* n_rp+1, in scalars */; const uint8_t* rp_challenges;
+  /* OPTIONAL device-side Fiat-Shamir.  When fs_blobs != NULL the library replays the Merlin transcripts,
+   * derives c / w / y / z / x / w / u_j and the random batch factors, and checks the main signatures' SHA3-512 on the
+   * device from the transactions' xtx1 wire bytes; the challenge / factor slots of eq_scalars, val_scalars, rp_scalars and
+   * rp_challenges are then ignored (may be zero).  fs_plan: 6 words per tx = eq_begin, val_begin, rp slot (0xffffffff none),
+   * rp challenge offset, main-signature slot (0xffffffff none), flags (bit 0: sigma / range stage reached). */
+  const uint8_t* fs_blobs; const uint64_t* fs_blob_off /* n_tx+1 */; const uint32_t* fs_plan; uint8_t fs_seed[32];
+  /* OPTIONAL device-side layout (fast path; requires fs_blobs; SURVEY.md 8 f.2 in spirit).  When layout_on_device != 0 the
+   * library also builds the point table and every per-proof / signature array from the blobs (kernel k_layout), so
+   * points / sig_* / eq_* / val_* / rp_points / rp_scalars may be NULL.  The host supplies counts (n_points, n_sigs, n_eq, n_val,
+   * n_rp), rp_m, rp_point_off, rp_chal_off, the balance-chain ops, fs_plan with EIGHT words per tx (the six above + point base
+   * + first balance-op index; the per-tx point layout is documented at k_layout) and the state-derived encodings
+   * (initial balance halves) region_b, placed at point indices [n_points - n_region_b, n_points). */
+  uint32_t layout_on_device; uint32_t n_region_b; const uint8_t* region_b;
 } xhe_batch;
 
 typedef struct xhe_verdict {
@@ -107,6 +120,8 @@ typedef struct xhe_verdict {
   uint8_t* point_ok;             /* n_points: decompression flags (caller-allocated) */
   uint8_t* sig_r;                /* n_sigs x 32: compressed r_i (caller-allocated) */
   uint8_t* op_out;               /* n_ops x 32: compressed chain outputs = updated balance halves (caller-allocated) */
+  uint8_t* sig_ok;               /* n_sigs: filled only in device Fiat-Shamir mode, for the main-signature slots (caller-allocated, optional) */
+  uint32_t device_flags;         /* device-layout mode: bit 0 identity-encoded Y/A/S/T/L/R, bit 1 some point failed to decompress, bit 2 some signature mismatched */
 } xhe_verdict;
 
 /* returns XHE_OK when the device work completed (verdict fields filled) -- the accept/reject decision and its error

@@ -28,6 +28,18 @@ def both(ctx, world, txs, expect=None):
     hl = world.host_ledger()
     code, idx, tm = verifier.verify_batch(ctx, txs, hl, seed=SEED, threads=4)
     assert (code, idx) == want, (code, idx, want)
+    hl_dev = world.host_ledger()                      # same batch with device-side Fiat-Shamir: same verdict, same state
+    code_d, idx_d, _ = verifier.verify_batch(ctx, txs, hl_dev, seed=SEED, threads=4, fiat_shamir="device")
+    assert (code_d, idx_d) == want, ("device fiat-shamir", code_d, idx_d, want)
+    assert hl_dev.dump() == hl.dump()
+    hl_fast = world.host_ledger()                     # optimistic device-layout path (falls back to the exact path on any failure)
+    code_f, idx_f, tm_f = verifier.verify_batch(ctx, txs, hl_fast, seed=SEED, threads=4, fiat_shamir="fast")
+    assert (code_f, idx_f) == want, ("fast path", code_f, idx_f, want)
+    assert hl_fast.dump() == hl.dump()
+    if code == OK and txs and not any(t[1] == 4 or t[3] != 0xFF for t in txs) and not world.multisig:
+        assert tm_f["fast_path"], "an honest non-multisig batch must be decided by the fast path"
+    if code != OK:
+        assert not tm_f["fast_path"]
     if expect is not None:
         assert code == expect
     if code == OK:
@@ -45,6 +57,9 @@ def test_minted_batches_accept(ctx):
         code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED)
         assert (code, idx) == (OK, -1)
         assert hl.dump() == sorted(ol.dump())
+        hf = verifier.Ledger(); hf.import_records(b.ledger().dump())
+        code, idx, tm = verifier.verify_batch(ctx, b.blobs, hf, seed=SEED, fiat_shamir="fast")
+        assert (code, idx) == (OK, -1) and tm["fast_path"] and hf.dump() == sorted(ol.dump())
 
 
 def test_mixed_party_sizes_in_one_batch(ctx):
@@ -153,6 +168,26 @@ def test_apply_without_verify_matches_oracle(ctx):
     hl = w.host_ledger()
     assert verifier.apply_without_verify(ctx, txs, hl) == 0
     assert hl.dump() == sorted(ol.dump())
+
+
+def test_device_fiat_shamir_matches_host(ctx):
+    """both modes derive the same challenges and batch factors: the partial MSM encodings of a (deliberately invalid) shard
+    are byte-identical, not just the verdicts"""
+    from xelis_he_b200 import verifier
+    b = oracle.mint_transfers(91, 9, 2, 3, threads=8)
+    blobs = list(b.blobs)
+    blobs[4] = _mut(blobs[4], 64 + 160 + 128)      # corrupt a validity-proof response: the sigma partial is no longer the identity
+    outs = []
+    for mode in ("host", "device"):
+        hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+        outs.append(verifier.verify_batch_partial(ctx, blobs, hl, seed=SEED, threads=3, fiat_shamir=mode)[:4])
+    assert outs[0] == outs[1] and outs[0][0] == SIG and outs[0][1] == 4 and outs[0][2] != bytes(32)
+    swapped = [b.blobs[1], b.blobs[0]] + b.blobs[2:]          # valid txs: partials are the identity in both modes
+    for mode in ("host", "device", "fast"):
+        hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+        r = verifier.verify_batch_partial(ctx, swapped, hl, seed=SEED, fiat_shamir=mode)
+        assert r[:4] == (0, -1, bytes(32), bytes(32))
+        assert r[4]["fast_path"] == (mode == "fast")
 
 
 def test_verdict_partials_combine(ctx):

@@ -63,6 +63,8 @@ extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   if (ctx->d_gens_niels) cudaFree(ctx->d_gens_niels);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (auto& st : ctx->aux) if (st) cudaStreamDestroy(st);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   delete ctx;
 }
 extern "C" const char* xhe_last_error(const xhe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }

@@ -19,6 +19,13 @@ using namespace xhe;
 
 int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag);
 extern "C" size_t xhe_msm_workspace_bytes(const xhe_ctx*, size_t n);
+int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed,
+                               uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_rp_chal, const uint32_t* d_rp_m);
+int32_t xhe_launch_sig_hash(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_sig_r, const uint32_t* d_sig_e, uint8_t* d_sig_ok);
+int32_t xhe_launch_layout(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t n_tx, uint32_t n_points, uint8_t* d_enc,
+                          uint32_t* d_sig_idx, uint32_t n_eq, uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_range_idx, const uint32_t* d_rp_pt_off,
+                          uint32_t* d_sig_s, uint32_t* d_sig_e, uint32_t* d_sig_pk, uint32_t* d_viol);
+int32_t xhe_launch_any_zero(xhe_ctx* ctx, const uint8_t* d_flags, uint32_t n, uint32_t bit, uint32_t* d_viol);
 
 namespace {
 
@@ -386,12 +393,13 @@ struct DeviceBatch {
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
   long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
+  bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok; unsigned long long* d_blob_off; uint32_t* d_fs_plan; size_t blob_bytes = 0;
 };
 
 // stage 1: allocate from the ctx arena and upload the host description
 extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   if (!ctx || !b) return XHE_E_ARG;
-  if (b->n_points == 0 || !b->points) { ctx->err = "verify_batch: point table must contain the identity at index 0"; return XHE_E_ARG; }
+  if (b->n_points == 0 || (!b->points && !(b->layout_on_device && b->fs_blobs))) { ctx->err = "verify_batch: point table must contain the identity at index 0"; return XHE_E_ARG; }
   int32_t rc = ensure_tables(ctx); if (rc) return rc;
   cudaStream_t st = ctx->stream;
   if (!ctx->resident) ctx->resident = new DeviceBatch();
@@ -411,6 +419,10 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * 4) : 0;
   D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_range);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
+  D.fs = b->fs_blobs != nullptr && b->n_tx > 0; D.blob_bytes = D.fs ? (size_t)b->fs_blob_off[b->n_tx] : 0;
+  D.layout = D.fs && b->layout_on_device != 0; D.plan_stride = D.layout ? 8 : 6;
+  if (b->layout_on_device && !D.fs) { ctx->err = "verify_batch: layout_on_device needs fs_blobs"; return XHE_E_ARG; }
+  if (D.layout && (b->n_region_b > b->n_points - 1 || (b->n_region_b && !b->region_b))) { ctx->err = "verify_batch: bad region_b"; return XHE_E_ARG; }
   const size_t n_pts_total = D.n_pts_total, n_sigma = D.n_sigma, n_range = D.n_range, n_dyn = D.n_dyn, n_chal = D.n_chal, n_terms = D.n_terms; const uint32_t Nmax = D.Nmax;
   size_t need = 32 * (size_t)b->n_points + 64 * n_pts_total + 96 * n_pts_total + b->n_points
               + (size_t)b->n_sigs * (32 + 32 + 4 + 32 + 16 * 128)
@@ -418,7 +430,8 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
               + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
               + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * RP_DER + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
-              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + 4096 + 512 * 64;
+              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + 4096 + 512 * 64
+              + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs;
   if (ctx->scratch_bytes < need) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
@@ -439,14 +452,24 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
   TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
   TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range);
-  UP(D.d_enc, b->points, 32 * (size_t)b->n_points);
-  UP(D.d_sig_s, b->sig_s, 32 * (size_t)b->n_sigs); UP(D.d_sig_e, b->sig_e, 32 * (size_t)b->n_sigs); UP(D.d_sig_pk, b->sig_pk, 4 * (size_t)b->n_sigs);
+  TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs);
+  if (D.fs) { UP(D.d_blobs, b->fs_blobs, D.blob_bytes); UP(D.d_blob_off, b->fs_blob_off, 8 * ((size_t)b->n_tx + 1)); UP(D.d_fs_plan, b->fs_plan, 4 * (size_t)D.plan_stride * b->n_tx); UP(D.d_seed, b->fs_seed, 32); }
+  if (!D.layout) {
+    UP(D.d_enc, b->points, 32 * (size_t)b->n_points);
+    UP(D.d_sig_s, b->sig_s, 32 * (size_t)b->n_sigs); UP(D.d_sig_e, b->sig_e, 32 * (size_t)b->n_sigs); UP(D.d_sig_pk, b->sig_pk, 4 * (size_t)b->n_sigs);
+  } else {
+    XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_enc, 0, 32, st));                                               // point 0 = identity
+    UP(D.d_enc + 32 * (size_t)(b->n_points - b->n_region_b), b->region_b, 32 * (size_t)b->n_region_b);    // state-derived points
+  }
   if (b->n_ops) { UP(D.d_ptr_init, b->op_prev, 8 * (size_t)b->n_ops); UP(D.d_amount, b->op_amount, 8 * (size_t)b->n_ops); UP(D.d_term_off, b->op_term_off, 4 * ((size_t)b->n_ops + 1)); UP(D.d_terms, b->op_terms, 4 * n_terms); }
-  UP(D.d_eq_sc, b->eq_scalars, 192 * (size_t)b->n_eq); UP(D.d_val_sc, b->val_scalars, 160 * (size_t)b->n_val);
-  UP(D.d_sig_idx, b->eq_points, 28 * (size_t)b->n_eq); UP(D.d_sig_idx + 7 * (size_t)b->n_eq, b->val_points, 32 * (size_t)b->n_val);
+  if (!D.layout) {
+    UP(D.d_eq_sc, b->eq_scalars, 192 * (size_t)b->n_eq); UP(D.d_val_sc, b->val_scalars, 160 * (size_t)b->n_val);
+    UP(D.d_sig_idx, b->eq_points, 28 * (size_t)b->n_eq); UP(D.d_sig_idx + 7 * (size_t)b->n_eq, b->val_points, 32 * (size_t)b->n_val);
+  }
   if (b->n_rp) {
     UP(D.d_m, b->rp_m, 4 * (size_t)b->n_rp); UP(D.d_pt_off, b->rp_point_off, 4 * ((size_t)b->n_rp + 1)); UP(D.d_ch_off, b->rp_chal_off, 4 * ((size_t)b->n_rp + 1));
-    UP(D.d_rp_sc, b->rp_scalars, 224 * (size_t)b->n_rp); UP(D.d_chal, b->rp_challenges, 32 * n_chal); UP(D.d_range_idx, b->rp_points, 4 * n_dyn);
+    if (!D.layout) { UP(D.d_rp_sc, b->rp_scalars, 224 * (size_t)b->n_rp); UP(D.d_range_idx, b->rp_points, 4 * n_dyn); }
+    if (!D.fs) UP(D.d_chal, b->rp_challenges, 32 * n_chal);
   }
 #undef TAKE
 #undef UP
@@ -455,26 +478,63 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
 extern "C" size_t xhe_batch_h2d_bytes(const xhe_ctx* ctx) {
   if (!ctx || !ctx->resident) return 0;
   const DeviceBatch& D = *(const DeviceBatch*)ctx->resident; const xhe_batch& b = D.h;
+  if (D.layout) return D.blob_bytes + 8 * ((size_t)b.n_tx + 1) + 32 * (size_t)b.n_tx + 32 + 32 * (size_t)b.n_region_b + (size_t)b.n_ops * 16 + 4 * ((size_t)b.n_ops + 1) + 4 * D.n_terms + 12 * (size_t)b.n_rp + 8;
   return 32 * (size_t)b.n_points + (size_t)b.n_sigs * 68 + (size_t)b.n_ops * 16 + 4 * ((size_t)b.n_ops + 1) + 4 * D.n_terms + 220 * (size_t)b.n_eq + 192 * (size_t)b.n_val
-       + (size_t)b.n_rp * (4 + 8 + 224) + 32 * D.n_chal + 4 * D.n_dyn;
+       + (size_t)b.n_rp * (4 + 8 + 224) + (D.fs ? 0 : 32 * D.n_chal) + 4 * D.n_dyn + (D.fs ? D.blob_bytes + 32 * (size_t)b.n_tx + 40 : 0);
 }
 extern "C" size_t xhe_batch_d2h_bytes(const xhe_ctx* ctx) {
   if (!ctx || !ctx->resident) return 0;
   const xhe_batch& b = ((const DeviceBatch*)ctx->resident)->h;
-  return 512 + b.n_points + 32 * (size_t)b.n_sigs + 32 * (size_t)b.n_ops;
+  return 512 + b.n_points + 32 * (size_t)b.n_sigs + 32 * (size_t)b.n_ops + (((const DeviceBatch*)ctx->resident)->fs ? b.n_sigs : 0);
 }
 
-// stage 2: kernels only, on the resident batch (re-runnable: inputs are never overwritten)
+// stage 2: kernels only, on the resident batch (re-runnable: inputs are never overwritten).
+// Four independent pipelines run on separate streams and join at the end, so the latency-bound tails (single-thread Horner,
+// one-thread-per-signature / per-transcript kernels) overlap the throughput-bound kernels of the other pipelines:
+//   main : decompress -> balance chains -> sigma weights -> sigma MSM
+//   aux0 : Fiat-Shamir transcripts (device mode)
+//   aux1 : (after decompress) signature r -> signature hash
+//   aux2 : (after decompress + transcripts) range-proof scalars -> range MSM
 extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   if (!ctx || !ctx->resident) return XHE_E_ARG;
   DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h;
   xhe_tables* T = g_tables[ctx->device];
-  cudaStream_t st = ctx->stream; int32_t rc;
+  int32_t rc;
   const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_range = D.n_range; const uint32_t Nmax = D.Nmax;
+  if (!ctx->aux[0]) { for (auto& s : ctx->aux) XHE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  cudaStream_t main_st = ctx->stream, s_fs = ctx->aux[0], s_sig = ctx->aux[1], s_rp = ctx->aux[2];
+  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4];
+  struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
+  XHE_CUDA_OK(ctx, cudaEventRecord(e_start, main_st));
+  // ---- aux0: transcripts
+  if (D.fs) {
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_fs, e_start, 0));
+    ctx->stream = s_fs;
+    rc = xhe_launch_fiat_shamir(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_seed, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_chal, D.d_m); if (rc) return rc;
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_fs, s_fs));
+  }
+  // ---- main: (fast path) build the tables from the blobs, then decompress
+  ctx->stream = main_st;
+  if (D.layout) { rc = xhe_launch_layout(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, b->n_tx, b->n_points, D.d_enc, D.d_sig_idx, b->n_eq, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_range_idx, D.d_pt_off,
+                                         D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_results + 98); if (rc) return rc; }
   { XheTimed t(ctx, "k_decompress", 12632.0 * b->n_points);
     rc = xhe_decompress_dev(ctx, D.d_enc, b->n_points, D.d_aff, D.d_niels, D.d_ok); if (rc) return rc; }
-  if (b->n_sigs) { XheTimed t(ctx, "k_sig_r", 160000.0 * b->n_sigs);
-    k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, st>>>(D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_aff, D.d_ok, T->tabH, b->n_sigs, D.d_sig_r, D.d_sig_tab); XHE_LAUNCHED(ctx); }
+  if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_ok, b->n_points, 1, D.d_results + 98); if (rc) return rc; }
+  XHE_CUDA_OK(ctx, cudaEventRecord(e_dec, main_st));
+  // ---- aux1: signatures
+  if (b->n_sigs) {
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_dec, 0));
+    ctx->stream = s_sig;
+    { XheTimed t(ctx, "k_sig_r", 160000.0 * b->n_sigs);
+      k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, s_sig>>>(D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_aff, D.d_ok, T->tabH, b->n_sigs, D.d_sig_r, D.d_sig_tab); XHE_LAUNCHED(ctx); }
+    if (D.fs) { XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sig_ok, 0, b->n_sigs, s_sig)); rc = xhe_launch_sig_hash(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_sig_r, D.d_sig_e, D.d_sig_ok); if (rc) return rc;
+                if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_sig_ok, b->n_sigs, 2, D.d_results + 98); if (rc) return rc; } }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_sig, s_sig));
+  }
+  // ---- main: balance chains (their outputs are sigma MSM operands)
+  ctx->stream = main_st;
+  cudaStream_t st = main_st;
   if (b->n_ops) {
     XheTimed t(ctx, "balance_chain", (504.0 * 2 + 2 * 12688.0) * b->n_ops);
     XHE_CUDA_OK(ctx, cudaMemcpyAsync(D.d_ptr_a, D.d_ptr_init, 8 * (size_t)b->n_ops, cudaMemcpyDeviceToDevice, st));
@@ -486,10 +546,36 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     }
     k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, D.d_aff, D.d_niels, D.d_op_out); XHE_LAUNCHED(ctx);
   }
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, st));
+  // ---- aux2: range proofs (independent of the balance chains: they only reference input points)
+  if (b->n_rp) {
+    XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], main_st));          // results buffer cleared + decompress done
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, ctx->ev[5], 0));
+    if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_fs, 0));
+    ctx->stream = s_rp; st = s_rp;
+    { XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
+      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
+    size_t smem = 64 * (size_t)Nmax;
+    if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * (double)n_dyn);
+      k_rp_gens<<<D.rp_grid, RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.d_part); XHE_LAUNCHED(ctx); }
+    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
+    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
+    const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
+    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
+    k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
+    { XheTimed t(ctx, "msm_range", 8064.0 * n_range + 6.04e8);
+      rc = xhe_launch_msm_ex(ctx, D.d_range_sc, D.d_range_niels, n_range, D.d_ws2, D.ws_range, D.d_results + 48, D.d_results + 56, D.d_results + 64, D.d_results + 97); if (rc) return rc; }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
+  }
+  // ---- main: sigma proofs -> MSM
+  ctx->stream = main_st; st = main_st;
   {
     uint32_t np = b->n_eq + b->n_val;
     if (np) {
+      if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_fs, 0));
       { XheTimed t(ctx, "k_sigma_weights", 136.0 * 14 * np);
         k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(D.d_eq_sc, b->n_eq, D.d_val_sc, b->n_val, D.d_sigma_sc, D.d_gh); XHE_LAUNCHED(ctx); }
       k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx);
@@ -502,24 +588,10 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
     rc = xhe_launch_msm_ex(ctx, D.d_sigma_sc, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, D.d_results + 96); if (rc) return rc;
   }
-  if (b->n_rp) {
-    { XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
-      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
-    size_t smem = 64 * (size_t)Nmax;
-    if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * (double)n_dyn /* ~6 products per generator index; refined in DESIGN.md */);
-      k_rp_gens<<<D.rp_grid, RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.d_part); XHE_LAUNCHED(ctx); }
-    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
-    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
-    const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
-    k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
-    XheTimed t(ctx, "msm_range", 8064.0 * n_range + 6.04e8);
-    rc = xhe_launch_msm_ex(ctx, D.d_range_sc, D.d_range_niels, n_range, D.d_ws2, D.ws_range, D.d_results + 48, D.d_results + 56, D.d_results + 64, D.d_results + 96); if (rc) return rc;
-  }
+  // ---- join
+  if (b->n_sigs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sig, 0));
+  if (b->n_rp) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_rp, 0));
+  if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_fs, 0));
   XHE_CUDA_OK(ctx, cudaGetLastError());
   return XHE_OK;
 }
@@ -533,8 +605,10 @@ extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, D.d_ok, b->n_points, cudaMemcpyDeviceToHost, st));
   if (v->sig_r && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_r, D.d_sig_r, 32 * (size_t)b->n_sigs, cudaMemcpyDeviceToHost, st));
   if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, D.d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
+  if (v->sig_ok && D.fs && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_ok, D.d_sig_ok, b->n_sigs, cudaMemcpyDeviceToHost, st));
   XHE_CUDA_OK(ctx, cudaStreamSynchronize(st));
-  if (h_res[96]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
+  if (h_res[96] | h_res[97]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
+  v->device_flags = h_res[98];
   memcpy(v->sigma_enc, h_res, 32); v->sigma_is_identity = (int32_t)h_res[8]; memcpy(v->sigma_ext, h_res + 16, 128);
   if (b->n_rp) { memcpy(v->range_enc, h_res + 48, 32); v->range_is_identity = (int32_t)h_res[56]; memcpy(v->range_ext, h_res + 64, 128); }
   else { memset(v->range_enc, 0, 32); v->range_is_identity = 1; memset(v->range_ext, 0, 128); ((uint32_t*)v->range_ext)[8] = 1; ((uint32_t*)v->range_ext)[16] = 1; }

@@ -30,6 +30,8 @@ struct xhe_ctx {
   struct Pending { int timer; cudaEvent_t e0, e1; };
   std::vector<Pending> pending;
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};          // side streams for the independent pipelines of xhe_batch_run
+  cudaEvent_t ev[8] = {nullptr};
 };
 
 // scoped timing of one kernel launch on ctx->stream (no-op unless ctx->timing)

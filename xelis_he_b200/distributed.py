@@ -48,12 +48,12 @@ def all_gather_records(local_record, group=None, device=None):
     return [raw[i * n:(i + 1) * n] for i in range(world)]
 
 
-def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None, seed=None, threads=0, prepared=None, commit=True):
+def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None, seed=None, threads=0, prepared=None, commit=True, fiat_shamir="host"):
     """Transaction::verify_batch over a batch sharded across the ranks of `group`.  Returns (code, global first failing tx,
     timings).  On accept every rank commits its own shard's balance updates to its ledger."""
     import torch
     from . import verifier
-    code, idx, s_enc, r_enc, tm = verifier.verify_batch_partial(ctx, shard_blobs, ledger, seed=seed, threads=threads, prepared=prepared)
+    code, idx, s_enc, r_enc, tm = verifier.verify_batch_partial(ctx, shard_blobs, ledger, seed=seed, threads=threads, prepared=prepared, fiat_shamir=fiat_shamir)
     records = all_gather_records(pack_local(code, idx, shard_offset, s_enc, r_enc), group, torch.device("cuda", torch.cuda.current_device()))
     one = (1).to_bytes(32, "little")
     verdict = decide(records, lambda encs: ctx.msm(one * len(encs), b"".join(encs))[1])

@@ -72,9 +72,11 @@ struct TxView {   // parsed xtx1 blob (pointers into the caller's buffer)
   uint32_t n_transfers() const { return type == 0 ? count : 0; }
 };
 
-struct BatchTimings { double parse_ms = 0, resolve_ms = 0, transcript_ms = 0, device_ms = 0, finish_ms = 0, total_ms = 0; uint64_t keccak_f = 0; };
+struct BatchTimings { bool used_fast_path = false; double parse_ms = 0, resolve_ms = 0, transcript_ms = 0, device_ms = 0, finish_ms = 0, total_ms = 0; uint64_t keccak_f = 0; };
 struct BatchOptions { int threads = 0; const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool apply_state = true;
-                      uint8_t* partial_out = nullptr; /* 64 B: shard mode, see verify_batch */ };
+                      uint8_t* partial_out = nullptr; /* 64 B: shard mode, see verify_batch */
+                      bool device_fiat_shamir = false; /* transcripts, batch factors and main-signature hashes on the GPU */
+                      bool fast_path = false; /* optimistic device-layout path first (implies device Fiat-Shamir); the exact path decides on any failure */ };
 
 // Transaction::verify_batch.  Returns XHE_OK or the verdict code; *fail_index = first failing tx (-1 for the two
 // batch-level MSM checks, as in the reference where those errors carry no tx).

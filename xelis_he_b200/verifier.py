@@ -31,11 +31,16 @@ def _lib():
     lib.xheh_verify_batch.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double)]
     lib.xheh_verify_batch_partial.restype = C.c_int32
     lib.xheh_verify_batch_partial.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
+    lib.xheh_verify_batch_ex.restype = C.c_int32
+    lib.xheh_verify_batch_ex.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.c_uint32, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
     lib.xheh_commit_pending.restype = C.c_int32; lib.xheh_commit_pending.argtypes = [vp, vp]
     lib.xheh_apply_without_verify.restype = C.c_int32
     lib.xheh_apply_without_verify.argtypes = [vp, vp, vp, vp, sz]
     lib._xheh_ready = True
     return lib
+
+
+_MODE_FLAGS = {"host": 0, "device": 1, "fast": 5}
 
 
 class Ledger:
@@ -90,20 +95,23 @@ class _Blobs:
         self.n = n
 
 
-def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None):
-    """Transaction::verify_batch.  Returns (code, first_failing_tx, timings dict); code 0 = Ok, >0 = verdicts (ERR_NAMES)."""
+def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host"):
+    """Transaction::verify_batch.  Returns (code, first_failing_tx, timings dict); code 0 = Ok, >0 = verdicts (ERR_NAMES).
+    fiat_shamir = "host" (Merlin transcripts on host threads, north_star's split), "device"  or "fast"
+    (device transcripts + device-side batch layout, optimistic; any failure is re-decided by the exact path)."""
     lib = _lib()
     bl = prepared or _Blobs(blobs)
     fi = C.c_long(-1)
     tm = (C.c_double * 7)()
-    rc = lib.xheh_verify_batch(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, C.byref(fi), tm)
+    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, _MODE_FLAGS[fiat_shamir], C.byref(fi), tm, None)
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
-    return rc, fi.value, dict(zip(keys, tm))
+    d = dict(zip(keys, tm)); d["fast_path"] = d["keccak_f"] < 0
+    return rc, fi.value, d
 
 
-def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None):
+def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host"):
     """Shard mode for multi-GPU batches: (local code, first failing local tx, sigma partial enc, range partial enc, timings).
     The sigma / range identity decisions are left to the caller (xelis_he_b200.distributed); balance updates are held back
     until commit_pending()."""
@@ -112,11 +120,12 @@ def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None
     fi = C.c_long(-1)
     tm = (C.c_double * 7)()
     part = C.create_string_buffer(64)
-    rc = lib.xheh_verify_batch_partial(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, C.byref(fi), tm, part)
+    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, 2 | _MODE_FLAGS[fiat_shamir], C.byref(fi), tm, part)
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
-    return rc, fi.value, part.raw[:32], part.raw[32:], dict(zip(keys, tm))
+    d = dict(zip(keys, tm)); d["fast_path"] = d["keccak_f"] < 0
+    return rc, fi.value, part.raw[:32], part.raw[32:], d
 
 
 def commit_pending(ctx, ledger):
