@@ -5,16 +5,16 @@ ctx = xhe.Ctx(0, party_capacity=0)
 lib = ctx.lib
 lib.xhe_bench_op.restype = C.c_int32
 lib.xhe_bench_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-names = ["fe_mul", "fe_sq", "ge_double", "ge_madd", "ge_add"]
+names = ["fe_mul", "fe_sq", "ge_double", "ge_madd", "ge_add", "fe_add", "quad_double", "quad_add", "quad_madd"]
 res = {}
 GHZ = 1.92
 for op, name in enumerate(names):
     row = {}
     # (threads/block, blocks/SM): resident warps per SMSP = tpb/32*bps/4 if registers allow
-    for tpb, bps in ((128, 1), (128, 2), (128, 4), (128, 6), (128, 8), (128, 12), (128, 16)):
+    for tpb, bps in ((32, 1), (128, 1), (128, 2), (128, 4)):
         c = (C.c_double * 2)()
         rc = lib.xhe_bench_op(ctx.p, op, tpb, 148 * bps, 1000, c)
-        row[f"{bps}w"] = (round(c[0]), round(c[1] * GHZ)) if rc == 0 else rc   # (warp-0 latency cycles, cycles per warp-op per SMSP from wall time)
+        row[f"{tpb}x{bps}"] = (round(c[0]), round(c[1] * GHZ)) if rc == 0 else rc   # (warp-0 latency cycles, cycles per warp-op per SMSP from wall time)
     res[name] = row
     print(name, row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True); json.dump(res, open("gpurun_out/op_bench.json", "w"), indent=1)

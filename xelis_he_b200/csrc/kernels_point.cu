@@ -2,6 +2,7 @@
 // the integer-pipe microbenchmarks.  One thread per point; these kernels are bound by the integer-multiply pipe
 // (one invsqrt = 254 S + 11 M ~ 12k limb products per point against 32-128 B of traffic).
 #include "xhe_internal.cuh"
+#include "quad.cuh"
 using namespace xhe;
 
 #define XHE_PT_THREADS 128
@@ -251,6 +252,9 @@ __global__ void k_bench_op(uint32_t* out, const uint32_t* in, int iters, unsigne
     else if (OP == 3) p = ge_madd(p, q);
     else if (OP == 4) p = ge_add(p, p);
     else if (OP == 5) a = fe_add(a, b);
+    else if (OP == 6) p = quad_double(p);
+    else if (OP == 7) p = quad_add(p, p);
+    else if (OP == 8) p = quad_madd(p, q);
   }
   unsigned long long t1 = clock64();
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
@@ -275,6 +279,9 @@ extern "C" int32_t xhe_bench_op(xhe_ctx* ctx, int op, int threads_per_block, int
       case 2: k_bench_op<2><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
       case 3: k_bench_op<3><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
       case 4: k_bench_op<4><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
+      case 6: k_bench_op<6><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
+      case 7: k_bench_op<7><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
+      case 8: k_bench_op<8><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
       default: k_bench_op<5><<<blocks, threads_per_block, 0, ctx->stream>>>(d_out, d_in, iters, d_c); break;
     }
     cudaEventRecord(e1, ctx->stream);

@@ -17,6 +17,7 @@
 //
 // Algorithmic work: n*W mixed adds of 7 M = 504 limb products each dominate.
 #include "xhe_internal.cuh"
+#include "quad.cuh"
 #include <algorithm>
 #include <vector>
 #include <string.h>
@@ -307,16 +308,19 @@ __global__ void __launch_bounds__(128) k_msm_nodes(const uint32_t* __restrict__ 
   }
 }
 
-// final: one node per window.  S_w = wsum + run (bucket b carries multiplier b+1); result = sum_w 2^(c w) S_w
-__global__ void k_msm_horner(const uint32_t* __restrict__ nodes, int W, int c, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// final: one node per window.  S_w = wsum + run (bucket b carries multiplier b+1); result = sum_w 2^(c w) S_w by Horner.
+// 254 sequential doublings: a pure latency chain, so one quad (4 lanes) shares every point operation (quad.cuh).
+__global__ void __launch_bounds__(32) k_msm_horner(const uint32_t* __restrict__ nodes, int W, int c, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
   ge acc = ge_identity();
   for (int w = W - 1; w >= 0; w--) {
-    for (int k = 0; k < c; k++) acc = ge_double(acc);
+    if (w != W - 1) for (int k = 0; k < c; k++) acc = quad_double(acc);
     ge run, wsum; ld_ge(run, nodes + 64 * (size_t)w); ld_ge(wsum, nodes + 64 * (size_t)w + 32);
-    acc = ge_add(acc, ge_add(run, wsum));
+    acc = quad_add(acc, quad_add(run, wsum));
   }
-  if (out_ext) st_ge(out_ext, acc);
+  if (threadIdx.x != 0) return;
+  if (out_ext) {   // canonical coordinates so any consumer (other ranks, the CPU oracle) can read them
+    st_fe(out_ext, fe_freeze(acc.X)); st_fe(out_ext + 8, fe_freeze(acc.Y)); st_fe(out_ext + 16, fe_freeze(acc.Z)); st_fe(out_ext + 24, fe_freeze(acc.T));
+  }
   if (out_enc) encode_words(out_enc, acc);
   if (is_identity) *is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }

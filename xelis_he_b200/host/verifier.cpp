@@ -263,7 +263,7 @@ int commit_pending(xhe_ctx* ctx, VerificationState& state) {
 // error precedence.  Multisig accounts / multisig transactions always take the exact path.
 // ------------------------------------------------------------------------------------------------------------------
 struct FastCache {
-  PinnedVec<uint8_t> blob, region_b; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
+  PinnedVec<uint8_t> blob, region_b, op_out; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
 };
 static std::unordered_map<xhe_ctx*, FastCache*> g_fast_cache;
 static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g_cache_mu); FastCache*& c = g_fast_cache[ctx]; if (!c) c = new FastCache(); return *c; }
@@ -355,7 +355,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   xb.n_eq = n_eq; xb.n_val = n_val; xb.n_rp = (uint32_t)n; xb.rp_m = F.rp_m.data(); xb.rp_point_off = F.rp_pt_off.data(); xb.rp_chal_off = F.rp_ch_off.data();
   xb.fs_blobs = F.blob.data(); xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32);
   xb.layout_on_device = 1; xb.n_region_b = n_rb; xb.region_b = F.region_b.data();
-  std::vector<uint8_t> op_out(32 * (size_t)xb.n_ops + 1);
+  PinnedVec<uint8_t>& op_out = F.op_out; op_out.n = 0; op_out.reserve(32 * (size_t)xb.n_ops + 64); op_out.n = 32 * (size_t)xb.n_ops;
   xhe_verdict v; memset(&v, 0, sizeof v); v.op_out = op_out.data();
   int32_t rc = xhe_verify_batch(ctx, &xb, &v);
   double t4 = now_ms();
@@ -367,7 +367,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   if (shard) {
     memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32);
     std::lock_guard<std::mutex> g(g_pending_mu);
-    Pending& Pn = g_pending[ctx]; Pn.updates.clear(); Pn.op_out = op_out;
+    Pending& Pn = g_pending[ctx]; Pn.updates.clear(); Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size());
     for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; Pn.updates.push_back(su); }
   } else if (opt.apply_state) {
     for (const Upd& u : updates) {
