@@ -48,13 +48,60 @@ def all_gather_records(local_record, group=None, device=None):
     return [raw[i * n:(i + 1) * n] for i in range(world)]
 
 
-def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None, seed=None, threads=0, prepared=None, commit=True, fiat_shamir="host"):
+class OrderedGatherer:
+    """All-gathers for several batches in flight.  NCCL collectives must be issued in the same order on every rank, so the
+    worker threads never call NCCL themselves: they submit (sequence number, record) and one thread per process performs the
+    all-gathers strictly in sequence order on a single communicator."""
+
+    def __init__(self, group=None, device=None):
+        import threading
+        self.group, self.device = group, device
+        self.cv = threading.Condition()
+        self.pending, self.results, self.next_seq, self.stop = {}, {}, 0, False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        import torch
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        while True:
+            with self.cv:
+                while self.next_seq not in self.pending and not self.stop:
+                    self.cv.wait(0.05)
+                if self.stop and self.next_seq not in self.pending:
+                    return
+                rec = self.pending.pop(self.next_seq)
+            out = all_gather_records(rec, self.group, self.device)
+            with self.cv:
+                self.results[self.next_seq] = out
+                self.next_seq += 1
+                self.cv.notify_all()
+
+    def gather(self, seq, record):
+        with self.cv:
+            self.pending[seq] = record
+            self.cv.notify_all()
+            while seq not in self.results:
+                self.cv.wait(0.05)
+            return self.results.pop(seq)
+
+    def close(self):
+        with self.cv:
+            self.stop = True
+            self.cv.notify_all()
+        self.thread.join(5)
+
+
+def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None, seed=None, threads=0, prepared=None, commit=True, fiat_shamir="host", gather=None):
     """Transaction::verify_batch over a batch sharded across the ranks of `group`.  Returns (code, global first failing tx,
-    timings).  On accept every rank commits its own shard's balance updates to its ledger."""
+    timings).  On accept every rank commits its own shard's balance updates to its ledger.  `gather` (record -> list of
+    records) replaces the direct all-gather when several batches are in flight (OrderedGatherer)."""
     import torch
     from . import verifier
     code, idx, s_enc, r_enc, tm = verifier.verify_batch_partial(ctx, shard_blobs, ledger, seed=seed, threads=threads, prepared=prepared, fiat_shamir=fiat_shamir)
-    records = all_gather_records(pack_local(code, idx, shard_offset, s_enc, r_enc), group, torch.device("cuda", torch.cuda.current_device()))
+    rec = pack_local(code, idx, shard_offset, s_enc, r_enc)
+    records = gather(rec) if gather else all_gather_records(rec, group, torch.device("cuda", torch.cuda.current_device()))
     one = (1).to_bytes(32, "little")
     verdict = decide(records, lambda encs: ctx.msm(one * len(encs), b"".join(encs))[1])
     if verdict[0] == OK and commit:
