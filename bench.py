@@ -198,7 +198,6 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     barrier()
     launches0 = ctx.launches
-    lib.xhe_ctx_timing(ctx.p, 1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     rec_local = torch.zeros(80, dtype=torch.uint8, device="cuda"); rec_all = torch.zeros(80 * world, dtype=torch.uint8, device="cuda")
     ts = streams[0]
@@ -213,10 +212,19 @@ def main():
     torch.cuda.synchronize()
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     launches = ctx.launches - launches0
+    # isolated per-kernel durations for the roofline: the same steps with the pipelines serialised on one stream and
+    # CUDA events around the main kernels (timers under stream concurrency would include the overlapped neighbours)
+    lib.xhe_ctx_set_serial.argtypes = [C.c_void_p, C.c_int]
+    lib.xhe_ctx_set_serial(ctx.p, 1); lib.xhe_ctx_timing(ctx.p, 1)
+    with torch.cuda.stream(ts):
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            assert lib.xhe_batch_run(ctx.p) == 0
+    torch.cuda.synchronize()
     names = (C.c_char_p * 16)(); kms = (C.c_double * 16)(); kl = (C.c_uint64 * 16)(); ku = (C.c_double * 16)()
     nk = lib.xhe_ctx_timing_read(ctx.p, names, kms, kl, ku, 16)
     kernels = {names[i].decode(): {"ms_per_step": kms[i] / args.steps, "launches": int(kl[i]), "alg_lp_per_step": ku[i] / args.steps} for i in range(nk)}
-    lib.xhe_ctx_timing(ctx.p, 0)
+    lib.xhe_ctx_timing(ctx.p, 0); lib.xhe_ctx_set_serial(ctx.p, 0)
     barrier()
     # ---- timed region 2: end to end through the host API, host buffers in, verdict out (e2e).
     # (a) one call at a time (latency); (b) two batches in flight on two contexts of the same GPU, so the host phase of
@@ -238,11 +246,11 @@ def main():
     gatherer = xd.OrderedGatherer(None, torch.device("cuda", local)) if (dist and pipelined) else None   # one thread issues the NCCL all-gathers in sequence order
     wthreads = max(1, host_threads // nfl)
 
-    def worker(widx, nsteps, out):
+    def worker(widx, nsteps, out, ledgers=None):
         c = workers[widx]
         torch.cuda.set_device(local)
         for s in range(nsteps):
-            led = ledger0.clone()
+            led = ledgers[s] if ledgers else ledger0.clone()      # fresh state per step (cloned before the clock starts)
             if dist:
                 seq = seq_base[0] + s * nfl + widx
                 code, idx, _ = xd.verify_batch_distributed(c, None, led, rank * args.txs, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, commit=False, fiat_shamir=args.fiat_shamir,
@@ -262,7 +270,8 @@ def main():
         barrier()
         outs = [[] for _ in range(nfl)]
         counts = [args.steps // nfl + (1 if w < args.steps % nfl else 0) for w in range(nfl)]
-        th = [threading.Thread(target=worker, args=(w, counts[w], outs[w])) for w in range(nfl)]
+        fresh = [[ledger0.clone() for _ in range(counts[w])] for w in range(nfl)]
+        th = [threading.Thread(target=worker, args=(w, counts[w], outs[w], fresh[w])) for w in range(nfl)]
         t0 = time.perf_counter()
         for t_ in th:
             t_.start()
@@ -308,9 +317,11 @@ def main():
     leaf = {n: v for n, v in kernels.items() if n not in ("msm_sigma", "msm_range")}
     dom = max(leaf, key=lambda n: leaf[n]["ms_per_step"])
     ach = leaf[dom]["alg_lp_per_step"] / (leaf[dom]["ms_per_step"] * 1e-3)
+    work = {n: {"ms": round(v["ms_per_step"], 4), "TLP_s": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12, 3), "frac": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / peak_wide, 4)}
+            for n, v in leaf.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
     roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide,
                 "peak_source": "measured live: IMAD.WIDE.U32 microkernel (plain accumulate form)", "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": ach / peak_chain,
-                "traffic": None, "note": "carry-predicated IMAD.WIDE (the form a radix-2^32 multiply needs) issues at half rate on sm_100a; see DESIGN.md"}
+                "traffic": None, "per_kernel_isolated": work, "note": "carry-predicated IMAD.WIDE (the form a radix-2^32 multiply needs) issues at half rate on sm_100a; see DESIGN.md"}
     line = {"metric": "verified TX/s (10k-transfer batch)", "value": value, "unit": "TX/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 2500.0, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
             "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic (valid TXs minted by the oracle prover; ranks share one minted batch)", "config": config,
@@ -318,7 +329,7 @@ def main():
                     "single_call": {"value": args.txs * args.steps / single_s, "ms_per_step": 1e3 * single_s / args.steps},
                     "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": phases.get("keccak_f", 0) / args.txs,
                     "fiat_shamir": args.fiat_shamir, "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_ms_per_step": {n: round(v["ms_per_step"], 4) for n, v in kernels.items()},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_ms_per_step_isolated": {n: round(v["ms_per_step"], 4) for n, v in kernels.items()},
             "mint_seconds": round(t_mint, 1), "host_cores": ncpu}
     if world > 1:
         line["collective"] = {"what": "one all_gather of 80 B per rank per batch (verdict + partial sigma / range MSM encodings) over NCCL, inside both timed regions"}

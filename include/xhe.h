@@ -144,6 +144,8 @@ int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate);
 /* CUDA-event timing of the main kernels of xhe_batch_run / the MSM (roofline evidence): enable, run, then read.
  * units[i] = algorithmic limb products (DESIGN.md work model) accumulated for kernel i. */
 int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable);
+/* run the independent pipelines of xhe_batch_run back to back on one stream (isolated per-kernel timing; slower) */
+int32_t xhe_ctx_set_serial(xhe_ctx* ctx, int serial);
 int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap);
 /* self-test of the arithmetic layer: runs op (tests/hostemu op codes) on n operand pairs on the device */
 int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);

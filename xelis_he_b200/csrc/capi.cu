@@ -71,6 +71,7 @@ extern "C" const char* xhe_last_error(const xhe_ctx* ctx) { return ctx ? ctx->er
 extern "C" int32_t xhe_ctx_set_stream(xhe_ctx* ctx, void* s) { if (!ctx) return XHE_E_ARG; ctx->stream = (cudaStream_t)s; return XHE_OK; }
 extern "C" int32_t xhe_ctx_sync(xhe_ctx* ctx) { if (!ctx) return XHE_E_ARG; XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); return XHE_OK; }
 extern "C" uint64_t xhe_ctx_launch_count(const xhe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int32_t xhe_ctx_set_serial(xhe_ctx* ctx, int serial) { if (!ctx) return XHE_E_ARG; ctx->serial = serial != 0; return XHE_OK; }
 extern "C" int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable) {
   if (!ctx) return XHE_E_ARG;
   for (auto& p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }

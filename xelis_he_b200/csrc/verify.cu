@@ -397,7 +397,7 @@ struct DeviceBatch {
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
   long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
-  bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok; unsigned long long* d_blob_off; uint32_t* d_fs_plan; size_t blob_bytes = 0;
+  double sum_m = 0; bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok; unsigned long long* d_blob_off; uint32_t* d_fs_plan; size_t blob_bytes = 0;
 };
 
 // stage 1: allocate from the ctx arena and upload the host description
@@ -408,12 +408,13 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   cudaStream_t st = ctx->stream;
   if (!ctx->resident) ctx->resident = new DeviceBatch();
   DeviceBatch& D = *(DeviceBatch*)ctx->resident;
-  D.h = *b;
+  D.h = *b; D.sum_m = 0;
   uint32_t m_max = 1;
   for (uint32_t p = 0; p < b->n_rp; p++) {
     uint32_t m = b->rp_m[p];
     if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity || 64u * m > 2048u) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs a power of two <= min(party_capacity, 32))"; return XHE_E_ARG; }
     if (m > m_max) m_max = m;
+    D.sum_m += m;
   }
   D.Nmax = 64 * m_max;
   D.n_pts_total = (size_t)b->n_points + b->n_ops;
@@ -506,7 +507,8 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   int32_t rc;
   const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_range = D.n_range; const uint32_t Nmax = D.Nmax;
   if (!ctx->aux[0]) { for (auto& s : ctx->aux) XHE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
-  static const bool serial = getenv("XHE_SERIAL") != nullptr;      // diagnostics: run the pipelines back to back on one stream
+  static const bool serial_env = getenv("XHE_SERIAL") != nullptr;
+  const bool serial = serial_env || ctx->serial;                   // diagnostics / isolated kernel timing: one stream, back to back
   cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2];
   cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
@@ -561,7 +563,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
       k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
     size_t smem = 64 * (size_t)Nmax;
     if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * (double)n_dyn);
+    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // ~6 mod-l products per generator index, 64*m indices per proof
       k_rp_gens<<<D.rp_grid, RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.d_part); XHE_LAUNCHED(ctx); }
     k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
     k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);

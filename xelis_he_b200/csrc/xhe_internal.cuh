@@ -24,6 +24,7 @@ struct xhe_ctx {
   void* h_pinned = nullptr; size_t pinned_bytes = 0;         // grow-only pinned staging
   // optional CUDA-event timing of the main kernels (bench.py roofline): accumulated since the last reset
   bool timing = false;
+  bool serial = false;                                        // diagnostics: run the pipelines of xhe_batch_run back to back on one stream
   struct KernelTimer { const char* name; double ms = 0; uint64_t launches = 0; double units = 0; };
   KernelTimer timers[16];
   int n_timers = 0;
