@@ -33,7 +33,8 @@ def parse_args():
     ap.add_argument("--shape", default="a1k1")
     ap.add_argument("--cpu-sample", type=int, default=2500, help="transactions per host thread in the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the MSM points/s and ciphertext-update (HBM) side measurements")
+    ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
     ap.add_argument("--fiat-shamir", default="fast", choices=["fast", "device", "host"], help="where the Merlin transcripts run (host = north_star split; device = SURVEY 8 f.1)")
     return ap.parse_args()
 
@@ -83,6 +84,57 @@ def cpu_baseline(batch, threads, sample):
             "sample": f"{threads} threads x verify_batch({sub.n} tx) of the same workload, scalar 64-bit backend, no SIMD; CPU restatement, not curve25519-dalek",
             "seconds": t, "readme_figure_tx_s_per_thread": 2500}
 
+
+
+def secondary_metrics(lib, ctx, stream, hbm_peak_gbs):
+    """BASELINE.json's other single-GPU figures, measured live on the device (CUDA events on the ctx stream, L2-sized
+    inputs): MSM points/s on 2^20 resident points (config 2) and the resident ciphertext update (config 4, HBM-bound)."""
+    import ctypes as C
+    import torch
+    out = {}
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    n = 1 << 20
+
+    def timed(fn, iters=5, warm=3):
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                assert fn() == 0
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters):
+                assert fn() == 0
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    with torch.cuda.stream(stream):
+        uni = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=g)
+        enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda"); aff = torch.empty((n, 16), dtype=torch.int32, device="cuda")
+        niels = torch.empty((n, 24), dtype=torch.int32, device="cuda"); ok = torch.empty((n,), dtype=torch.uint8, device="cuda")
+        sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g); sc[:, 31] &= 0x0F      # < 2^252 < l
+        assert lib.xhe_from_uniform_dev(ctx.p, uni.data_ptr(), n, enc.data_ptr()) == 0
+        assert lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()) == 0
+    lib.xhe_msm_workspace_bytes.restype = C.c_size_t; lib.xhe_msm_workspace_bytes.argtypes = [C.c_void_p, C.c_size_t]
+    wsb = lib.xhe_msm_workspace_bytes(ctx.p, n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda"); res = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    lib.xhe_msm_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    ms = timed(lambda: lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32))
+    out["msm_2p20"] = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3, "alg_TLP_s": (8064.0 * n + 6.04e8) / ms / 1e9,
+                       "note": "resident decompressed points (affine Niels, 96 MB > L2... operands re-read from L2/HBM), 253-bit scalars; bit-exactness vs the oracle is tests/test_gpu_msm.py"}
+    ms = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()))
+    out["decompress_2p20"] = {"ms": ms, "points_per_s": n / ms * 1e3}
+    del uni, aff, ws
+    na = 1 << 20
+    balr = torch.randint(0, 2**31 - 1, (4, 2 * na, 8), dtype=torch.int32, device="cuda", generator=g)
+    dn = torch.randint(0, 2**31 - 1, (3, 2 * na, 8), dtype=torch.int32, device="cuda", generator=g)
+    sub = torch.randint(0, 2, (na,), dtype=torch.uint8, device="cuda", generator=g)
+    lib.xhe_ct_update_resident_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    ms = timed(lambda: lib.xhe_ct_update_resident_dev(ctx.p, balr.data_ptr(), dn.data_ptr(), sub.data_ptr(), na), iters=10)
+    bytes_per_account = 2 * (128 + 128 + 96)       # two points per account: extended balance read + write, affine-Niels delta read
+    gbs = na * bytes_per_account / ms / 1e6
+    out["ct_update_resident_1M"] = {"accounts": na, "ms": ms, "accounts_per_s": na / ms * 1e3,
+                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s", "frac": gbs / hbm_peak_gbs, "traffic": None,
+                                                 "algorithmic_bytes_per_account": bytes_per_account, "working_set_mb": na * bytes_per_account / 1e6}}
+    return out
 
 def main():
     # exactly one JSON line may reach stdout: libraries (NCCL's version banner, torchrun) write there too, so everything else
@@ -225,6 +277,18 @@ def main():
     nk = lib.xhe_ctx_timing_read(ctx.p, names, kms, kl, ku, 16)
     kernels = {names[i].decode(): {"ms_per_step": kms[i] / args.steps, "launches": int(kl[i]), "alg_lp_per_step": ku[i] / args.steps} for i in range(nk)}
     lib.xhe_ctx_timing(ctx.p, 0); lib.xhe_ctx_set_serial(ctx.p, 0)
+    # where each kernel sits inside one concurrent step (four stream pipelines): start/end in ms from the step start
+    lib.xhe_ctx_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+    lib.xhe_ctx_timing(ctx.p, 1)
+    with torch.cuda.stream(ts):
+        flush.fill_(1)
+        assert lib.xhe_batch_run(ctx.p) == 0
+    torch.cuda.synchronize()
+    lib.xhe_ctx_timing_read(ctx.p, names, kms, kl, ku, 16)
+    tn = (C.c_char_p * 64)(); t0s = (C.c_float * 64)(); t1s = (C.c_float * 64)()
+    nt = lib.xhe_ctx_timeline(ctx.p, tn, t0s, t1s, 64)
+    timeline = sorted([[tn[i].decode(), round(t0s[i], 3), round(t1s[i], 3)] for i in range(max(nt, 0))], key=lambda r: r[1])
+    lib.xhe_ctx_timing(ctx.p, 0)
     barrier()
     # ---- timed region 2: end to end through the host API, host buffers in, verdict out (e2e).
     # (a) one call at a time (latency); (b) two batches in flight on two contexts of the same GPU, so the host phase of
@@ -256,9 +320,11 @@ def main():
                 code, idx, _ = xd.verify_batch_distributed(c, None, led, rank * args.txs, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, commit=False, fiat_shamir=args.fiat_shamir,
                                                            gather=(lambda rec, q=seq: gatherer.gather(q, rec)) if gatherer else None)
             else:
-                code, idx, _ = verifier.verify_batch(c, None, led, seed=b"p%d-%d" % (widx, s), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
+                code, idx, tmw = verifier.verify_batch(c, None, led, seed=b"p%d-%d" % (widx, s), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
+                pipe_phases.append(tmw)
             out.append((code, idx))
     seq_base = [0]
+    pipe_phases = []
     if pipelined:
         # warm-up of the extra contexts: every slot runs one batch (same sequence numbering on all ranks)
         wth = [threading.Thread(target=worker, args=(w, 1, [])) for w in range(nfl)]
@@ -268,6 +334,7 @@ def main():
             t_.join()
         seq_base[0] = nfl
         barrier()
+        pipe_phases.clear()
         outs = [[] for _ in range(nfl)]
         counts = [args.steps // nfl + (1 if w < args.steps % nfl else 0) for w in range(nfl)]
         fresh = [[ledger0.clone() for _ in range(counts[w])] for w in range(nfl)]
@@ -283,8 +350,22 @@ def main():
         assert all(o == (0, -1) for o in flat) and len(flat) == args.steps
         if gatherer:
             gatherer.close()
+        # device-side ceiling of that pipeline: every context re-runs its resident batch, all streams in flight at once
+        rounds = max(2, args.steps // nfl)
+        torch.cuda.synchronize()
+        c0 = torch.cuda.Event(enable_timing=True); c0.record(streams[0])
+        for _ in range(rounds):
+            for c in workers:
+                assert lib.xhe_batch_run(c.p) == 0
+        cends = []
+        for st_ in streams[:nfl]:
+            e_ = torch.cuda.Event(enable_timing=True); e_.record(st_); cends.append(e_)
+        torch.cuda.synchronize()
+        conc_ms = max(c0.elapsed_time(e_) for e_ in cends)
+        concurrent_value = args.txs * rounds * nfl / (conc_ms * 1e-3)
     else:
         e2e_s = single_s
+        concurrent_value = None
     barrier()
     # the other Fiat-Shamir placement, for the record (3 steps)
     other = "host" if args.fiat_shamir != "host" else "fast"
@@ -314,25 +395,35 @@ def main():
     e2e = total_tx / (e2e_ms_max * 1e-3)
     # ---- roofline of the dominant kernel (integer-multiply pipe; tensor cores unused by design)
     peak_wide = ctx.int_peak(2); peak_chain = ctx.int_peak(3)
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6553.9          # the figure MEASURED_PEAKS.json held when this was written
     leaf = {n: v for n, v in kernels.items() if n not in ("msm_sigma", "msm_range")}
-    dom = max(leaf, key=lambda n: leaf[n]["ms_per_step"])
+    # dominant kernel = the one carrying the largest share of the step's algorithmic work (limb products); the per-kernel
+    # table below lists every timed kernel, including the latency-bound one-thread-per-item kernels
+    dom = max(leaf, key=lambda n: leaf[n]["alg_lp_per_step"])
     ach = leaf[dom]["alg_lp_per_step"] / (leaf[dom]["ms_per_step"] * 1e-3)
     work = {n: {"ms": round(v["ms_per_step"], 4), "TLP_s": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12, 3), "frac": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / peak_wide, 4)}
             for n, v in leaf.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
-    roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide,
+    roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide, "share_of_step_work": leaf[dom]["alg_lp_per_step"] / max(1.0, sum(v["alg_lp_per_step"] for n, v in leaf.items())),
                 "peak_source": "measured live: IMAD.WIDE.U32 microkernel (plain accumulate form)", "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": ach / peak_chain,
                 "traffic": None, "per_kernel_isolated": work, "note": "carry-predicated IMAD.WIDE (the form a radix-2^32 multiply needs) issues at half rate on sm_100a; see DESIGN.md"}
     line = {"metric": "verified TX/s (10k-transfer batch)", "value": value, "unit": "TX/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 2500.0, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
             "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic (valid TXs minted by the oracle prover; ranks share one minted batch)", "config": config,
             "e2e": {"value": e2e, "unit": "TX/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps, "host_threads": host_threads, "batches_in_flight": nfl,
                     "single_call": {"value": args.txs * args.steps / single_s, "ms_per_step": 1e3 * single_s / args.steps},
                     "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": phases.get("keccak_f", 0) / args.txs,
+                    "phases_ms_pipelined_mean": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None,
                     "fiat_shamir": args.fiat_shamir, "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
+            "value_batches_in_flight": {"value_this_rank": concurrent_value, "unit": "TX/s", "contexts": nfl, "note": "device-resident batches of all contexts in flight at once (no L2 flush); the GPU-side ceiling of the pipelined e2e"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_ms_per_step_isolated": {n: round(v["ms_per_step"], 4) for n, v in kernels.items()},
-            "mint_seconds": round(t_mint, 1), "host_cores": ncpu}
+            "timeline_ms_one_step": timeline, "mint_seconds": round(t_mint, 1), "host_cores": ncpu}
     if world > 1:
         line["collective"] = {"what": "one all_gather of 80 B per rank per batch (verdict + partial sigma / range MSM encodings) over NCCL, inside both timed regions"}
+    if world == 1 and not args.no_secondary:
+        line["secondary"] = secondary_metrics(lib, ctx, ts, hbm_peak)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(batch, ncpu, args.cpu_sample)
     emit(line)

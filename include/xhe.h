@@ -147,6 +147,9 @@ int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable);
 /* run the independent pipelines of xhe_batch_run back to back on one stream (isolated per-kernel timing; slower) */
 int32_t xhe_ctx_set_serial(xhe_ctx* ctx, int serial);
 int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap);
+/* start/end (ms since the start of the run) of every timed kernel of the last timed xhe_batch_run, as gathered by the
+ * last xhe_ctx_timing_read; returns the number of spans written (diagnostics for the stream pipelines) */
+int32_t xhe_ctx_timeline(xhe_ctx* ctx, const char** names, float* t0, float* t1, int cap);
 /* self-test of the arithmetic layer: runs op (tests/hostemu op codes) on n operand pairs on the device */
 int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
 

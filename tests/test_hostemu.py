@@ -52,6 +52,18 @@ def test_scalar_and_point_ops(emu):
         for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "inv"), (4, "neg")):
             assert scop(op, a, b) == oracle.sc_op(name, a, b)
         assert scop(5, rnd[64 * i:64 * i + 32], rnd[64 * i + 32:64 * i + 64]) == a
+    # edge values against Python integers: extremes of every carry path of the Montgomery reduction
+    L = 2**252 + 27742317777372353535851937790883648493
+    le = lambda v: v.to_bytes(32, "little")
+    edge = [0, 1, 2, L - 1, L - 2, 2**252, 2**252 - 1, 2**128 - 1, (L - 1) ^ (2**125), 2**32 - 1, L >> 1]
+    for a in edge:
+        for b in edge:
+            assert scop(2, le(a), le(b)) == le(a * b % L), (a, b)
+        if a:
+            assert scop(3, le(a)) == le(pow(a, L - 2, L))
+    for lo, hi in ((2**256 - 1, 2**256 - 1), (0, 2**256 - 1), (2**256 - 1, 0), (L, L), (2**255, 2**255)):
+        assert scop(5, le(lo), le(hi)) == le((lo + (hi << 256)) % L)
+        assert scop(6, le(lo)) == le(lo % L)
     pts = [oracle.from_uniform(rnd[64 * i:64 * i + 64]) for i in range(24)]
     for i in range(0, 24, 2):
         a, b = pts[i], pts[i + 1]; o = (C.c_uint8 * 32)()

@@ -83,10 +83,28 @@ extern "C" int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable) {
 extern "C" int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap) {
   if (!ctx) return XHE_E_ARG;
   XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  for (auto& p : ctx->pending) { float t = 0; cudaEventElapsedTime(&t, p.e0, p.e1); ctx->timers[p.timer].ms += t; cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
-  ctx->pending.clear();
+  for (auto* s : ctx->aux) if (s) XHE_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  ctx->timeline.clear();
+  for (size_t i = 0; i < ctx->pending.size(); i++) {
+    auto& p = ctx->pending[i];
+    float t = 0; cudaEventElapsedTime(&t, p.e0, p.e1); ctx->timers[p.timer].ms += t;
+    if (ctx->tl_base && i >= ctx->tl_mark) {
+      float a = 0, b = 0;
+      if (cudaEventElapsedTime(&a, ctx->tl_base, p.e0) == cudaSuccess && cudaEventElapsedTime(&b, ctx->tl_base, p.e1) == cudaSuccess) ctx->timeline.push_back({ctx->timers[p.timer].name, a, b});
+    }
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  (void)cudaGetLastError();
+  ctx->pending.clear(); ctx->tl_mark = 0;
   int n = ctx->n_timers < cap ? ctx->n_timers : cap;
   for (int i = 0; i < n; i++) { names[i] = ctx->timers[i].name; ms[i] = ctx->timers[i].ms; launches[i] = ctx->timers[i].launches; units[i] = ctx->timers[i].units; }
+  return n;
+}
+// spans (ms from the start of the last timed xhe_batch_run) gathered by the last xhe_ctx_timing_read
+extern "C" int32_t xhe_ctx_timeline(xhe_ctx* ctx, const char** names, float* t0, float* t1, int cap) {
+  if (!ctx) return XHE_E_ARG;
+  int n = (int)ctx->timeline.size() < cap ? (int)ctx->timeline.size() : cap;
+  for (int i = 0; i < n; i++) { names[i] = ctx->timeline[i].name; t0[i] = ctx->timeline[i].t0; t1[i] = ctx->timeline[i].t1; }
   return n;
 }
 extern "C" const void* xhe_ctx_generators_dev(const xhe_ctx* ctx, size_t* n) { if (n) *n = ctx->n_gens; return ctx->d_gens_niels; }

@@ -371,7 +371,8 @@ XHE_HD fe fe_reduce512(const uint32_t* t) {
   return r;
 }
 
-XHE_HD fe fe_mul(const fe& a, const fe& b) {
+// t[0..15] = a[0..7] * b[0..7] (full 512-bit product)
+XHE_HD void mul512(uint32_t* t, const uint32_t* a, const uint32_t* b) {
   // product a[j]*b[i] lands at limb i+j: even positions accumulate in ev[], odd in od[] (od[k] is limb k+1), so
   // every product is an aligned 64-bit slot and ptxas emits one IMAD.WIDE.U32(.X) per limb product.
   uint32_t ev[16], od[16];
@@ -379,23 +380,27 @@ XHE_HD fe fe_mul(const fe& a, const fe& b) {
   for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
-    mad4w(ev + i, ev[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-    mad4w(od + i, od[i + 8], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-    if (i + 10 < 16) mad4w(ev + i + 2, ev[i + 10], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
-    else mad4w_nc(ev + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
-    mad4w(od + i, od[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+    mad4w(ev + i, ev[i + 8], a[0], a[2], a[4], a[6], b[i]);
+    mad4w(od + i, od[i + 8], a[1], a[3], a[5], a[7], b[i]);
+    if (i + 10 < 16) mad4w(ev + i + 2, ev[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
+    else mad4w_nc(ev + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
+    mad4w(od + i, od[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
   }
-  uint32_t t[16];
   merge16(t, ev, od);
+}
+
+XHE_HD fe fe_mul(const fe& a, const fe& b) {
+  uint32_t t[16];
+  mul512(t, a.v, b.v);
   return fe_reduce512(t);
 }
 
-XHE_HD fe fe_sq(const fe& a) {
-  // 28 cross products x[i]*x[j] (i<j) in even/odd chains, doubled, plus the 8 squares: 36 IMAD.WIDE (+8 fold).
+// t[0..15] = x[0..7]^2
+XHE_HD void sq512(uint32_t* t, const uint32_t* x) {
+  // 28 cross products x[i]*x[j] (i<j) in even/odd chains, doubled, plus the 8 squares: 36 IMAD.WIDE.
   uint32_t ev[16], od[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
-  const uint32_t* x = a.v;
   // limb position p = i+j; p even -> slot ev[p], p odd -> slot od[p-1]
   mad4w(od + 0, od[8], x[1], x[3], x[5], x[7], x[0]);   // p = 1,3,5,7
   mad3w(ev + 2, ev[8], x[2], x[4], x[6], x[0]);         // p = 2,4,6
@@ -410,7 +415,6 @@ XHE_HD fe fe_sq(const fe& a) {
   mad1w(od + 10, od[12], x[6], x[5]);                   // p = 11
   mad1w(ev + 12, ev[14], x[7], x[5]);                   // p = 12
   mad1w_nc(od + 12, x[7], x[6]);                        // p = 13
-  uint32_t t[16];
   merge16(t, ev, od);
   // t = 2t (t < 2^511)
   {
@@ -451,6 +455,11 @@ XHE_HD fe fe_sq(const fe& a) {
     }
   }
 #endif
+}
+
+XHE_HD fe fe_sq(const fe& a) {
+  uint32_t t[16];
+  sq512(t, a.v);
   return fe_reduce512(t);
 }
 

@@ -66,34 +66,62 @@ XHE_HD sc sc_sub(const sc& a, const sc& b) {  // inputs < l
 }
 XHE_HD sc sc_neg(const sc& a) { return sc_sub(sc_zero(), a); }
 
-// Montgomery product a*b*R^-1 mod l for a*b < l*R; result < l.  CIOS, one 32-bit row at a time.
-XHE_HD sc sc_montmul(const sc& a, const sc& b) {
-  uint32_t t[10];
+// Montgomery reduction (t + M*l) / 2^256 of a 16-limb t < l*2^256; result < l.  M = sum m_i 2^(32 i) is fixed one
+// limb at a time (m_i = limb_i * (-l^-1) mod 2^32).  Because l = 2^252 + c with c < 2^125, M*l splits into M*c (8 rows of
+// four limb products, kept in their own even/odd slot arrays so that every chain's carry word is still untouched when
+// the chain ends) and M << 252 (shifts only).  `carry` tracks what the cancelled low limbs pushed upward.
+XHE_HD sc sc_redc(const uint32_t* t) {
+  uint32_t re[14], ro[14], m[9];
 #pragma unroll
-  for (int i = 0; i < 10; i++) t[i] = 0;
+  for (int i = 0; i < 14; i++) { re[i] = 0; ro[i] = 0; }
+  const uint32_t c0 = 0x5cf5d3edu, c1 = 0x5812631au, c2 = 0xa2f79cd6u, c3 = 0x14def9deu;
+  uint32_t carry = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    // t += a * b[i]
-    uint64_t c = 0;
+    // limb i of t + M*c + (M << 252), before and after this row's contribution (which clears its low word)
+    uint32_t fix = (i == 7) ? (uint32_t)(m[0] << 28) : 0u;
+    uint64_t x = (uint64_t)t[i] + re[i] + carry + fix;
+    if (i > 0) x += ro[i - 1];
+    m[i] = (uint32_t)x * XHE_SC_LFACTOR;
+    if ((i & 1) == 0) {
+      mad2w(re + i, re[i + 4], c0, c2, m[i]);
+      mad2w(ro + i, ro[i + 4], c1, c3, m[i]);
+    } else {
+      mad2w(ro + i - 1, ro[i + 3], c0, c2, m[i]);
+      mad2w(re + i + 1, re[i + 5], c1, c3, m[i]);
+    }
+    uint64_t y = (uint64_t)t[i] + re[i] + carry + fix;
+    if (i > 0) y += ro[i - 1];
+    carry = (uint32_t)(y >> 32);
+  }
+  m[8] = 0;
+  // limbs 8..15: t_hi + (M*c)_hi + (M << 252)_hi + carry
+  uint32_t h[8], u[8], v[8], w[8], z[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
-    c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
-    // m = t[0] * (-l^-1) mod 2^32 ; t = (t + m*l) / 2^32.  l = c0..c3 + 2^252
-    uint32_t m = t[0] * XHE_SC_LFACTOR;
-    c = (uint64_t)m * SC_L[0] + t[0]; c >>= 32;
-#pragma unroll
-    for (int j = 1; j < 4; j++) { c += (uint64_t)m * SC_L[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-#pragma unroll
-    for (int j = 4; j < 7; j++) { c += t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-    c += (uint64_t)m * 0x10000000u + t[7]; t[6] = (uint32_t)c; c >>= 32;
-    c += t[8]; t[7] = (uint32_t)c; c >>= 32;
-    t[8] = t[9] + (uint32_t)c;
+  for (int k = 0; k < 8; k++) {
+    h[k] = (m[k] >> 4) | (m[k + 1] << 28);
+    u[k] = 8 + k < 14 ? re[8 + k] : 0;
+    v[k] = 7 + k < 14 ? ro[7 + k] : 0;
   }
   sc r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = t[i];
-  sc_csub_l(r.v, t[8]);
+  add8(w, t + 8, h);
+  add8(z, u, v);
+  add8(r.v, w, z);
+  addw8(r.v, carry);      // the total is < 2l < 2^254: none of these carries out
+  sc_csub_l(r.v, 0);
   return r;
+}
+
+// Montgomery product a*b*R^-1 mod l (R = 2^256) for a*b < l*R; result < l
+XHE_HD sc sc_montmul(const sc& a, const sc& b) {
+  uint32_t t[16];
+  mul512(t, a.v, b.v);
+  return sc_redc(t);
+}
+XHE_HD sc sc_montsq(const sc& a) {
+  uint32_t t[16];
+  sq512(t, a.v);
+  return sc_redc(t);
 }
 XHE_HD sc sc_to_mont(const sc& a) { return sc_montmul(a, sc_load_const(SC_RR)); }         // a*R
 XHE_HD sc sc_from_mont(const sc& a) { sc one = sc_zero(); one.v[0] = 1; return sc_montmul(a, one); }
@@ -105,7 +133,7 @@ XHE_HD sc sc_reduce512(const sc& lo, const sc& hi) { return sc_add(sc_montmul(lo
 XHE_HD sc sc_mont_invert(const sc& a) {
   sc acc = sc_load_const(SC_R1);
   for (int i = 252; i >= 0; i--) {
-    acc = sc_montmul(acc, acc);
+    acc = sc_montsq(acc);
     uint32_t w = SC_L[i >> 5] - ((i >> 5) == 0 ? 2u : 0u);  // (l-2): only limb 0 changes (0x5cf5d3ed - 2, no borrow)
     if ((w >> (i & 31)) & 1u) acc = sc_montmul(acc, a);
   }

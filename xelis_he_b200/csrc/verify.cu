@@ -143,9 +143,11 @@ __global__ void __launch_bounds__(128) k_op_finish(const uint32_t* __restrict__ 
   ge_aff ia; ld_fe(ia.x, pt_aff + 16 * (size_t)init); ld_fe(ia.y, pt_aff + 16 * (size_t)init + 8);
   ge a; ld_ge(a, acc + 32 * (size_t)j);
   ge r = ge_add(ge_from_affine(ia), a);
-  encode_words(out_enc + 32 * (size_t)j, r);
-  fe zi = fe_invert(r.Z);
-  ge_aff ra; ra.x = fe_mul(r.X, zi); ra.y = fe_mul(r.Y, zi);
+  // the encode's inverse square root also yields 1/Z (z_inv = den1*den2*T = T/(XY) = 1/Z) whenever X*Y != 0; the points
+  // with X*Y == 0 (the four-element identity coset) take the explicit inversion
+  ge_aff ra;
+  encode_words(out_enc + 32 * (size_t)j, r, &ra);
+  if (fe_iszero(fe_mul(r.X, r.Y))) { fe zi = fe_invert(r.Z); ra.x = fe_mul(r.X, zi); ra.y = fe_mul(r.Y, zi); }
   size_t slot = (size_t)n_points + j;
   st_fe(pt_aff + 16 * slot, ra.x); st_fe(pt_aff + 16 * slot + 8, ra.y);
   st_niels(pt_niels + 24 * slot, niels_from_affine(ra));
@@ -226,10 +228,14 @@ __global__ void __launch_bounds__(256) k_reduce_scalars(const uint32_t* __restri
 }
 
 // ---- range proofs ----------------------------------------------------------------------------------------------------
-// per-proof derived scalars written by k_rp_prep (all in MONTGOMERY form unless noted), RP_DER scalars per proof:
-enum { D_ALLINV = 0, D_YINV, D_RZ /* rho z */, D_RA /* rho a */, D_RB /* rho b */, D_RZZ /* rho z^2 */, D_Z, D_USQ /* lg entries */ };
+// per-proof derived scalars written by k_rp_prep, RP_DER scalars per proof.  M = Montgomery form, P = plain form: a
+// Montgomery product of a P and an M operand is the plain product, which lets k_rp_gens emit plain weights directly.
+enum { D_ALLINV = 0 /* M */, D_YINV /* M */, D_RZ /* P rho z */, D_RA /* P rho a */, D_RB /* P rho b */, D_RZZ /* unused */, D_Z /* M */, D_USQ /* M, lg entries */ };
 #define RP_MAX_LG 16
-#define RP_DER (7 + 2 * RP_MAX_LG)   // + u_j^2 [lg], y_inv^(2^j) [lg]
+#define RP_MAX_M 32
+#define D_YPW (D_USQ + RP_MAX_LG)        // M: y_inv^(2^j), lg entries
+#define D_RZZJ (D_USQ + 2 * RP_MAX_LG)   // P: rho z^2 z^j, m entries
+#define RP_DER (7 + 2 * RP_MAX_LG + RP_MAX_M)
 
 __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ sc_in /* 7 per proof */, const uint32_t* __restrict__ chal_off,
                                                 const uint32_t* __restrict__ chal, const uint32_t* __restrict__ dyn_off /* term offset per proof */, uint32_t n_rp,
@@ -263,15 +269,16 @@ __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_a
   uint32_t* d = der + 8 * (size_t)RP_DER * p;
   sc zzm = mmul(zm, zm);
   st_sc(d + 8 * D_ALLINV, allinv); st_sc(d + 8 * D_YINV, yinv);
-  st_sc(d + 8 * D_RZ, mmul(rm, zm)); st_sc(d + 8 * D_RA, mmul(rm, am)); st_sc(d + 8 * D_RB, mmul(rm, bm)); st_sc(d + 8 * D_RZZ, mmul(rm, zzm)); st_sc(d + 8 * D_Z, zm);
-  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), mmul(um[j], um[j])); st_sc(d + 8 * (D_USQ + RP_MAX_LG + j), yp); yp = mmul(yp, yp); } }
+  st_sc(d + 8 * D_RZ, mmul(rho, zm)); st_sc(d + 8 * D_RA, mmul(rho, am)); st_sc(d + 8 * D_RB, mmul(rho, bm)); st_sc(d + 8 * D_Z, zm);
+  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), sc_montsq(um[j])); st_sc(d + 8 * (D_YPW + j), yp); yp = sc_montsq(yp); } }
   // dynamic scalars (plain form): A: rho ; S: rho x ; T1: rho c x ; T2: rho c x^2 ; L_j: rho u_j^2 ; R_j: rho u_j^-2 ; V_j: rho c z^2 z^j
   uint32_t* o = dyn_sc + 8 * (size_t)dyn_off[p];
   sc rx = mmul(rm, xm), rcx = mmul(rx, cm), rcxx = mmul(rcx, xm);
   st_sc(o, rho); st_sc(o + 8, sc_from_mont(rx)); st_sc(o + 16, sc_from_mont(rcx)); st_sc(o + 24, sc_from_mont(rcxx));
   for (int j = 0; j < lg; j++) { st_sc(o + 8 * (4 + j), sc_from_mont(mmul(rm, mmul(um[j], um[j])))); st_sc(o + 8 * (4 + lg + j), sc_from_mont(mmul(rm, mmul(uinv[j], uinv[j])))); }
   sc rczz = mmul(mmul(rm, cm), zzm), zj = onem, sum_z = sc_zero();
-  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), sc_from_mont(mmul(rczz, zj))); sum_z = sc_add(sum_z, zj); zj = mmul(zj, zm); }
+  sc rzz_p = mmul(rho, zzm);
+  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), sc_from_mont(mmul(rczz, zj))); st_sc(d + 8 * (D_RZZJ + j), mmul(rzz_p, zj)); sum_z = sc_add(sum_z, zj); zj = mmul(zj, zm); }
   // delta(y,z) = (z - z^2) * sum_{i<N} y^i - z^3 * (2^64 - 1) * sum_{j<m} z^j
   sc yN = ym; for (int j = 0; j < lg; j++) yN = mmul(yN, yN);
   sc sum_y = y_is_one ? mmul(sc_from_u64(N), RR) : mmul(sc_sub(yN, onem), ym1inv);
@@ -291,39 +298,58 @@ __global__ void k_pow2_table(uint32_t* __restrict__ tab) {
   st_sc(tab + 8 * k, sc_montmul(v, sc_load_const(SC_RR)));
 }
 
-// persistent blocks: block b handles proofs b, b+grid, ...; accumulates rho*(-z - a s_i) and rho*(z + y^-i (z^2 z^j 2^k - b s_{N-1-i}))
-// into its private partial buffer part[b][2*Nmax] (plain form).  s-vector and y^-i by doubling DP in shared memory.
-#define RPG_THREADS 256
+// One warp per proof (warp w takes proofs w, w + #warps, ...): accumulates rho*(-z - a s_i) and
+// rho*(z + y^-i (z^2 z^j 2^k - b s_{N-1-i})) for every generator index i = 64 j + k into the warp's private row
+// part[w][2*Nmax] (plain form).  The s-vector and the powers of y^-1 are products over the set bits of i: the low (up to
+// seven) bits by a doubling table in the warp's shared-memory slice, the remaining bits as one factor per 128-index chunk.
+#define RPG_WARPS 4
+#define RPG_THREADS (32 * RPG_WARPS)
+#define RPG_CHUNK 128
 __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
-                                                         uint32_t Nmax, uint32_t* __restrict__ part) {
-  extern __shared__ uint32_t sm[];           // s[N] then ypow[N], 8 words each (Montgomery form)
-  uint32_t* my = part + 8 * (size_t)blockIdx.x * 2 * Nmax;
-  for (uint32_t i = threadIdx.x; i < 2 * Nmax; i += RPG_THREADS) st_sc(my + 8 * i, sc_zero());
-  for (uint32_t p = blockIdx.x; p < n_rp; p += gridDim.x) {
-    uint32_t m = m_arr[p]; int lg = 6 + (31 - __clz(m)); uint32_t N = 64u * m;
+                                                         uint32_t Nmax, uint32_t n_rows, uint32_t* __restrict__ part) {
+  extern __shared__ uint32_t sm[];           // per warp: t[128] then yl[128], 8 words each (Montgomery form)
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, row = blockIdx.x * RPG_WARPS + wib;
+  if (row >= n_rows) return;
+  uint32_t* t = sm + (size_t)wib * 2 * RPG_CHUNK * 8; uint32_t* yl = t + RPG_CHUNK * 8;
+  uint32_t* my = part + 8 * (size_t)row * 2 * Nmax;
+  for (uint32_t i = lane; i < 2 * Nmax; i += 32) st_sc(my + 8 * i, sc_zero());
+  for (uint32_t p = row; p < n_rp; p += n_rows) {
+    const uint32_t m = m_arr[p]; const int lg = 6 + (31 - __clz(m)), lgc = lg < 7 ? lg : 7; const uint32_t N = 64u * m, Cn = 1u << lgc, Q = N >> lgc;
     const uint32_t* d = der + 8 * (size_t)RP_DER * p;
-    uint32_t *s = sm, *yp = sm + 8 * (size_t)N;
-    __syncthreads();
-    if (threadIdx.x == 0) { sc a0; ld_sc(a0, d + 8 * D_ALLINV); st_sc(s, a0); st_sc(yp, mont_one()); }
-    __syncthreads();
-    for (int r = 0; r < lg; r++) {
-      sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - r))); ld_sc(ypw, d + 8 * (D_USQ + RP_MAX_LG + r));
-      uint32_t half = 1u << r;
-      for (uint32_t i = half + threadIdx.x; i < 2 * half; i += RPG_THREADS) {
-        sc a, b; ld_sc_rw(a, s + 8 * (i - half)); ld_sc_rw(b, yp + 8 * (i - half));
-        st_sc(s + 8 * i, mmul(a, usq)); st_sc(yp + 8 * i, mmul(b, ypw));
+    sc allinv; ld_sc(allinv, d + 8 * D_ALLINV);
+    __syncwarp();
+    if (lane == 0) { st_sc(t, Q == 1 ? allinv : mont_one()); st_sc(yl, mont_one()); }
+    __syncwarp();
+    for (int r = 0; r < lgc; r++) {
+      sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - r))); ld_sc(ypw, d + 8 * (D_YPW + r));
+      const uint32_t half = 1u << r;
+      for (uint32_t i = half + lane; i < 2 * half; i += 32) {
+        sc a, b; ld_sc_rw(a, t + 8 * (i - half)); ld_sc_rw(b, yl + 8 * (i - half));
+        st_sc(t + 8 * i, mmul(a, usq)); st_sc(yl + 8 * i, mmul(b, ypw));
       }
-      __syncthreads();
+      __syncwarp();
     }
-    sc rz, ra, rb, rzz, zm; ld_sc(rz, d + 8 * D_RZ); ld_sc(ra, d + 8 * D_RA); ld_sc(rb, d + 8 * D_RB); ld_sc(rzz, d + 8 * D_RZZ); ld_sc(zm, d + 8 * D_Z);
-    for (uint32_t i = threadIdx.x; i < N; i += RPG_THREADS) {
-      uint32_t j = i >> 6, k = i & 63;
-      sc zj = mont_one(); for (uint32_t q = 0; q < j; q++) zj = mmul(zj, zm);      // z^j (j < m, small)
-      sc si, sr, ypi, p2; ld_sc_rw(si, s + 8 * i); ld_sc_rw(sr, s + 8 * (N - 1 - i)); ld_sc_rw(ypi, yp + 8 * i); ld_sc(p2, pow2m + 8 * k);
-      sc gi = sc_neg(sc_add(rz, mmul(ra, si)));
-      sc hi = sc_add(rz, mmul(ypi, sc_sub(mmul(mmul(rzz, zj), p2), mmul(rb, sr))));
-      sc g0, h0; ld_sc_rw(g0, my + 8 * i); ld_sc_rw(h0, my + 8 * (Nmax + i));
-      st_sc(my + 8 * i, sc_add(g0, sc_from_mont(gi))); st_sc(my + 8 * (Nmax + i), sc_add(h0, sc_from_mont(hi)));
+    sc rz, ra, rb; ld_sc(rz, d + 8 * D_RZ); ld_sc(ra, d + 8 * D_RA); ld_sc(rb, d + 8 * D_RB);
+    for (uint32_t q = 0; q < Q; q++) {
+      // factors of the chunk's high index bits (bit lgc + b of i pairs with u_{lg-1-lgc-b}): s base for q and for the
+      // mirrored chunk Q-1-q, and y^-(q * 2^lgc)
+      sc sb = allinv, sbr = allinv, yb = mont_one();
+      if (Q > 1) {
+        for (int b = 0; lgc + b < lg; b++) {
+          sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - lgc - b))); ld_sc(ypw, d + 8 * (D_YPW + lgc + b));
+          if ((q >> b) & 1u) { sb = mmul(sb, usq); yb = mmul(yb, ypw); } else sbr = mmul(sbr, usq);
+        }
+      }
+      for (uint32_t il = lane; il < Cn; il += 32) {
+        const uint32_t i = (q << lgc) + il, j = i >> 6, k = i & 63;
+        sc si, sr, ypi, p2, rzzj;
+        ld_sc_rw(si, t + 8 * il); ld_sc_rw(sr, t + 8 * (Cn - 1 - il)); ld_sc_rw(ypi, yl + 8 * il); ld_sc(p2, pow2m + 8 * k); ld_sc(rzzj, d + 8 * (D_RZZJ + j));
+        if (Q > 1) { si = mmul(si, sb); sr = mmul(sr, sbr); ypi = mmul(ypi, yb); }
+        sc gi = sc_neg(sc_add(rz, mmul(ra, si)));
+        sc hi = sc_add(rz, mmul(ypi, sc_sub(mmul(rzzj, p2), mmul(rb, sr))));
+        sc g0, h0; ld_sc_rw(g0, my + 8 * i); ld_sc_rw(h0, my + 8 * (Nmax + i));
+        st_sc(my + 8 * i, sc_add(g0, gi)); st_sc(my + 8 * (Nmax + i), sc_add(h0, hi));
+      }
     }
   }
 }
@@ -421,7 +447,10 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   D.n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val; D.n_sigma = D.n_sigma_terms + 2;
   D.n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0; D.n_range = D.n_dyn + (b->n_rp ? 2 * (size_t)D.Nmax + 2 : 0);
   D.n_chal = b->n_rp ? b->rp_chal_off[b->n_rp] : 0;
-  D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * 4) : 0;
+  // rows of per-warp partial sums for k_rp_gens: one resident wave of warps, capped so the partial buffer stays within 64 MiB
+  static int gens_blocks_per_sm = 0;
+  if (!gens_blocks_per_sm) { int nb = 0; XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32)); gens_blocks_per_sm = nb > 0 ? nb : 1; }
+  D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS), std::max<size_t>(64, ((size_t)64 << 20) / (64 * (size_t)D.Nmax))) : 0;
   D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_range);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
   D.fs = b->fs_blobs != nullptr && b->n_tx > 0; D.blob_bytes = D.fs ? (size_t)b->fs_blob_off[b->n_tx] : 0;
@@ -506,13 +535,19 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   xhe_tables* T = g_tables[ctx->device];
   int32_t rc;
   const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_range = D.n_range; const uint32_t Nmax = D.Nmax;
-  if (!ctx->aux[0]) { for (auto& s : ctx->aux) XHE_CUDA_OK(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  if (!ctx->aux[0]) {
+    // the transcript and range pipelines form the longest dependency chain of a step: give their blocks priority
+    int lo_pri = 0, hi_pri = 0; XHE_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[0], cudaStreamNonBlocking, hi_pri));
+    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[1], cudaStreamNonBlocking, lo_pri));
+    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[2], cudaStreamNonBlocking, hi_pri)); for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
   static const bool serial_env = getenv("XHE_SERIAL") != nullptr;
   const bool serial = serial_env || ctx->serial;                   // diagnostics / isolated kernel timing: one stream, back to back
   cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2];
   cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
   XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
+  if (ctx->timing) { if (!ctx->tl_base) XHE_CUDA_OK(ctx, cudaEventCreate(&ctx->tl_base)); XHE_CUDA_OK(ctx, cudaEventRecord(ctx->tl_base, main_st)); ctx->tl_mark = ctx->pending.size(); }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_start, main_st));
   // ---- aux0: transcripts
   if (D.fs) {
@@ -525,6 +560,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   ctx->stream = main_st;
   if (D.layout) { rc = xhe_launch_layout(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, b->n_tx, b->n_points, D.d_enc, D.d_sig_idx, b->n_eq, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_range_idx, D.d_pt_off,
                                          D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_results + 98); if (rc) return rc; }
+  XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], main_st));            // results cleared, per-proof tables in place
   { XheTimed t(ctx, "k_decompress", 12632.0 * b->n_points);
     rc = xhe_decompress_dev(ctx, D.d_enc, b->n_points, D.d_aff, D.d_niels, D.d_ok); if (rc) return rc; }
   if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_ok, b->n_points, 1, D.d_results + 98); if (rc) return rc; }
@@ -555,19 +591,20 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   }
   // ---- aux2: range proofs (independent of the balance chains: they only reference input points)
   if (b->n_rp) {
-    XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], main_st));          // results buffer cleared + decompress done
+    // the scalar half (k_rp_prep, k_rp_gens, reductions) needs only the challenges; the decompressed points are first
+    // touched by k_gather_niels
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, ctx->ev[5], 0));
     if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_fs, 0));
     ctx->stream = s_rp; st = s_rp;
     { XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
       k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
-    size_t smem = 64 * (size_t)Nmax;
-    if (smem > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32;
     { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // ~6 mod-l products per generator index, 64*m indices per proof
-      k_rp_gens<<<D.rp_grid, RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.d_part); XHE_LAUNCHED(ctx); }
+      k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
     k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
     k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
     k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dec, 0));
     k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
     const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
     k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);

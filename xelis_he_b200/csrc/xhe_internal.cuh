@@ -30,6 +30,10 @@ struct xhe_ctx {
   int n_timers = 0;
   struct Pending { int timer; cudaEvent_t e0, e1; };
   std::vector<Pending> pending;
+  // timeline of the last timed xhe_batch_run (start/end of every timed kernel relative to the start of the run)
+  cudaEvent_t tl_base = nullptr; size_t tl_mark = 0;
+  struct Span { const char* name; float t0, t1; };
+  std::vector<Span> timeline;
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};          // side streams for the independent pipelines of xhe_batch_run
   cudaEvent_t ev[8] = {nullptr};

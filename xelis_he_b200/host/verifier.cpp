@@ -264,6 +264,7 @@ int commit_pending(xhe_ctx* ctx, VerificationState& state) {
 // ------------------------------------------------------------------------------------------------------------------
 struct FastCache {
   PinnedVec<uint8_t> blob, region_b, op_out; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
+  FlatTable<64, Chain> chains;       // (account, asset) -> tail of its balance chain inside the batch
 };
 static std::unordered_map<xhe_ctx*, FastCache*> g_fast_cache;
 static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g_cache_mu); FastCache*& c = g_fast_cache[ctx]; if (!c) c = new FastCache(); return *c; }
@@ -284,15 +285,24 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   F.off.resize(n + 1); F.plan.resize(8 * n); F.rp_m.resize(n); F.rp_pt_off.resize(n + 1); F.rp_ch_off.resize(n + 1);
   F.region_b.clear(); F.terms.clear(); F.term_off.clear(); F.prev.clear(); F.amount.clear();
   F.term_off.push_back(0);
-  std::unordered_map<Ct64, Chain, KeyHash> chains; chains.reserve(4 * n);
+  FlatTable<64, Chain>& chains = F.chains; chains.clear(); chains.reserve(4 * n);
   struct Upd { const uint8_t *account, *asset; Role role; uint32_t op_c; };
   std::vector<Upd> updates; updates.reserve(3 * n);
   const long long RB = (long long)1 << 40;     // marks "region B slot j" until the region-A size is known
   uint32_t pt = 1, n_eq = 0, n_val = 0, max_chain = 1; uint64_t off = 0;
   F.rp_pt_off[0] = 0; F.rp_ch_off[0] = 0;
   std::vector<Bytes32> signers;
+  // the walk below is one dependent hash lookup after another: announce the lookups a few transactions ahead
+  const size_t AHEAD = 6;
+  auto announce = [&](const TxView& tx) {
+    state.prefetch_account(tx.source);
+    for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); Ct64 kk = MockLedger::key(tx.source, tx.sc + 256 * q); chains.prefetch(kk.data()); }
+    for (uint32_t t = 0; t < tx.n_transfers(); t++) { const TransferView& tr = tx.transfers[t]; state.prefetch_balance(tr.dest, tr.asset); Ct64 kk = MockLedger::key(tr.dest, tr.asset); chains.prefetch(kk.data()); }
+  };
+  for (size_t i = 0; i < n && i < AHEAD; i++) announce(txs[i]);
   for (size_t i = 0; i < n; i++) {
     const TxView& tx = txs[i];
+    if (i + AHEAD < n) announce(txs[i + AHEAD]);
     if (tx.type == 4 || tx.n_ms >= 0) return 0;                               // multisig: exact path
     uint64_t nonce;
     if (!state.get_account_nonce(tx.source, &nonce) || nonce != tx.nonce) return 0;
@@ -308,9 +318,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     F.off[i] = off; off += (lens[i] + 15) & ~(size_t)15;
     const uint32_t iT = pt + 1;
     auto touch = [&](const uint8_t* account, const uint8_t* asset, Role role, long long* pc, long long* pd) -> Chain* {
-      auto ins = chains.try_emplace(MockLedger::key(account, asset));
-      Chain& c = ins.first->second;
-      if (ins.second) {
+      Ct64 kk = MockLedger::key(account, asset); bool fresh = false;
+      Chain& c = *chains.insert(kk.data(), &fresh);
+      if (fresh) {
         uint8_t ct[64];
         if (!state.get_account_balance(account, asset, role, ct)) return nullptr;
         long long j = (long long)(F.region_b.size() / 32); F.region_b.append(ct, 64);
@@ -370,7 +380,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     Pending& Pn = g_pending[ctx]; Pn.updates.clear(); Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size());
     for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; Pn.updates.push_back(su); }
   } else if (opt.apply_state) {
-    for (const Upd& u : updates) {
+    for (size_t j = 0; j < updates.size(); j++) {
+      const Upd& u = updates[j];
+      if (j + 8 < updates.size()) state.prefetch_balance(updates[j + 8].account, updates[j + 8].asset);
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 64);       // commitment op and handle op are adjacent
       if (!state.update_account_balance(u.account, u.asset, ct, u.role)) { *rc_out = XHE_ERR_STATE; return 0; }
     }
@@ -766,15 +778,16 @@ extern "C" {
 void* xheh_ledger_new() { return new MockLedger(); }
 void* xheh_ledger_clone(const void* l) { return new MockLedger(*(const MockLedger*)l); }
 void xheh_ledger_free(void* l) { delete (MockLedger*)l; }
-void xheh_ledger_set_balance(void* l, const uint8_t* pk, const uint8_t* asset, const uint8_t* ct) { Ct64 v; memcpy(v.data(), ct, 64); ((MockLedger*)l)->balances[MockLedger::key(pk, asset)] = v; }
+void xheh_ledger_set_balance(void* l, const uint8_t* pk, const uint8_t* asset, const uint8_t* ct) { ((MockLedger*)l)->set_balance(pk, asset, ct); }
 int xheh_ledger_get_balance(void* l, const uint8_t* pk, const uint8_t* asset, uint8_t* ct) { return ((MockLedger*)l)->get_account_balance(pk, asset, Sender, ct) ? 1 : 0; }
-void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { Bytes32 k; memcpy(k.data(), pk, 32); ((MockLedger*)l)->nonces[k] = nonce; }
+void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { ((MockLedger*)l)->set_nonce(pk, nonce); }
 void xheh_ledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { ((MockLedger*)l)->set_multisig_for_account(pk, signers, n, threshold); }
 int xheh_ledger_has_multisig(void* l, const uint8_t* pk) { std::vector<Bytes32> s; uint8_t t; bool p; ((MockLedger*)l)->get_multisig_for_account(pk, &s, &t, &p); return p ? 1 : 0; }
 size_t xheh_ledger_size(void* l) { return ((MockLedger*)l)->balances.size(); }
 // bulk import of records (pk[32] asset[32] ct[64]) and nonce-0 accounts
-void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; L->balances.reserve(L->balances.size() + n); for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; xheh_ledger_set_balance(l, r, r + 32, r + 64); Bytes32 k; memcpy(k.data(), r, 32); L->nonces.emplace(k, 0); } }
-size_t xheh_ledger_export(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; for (auto& kv : L->balances) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, kv.first.data(), 64); memcpy(out + 128 * i + 64, kv.second.data(), 64); } i++; } return i; }
+void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; L->balances.reserve(L->balances.size() + n); L->nonces.reserve(L->nonces.size() + n);
+  for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; L->set_balance(r, r + 32, r + 64); bool fresh = false; uint64_t* v = L->nonces.insert(r, &fresh); if (fresh) *v = 0; } }
+size_t xheh_ledger_export(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; L->balances.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
 // timings: parse, resolve, transcript, device, finish, total (ms), keccak permutations
 int32_t xheh_verify_batch(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, long* fail_index, double* timings7) {
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len;

@@ -17,6 +17,7 @@
 #include <string.h>
 #include <array>
 #include <string>
+#include <algorithm>
 #include <unordered_map>
 #include <vector>
 #include "../../include/xhe.h"
@@ -35,31 +36,89 @@ struct VerificationState {               // src/tx/verify.rs:25-77; every call r
   virtual bool update_account_nonce(const uint8_t account[32], uint64_t nonce) = 0;
   virtual bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) = 0;
   virtual bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) = 0;
+  // optional hints (not part of the reference trait): the batch front end announces the lookups it is about to make
+  virtual void prefetch_account(const uint8_t[32]) const {}
+  virtual void prefetch_balance(const uint8_t[32], const uint8_t[32]) const {}
 };
 
 struct KeyHash { size_t operator()(const Ct64& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); uint64_t g; memcpy(&g, k.data() + 37, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull ^ g); } };
 struct Key32Hash { size_t operator()(const Bytes32& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
 
+// Open-addressing table with inline keys (linear probing, one tag byte per slot, no erase): a lookup touches one tag
+// line and one entry, and the slot of a key can be prefetched from its hash alone -- what the batch front end needs
+// when it walks 10^4 transactions' accounts in order.
+template <size_t KB, typename V>
+class FlatTable {
+ public:
+  struct alignas(KB >= 64 ? 64 : 8) Entry { std::array<uint8_t, KB> key; V val; };
+  static uint64_t hash(const uint8_t* k) {     // keys are (concatenations of) compressed points / asset hashes: already uniform
+    uint64_t h; memcpy(&h, k + 5, 8);
+    if (KB >= 64) { uint64_t g; memcpy(&g, k + 37, 8); h = h * 0x9E3779B97F4A7C15ull ^ g; }
+    return h * 0xD6E8FEB86659FD93ull;
+  }
+  size_t size() const { return count_; }
+  void reserve(size_t n) { size_t cap = 16; while (cap < 2 * n) cap <<= 1; if (cap > tags_.size()) rehash(cap); }
+  V* find(const uint8_t* k) {
+    if (tags_.empty()) return nullptr;
+    const uint64_t h = hash(k); const size_t mask = tags_.size() - 1; const uint8_t tag = (uint8_t)(h >> 57) | 0x80;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      const uint8_t c = tags_[i];
+      if (c == 0) return nullptr;
+      if (c == tag && !memcmp(entries_[i].key.data(), k, KB)) return &entries_[i].val;
+    }
+  }
+  const V* find(const uint8_t* k) const { return const_cast<FlatTable*>(this)->find(k); }
+  // returns the value slot; *inserted tells whether the key was new (its value is then value-initialised)
+  V* insert(const uint8_t* k, bool* inserted = nullptr) {
+    if (2 * (count_ + 1) > tags_.size()) rehash(tags_.empty() ? 16 : 2 * tags_.size());
+    const uint64_t h = hash(k); const size_t mask = tags_.size() - 1; const uint8_t tag = (uint8_t)(h >> 57) | 0x80;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      const uint8_t c = tags_[i];
+      if (c == 0) { tags_[i] = tag; memcpy(entries_[i].key.data(), k, KB); entries_[i].val = V(); count_++; if (inserted) *inserted = true; return &entries_[i].val; }
+      if (c == tag && !memcmp(entries_[i].key.data(), k, KB)) { if (inserted) *inserted = false; return &entries_[i].val; }
+    }
+  }
+  void prefetch(const uint8_t* k) const {
+    if (tags_.empty()) return;
+    const size_t i = (size_t)hash(k) & (tags_.size() - 1);
+    __builtin_prefetch(&tags_[i]); const char* e = (const char*)&entries_[i]; __builtin_prefetch(e); if (sizeof(Entry) > 64) __builtin_prefetch(e + 64);
+  }
+  void clear() { std::fill(tags_.begin(), tags_.end(), 0); count_ = 0; }
+  template <typename F> void for_each(F f) const { for (size_t i = 0; i < tags_.size(); i++) if (tags_[i]) f(entries_[i].key.data(), entries_[i].val); }
+ private:
+  void rehash(size_t cap) {
+    std::vector<uint8_t> ot; std::vector<Entry> oe; ot.swap(tags_); oe.swap(entries_);
+    tags_.assign(cap, 0); entries_.resize(cap); count_ = 0;
+    for (size_t i = 0; i < ot.size(); i++) if (ot[i]) *insert(oe[i].key.data()) = oe[i].val;
+  }
+  std::vector<uint8_t> tags_; std::vector<Entry> entries_; size_t count_ = 0;
+};
+
 class MockLedger : public VerificationState {   // src/lib.rs:106-201
  public:
-  std::unordered_map<Ct64, Ct64, KeyHash> balances;   // key = account || asset
-  std::unordered_map<Bytes32, uint64_t, Key32Hash> nonces;
+  FlatTable<64, Ct64> balances;                 // key = account || asset
+  FlatTable<32, uint64_t> nonces;
   std::unordered_map<Bytes32, std::pair<std::vector<Bytes32>, uint8_t>, Key32Hash> multisig;
   static Ct64 key(const uint8_t a[32], const uint8_t b[32]) { Ct64 k; memcpy(k.data(), a, 32); memcpy(k.data() + 32, b, 32); return k; }
+  void set_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t ct[64]) { memcpy(balances.insert(key(account, asset).data())->data(), ct, 64); }
+  void set_nonce(const uint8_t account[32], uint64_t nonce) { *nonces.insert(account) = nonce; }
   bool get_account_balance(const uint8_t account[32], const uint8_t asset[32], Role, uint8_t out_ct[64]) override {
-    auto it = balances.find(key(account, asset)); if (it == balances.end()) return false; memcpy(out_ct, it->second.data(), 64); return true; }
+    const Ct64* v = balances.find(key(account, asset).data()); if (!v) return false; memcpy(out_ct, v->data(), 64); return true; }
   bool update_account_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t new_ct[64], Role) override {
-    auto it = balances.find(key(account, asset)); if (it == balances.end()) return false; memcpy(it->second.data(), new_ct, 64); return true; }
-  bool get_account_nonce(const uint8_t account[32], uint64_t* nonce) override { Bytes32 k; memcpy(k.data(), account, 32); auto it = nonces.find(k); if (it == nonces.end()) return false; *nonce = it->second; return true; }
-  bool update_account_nonce(const uint8_t account[32], uint64_t nonce) override { Bytes32 k; memcpy(k.data(), account, 32); auto it = nonces.find(k); if (it == nonces.end()) return false; it->second = nonce; return true; }
+    Ct64* v = balances.find(key(account, asset).data()); if (!v) return false; memcpy(v->data(), new_ct, 64); return true; }
+  bool get_account_nonce(const uint8_t account[32], uint64_t* nonce) override { const uint64_t* v = nonces.find(account); if (!v) return false; *nonce = *v; return true; }
+  bool update_account_nonce(const uint8_t account[32], uint64_t nonce) override { uint64_t* v = nonces.find(account); if (!v) return false; *v = nonce; return true; }
   bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) override {
     Bytes32 k; memcpy(k.data(), account, 32);
     if (n == 0) { multisig.erase(k); return true; }
     std::vector<Bytes32> v(n); for (size_t i = 0; i < n; i++) memcpy(v[i].data(), signers + 32 * i, 32);
     multisig[k] = std::make_pair(v, threshold); return true; }
   bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) override {
+    if (multisig.empty()) { *present = false; return true; }
     Bytes32 k; memcpy(k.data(), account, 32); auto it = multisig.find(k); *present = it != multisig.end();
     if (*present) { *signers = it->second.first; *threshold = it->second.second; } return true; }
+  void prefetch_account(const uint8_t account[32]) const override { nonces.prefetch(account); }
+  void prefetch_balance(const uint8_t account[32], const uint8_t asset[32]) const override { balances.prefetch(key(account, asset).data()); }
 };
 
 struct TransferView { const uint8_t *asset, *dest, *commitment, *sender_handle, *receiver_handle, *proof, *extra; uint32_t extra_len; bool has_extra; };
