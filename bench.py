@@ -317,8 +317,9 @@ def main():
             led = ledgers[s] if ledgers else ledger0.clone()      # fresh state per step (cloned before the clock starts)
             if dist:
                 seq = seq_base[0] + s * nfl + widx
-                code, idx, _ = xd.verify_batch_distributed(c, None, led, rank * args.txs, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, commit=False, fiat_shamir=args.fiat_shamir,
+                code, idx, tmw = xd.verify_batch_distributed(c, None, led, rank * args.txs, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, commit=True, fiat_shamir=args.fiat_shamir,
                                                            gather=(lambda rec, q=seq: gatherer.gather(q, rec)) if gatherer else None)
+                pipe_phases.append(tmw)
             else:
                 code, idx, tmw = verifier.verify_batch(c, None, led, seed=b"p%d-%d" % (widx, s), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
                 pipe_phases.append(tmw)

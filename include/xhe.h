@@ -136,6 +136,10 @@ size_t  xhe_batch_h2d_bytes(const xhe_ctx* ctx);
 size_t  xhe_batch_d2h_bytes(const xhe_ctx* ctx);
 /* K7: add n partial sums (n x 128 B as produced in *_ext) and test the Ristretto identity; out_enc optional */
 int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t out_enc[32], int32_t* is_identity);
+/* Cross-rank decision of a sharded batch: sum of n <= 224 canonical encodings -- the per-rank partial
+ * results of the sigma or range MSM (src/proofs.rs:49-67 decides on the identity of the total) -- as one 32-thread
+ * kernel with no allocation.  *all_valid = 0 if an encoding does not decode (such inputs are left out of the sum). */
+int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t out_enc[32], int32_t* is_identity, int32_t* all_valid);
 
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns

@@ -118,3 +118,21 @@ def test_int_peak_reports(ctx):
     rates = [ctx.int_peak(w) for w in range(3)]
     print("int peak (inst/s): IMAD.lo %.3e IMAD.HI %.3e IMAD.WIDE %.3e" % tuple(rates))
     assert all(r > 1e11 for r in rates)
+
+
+def test_sum_encodings_parity(ctx):
+    """cross-rank combination of partial MSM results: sum of encodings == oracle point additions; identity and bad input"""
+    import oracle
+    rnd = hashlib.shake_256(b"sum-enc").digest(64 * 40)
+    pts = [oracle.from_uniform(rnd[64 * i:64 * i + 64]) for i in range(40)]
+    ident = bytes(32)
+    for n in (0, 1, 2, 8, 33, 40):
+        want = ident
+        for p in pts[:n]:
+            want = oracle.point_add(want, p)
+        enc, is_id = ctx.sum_encodings(b"".join(pts[:n]))
+        assert enc == want and is_id == (want == ident)
+    a = pts[0]; neg_a = oracle.point_add(ident, a, sub=True)
+    assert ctx.sum_encodings(a + pts[1] + neg_a + oracle.point_add(ident, pts[1], sub=True)) == (ident, True)
+    bad = b"\xff" * 32                       # non-canonical field element: not a valid encoding
+    assert ctx.sum_encodings(a + bad + neg_a)[1] is False

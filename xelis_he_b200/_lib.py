@@ -48,6 +48,7 @@ def load_library():
         "xhe_msm_workspace_bytes": (sz, [vp, sz]),
         "xhe_msm_dev": (i32, [vp, vp, vp, sz, vp, sz, vp, vp]),
         "xhe_msm_vartime": (i32, [vp, u8p, u8p, sz, vp, C.POINTER(C.c_int32)]),
+        "xhe_sum_encodings": (i32, [vp, u8p, sz, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
         "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),
@@ -128,6 +129,15 @@ class Ctx:
         if rc != 0:
             raise XheError(rc, self.lib.xhe_last_error(self.p).decode())
         return out.raw, bool(ident.value)
+
+    def sum_encodings(self, encodings: bytes):
+        """Sum of canonical Ristretto encodings (per-rank partial MSM results): returns (encoding of the sum, is_identity and
+        all inputs valid).  One small kernel, no allocation -- safe to call between batches in flight."""
+        n = len(encodings) // 32
+        out = C.create_string_buffer(32)
+        ident, valid = C.c_int32(0), C.c_int32(0)
+        self._chk(self.lib.xhe_sum_encodings(self.p, encodings, n, out, C.byref(ident), C.byref(valid)))
+        return out.raw, bool(ident.value) and bool(valid.value)
 
     def msm_plan(self, n):
         c, w = C.c_int(), C.c_int()

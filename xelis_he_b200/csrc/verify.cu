@@ -374,6 +374,28 @@ __global__ void k_combine(const uint32_t* __restrict__ ext, uint32_t n, uint8_t*
   *is_id = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }
 
+// sum of up to 32 * k Ristretto encodings (one warp: lanes decode in parallel, lane 0 adds): out = 32 B encoding of the
+// sum, then a word "sum is the identity", then a word "every encoding decoded"
+__global__ void __launch_bounds__(32) k_sum_encodings(const uint8_t* __restrict__ enc, uint32_t n, uint8_t* __restrict__ out) {
+  __shared__ uint32_t pts[32 * 16]; __shared__ uint32_t okw[32];
+  ge acc = ge_identity(); uint32_t all_ok = 1;
+  for (uint32_t base = 0; base < n; base += 32) {
+    uint32_t i = base + threadIdx.x; ge_aff a; bool ok = true;
+    if (i < n) { ok = decode_words(a, enc + 32 * (size_t)i); for (int q = 0; q < 8; q++) { pts[16 * threadIdx.x + q] = a.x.v[q]; pts[16 * threadIdx.x + 8 + q] = a.y.v[q]; } }
+    okw[threadIdx.x] = ok ? 1u : 0u;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      for (uint32_t k = 0; k < 32 && base + k < n; k++) {
+        if (!okw[k]) { all_ok = 0; continue; }
+        ge_aff b; for (int q = 0; q < 8; q++) { b.x.v[q] = pts[16 * k + q]; b.y.v[q] = pts[16 * k + 8 + q]; }
+        acc = ge_add(acc, ge_from_affine(b));
+      }
+    }
+    __syncwarp();
+  }
+  if (threadIdx.x == 0) { encode_words(out, acc); ((uint32_t*)out)[8] = ge_ristretto_is_identity(acc) ? 1u : 0u; ((uint32_t*)out)[9] = all_ok; }
+}
+
 inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 struct Arena {   // bump allocator over one cudaMalloc'd block (grow-only, owned by the ctx)
@@ -412,6 +434,22 @@ extern "C" int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t
   cudaFree(d);
   if (out_enc) memcpy(out_enc, h, 32);
   uint32_t f; memcpy(&f, h + 32, 4); *is_identity = (int32_t)f;
+  return XHE_OK;
+}
+
+// Sum of n <= 224 canonical Ristretto encodings (the per-rank partial MSM results of a sharded batch): encoding of the sum,
+// whether it is the identity, whether all inputs decoded.  No allocation, one 32-thread kernel, synchronous.
+extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t out_enc[32], int32_t* is_identity, int32_t* all_valid) {
+  if (!ctx || !is_identity || (n && !enc) || n > 224) return XHE_E_ARG;
+  if (!ctx->d_small) XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_small, 8192));
+  uint8_t* d = (uint8_t*)ctx->d_small; uint8_t* dout = d + 7168;
+  if (n) XHE_CUDA_OK(ctx, cudaMemcpyAsync(d, enc, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_sum_encodings<<<1, 32, 0, ctx->stream>>>(d, (uint32_t)n, dout); XHE_LAUNCHED(ctx);
+  uint8_t h[40];
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h, dout, 40, cudaMemcpyDeviceToHost, ctx->stream));
+  XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (out_enc) memcpy(out_enc, h, 32);
+  uint32_t f, v; memcpy(&f, h + 32, 4); memcpy(&v, h + 36, 4); *is_identity = (int32_t)f; if (all_valid) *all_valid = (int32_t)v;
   return XHE_OK;
 }
 

@@ -34,6 +34,7 @@ struct xhe_ctx {
   cudaEvent_t tl_base = nullptr; size_t tl_mark = 0;
   struct Span { const char* name; float t0, t1; };
   std::vector<Span> timeline;
+  void* d_small = nullptr;                                    // 8 KiB device scratch for the tiny cross-rank combination (xhe_sum_encodings)
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};          // side streams for the independent pipelines of xhe_batch_run
   cudaEvent_t ev[8] = {nullptr};

@@ -241,14 +241,18 @@ std::unordered_map<xhe_ctx*, Pending> g_pending;
 }  // namespace
 
 int commit_pending(xhe_ctx* ctx, VerificationState& state) {
-  std::lock_guard<std::mutex> g(g_pending_mu);
-  auto it = g_pending.find(ctx);
-  if (it == g_pending.end()) return XHE_E_ARG;
-  for (const StateUpdate& u : it->second.updates) {
-    uint8_t ct[64]; memcpy(ct, &it->second.op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &it->second.op_out[32 * (size_t)u.op_d], 32);
+  Pending P;
+  { std::lock_guard<std::mutex> g(g_pending_mu);          // the lock only covers the hand-over, not the state walk
+    auto it = g_pending.find(ctx);
+    if (it == g_pending.end()) return XHE_E_ARG;
+    P = std::move(it->second); g_pending.erase(it); }
+  const size_t n = P.updates.size();
+  for (size_t j = 0; j < n; j++) {
+    const StateUpdate& u = P.updates[j];
+    if (j + 8 < n) state.prefetch_balance(P.updates[j + 8].account.data(), P.updates[j + 8].asset.data());
+    uint8_t ct[64]; memcpy(ct, &P.op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &P.op_out[32 * (size_t)u.op_d], 32);
     if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
   }
-  g_pending.erase(it);
   return XHE_OK;
 }
 
@@ -376,9 +380,10 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   if (!shard && (!v.sigma_is_identity || !v.range_is_identity)) return 0;
   if (shard) {
     memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32);
-    std::lock_guard<std::mutex> g(g_pending_mu);
-    Pending& Pn = g_pending[ctx]; Pn.updates.clear(); Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size());
+    Pending Pn; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.updates.reserve(updates.size());
     for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; Pn.updates.push_back(su); }
+    std::lock_guard<std::mutex> g(g_pending_mu);
+    g_pending[ctx] = std::move(Pn);
   } else if (opt.apply_state) {
     for (size_t j = 0; j < updates.size(); j++) {
       const Upd& u = updates[j];
@@ -703,8 +708,9 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   if (verdict == XHE_OK) { for (size_t i = 0; i < n_reached; i++) if (plan[i].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
   if (verdict == XHE_OK && !shard && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;               // src/tx/verify.rs:504-514
   if (shard) {
+    Pending Pn; Pn.updates = B.updates; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size());
     std::lock_guard<std::mutex> g(g_pending_mu);
-    Pending& P = g_pending[ctx]; P.updates = B.updates; P.op_out = op_out;
+    g_pending[ctx] = std::move(Pn);
   } else if (verdict == XHE_OK && opt.apply_state) {
     for (const StateUpdate& u : B.updates) {
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
