@@ -201,3 +201,42 @@ def test_verdict_partials_combine(ctx):
     out = (C.c_uint8 * 32)(); flag = C.c_int32(0)
     assert lib.xhe_combine_partials(ctx.p, bytes(ident) * 3, 3, out, C.byref(flag)) == 0
     assert flag.value == 1 and bytes(out) == bytes(32)
+
+
+def test_large_batch_size_independent_properties(ctx):
+    """2,000-transfer batch (the bench workload's shape at a size the oracle still checks in seconds): accept through the
+    fast path, every updated ciphertext equal to the oracle's apply_without_verify, and a tampered transaction deep inside
+    the batch rejected at the index and with the code the oracle reports (exact-path fallback)."""
+    from xelis_he_b200 import verifier
+    T = 2000
+    b = oracle.mint_transfers(91, T, 1, 1, threads=16)
+    hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+    code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir="fast")
+    assert (code, idx) == (OK, -1) and tm["fast_path"]
+    ol = b.ledger()
+    for blob in b.blobs:
+        assert oracle.apply_without_verify(blob, ol) == 0
+    assert hl.dump() == sorted(ol.dump())
+    # idempotence of the verdict under a different batch-factor seed, and the host-transcript split agrees
+    hl2 = verifier.Ledger(); hl2.import_records(b.ledger().dump())
+    assert verifier.verify_batch(ctx, b.blobs, hl2, seed=b"another seed", fiat_shamir="host")[:2] == (OK, -1)
+    assert hl2.dump() == hl.dump()
+    bad = list(b.blobs); victim = 1617
+    t = bytearray(bad[victim]); t[-1] ^= 0x01; bad[victim] = bytes(t)           # last byte of the signature
+    hl3 = verifier.Ledger(); hl3.import_records(b.ledger().dump())
+    got = verifier.verify_batch(ctx, bad, hl3, seed=SEED, fiat_shamir="fast")
+    assert got[:2] == oracle.verify_batch(bad[:victim + 1], b.slice(victim + 1).ledger()) == (1, victim)
+    assert not got[2]["fast_path"]
+
+
+def test_long_single_sender_chain(ctx):
+    """C3's one-sender variant: 256 transactions spending from one account, so every source balance is the output of the
+    previous transaction (pointer-jumping prefix over a chain of length T)."""
+    from xelis_he_b200 import verifier
+    b = oracle.mint_chain(77, 256, 1)
+    ol = b.ledger()
+    assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
+    for mode in ("fast", "host"):
+        hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+        assert verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir=mode)[:2] == (OK, -1)
+        assert hl.dump() == sorted(ol.dump())

@@ -11,7 +11,9 @@ namespace {
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
-__device__ void keccak_f1600(uint64_t* st) {
+// (kept out of line, like the sponge operations below: one thread per transaction walks ~100 transcript operations, and with
+// everything inlined the kernel grew to ~120k instructions and stalled on instruction fetch)
+__device__ __noinline__ void keccak_f1600(uint64_t* st) {
   const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
                            0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
                            0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
@@ -41,22 +43,67 @@ __device__ void keccak_f1600(uint64_t* st) {
   for (int i = 0; i < 25; i++) st[i] = s[i];
 }
 
-struct Sponge {   // byte-granular sponge over a local-memory state
+// up to eight message bytes as one little-endian word: the loads are independent of each other (one memory round trip),
+// word loads when the pointer allows it
+__device__ __forceinline__ uint64_t load_le(const uint8_t* d, uint32_t nb) {
+  if (nb == 8 && (((uintptr_t)d) & 3) == 0) { const uint32_t* w = (const uint32_t*)d; return (uint64_t)w[0] | ((uint64_t)w[1] << 32); }
+  uint64_t v = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i++) if (i < nb) v |= (uint64_t)d[i] << (8 * i);
+  return v;
+}
+
+struct Sponge {   // sponge over a local-memory state; absorbs and squeezes up to eight bytes per state access
   uint64_t st[25]; uint32_t pos, rate;
   __device__ void init(uint32_t r) { for (int i = 0; i < 25; i++) st[i] = 0; pos = 0; rate = r; }
   __device__ __forceinline__ void xor_byte(uint32_t p, uint8_t v) { st[p >> 3] ^= (uint64_t)v << ((p & 7) * 8); }
   __device__ __forceinline__ uint8_t get_byte(uint32_t p) const { return (uint8_t)(st[p >> 3] >> ((p & 7) * 8)); }
-  __device__ void absorb(const uint8_t* d, uint32_t n) { for (uint32_t i = 0; i < n; i++) { xor_byte(pos++, d[i]); if (pos == rate) { keccak_f1600(st); pos = 0; } } }
+  // XOR the nb <= 8 low bytes of w (upper bytes zero) into the state at byte position p
+  __device__ __forceinline__ void xor_word(uint32_t p, uint64_t w, uint32_t nb) {
+    const uint32_t o = p & 7, sh = o * 8;
+    st[p >> 3] ^= w << sh;
+    if (o + nb > 8) st[(p >> 3) + 1] ^= w >> (64 - sh);
+  }
+  // the nb <= 8 state bytes at position p as a little-endian word
+  __device__ __forceinline__ uint64_t get_word(uint32_t p, uint32_t nb) const {
+    const uint32_t o = p & 7, sh = o * 8;
+    uint64_t v = st[p >> 3] >> sh;
+    if (o + nb > 8) v |= st[(p >> 3) + 1] << (64 - sh);
+    return nb < 8 ? v & ((1ull << (8 * nb)) - 1) : v;
+  }
+  __device__ __noinline__ void absorb(const uint8_t* d, uint32_t n) {
+    while (n) {
+      uint32_t nb = min(min(8u, n), rate - pos);
+      xor_word(pos, load_le(d, nb), nb);
+      pos += nb; d += nb; n -= nb;
+      if (pos == rate) { keccak_f1600(st); pos = 0; }
+    }
+  }
   __device__ void finish(uint8_t dom) { xor_byte(pos, dom); xor_byte(rate - 1, 0x80); keccak_f1600(st); pos = 0; }
-  __device__ void squeeze(uint8_t* o, uint32_t n) { for (uint32_t i = 0; i < n; i++) { if (pos == rate) { keccak_f1600(st); pos = 0; } o[i] = get_byte(pos++); } }
+  __device__ __noinline__ void squeeze(uint8_t* o, uint32_t n) {
+    while (n) {
+      if (pos == rate) { keccak_f1600(st); pos = 0; }
+      uint32_t nb = min(min(8u, n), rate - pos);
+      uint64_t v = get_word(pos, nb);
+      for (uint32_t i = 0; i < nb; i++) o[i] = (uint8_t)(v >> (8 * i));
+      pos += nb; o += nb; n -= nb;
+    }
+  }
 };
 
 struct Merlin {   // STROBE-128 / "Merlin v1.0"
   Sponge s; uint8_t pos_begin;
   enum { R = 166, F_I = 1, F_A = 2, F_C = 4, F_M = 16, F_K = 32 };
-  __device__ void run_f() { s.xor_byte(s.pos, pos_begin); s.xor_byte(s.pos + 1, 0x04); s.xor_byte(R + 1, 0x80); keccak_f1600(s.st); s.pos = 0; pos_begin = 0; }
-  __device__ void absorb(const uint8_t* d, uint32_t n) { for (uint32_t i = 0; i < n; i++) { s.xor_byte(s.pos++, d[i]); if (s.pos == R) run_f(); } }
-  __device__ void begin_op(uint8_t flags) {
+  __device__ __noinline__ void run_f() { s.xor_byte(s.pos, pos_begin); s.xor_byte(s.pos + 1, 0x04); s.xor_byte(R + 1, 0x80); keccak_f1600(s.st); s.pos = 0; pos_begin = 0; }
+  __device__ __noinline__ void absorb(const uint8_t* d, uint32_t n) {
+    while (n) {
+      uint32_t nb = min(min(8u, n), (uint32_t)R - s.pos);
+      s.xor_word(s.pos, load_le(d, nb), nb);
+      s.pos += nb; d += nb; n -= nb;
+      if (s.pos == R) run_f();
+    }
+  }
+  __device__ __noinline__ void begin_op(uint8_t flags) {
     uint8_t h[2] = {pos_begin, flags}; pos_begin = (uint8_t)(s.pos + 1);
     absorb(h, 2);
     if ((flags & (F_C | F_K)) && s.pos != 0) run_f();
@@ -72,19 +119,27 @@ struct Merlin {   // STROBE-128 / "Merlin v1.0"
     const uint8_t ds[7] = {'d', 'o', 'm', '-', 's', 'e', 'p'};
     append(ds, 7, (const uint8_t*)label, llen);
   }
-  __device__ void append(const uint8_t* label, uint32_t llen, const uint8_t* msg, uint32_t n) {
+  __device__ __noinline__ void append(const uint8_t* label, uint32_t llen, const uint8_t* msg, uint32_t n) {
     uint8_t le[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
     meta_ad(label, llen, false); meta_ad(le, 4, true);
     begin_op(F_A); absorb(msg, n);
   }
   __device__ void append_u64(const uint8_t* label, uint32_t llen, uint64_t v) { uint8_t le[8]; for (int i = 0; i < 8; i++) le[i] = (uint8_t)(v >> (8 * i)); append(label, llen, le, 8); }
   // 64 challenge bytes reduced mod l (ProtocolTranscript::challenge_scalar, src/transcript.rs:46-51) -> 8 words
-  __device__ void challenge_scalar(const uint8_t* label, uint32_t llen, uint32_t* out8) {
+  __device__ __noinline__ void challenge_scalar(const uint8_t* label, uint32_t llen, uint32_t* out8) {
     uint8_t le[4] = {64, 0, 0, 0};
     meta_ad(label, llen, false); meta_ad(le, 4, true);
     begin_op(F_I | F_A | F_C);
-    uint8_t b[64];
-    for (int i = 0; i < 64; i++) { b[i] = s.get_byte(s.pos); s.xor_byte(s.pos, b[i]); s.pos++; if (s.pos == R) run_f(); }
+    // PRF output: the state bytes are read out and cleared (STROBE squeeze with the C flag), eight at a time
+    uint8_t b[64]; uint32_t got = 0;
+    while (got < 64) {
+      uint32_t nb = min(8u, min(64u - got, (uint32_t)R - s.pos));
+      uint64_t v = s.get_word(s.pos, nb);
+      s.xor_word(s.pos, v, nb);
+      for (uint32_t i = 0; i < nb; i++) b[got + i] = (uint8_t)(v >> (8 * i));
+      got += nb; s.pos += nb;
+      if (s.pos == R) run_f();
+    }
     sc lo = sc_frombytes(b), hi = sc_frombytes(b + 32);
     sc r = sc_reduce512(lo, hi);
     for (int i = 0; i < 8; i++) out8[i] = r.v[i];

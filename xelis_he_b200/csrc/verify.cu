@@ -45,6 +45,11 @@ __device__ __forceinline__ void st_sc(uint32_t* p, const sc& r) {
 }
 __device__ __forceinline__ sc mmul(const sc& a, const sc& b) { return sc_montmul(a, b); }
 __device__ __forceinline__ sc mont_one() { return sc_load_const(SC_R1); }
+// out-of-line variants for the one-thread-per-proof kernels, which are bound by instruction fetch when ~60 products are inlined
+__device__ __noinline__ sc mmul_call(const sc& a, const sc& b) { return sc_montmul(a, b); }
+__device__ __noinline__ sc msq_call(const sc& a) { return sc_montsq(a); }
+__device__ __noinline__ sc minv_call(const sc& a) { return sc_mont_invert(a); }
+__device__ __forceinline__ sc from_mont_call(const sc& a) { sc one = sc_zero(); one.v[0] = 1; return mmul_call(a, one); }
 
 // ---- fixed-base tables (built once per ctx) -------------------------------------------------------------------------
 // tab8[w][j-1] = j * 2^(8w) * base as affine Niels, w < nwin, j = 1..255
@@ -249,46 +254,46 @@ __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_a
   const uint32_t* ch = chal + 8 * (size_t)chal_off[p];
   sc y, z, x, w; ld_sc(y, ch); ld_sc(z, ch + 8); ld_sc(x, ch + 16); ld_sc(w, ch + 24);
   // to Montgomery form
-  sc ym = mmul(y, RR), zm = mmul(z, RR), xm = mmul(x, RR), wm = mmul(w, RR), am = mmul(a, RR), bm = mmul(b, RR), cm = mmul(c, RR), rm = mmul(rho, RR);
+  sc ym = mmul_call(y, RR), zm = mmul_call(z, RR), xm = mmul_call(x, RR), wm = mmul_call(w, RR), am = mmul_call(a, RR), bm = mmul_call(b, RR), cm = mmul_call(c, RR), rm = mmul_call(rho, RR);
   sc onem = mont_one();
   // batch inversion of u_0..u_{lg-1}, y, (y - 1)
   sc um[RP_MAX_LG + 2], pre[RP_MAX_LG + 2];
-  for (int j = 0; j < lg; j++) { sc u; ld_sc(u, ch + 32 + 8 * j); um[j] = mmul(u, RR); }
+  for (int j = 0; j < lg; j++) { sc u; ld_sc(u, ch + 32 + 8 * j); um[j] = mmul_call(u, RR); }
   um[lg] = ym; um[lg + 1] = sc_sub(ym, onem);
   bool y_is_one = sc_iszero(um[lg + 1]);
   if (y_is_one) um[lg + 1] = onem;
   sc accp = onem;
-  for (int j = 0; j < lg + 2; j++) { pre[j] = accp; accp = mmul(accp, um[j]); }
-  sc inv = sc_mont_invert(accp);
+  for (int j = 0; j < lg + 2; j++) { pre[j] = accp; accp = mmul_call(accp, um[j]); }
+  sc inv = minv_call(accp);
   sc uinv[RP_MAX_LG + 2];
-  for (int j = lg + 1; j >= 0; j--) { uinv[j] = mmul(inv, pre[j]); inv = mmul(inv, um[j]); }
+  for (int j = lg + 1; j >= 0; j--) { uinv[j] = mmul_call(inv, pre[j]); inv = mmul_call(inv, um[j]); }
   // allinv = prod u_j^-1
   sc allinv = onem;
-  for (int j = 0; j < lg; j++) allinv = mmul(allinv, uinv[j]);
+  for (int j = 0; j < lg; j++) allinv = mmul_call(allinv, uinv[j]);
   sc yinv = uinv[lg], ym1inv = uinv[lg + 1];
   uint32_t* d = der + 8 * (size_t)RP_DER * p;
-  sc zzm = mmul(zm, zm);
+  sc zzm = mmul_call(zm, zm);
   st_sc(d + 8 * D_ALLINV, allinv); st_sc(d + 8 * D_YINV, yinv);
-  st_sc(d + 8 * D_RZ, mmul(rho, zm)); st_sc(d + 8 * D_RA, mmul(rho, am)); st_sc(d + 8 * D_RB, mmul(rho, bm)); st_sc(d + 8 * D_Z, zm);
-  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), sc_montsq(um[j])); st_sc(d + 8 * (D_YPW + j), yp); yp = sc_montsq(yp); } }
+  st_sc(d + 8 * D_RZ, mmul_call(rho, zm)); st_sc(d + 8 * D_RA, mmul_call(rho, am)); st_sc(d + 8 * D_RB, mmul_call(rho, bm)); st_sc(d + 8 * D_Z, zm);
+  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), msq_call(um[j])); st_sc(d + 8 * (D_YPW + j), yp); yp = msq_call(yp); } }
   // dynamic scalars (plain form): A: rho ; S: rho x ; T1: rho c x ; T2: rho c x^2 ; L_j: rho u_j^2 ; R_j: rho u_j^-2 ; V_j: rho c z^2 z^j
   uint32_t* o = dyn_sc + 8 * (size_t)dyn_off[p];
-  sc rx = mmul(rm, xm), rcx = mmul(rx, cm), rcxx = mmul(rcx, xm);
-  st_sc(o, rho); st_sc(o + 8, sc_from_mont(rx)); st_sc(o + 16, sc_from_mont(rcx)); st_sc(o + 24, sc_from_mont(rcxx));
-  for (int j = 0; j < lg; j++) { st_sc(o + 8 * (4 + j), sc_from_mont(mmul(rm, mmul(um[j], um[j])))); st_sc(o + 8 * (4 + lg + j), sc_from_mont(mmul(rm, mmul(uinv[j], uinv[j])))); }
-  sc rczz = mmul(mmul(rm, cm), zzm), zj = onem, sum_z = sc_zero();
-  sc rzz_p = mmul(rho, zzm);
-  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), sc_from_mont(mmul(rczz, zj))); st_sc(d + 8 * (D_RZZJ + j), mmul(rzz_p, zj)); sum_z = sc_add(sum_z, zj); zj = mmul(zj, zm); }
+  sc rx = mmul_call(rm, xm), rcx = mmul_call(rx, cm), rcxx = mmul_call(rcx, xm);
+  st_sc(o, rho); st_sc(o + 8, from_mont_call(rx)); st_sc(o + 16, from_mont_call(rcx)); st_sc(o + 24, from_mont_call(rcxx));
+  for (int j = 0; j < lg; j++) { st_sc(o + 8 * (4 + j), from_mont_call(mmul_call(rm, mmul_call(um[j], um[j])))); st_sc(o + 8 * (4 + lg + j), from_mont_call(mmul_call(rm, mmul_call(uinv[j], uinv[j])))); }
+  sc rczz = mmul_call(mmul_call(rm, cm), zzm), zj = onem, sum_z = sc_zero();
+  sc rzz_p = mmul_call(rho, zzm);
+  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), from_mont_call(mmul_call(rczz, zj))); st_sc(d + 8 * (D_RZZJ + j), mmul_call(rzz_p, zj)); sum_z = sc_add(sum_z, zj); zj = mmul_call(zj, zm); }
   // delta(y,z) = (z - z^2) * sum_{i<N} y^i - z^3 * (2^64 - 1) * sum_{j<m} z^j
-  sc yN = ym; for (int j = 0; j < lg; j++) yN = mmul(yN, yN);
-  sc sum_y = y_is_one ? mmul(sc_from_u64(N), RR) : mmul(sc_sub(yN, onem), ym1inv);
-  sc two64m1 = mmul(sc_from_u64(0xffffffffffffffffull), RR);
-  sc delta = sc_sub(mmul(sc_sub(zm, zzm), sum_y), mmul(mmul(mmul(zzm, zm), two64m1), sum_z));
+  sc yN = ym; for (int j = 0; j < lg; j++) yN = mmul_call(yN, yN);
+  sc sum_y = y_is_one ? mmul_call(sc_from_u64(N), RR) : mmul_call(sc_sub(yN, onem), ym1inv);
+  sc two64m1 = mmul_call(sc_from_u64(0xffffffffffffffffull), RR);
+  sc delta = sc_sub(mmul_call(sc_sub(zm, zzm), sum_y), mmul_call(mmul_call(mmul_call(zzm, zm), two64m1), sum_z));
   // B (G): rho (w (t_x - a b) + c (delta - t_x)) ; B_blinding (H): rho (-e_bl - c t_x_bl)
-  sc txm = mmul(t_x, RR);
-  sc gB = mmul(rm, sc_add(mmul(wm, sc_sub(txm, mmul(am, bm))), mmul(cm, sc_sub(delta, txm))));
-  sc hB = mmul(rm, sc_neg(sc_add(mmul(e_bl, RR), mmul(cm, mmul(t_x_bl, RR)))));
-  st_sc(gh + 16 * (size_t)p, sc_from_mont(gB)); st_sc(gh + 16 * (size_t)p + 8, sc_from_mont(hB));
+  sc txm = mmul_call(t_x, RR);
+  sc gB = mmul_call(rm, sc_add(mmul_call(wm, sc_sub(txm, mmul_call(am, bm))), mmul_call(cm, sc_sub(delta, txm))));
+  sc hB = mmul_call(rm, sc_neg(sc_add(mmul_call(e_bl, RR), mmul_call(cm, mmul_call(t_x_bl, RR)))));
+  st_sc(gh + 16 * (size_t)p, from_mont_call(gB)); st_sc(gh + 16 * (size_t)p + 8, from_mont_call(hB));
 }
 
 // 2^k in Montgomery form for k < 64 (filled once per ctx)
