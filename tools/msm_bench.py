@@ -14,9 +14,9 @@ variant = int(os.environ.get('XHE_ACC_VARIANT', '4'))
 lib.xhe_msm_set_variant(variant)
 res = {"imad_wide_peak": peak, "variant": variant}
 g = torch.Generator(device="cuda"); g.manual_seed(1)
-logs = [int(a) for a in sys.argv[1:]] or [16, 18, 20, 22]
+logs = [float(a) for a in sys.argv[1:]] or [16, 18, 20, 22]
 for logn in logs:
-    n = 1 << logn
+    n = int(round(2 ** logn)); logn = int(logn) if float(logn).is_integer() else logn
     uni = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=g)
     enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
     niels = torch.empty((n, 24), dtype=torch.int32, device="cuda")

@@ -16,6 +16,7 @@
 //   k_msm_horner    1 thread     : sum_w 2^(c w) S_w by Horner, ristretto encode, identity flag
 //
 // Algorithmic work: n*W mixed adds of 7 M = 504 limb products each dominate.
+#include <stdlib.h>
 #include "xhe_internal.cuh"
 #include "quad.cuh"
 #include <algorithm>
@@ -41,11 +42,17 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 MsmPlan make_plan(size_t n) {
   MsmPlan p;
-  // cost model in units of one mixed add: W * (n + 3 * 2^(c-1)); c in [4, 18]
+  // cost model in units of one mixed add: W * (n + K * 2^(c-1)); c in [4, 18].  K = what one bucket costs in the reduction
+  // stages relative to one accumulated entry.  Measured on B200 (tools/msm_bench.py sweep, profiles/r01_msm_window_sweep.md):
+  // below 2^19 points the latency of the per-window stages dominates and fewer, larger windows win (K = 3 picks c = 13 at
+  // 2^16, 15 at 2^18); above, the reduction's ~1.35 ns per bucket against ~0.1 ns per entry makes K = 12 the better fit
+  // (c = 15 at 2^20, 16 at 2^22).  Buckets must stay below ~100 entries on average: longer ones take the heavy-bucket path.
+  static const double K_env = getenv("XHE_MSM_BUCKET_COST") ? atof(getenv("XHE_MSM_BUCKET_COST")) : 0.0;
+  const double K = K_env > 0 ? K_env : (n >= ((size_t)1 << 19) ? 12.0 : 3.0);
   double best = 1e300; int bc = 8;
   for (int c = 4; c <= 18; c++) {
     int W = (254 + c - 1) / c;
-    double cost = (double)W * ((double)n + 3.0 * (double)(1u << (c - 1)));
+    double cost = (double)W * ((double)n + K * (double)(1u << (c - 1)));
     if (cost < best) { best = cost; bc = c; }
   }
   p.c = bc; p.W = (254 + bc - 1) / bc; p.B = 1u << (bc - 1); p.total_buckets = (size_t)p.W * p.B;
