@@ -55,6 +55,7 @@ MsmPlan make_plan(size_t n) {
     double cost = (double)W * ((double)n + K * (double)(1u << (c - 1)));
     if (cost < best) { best = cost; bc = c; }
   }
+  if (n <= 4096 && bc < 8) bc = 8;   // tiny inputs are pure latency: fewer windows shorten the per-window stages and the Horner chain
   p.c = bc; p.W = (254 + bc - 1) / bc; p.B = 1u << (bc - 1); p.total_buckets = (size_t)p.W * p.B;
   p.seg_log = std::min(3, bc - 1);
   size_t o = 0;
@@ -346,54 +347,81 @@ extern "C" void xhe_msm_set_variant(int v) { g_accum_variant = v; }
 extern "C" size_t xhe_msm_workspace_bytes(const xhe_ctx*, size_t n) { return make_plan(n).total; }
 extern "C" int32_t xhe_msm_plan(size_t n, int* c, int* W) { MsmPlan p = make_plan(n); if (c) *c = p.c; if (W) *W = p.W; return XHE_OK; }
 
-// d_out_ext (optional): the un-normalised extended result (128 B) for multi-GPU partial-sum combination
-int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag) {
+// The pipeline in two phases, so that a caller whose scalars are ready before its points (xhe_batch_run) can overlap them:
+//   xhe_msm_sort   -- steps 1-4: needs only the scalars (digit recoding, counting sort into bucket order, tile runs)
+//   xhe_msm_finish -- steps 5-9: needs the points; d_out_ext (optional) = the un-normalised extended result (128 B)
+namespace {
+struct MsmPtrs {
+  uint32_t *counts, *offsets, *cursor, *blocksums, *list, *glist, *runs, *run_off, *part, *part_g, *pstart, *pcount, *heavy, *nodes_a, *nodes_b, *flag;
+};
+inline MsmPtrs msm_ptrs(const MsmPlan& p, void* d_ws, void* d_bad_flag) {
+  uint8_t* ws = (uint8_t*)d_ws;
+  MsmPtrs q;
+  q.counts = (uint32_t*)(ws + p.off_counts); q.offsets = (uint32_t*)(ws + p.off_offsets); q.cursor = (uint32_t*)(ws + p.off_cursor);
+  q.blocksums = (uint32_t*)(ws + p.off_blocksums); q.list = (uint32_t*)(ws + p.off_list); q.glist = (uint32_t*)(ws + p.off_glist);
+  q.runs = (uint32_t*)(ws + p.off_runs); q.run_off = (uint32_t*)(ws + p.off_runoff); q.part = (uint32_t*)(ws + p.off_part); q.part_g = (uint32_t*)(ws + p.off_partg);
+  q.pstart = (uint32_t*)(ws + p.off_pstart); q.pcount = (uint32_t*)(ws + p.off_pcount); q.heavy = (uint32_t*)(ws + p.off_heavy);
+  q.nodes_a = (uint32_t*)(ws + p.off_nodes_a); q.nodes_b = (uint32_t*)(ws + p.off_nodes_b);
+  q.flag = d_bad_flag ? (uint32_t*)d_bad_flag : (uint32_t*)(ws + p.off_flag);
+  return q;
+}
+}  // namespace
+
+int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, size_t ws_bytes, void* d_bad_flag) {
+  if (!ctx) return XHE_E_ARG;
+  if (n == 0) return XHE_OK;
+  if (!d_scalars || !d_ws) return XHE_E_ARG;
+  if (n >= (1ull << 31)) return XHE_E_ARG;
+  cudaStream_t st = ctx->stream;
+  MsmPlan p = make_plan(n);
+  if (ws_bytes < p.total) { ctx->err = "msm workspace too small"; return XHE_E_ARG; }
+  MsmPtrs q = msm_ptrs(p, d_ws, d_bad_flag);
+  const size_t m = p.total_buckets;
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(q.counts, 0, 4 * (m + 1), st));
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(q.pcount, 0, 4 * m, st));
+  XHE_CUDA_OK(ctx, cudaMemsetAsync(q.heavy, 0, 4, st));
+  if (!d_bad_flag) XHE_CUDA_OK(ctx, cudaMemsetAsync(q.flag, 0, 4, st));
+  k_msm_count<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, q.counts, q.flag); XHE_LAUNCHED(ctx);
+  unsigned nb = nblk(m, SCAN_THREADS * SCAN_ITEMS);
+  if (nb > 4096) { ctx->err = "msm: too many buckets"; return XHE_E_ARG; }
+  k_scan_blocks<<<nb, SCAN_THREADS, 0, st>>>(q.counts, m, q.offsets, q.blocksums); XHE_LAUNCHED(ctx);
+  k_scan_totals<<<1, 1024, 0, st>>>(q.blocksums, (int)nb, q.offsets + m); XHE_LAUNCHED(ctx);
+  k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(q.offsets, m, q.blocksums, q.cursor); XHE_LAUNCHED(ctx);
+  k_msm_scatter<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, q.cursor, q.list, q.glist); XHE_LAUNCHED(ctx);
+  // offsets[m] = total number of non-zero digits (device-side); tiles beyond it are empty
+  k_msm_tile_runs<<<nblk(p.n_tiles + 1, 256), 256, 0, st>>>(q.glist, q.offsets + m, p.n_tiles, q.runs); XHE_LAUNCHED(ctx);
+  unsigned nbt = nblk(p.n_tiles + 1, SCAN_THREADS * SCAN_ITEMS);
+  if (nbt > 4096) { ctx->err = "msm: too many tiles"; return XHE_E_ARG; }
+  k_scan_blocks<<<nbt, SCAN_THREADS, 0, st>>>(q.runs, p.n_tiles + 1, q.run_off, q.blocksums); XHE_LAUNCHED(ctx);
+  k_scan_totals<<<1, 1024, 0, st>>>(q.blocksums, (int)nbt, (uint32_t*)((uint8_t*)d_ws + p.off_flag) + 2); XHE_LAUNCHED(ctx);
+  k_scan_add<<<nbt, SCAN_THREADS, 0, st>>>(q.run_off, p.n_tiles + 1, q.blocksums, nullptr); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext) {
   if (!ctx) return XHE_E_ARG;
   cudaStream_t st = ctx->stream;
   if (n == 0) { k_msm_empty<<<1, 1, 0, st>>>((uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK; }
-  if (!d_scalars || !d_niels || !d_ws) return XHE_E_ARG;
-  if (n >= (1ull << 31)) return XHE_E_ARG;
+  if (!d_niels || !d_ws) return XHE_E_ARG;
   MsmPlan p = make_plan(n);
   if (ws_bytes < p.total) { ctx->err = "msm workspace too small"; return XHE_E_ARG; }
-  uint8_t* ws = (uint8_t*)d_ws;
-  uint32_t *counts = (uint32_t*)(ws + p.off_counts), *offsets = (uint32_t*)(ws + p.off_offsets), *cursor = (uint32_t*)(ws + p.off_cursor),
-           *blocksums = (uint32_t*)(ws + p.off_blocksums), *list = (uint32_t*)(ws + p.off_list), *glist = (uint32_t*)(ws + p.off_glist),
-           *runs = (uint32_t*)(ws + p.off_runs), *run_off = (uint32_t*)(ws + p.off_runoff), *part = (uint32_t*)(ws + p.off_part), *part_g = (uint32_t*)(ws + p.off_partg),
-           *pstart = (uint32_t*)(ws + p.off_pstart), *pcount = (uint32_t*)(ws + p.off_pcount), *heavy = (uint32_t*)(ws + p.off_heavy), *nodes_a = (uint32_t*)(ws + p.off_nodes_a),
-           *nodes_b = (uint32_t*)(ws + p.off_nodes_b), *flag = d_bad_flag ? (uint32_t*)d_bad_flag : (uint32_t*)(ws + p.off_flag);
+  MsmPtrs q = msm_ptrs(p, d_ws, nullptr);
   const size_t m = p.total_buckets;
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, 4 * (m + 1), st));
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(pcount, 0, 4 * m, st));
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(heavy, 0, 4, st));
-  if (!d_bad_flag) XHE_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, 4, st));
-  k_msm_count<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, counts, flag); XHE_LAUNCHED(ctx);
-  unsigned nb = nblk(m, SCAN_THREADS * SCAN_ITEMS);
-  if (nb > 4096) { ctx->err = "msm: too many buckets"; return XHE_E_ARG; }
-  k_scan_blocks<<<nb, SCAN_THREADS, 0, st>>>(counts, m, offsets, blocksums); XHE_LAUNCHED(ctx);
-  k_scan_totals<<<1, 1024, 0, st>>>(blocksums, (int)nb, offsets + m); XHE_LAUNCHED(ctx);
-  k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(offsets, m, blocksums, cursor); XHE_LAUNCHED(ctx);
-  k_msm_scatter<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, cursor, list, glist); XHE_LAUNCHED(ctx);
-  // offsets[m] = total number of non-zero digits (device-side); tiles beyond it are empty
-  k_msm_tile_runs<<<nblk(p.n_tiles + 1, 256), 256, 0, st>>>(glist, offsets + m, p.n_tiles, runs); XHE_LAUNCHED(ctx);
-  unsigned nbt = nblk(p.n_tiles + 1, SCAN_THREADS * SCAN_ITEMS);
-  if (nbt > 4096) { ctx->err = "msm: too many tiles"; return XHE_E_ARG; }
-  k_scan_blocks<<<nbt, SCAN_THREADS, 0, st>>>(runs, p.n_tiles + 1, run_off, blocksums); XHE_LAUNCHED(ctx);
-  k_scan_totals<<<1, 1024, 0, st>>>(blocksums, (int)nbt, (uint32_t*)(ws + p.off_flag) + 2); XHE_LAUNCHED(ctx);
-  k_scan_add<<<nbt, SCAN_THREADS, 0, st>>>(run_off, p.n_tiles + 1, blocksums, nullptr); XHE_LAUNCHED(ctx);
   { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
   switch (g_accum_variant) {
-    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
-    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
-    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, list, glist, offsets + m, run_off, p.n_tiles, part, part_g); break;
+    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
   } }
   XHE_LAUNCHED(ctx);
-  k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(part_g, run_off + p.n_tiles, p.max_runs, pstart, pcount); XHE_LAUNCHED(ctx);
-  k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(pcount, m, heavy); XHE_LAUNCHED(ctx);
-  k_msm_fold_heavy<<<std::min<size_t>(m, 2048), FOLD_THREADS, 0, st>>>(part, pstart, pcount, heavy); XHE_LAUNCHED(ctx);
+  k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(q.part_g, q.run_off + p.n_tiles, p.max_runs, q.pstart, q.pcount); XHE_LAUNCHED(ctx);
+  k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(q.pcount, m, q.heavy); XHE_LAUNCHED(ctx);
+  k_msm_fold_heavy<<<std::min<size_t>(m, 2048), FOLD_THREADS, 0, st>>>(q.part, q.pstart, q.pcount, q.heavy); XHE_LAUNCHED(ctx);
   size_t n_nodes = m >> p.seg_log;
-  k_msm_seg<<<nblk(n_nodes, 128), 128, 0, st>>>(part, pstart, pcount, n_nodes, p.seg_log, nodes_a); XHE_LAUNCHED(ctx);
+  k_msm_seg<<<nblk(n_nodes, 128), 128, 0, st>>>(q.part, q.pstart, q.pcount, n_nodes, p.seg_log, q.nodes_a); XHE_LAUNCHED(ctx);
   uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;
-  uint32_t *cur = nodes_a, *nxt = nodes_b;
+  uint32_t *cur = q.nodes_a, *nxt = q.nodes_b;
   while (per_window > 1) {
     uint32_t parents = (per_window + 31) / 32;
     size_t warps = (size_t)parents * p.W;
@@ -403,6 +431,12 @@ int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_nie
   k_msm_horner<<<1, 32, 0, st>>>(cur, p.W, p.c, (uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx);
   XHE_CUDA_OK(ctx, cudaGetLastError());
   return XHE_OK;
+}
+
+int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag) {
+  if (n && (!d_scalars || !d_niels || !d_ws)) return XHE_E_ARG;
+  int32_t rc = xhe_msm_sort(ctx, d_scalars, n, d_ws, ws_bytes, d_bad_flag); if (rc) return rc;
+  return xhe_msm_finish(ctx, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, d_out_ext);
 }
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id) {
   return xhe_launch_msm_ex(ctx, d_scalars, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, nullptr, nullptr);

@@ -379,6 +379,17 @@ __global__ void k_combine(const uint32_t* __restrict__ ext, uint32_t n, uint8_t*
   *is_id = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }
 
+// sum of n partial extended points -> encoding, identity flag and canonical extended coordinates (the two halves of the
+// range-proof MSM; warp 0 lane 0 does the work)
+__global__ void k_combine_out(const uint32_t* __restrict__ ext, uint32_t n, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_id, uint32_t* __restrict__ out_ext) {
+  if (threadIdx.x || blockIdx.x) return;
+  ge acc = ge_identity();
+  for (uint32_t i = 0; i < n; i++) { ge p; ld_ge(p, ext + 32 * (size_t)i); acc = ge_add(acc, p); }
+  st_fe(out_ext, fe_freeze(acc.X)); st_fe(out_ext + 8, fe_freeze(acc.Y)); st_fe(out_ext + 16, fe_freeze(acc.Z)); st_fe(out_ext + 24, fe_freeze(acc.T));
+  encode_words(out_enc, acc);
+  *is_id = ge_ristretto_is_identity(acc) ? 1u : 0u;
+}
+
 // sum of up to 32 * k Ristretto encodings (one warp: lanes decode in parallel, lane 0 adds): out = 32 B encoding of the
 // sum, then a word "sum is the identity", then a word "every encoding decoded"
 __global__ void __launch_bounds__(32) k_sum_encodings(const uint8_t* __restrict__ enc, uint32_t n, uint8_t* __restrict__ out) {
@@ -462,7 +473,7 @@ extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n,
 struct DeviceBatch {
   xhe_batch h;                       // scalar fields (counts) copied from the host description; pointers unused
   uint32_t Nmax = 64, rp_grid = 0; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
-  uint8_t *d_enc, *d_ok, *d_sig_r, *d_op_out, *d_ws1, *d_ws2;
+  uint8_t *d_enc, *d_ok, *d_sig_r, *d_op_out, *d_ws1, *d_ws2, *d_ws3; uint32_t* d_rparts; size_t ws_static = 0;
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
   long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
@@ -494,7 +505,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   static int gens_blocks_per_sm = 0;
   if (!gens_blocks_per_sm) { int nb = 0; XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32)); gens_blocks_per_sm = nb > 0 ? nb : 1; }
   D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS), std::max<size_t>(64, ((size_t)64 << 20) / (64 * (size_t)D.Nmax))) : 0;
-  D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_range);
+  D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_dyn); D.ws_static = xhe_msm_workspace_bytes(ctx, D.n_range - D.n_dyn);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
   D.fs = b->fs_blobs != nullptr && b->n_tx > 0; D.blob_bytes = D.fs ? (size_t)b->fs_blob_off[b->n_tx] : 0;
   D.layout = D.fs && b->layout_on_device != 0; D.plan_stride = D.layout ? 8 : 6;
@@ -507,7 +518,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
               + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
               + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * RP_DER + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
-              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + 4096 + 512 * 64
+              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + D.ws_static + 8192 + 512 * 64
               + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs;
   if (ctx->scratch_bytes < need) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -528,7 +539,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   TAKE(uint32_t, d_results, 128); TAKE(uint8_t, d_ws1, D.ws_sigma);
   TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
   TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
-  TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range);
+  TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range); TAKE(uint8_t, d_ws3, D.ws_static); TAKE(uint32_t, d_rparts, 64);
   TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs);
   if (D.fs) { UP(D.d_blobs, b->fs_blobs, D.blob_bytes); UP(D.d_blob_off, b->fs_blob_off, 8 * ((size_t)b->n_tx + 1)); UP(D.d_fs_plan, b->fs_plan, 4 * (size_t)D.plan_stride * b->n_tx); UP(D.d_seed, b->fs_seed, 32); }
   if (!D.layout) {
@@ -577,40 +588,65 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h;
   xhe_tables* T = g_tables[ctx->device];
   int32_t rc;
-  const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_range = D.n_range; const uint32_t Nmax = D.Nmax;
+  const size_t n_sigma_terms = D.n_sigma_terms, n_sigma = D.n_sigma, n_dyn = D.n_dyn, n_static = D.n_range - D.n_dyn; const uint32_t Nmax = D.Nmax;
   if (!ctx->aux[0]) {
     // the transcript and range pipelines form the longest dependency chain of a step: give their blocks priority
     int lo_pri = 0, hi_pri = 0; XHE_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     // (measured: priorities move the step time by < 2 % either way; kept because they cost nothing)
-    const int p0 = hi_pri, p1 = lo_pri, p2 = hi_pri;
-    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[0], cudaStreamNonBlocking, p0));
-    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[1], cudaStreamNonBlocking, p1));
-    XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[2], cudaStreamNonBlocking, p2)); for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    const int pri[4] = {hi_pri, lo_pri, hi_pri, hi_pri};
+    for (int i = 0; i < 4; i++) XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, pri[i]));
+    for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   static const bool serial_env = getenv("XHE_SERIAL") != nullptr;
   const bool serial = serial_env || ctx->serial;                   // diagnostics / isolated kernel timing: one stream, back to back
-  cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2];
-  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4];
+  // Five dependent chains (the enqueue order below is a topological order, so the serial mode is the same code on one stream):
+  //   main : layout -> decompress -> balance chains -> [sigma sort done] gather -> sigma MSM accumulate/reduce
+  //   s_fs : transcripts -> sigma weights -> sigma MSM sort            (scalars only: runs beside the decompression)
+  //   s_sig: [decompress] signatures -> signature hashes
+  //   s_rp : [transcripts] range scalars -> static-generator weights -> MSM over the static generators -> [s_dyn] combine
+  //   s_dyn: [range scalars] sort -> [decompress] gather -> MSM over the proofs' own points
+  cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2], s_dyn = serial ? main_st : ctx->aux[3];
+  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
+  const uint32_t np = b->n_eq + b->n_val;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
   if (ctx->timing) { if (!ctx->tl_base) XHE_CUDA_OK(ctx, cudaEventCreate(&ctx->tl_base)); XHE_CUDA_OK(ctx, cudaEventRecord(ctx->tl_base, main_st)); ctx->tl_mark = ctx->pending.size(); }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_start, main_st));
-  // ---- aux0: transcripts
+  // ---- s_fs: transcripts
+  XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_fs, e_start, 0));
   if (D.fs) {
-    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_fs, e_start, 0));
     ctx->stream = s_fs;
     rc = xhe_launch_fiat_shamir(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_seed, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_chal, D.d_m); if (rc) return rc;
     XHE_CUDA_OK(ctx, cudaEventRecord(e_fs, s_fs));
   }
-  // ---- main: (fast path) build the tables from the blobs, then decompress
+  // ---- main: (fast path) build the tables from the blobs
   ctx->stream = main_st;
   if (D.layout) { rc = xhe_launch_layout(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, b->n_tx, b->n_points, D.d_enc, D.d_sig_idx, b->n_eq, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_range_idx, D.d_pt_off,
                                          D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_results + 98); if (rc) return rc; }
-  XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], main_st));            // results cleared, per-proof tables in place
+  XHE_CUDA_OK(ctx, cudaEventRecord(e_lay, main_st));               // results cleared, per-proof tables in place
+  // ---- s_fs: sigma-proof weights and the scalar half of their MSM
+  {
+    ctx->stream = s_fs; cudaStream_t st = s_fs;
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_fs, e_lay, 0));
+    if (np) {
+      { XheTimed t(ctx, "k_sigma_weights", 136.0 * 14 * np);
+        k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(D.d_eq_sc, b->n_eq, D.d_val_sc, b->n_val, D.d_sigma_sc, D.d_gh); XHE_LAUNCHED(ctx); }
+      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_gh, np, 2, 1, D.d_gh_part, 2); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_gh_part, 32, 2, 1, D.d_sigma_sc + 8 * n_sigma_terms, 2); XHE_LAUNCHED(ctx);
+    } else {
+      XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
+    }
+    { XheTimed t(ctx, "msm_sigma_sort", 0);
+      rc = xhe_msm_sort(ctx, D.d_sigma_sc, n_sigma, D.d_ws1, D.ws_sigma, D.d_results + 96); if (rc) return rc; }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_sgsort, s_fs));
+  }
+  // ---- main: decompress
+  ctx->stream = main_st;
   { XheTimed t(ctx, "k_decompress", 12632.0 * b->n_points);
     rc = xhe_decompress_dev(ctx, D.d_enc, b->n_points, D.d_aff, D.d_niels, D.d_ok); if (rc) return rc; }
   if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_ok, b->n_points, 1, D.d_results + 98); if (rc) return rc; }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_dec, main_st));
-  // ---- aux1: signatures
+  // ---- s_sig: signatures
   if (b->n_sigs) {
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_dec, 0));
     ctx->stream = s_sig;
@@ -622,9 +658,9 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   }
   // ---- main: balance chains (their outputs are sigma MSM operands)
   ctx->stream = main_st;
-  cudaStream_t st = main_st;
   if (b->n_ops) {
-    XheTimed t(ctx, "balance_chain", (504.0 * 2 + 2 * 12688.0) * b->n_ops);
+    cudaStream_t st = main_st;
+    XheTimed t(ctx, "balance_chain", (504.0 * 2 + 12688.0) * b->n_ops);
     XHE_CUDA_OK(ctx, cudaMemcpyAsync(D.d_ptr_a, D.d_ptr_init, 8 * (size_t)b->n_ops, cudaMemcpyDeviceToDevice, st));
     k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(D.d_term_off, D.d_terms, D.d_amount, D.d_niels, T->tabG, b->n_ops, D.d_acc_a); XHE_LAUNCHED(ctx);
     uint32_t *acc_cur = D.d_acc_a, *acc_nxt = D.d_acc_b; long long *ptr_cur = D.d_ptr_a, *ptr_nxt = D.d_ptr_b;
@@ -634,48 +670,55 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     }
     k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, D.d_aff, D.d_niels, D.d_op_out); XHE_LAUNCHED(ctx);
   }
-  // ---- aux2: range proofs (independent of the balance chains: they only reference input points)
+  // ---- range proofs.  Their MSM is computed as two partial sums: the proofs' own points (A, S, T1, T2, L_j, R_j, V_j --
+  // scalars known after k_rp_prep) on s_dyn, beside the static-generator weights (k_rp_gens) and the small MSM over the
+  // static generators on s_rp; k_combine_out adds the two.
   if (b->n_rp) {
-    // the scalar half (k_rp_prep, k_rp_gens, reductions) needs only the challenges; the decompressed points are first
-    // touched by k_gather_niels
-    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, ctx->ev[5], 0));
-    if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_fs, 0));
-    ctx->stream = s_rp; st = s_rp;
-    { XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
-      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
-    const size_t smem = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32;
-    { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // ~6 mod-l products per generator index, 64*m indices per proof
-      k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
-    k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
-    k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
-    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dec, 0));
-    k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, st>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
     const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
-    k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
-    k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
-    { XheTimed t(ctx, "msm_range", 8064.0 * n_range + 6.04e8);
-      rc = xhe_launch_msm_ex(ctx, D.d_range_sc, D.d_range_niels, n_range, D.d_ws2, D.ws_range, D.d_results + 48, D.d_results + 56, D.d_results + 64, D.d_results + 97); if (rc) return rc; }
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_lay, 0));
+    if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_fs, 0));
+    ctx->stream = s_rp;
+    { cudaStream_t st = s_rp;
+      XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
+      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_prep, s_rp));
+    // s_dyn
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_prep, 0));
+    ctx->stream = s_dyn;
+    { XheTimed t(ctx, "msm_range_dyn", 8064.0 * n_dyn + 6.04e8);
+      rc = xhe_msm_sort(ctx, D.d_range_sc, n_dyn, D.d_ws2, D.ws_range, D.d_results + 97); if (rc) return rc;
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_dec, 0));
+      k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, s_dyn>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
+      rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts); if (rc) return rc; }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_dyn, s_dyn));
+    // s_rp
+    ctx->stream = s_rp;
+    { cudaStream_t st = s_rp;
+      const size_t smem = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32;
+      { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // 6 mod-l products per generator index, 64*m indices per proof
+        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
+      k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+      k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
+      k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
+      k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
+      { XheTimed t(ctx, "msm_range_static", 0);
+        rc = xhe_launch_msm_ex(ctx, D.d_range_sc + 8 * n_dyn, D.d_range_niels + 24 * n_dyn, n_static, D.d_ws3, D.ws_static, nullptr, nullptr, D.d_rparts + 32, D.d_results + 97); if (rc) return rc; }
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dyn, 0));
+      k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
+    }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
   }
-  // ---- main: sigma proofs -> MSM
-  ctx->stream = main_st; st = main_st;
+  // ---- main: sigma MSM over the gathered operands (inputs and balance-chain outputs)
+  ctx->stream = main_st;
   {
-    uint32_t np = b->n_eq + b->n_val;
-    if (np) {
-      if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_fs, 0));
-      { XheTimed t(ctx, "k_sigma_weights", 136.0 * 14 * np);
-        k_sigma_weights<<<nblk(np, 128), 128, 0, st>>>(D.d_eq_sc, b->n_eq, D.d_val_sc, b->n_val, D.d_sigma_sc, D.d_gh); XHE_LAUNCHED(ctx); }
-      k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx);
-      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_gh, np, 2, 1, D.d_gh_part, 2); XHE_LAUNCHED(ctx);
-      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_gh_part, 32, 2, 1, D.d_sigma_sc + 8 * n_sigma_terms, 2); XHE_LAUNCHED(ctx);
-    } else {
-      XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
-    }
+    cudaStream_t st = main_st;
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sgsort, 0));
+    if (np) { k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx); }
     k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, D.d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
     XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
-    rc = xhe_launch_msm_ex(ctx, D.d_sigma_sc, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, D.d_results + 96); if (rc) return rc;
+    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16); if (rc) return rc;
   }
   // ---- join
   if (b->n_sigs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sig, 0));

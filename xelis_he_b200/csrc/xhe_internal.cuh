@@ -36,8 +36,8 @@ struct xhe_ctx {
   std::vector<Span> timeline;
   void* d_small = nullptr;                                    // 8 KiB device scratch for the tiny cross-rank combination (xhe_sum_encodings)
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};          // side streams for the independent pipelines of xhe_batch_run
-  cudaEvent_t ev[8] = {nullptr};
+  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; // side streams for the independent pipelines of xhe_batch_run
+  cudaEvent_t ev[12] = {nullptr};
 };
 
 // scoped timing of one kernel launch on ctx->stream (no-op unless ctx->timing)
@@ -112,4 +112,6 @@ __device__ __forceinline__ void st_ge(uint32_t* p, const ge& g) { st_fe(p, g.X);
 }  // namespace xhe
 
 // kernel launchers implemented across the .cu files
+int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, size_t ws_bytes, void* d_bad_flag);
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext);
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id);
