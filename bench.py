@@ -119,9 +119,20 @@ def secondary_metrics(lib, ctx, stream, hbm_peak_gbs):
     lib.xhe_msm_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     ms = timed(lambda: lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32))
     out["msm_2p20"] = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3, "alg_TLP_s": (8064.0 * n + 6.04e8) / ms / 1e9,
-                       "note": "resident decompressed points (affine Niels, 96 MB > L2... operands re-read from L2/HBM), 253-bit scalars; bit-exactness vs the oracle is tests/test_gpu_msm.py"}
-    ms = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()))
-    out["decompress_2p20"] = {"ms": ms, "points_per_s": n / ms * 1e3}
+                       "note": "resident decompressed points (affine Niels, 96 MB), uniform 252-bit scalars; bit-exactness against the oracle: tests/test_gpu_msm.py"}
+    ms_dec = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()))
+    out["decompress_2p20"] = {"ms": ms_dec, "points_per_s": n / ms_dec * 1e3, "alg_TLP_s": n * 12632.0 / ms_dec / 1e9}
+    ms_both = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr())
+                    or lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32))
+    out["msm_2p20"]["incl_decompression"] = {"ms": ms_both, "points_per_s": n / ms_both * 1e3}
+    # config 4, compressed I/O: 64-byte ciphertexts in and out (4 decodes + 2 encodes per account: integer-bound)
+    na_c = 1 << 19
+    subc = torch.randint(0, 2, (na_c,), dtype=torch.uint8, device="cuda", generator=g)
+    outb = torch.empty((na_c, 64), dtype=torch.uint8, device="cuda"); okb = torch.empty((na_c,), dtype=torch.uint8, device="cuda")
+    bal = enc[: 2 * na_c].reshape(na_c, 64); delta = enc.flip(0)[: 2 * na_c].reshape(na_c, 64).contiguous()
+    lib.xhe_ct_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    ms_c = timed(lambda: lib.xhe_ct_update_dev(ctx.p, bal.data_ptr(), delta.data_ptr(), subc.data_ptr(), na_c, outb.data_ptr(), okb.data_ptr()))
+    out["ct_update_compressed_512k"] = {"accounts": na_c, "ms": ms_c, "accounts_per_s": na_c / ms_c * 1e3, "alg_TLP_s": na_c * 76000.0 / ms_c / 1e9}
     del uni, aff, ws
     na = 1 << 20
     balr = torch.randint(0, 2**31 - 1, (4, 2 * na, 8), dtype=torch.int32, device="cuda", generator=g)
@@ -409,7 +420,8 @@ def main():
             for n, v in leaf.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
     roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide, "share_of_step_work": leaf[dom]["alg_lp_per_step"] / max(1.0, sum(v["alg_lp_per_step"] for n, v in leaf.items())),
                 "peak_source": "measured live: IMAD.WIDE.U32 microkernel (plain accumulate form)", "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": ach / peak_chain,
-                "traffic": None, "per_kernel_isolated": work, "note": "carry-predicated IMAD.WIDE (the form a radix-2^32 multiply needs) issues at half rate on sm_100a; see DESIGN.md"}
+                "traffic": 14.9e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress launch of this workload (profiles/r01_ncu_full_top_kernels.md); algorithmic bytes are 65.6 MB (32 B in, 160 B out per point): the outputs stay in the 126 MB L2",
+                "per_kernel_isolated": work, "note": "carry-predicated IMAD.WIDE (the form a radix-2^32 multiply needs) issues at half rate on sm_100a; see DESIGN.md"}
     line = {"metric": "verified TX/s (10k-transfer batch)", "value": value, "unit": "TX/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
             "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic (valid TXs minted by the oracle prover; ranks share one minted batch)", "config": config,

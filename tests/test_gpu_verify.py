@@ -240,3 +240,15 @@ def test_long_single_sender_chain(ctx):
         hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
         assert verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir=mode)[:2] == (OK, -1)
         assert hl.dump() == sorted(ol.dump())
+
+
+def test_mixed_batch_config5_flavour(ctx):
+    """Config 5 at a size the oracle's (sequential) builder mints in seconds: 96 transactions mixing multi-destination and
+    multi-asset transfers, burns, contract calls, deploys and multisig set-ups; accept run, then one tampered transaction per
+    class in the middle of the batch (the first failing index and code must match the oracle)."""
+    w, txs, _ = scenarios.mixed_types_world(96)
+    assert both(ctx, w, txs, OK) == (OK, -1)
+    for victim, off in ((37, -1), (50, 48), (63, 56)):                # signature byte, fee, nonce
+        bad = list(txs); t = bytearray(bad[victim]); t[off if off >= 0 else len(t) - 1] ^= 0x01; bad[victim] = bytes(t)
+        code, idx = both(ctx, w, bad)
+        assert idx == victim and code in (SIG, NONCE)
