@@ -31,7 +31,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--txs", type=int, default=10000)
     ap.add_argument("--shape", default="a1k1")
-    ap.add_argument("--cpu-sample", type=int, default=2500, help="transactions per host thread in the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="transactions per host thread in the CPU baseline (default: the whole batch in the cpu_baseline leg, 2,500 per step in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the MSM points/s and ciphertext-update (HBM) side measurements")
     ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
@@ -169,7 +169,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = min(args.cpu_sample, args.txs)
+        sample = min(args.cpu_sample or 2500, args.txs)
         batch = oracle.mint_transfers(77, sample, a, k, threads=ncpu)
         for _ in range(max(args.warmup, 1)):
             batch.verify_timed(ncpu)
@@ -438,7 +438,7 @@ def main():
     if world == 1 and not args.no_secondary:
         line["secondary"] = secondary_metrics(lib, ctx, ts, hbm_peak)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(batch, ncpu, args.cpu_sample)
+        line["cpu_baseline"] = cpu_baseline(batch, ncpu, args.cpu_sample or args.txs)
     emit(line)
     if dist:
         dist.destroy_process_group()
