@@ -318,7 +318,9 @@ def main():
     workers = [ctx] + [xhe.Ctx(local, party_capacity=max(m, 2)) for _ in range(nfl - 1)]
     for c in workers[1:]:
         streams.append(torch.cuda.Stream()); c.set_stream(streams[-1].cuda_stream)
-    gatherer = xd.OrderedGatherer(None, torch.device("cuda", local)) if (dist and pipelined) else None   # one thread issues the NCCL all-gathers in sequence order
+    # sharded + pipelined: the cross-rank decisions (ordered NCCL all-gathers, sum of the partial encodings, commit of the
+    # held-back balance updates) run on one thread per process, off the verification threads
+    decider = xd.AsyncDecider(xhe.Ctx(local, party_capacity=2), None, torch.device("cuda", local)) if (dist and pipelined) else None
     wthreads = max(1, host_threads // nfl)
 
     def worker(widx, nsteps, out, ledgers=None):
@@ -328,9 +330,11 @@ def main():
             led = ledgers[s] if ledgers else ledger0.clone()      # fresh state per step (cloned before the clock starts)
             if dist:
                 seq = seq_base[0] + s * nfl + widx
-                code, idx, tmw = xd.verify_batch_distributed(c, None, led, rank * args.txs, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, commit=True, fiat_shamir=args.fiat_shamir,
-                                                           gather=(lambda rec, q=seq: gatherer.gather(q, rec)) if gatherer else None)
+                code, idx, s_enc, r_enc, tmw = verifier.verify_batch_partial(c, None, led, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
+                decider.submit(seq, xd.pack_local(code, idx, rank * args.txs, s_enc, r_enc), verifier.take_pending(c), led)
                 pipe_phases.append(tmw)
+                out.append(seq)
+                continue
             else:
                 code, idx, tmw = verifier.verify_batch(c, None, led, seed=b"p%d-%d" % (widx, s), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
                 pipe_phases.append(tmw)
@@ -345,6 +349,8 @@ def main():
         for t_ in wth:
             t_.join()
         seq_base[0] = nfl
+        if decider:
+            assert all(v == (0, -1) for v in decider.drain(nfl).values())
         barrier()
         pipe_phases.clear()
         outs = [[] for _ in range(nfl)]
@@ -356,12 +362,15 @@ def main():
             t_.start()
         for t_ in th:
             t_.join()
+        verdicts = decider.drain(nfl + args.steps) if decider else None      # every batch decided and committed
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         flat = [o for oo in outs for o in oo]
-        assert all(o == (0, -1) for o in flat) and len(flat) == args.steps
-        if gatherer:
-            gatherer.close()
+        if decider:
+            assert len(flat) == args.steps and all(verdicts[q] == (0, -1) for q in flat)
+            decider.close()
+        else:
+            assert all(o == (0, -1) for o in flat) and len(flat) == args.steps
         # device-side ceiling of that pipeline: every context re-runs its resident batch, all streams in flight at once
         rounds = max(2, args.steps // nfl)
         torch.cuda.synchronize()

@@ -78,3 +78,67 @@ def test_decide_orders_checks_like_the_reference():
     assert xd.decide([xd.pack_local(6, -1, 0, z, z), xd.pack_local(0, -1, 5, nz, z)], ident) == (5, -1)
     assert xd.decide([ok, xd.pack_local(1, 3, 5, nz, nz)], ident) == (1, 8)                  # per-tx errors come first, global index
     assert xd.decide([xd.pack_local(9, 4, 0, z, z), xd.pack_local(1, 0, 5, z, z)], ident) == (9, 4)
+
+
+class _OracleSummer:
+    """stands in for the GPU context's sum_encodings in the CPU test of the decision thread"""
+
+    def sum_encodings(self, encodings):
+        import oracle
+        acc = bytes(32)
+        for i in range(0, len(encodings), 32):
+            acc = oracle.point_add(acc, encodings[i:i + 32])
+        return acc, acc == bytes(32)
+
+
+def _worker_async(rank, world, port, batches, q):
+    import threading
+    import torch.distributed as dist
+    import oracle
+    from xelis_he_b200 import distributed as xd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    decider = xd.AsyncDecider(_OracleSummer(), None, None)
+
+    def one(seq):
+        blobs, records = batches[seq]
+        led = oracle.Ledger()
+        for pk, asset, ct in records:
+            led.set_balance(pk, asset, ct); led.set_nonce(pk, 0)
+        n = len(blobs); lo, hi = n * rank // world, n * (rank + 1) // world
+        code, idx, s_enc, r_enc = oracle.verify_batch_partial(blobs[lo:hi], led, rng_seed=7 * seq + rank)
+        decider.submit(seq, xd.pack_local(code, idx, lo, s_enc, r_enc))
+    # several batches in flight, submitted from threads in a rank-dependent order: decisions still pair up by sequence number
+    order = list(range(len(batches)))
+    if rank:
+        order.reverse()
+    th = [threading.Thread(target=one, args=(s,)) for s in order]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    verdicts = decider.drain(len(batches), timeout=200)
+    decider.close()
+    q.put((rank, [verdicts[s] for s in range(len(batches))]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_async_decider_orders_decisions_across_ranks():
+    import oracle
+    import torch.multiprocessing as mp
+    good = oracle.mint_transfers(41, 6, 1, 1, threads=4)
+    other = oracle.mint_transfers(42, 4, 1, 3, threads=4)
+    bad = list(good.blobs); t = bytearray(bad[4]); t[-1] ^= 1; bad[4] = bytes(t)          # broken signature in the second shard
+    batches = [(good.blobs, good.ledger().dump()), (bad, good.ledger().dump()), (other.blobs, other.ledger().dump())]
+    want = [oracle.verify_batch(good.blobs, good.ledger()), oracle.verify_batch(bad, good.ledger()), oracle.verify_batch(other.blobs, other.ledger())]
+    assert want == [(0, -1), (1, 4), (0, -1)]
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue(); port = _free_port()
+    ps = [ctxm.Process(target=_worker_async, args=(r, 2, port, batches, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=240) for _ in range(2))
+    for p in ps:
+        p.join(60)
+    assert out[0] == out[1] == want

@@ -463,7 +463,7 @@ extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n,
   k_sum_encodings<<<1, 32, 0, ctx->stream>>>(d, (uint32_t)n, dout); XHE_LAUNCHED(ctx);
   uint8_t h[40];
   XHE_CUDA_OK(ctx, cudaMemcpyAsync(h, dout, 40, cudaMemcpyDeviceToHost, ctx->stream));
-  XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, ctx->stream));
   if (out_enc) memcpy(out_enc, h, 32);
   uint32_t f, v; memcpy(&f, h + 32, 4); memcpy(&v, h + 36, 4); *is_identity = (int32_t)f; if (all_valid) *all_valid = (int32_t)v;
   return XHE_OK;
@@ -732,13 +732,15 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
 extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (!ctx || !ctx->resident || !v) return XHE_E_ARG;
   DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h; cudaStream_t st = ctx->stream;
-  uint32_t h_res[128];
+  // pinned landing zone: a device-to-pageable copy would block (spinning) inside cudaMemcpyAsync until the batch is done
+  if (!ctx->h_res) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_res, 512, cudaHostAllocDefault));
+  uint32_t* h_res = ctx->h_res;
   XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, D.d_results, 512, cudaMemcpyDeviceToHost, st));
   if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, D.d_ok, b->n_points, cudaMemcpyDeviceToHost, st));
   if (v->sig_r && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_r, D.d_sig_r, 32 * (size_t)b->n_sigs, cudaMemcpyDeviceToHost, st));
   if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, D.d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
   if (v->sig_ok && D.fs && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_ok, D.d_sig_ok, b->n_sigs, cudaMemcpyDeviceToHost, st));
-  XHE_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
   if (h_res[96] | h_res[97]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
   v->device_flags = h_res[98];
   memcpy(v->sigma_enc, h_res, 32); v->sigma_is_identity = (int32_t)h_res[8]; memcpy(v->sigma_ext, h_res + 16, 128);

@@ -34,6 +34,8 @@ struct xhe_ctx {
   cudaEvent_t tl_base = nullptr; size_t tl_mark = 0;
   struct Span { const char* name; float t0, t1; };
   std::vector<Span> timeline;
+  cudaEvent_t sync_ev = nullptr;                              // blocking-sync event: host waits yield the core instead of spinning
+  uint32_t* h_res = nullptr;                                  // pinned 512-byte landing zone of a batch's result block
   void* d_small = nullptr;                                    // 8 KiB device scratch for the tiny cross-rank combination (xhe_sum_encodings)
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; // side streams for the independent pipelines of xhe_batch_run
@@ -64,6 +66,15 @@ struct XheTimed {
   } while (0)
 
 #define XHE_LAUNCHED(ctx) do { (ctx)->launches++; } while (0)
+
+// Wait for everything queued on `st`.  cudaStreamSynchronize spins on a core for the whole wait; with several batches in
+// flight (one host thread per context) those spinning threads starve the host phases of the other batches, so the hot
+// path waits on a blocking-sync event instead.
+inline cudaError_t xhe_wait_stream(xhe_ctx* ctx, cudaStream_t st) {
+  if (!ctx->sync_ev) { cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  cudaError_t e = cudaEventRecord(ctx->sync_ev, st); if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->sync_ev);
+}
 
 namespace xhe {
 

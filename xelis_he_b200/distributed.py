@@ -8,6 +8,7 @@ rank over NCCL (or gloo on CPU in the tests).  Ristretto encodings are canonical
 testing the identity is exactly the reference's `mega_check.is_identity()` on the whole batch (src/proofs.rs:49-67).
 NCCL has no user-defined reduction, hence all-gather + local add rather than an all-reduce.
 """
+import os
 import struct
 
 OK, GENERIC_PROOF, RANGE_PROOF = 0, 5, 6
@@ -34,17 +35,39 @@ def decide(records, sum_is_identity):
     return OK, -1
 
 
+_pinned = {}
+
+
 def all_gather_records(local_record, group=None, device=None):
+    """One all-gather of the fixed-size per-rank records.  On CUDA the record travels through pinned host buffers and the
+    host waits on a blocking-sync event: a synchronous copy to pageable memory would sit inside the driver for as long as
+    the slowest rank takes to arrive, and other threads' kernel launches (further batches in flight) queue up behind it."""
+    import threading
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    t = torch.frombuffer(bytearray(local_record), dtype=torch.uint8)
-    if device is not None:
-        t = t.to(device)
-    out = torch.empty(world * len(local_record), dtype=torch.uint8, device=t.device)
-    dist.all_gather_into_tensor(out, t, group=group)
-    raw = bytes(out.cpu().numpy())
     n = len(local_record)
+    if device is None or device.type != "cuda":
+        t = torch.frombuffer(bytearray(local_record), dtype=torch.uint8)
+        out = torch.empty(world * n, dtype=torch.uint8)
+        dist.all_gather_into_tensor(out, t, group=group)
+        raw = bytes(out.numpy())
+        return [raw[i * n:(i + 1) * n] for i in range(world)]
+    key = (threading.get_ident(), n, world, device.index)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = _pinned[key] = (torch.empty(n, dtype=torch.uint8, pin_memory=True), torch.empty(world * n, dtype=torch.uint8, pin_memory=True),
+                              torch.empty(n, dtype=torch.uint8, device=device), torch.empty(world * n, dtype=torch.uint8, device=device),
+                              torch.cuda.Event(blocking=True), torch.cuda.Stream(device=device))
+    h_in, h_out, d_in, d_out, ev, stream = buf
+    h_in.copy_(torch.frombuffer(bytearray(local_record), dtype=torch.uint8))
+    with torch.cuda.stream(stream):
+        d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in, group=group)
+        h_out.copy_(d_out, non_blocking=True)
+        ev.record(stream)
+    ev.synchronize()
+    raw = bytes(h_out.numpy())
     return [raw[i * n:(i + 1) * n] for i in range(world)]
 
 
@@ -85,6 +108,78 @@ class OrderedGatherer:
             while seq not in self.results:
                 self.cv.wait(0.05)
             return self.results.pop(seq)
+
+    def close(self):
+        with self.cv:
+            self.stop = True
+            self.cv.notify_all()
+        self.thread.join(5)
+
+
+class AsyncDecider:
+    """Cross-rank decisions off the verification threads.  A worker submits (sequence number, its shard's record, the
+    detached balance updates, the ledger they belong to) and moves on to its next batch; one thread per process all-gathers
+    the records strictly in sequence order (NCCL's ordering rule), sums the partial encodings on its own small context,
+    commits or drops the updates, and keeps the verdicts.  drain() waits for everything submitted so far."""
+
+    def __init__(self, ctx, group=None, device=None):
+        import threading
+        self.ctx, self.group, self.device = ctx, group, device
+        self.cv = threading.Condition()
+        self.pending, self.verdicts, self.next_seq, self.submitted, self.stop, self.error = {}, {}, 0, 0, False, None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        import torch
+        from . import verifier
+        try:
+            if self.device is not None and self.device.type == "cuda":
+                torch.cuda.set_device(self.device)
+            while True:
+                with self.cv:
+                    while self.next_seq not in self.pending and not self.stop:
+                        self.cv.wait(0.05)
+                    if self.next_seq not in self.pending:
+                        return
+                    rec, handle, ledger = self.pending.pop(self.next_seq)
+                if os.environ.get("XHE_DIAG_LOCAL_DECISION"):      # diagnostics: skip the exchange, decide on this rank's record alone
+                    records = [rec]
+                else:
+                    records = all_gather_records(rec, self.group, self.device)
+                verdict = decide(records, lambda encs: self.ctx.sum_encodings(b"".join(encs))[1])
+                if handle:
+                    if verdict[0] == OK and ledger is not None:
+                        verifier.commit_taken(handle, ledger)
+                    else:
+                        verifier.drop_taken(handle)
+                with self.cv:
+                    self.verdicts[self.next_seq] = verdict
+                    self.next_seq += 1
+                    self.cv.notify_all()
+        except Exception as e:          # surface the failure to drain() instead of hanging the workers
+            with self.cv:
+                self.error = e
+                self.cv.notify_all()
+
+    def submit(self, seq, record, handle=None, ledger=None):
+        with self.cv:
+            self.pending[seq] = (record, handle, ledger)
+            self.submitted += 1
+            self.cv.notify_all()
+
+    def drain(self, upto, timeout=120.0):
+        """wait until every sequence number below `upto` is decided; returns {seq: (code, first failing tx)}"""
+        import time
+        deadline = time.time() + timeout
+        with self.cv:
+            while self.next_seq < upto and self.error is None:
+                if time.time() > deadline:
+                    raise TimeoutError("cross-rank decisions did not complete")
+                self.cv.wait(0.05)
+            if self.error is not None:
+                raise self.error
+            return dict(self.verdicts)
 
     def close(self):
         with self.cv:

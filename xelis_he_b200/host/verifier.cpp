@@ -240,12 +240,7 @@ std::mutex g_pending_mu;
 std::unordered_map<xhe_ctx*, Pending> g_pending;
 }  // namespace
 
-int commit_pending(xhe_ctx* ctx, VerificationState& state) {
-  Pending P;
-  { std::lock_guard<std::mutex> g(g_pending_mu);          // the lock only covers the hand-over, not the state walk
-    auto it = g_pending.find(ctx);
-    if (it == g_pending.end()) return XHE_E_ARG;
-    P = std::move(it->second); g_pending.erase(it); }
+static int apply_pending(const Pending& P, VerificationState& state) {
   const size_t n = P.updates.size();
   for (size_t j = 0; j < n; j++) {
     const StateUpdate& u = P.updates[j];
@@ -254,6 +249,22 @@ int commit_pending(xhe_ctx* ctx, VerificationState& state) {
     if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
   }
   return XHE_OK;
+}
+// detach the held-back updates of ctx's last shard-mode batch (so the ctx can take the next batch before the cross-rank
+// decision arrives); nullptr if there are none
+static Pending* take_pending(xhe_ctx* ctx) {
+  std::lock_guard<std::mutex> g(g_pending_mu);          // the lock only covers the hand-over, not the state walk
+  auto it = g_pending.find(ctx);
+  if (it == g_pending.end()) return nullptr;
+  Pending* P = new Pending(std::move(it->second)); g_pending.erase(it);
+  return P;
+}
+int commit_pending(xhe_ctx* ctx, VerificationState& state) {
+  Pending* P = take_pending(ctx);
+  if (!P) return XHE_E_ARG;
+  int rc = apply_pending(*P, state);
+  delete P;
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -818,6 +829,10 @@ int32_t xheh_verify_batch_ex(xhe_ctx* ctx, void* ledger, const uint8_t* const* b
   return rc;
 }
 int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(ctx, *(MockLedger*)ledger); }
+// detached form: take the held-back updates now, commit (or drop) them when the cross-rank decision is known
+void* xheh_take_pending(xhe_ctx* ctx) { return take_pending(ctx); }
+int32_t xheh_commit_taken(void* pending, void* ledger) { if (!pending) return XHE_E_ARG; Pending* P = (Pending*)pending; int rc = apply_pending(*P, *(MockLedger*)ledger); delete P; return rc; }
+void xheh_drop_taken(void* pending) { delete (Pending*)pending; }
 int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(MockLedger*)ledger); }
 // host-only helpers exposed for CPU tests of the host logic
 void xheh_merlin_test(const char* proto, const char* label, const uint8_t* msg, size_t n, const char* chal_label, uint8_t* out, size_t outlen) { Transcript t(proto); t.append(label, msg, n); t.challenge(chal_label, out, outlen); }

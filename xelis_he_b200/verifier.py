@@ -132,6 +132,27 @@ def commit_pending(ctx, ledger):
     return _lib().xheh_commit_pending(ctx.p, ledger.ptr)
 
 
+def take_pending(ctx):
+    """Detach the balance updates the last shard-mode batch on `ctx` held back, so the context can take its next batch
+    before the cross-rank decision is known.  Commit them with commit_taken or release them with drop_taken."""
+    lib = _lib()
+    lib.xheh_take_pending.restype = C.c_void_p; lib.xheh_take_pending.argtypes = [C.c_void_p]
+    return lib.xheh_take_pending(ctx.p)
+
+
+def commit_taken(handle, ledger):
+    lib = _lib()
+    lib.xheh_commit_taken.restype = C.c_int32; lib.xheh_commit_taken.argtypes = [C.c_void_p, C.c_void_p]
+    return lib.xheh_commit_taken(handle, ledger.ptr)
+
+
+def drop_taken(handle):
+    lib = _lib()
+    lib.xheh_drop_taken.restype = None; lib.xheh_drop_taken.argtypes = [C.c_void_p]
+    if handle:
+        lib.xheh_drop_taken(handle)
+
+
 def verify(ctx, blob, ledger, seed=None):
     return verify_batch(ctx, [blob], ledger, seed)[:2]
 
