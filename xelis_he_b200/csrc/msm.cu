@@ -35,7 +35,7 @@ struct MsmPlan {
   int seg_log;          // log2 of buckets per level-1 segment
   // workspace offsets (bytes)
   size_t n_tiles, max_runs;
-  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_glist, off_runs, off_runoff, off_part, off_partg, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_flag, total;
+  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_tileg0, off_runs, off_runoff, off_part, off_partg, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_flag, total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -67,7 +67,7 @@ MsmPlan make_plan(size_t n) {
   p.n_tiles = (nw + MSM_TILE - 1) / MSM_TILE;
   p.max_runs = p.n_tiles + std::min(p.total_buckets, nw) + 1;
   p.off_list = o; o = align_up(o + 4 * nw + 4, 256);
-  p.off_glist = o; o = align_up(o + 4 * nw + 4, 256);
+  p.off_tileg0 = o; o = align_up(o + 4 * (p.n_tiles + 1), 256);       // tile_g0: bucket of each tile's first entry
   p.off_runs = o; o = align_up(o + 4 * (p.n_tiles + 1), 256);
   p.off_runoff = o; o = align_up(o + 4 * (p.n_tiles + 1), 256);
   p.off_part = o; o = align_up(o + 128 * p.max_runs, 256);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_msm_count(const uint32_t* __restrict__ 
   });
 }
 
-__global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* __restrict__ cursor, uint32_t* __restrict__ list, uint32_t* __restrict__ glist) {
+__global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t s[8];
@@ -127,8 +127,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict_
     if (d != 0) {
       uint32_t g = (uint32_t)w * B + (uint32_t)((d < 0 ? -d : d) - 1);
       uint32_t pos = atomicAdd(&cursor[g], 1u);
-      list[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
-      glist[pos] = g;
+      list[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);     // the bucket of a position follows from the offsets: no second array
     }
   });
 }
@@ -176,17 +175,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict_
 }
 
 // ---- balanced accumulation: fixed-size tiles of the bucket-sorted entry list ----------------------------------------
-// runs[t] = number of maximal same-bucket runs inside tile t (a run is one partial sum)
-__global__ void __launch_bounds__(256) k_msm_tile_runs(const uint32_t* __restrict__ glist, const uint32_t* __restrict__ total_entries, size_t n_tiles, uint32_t* __restrict__ runs) {
+// Bucket g owns the positions [offsets[g], offsets[g+1]) of the sorted list (offsets[m] = number of entries).
+// bucket_of: the bucket that contains position pos, searched in (lo_hint, m); requires offsets[lo_hint] <= pos.
+__device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ offsets, uint32_t m, uint32_t pos, uint32_t lo_hint) {
+  uint32_t lo = lo_hint + 1, hi = m;                 // smallest idx in [lo, hi] with offsets[idx] > pos
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) > pos) hi = mid; else lo = mid + 1; }
+  return lo - 1;
+}
+// the bucket that starts at position pos, given that bucket g ends there: usually g + 1; a binary search skips empty buckets
+__device__ __forceinline__ uint32_t next_bucket(const uint32_t* __restrict__ offsets, uint32_t m, uint32_t pos, uint32_t g) {
+  return __ldg(offsets + g + 2) > pos ? g + 1 : bucket_of(offsets, m, pos, g + 1);
+}
+// runs[t] = number of maximal same-bucket runs inside tile t (a run is one partial sum); tile_g0[t] = bucket of its first entry
+__global__ void __launch_bounds__(256) k_msm_tile_runs(const uint32_t* __restrict__ offsets, uint32_t m, size_t n_tiles, uint32_t* __restrict__ runs, uint32_t* __restrict__ tile_g0) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
-  uint32_t N = *total_entries;
+  uint32_t N = __ldg(offsets + m);
   size_t start = t * MSM_TILE;
   uint32_t cnt = 0;
   if (t < n_tiles && start < N) {
-    size_t end = min((size_t)N, start + MSM_TILE);
-    uint32_t prev = glist[start]; cnt = 1;
-    for (size_t p = start + 1; p < end; p++) { uint32_t cur = glist[p]; cnt += (cur != prev); prev = cur; }
+    uint32_t end = (uint32_t)min((size_t)N, start + MSM_TILE);
+    uint32_t g = bucket_of(offsets, m, (uint32_t)start, 0);
+    tile_g0[t] = g; cnt = 1;
+    uint32_t nb = __ldg(offsets + g + 1);
+    while (nb < end) { g = next_bucket(offsets, m, nb, g); nb = __ldg(offsets + g + 1); cnt++; }
   }
   runs[t] = cnt;
 }
@@ -195,26 +207,28 @@ __global__ void __launch_bounds__(256) k_msm_tile_runs(const uint32_t* __restric
 // point prefetched under the current addition) and accumulates 7 M mixed additions in registers; a partial sum is
 // flushed whenever the bucket id changes.  Every lane does the same number of additions: no divergence on bucket size.
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* __restrict__ niels, const uint32_t* __restrict__ list, const uint32_t* __restrict__ glist,
-                                                              const uint32_t* __restrict__ total_entries, const uint32_t* __restrict__ run_off, size_t n_tiles,
+__global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* __restrict__ niels, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offsets, uint32_t m,
+                                                              const uint32_t* __restrict__ tile_g0, const uint32_t* __restrict__ run_off, size_t n_tiles,
                                                               uint32_t* __restrict__ part, uint32_t* __restrict__ part_g) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  uint32_t N = *total_entries;
+  uint32_t N = __ldg(offsets + m);
   size_t start = t * MSM_TILE;
   if (start >= N) return;
   uint32_t cnt = (uint32_t)(min((size_t)N, start + MSM_TILE) - start);
   uint32_t slot = run_off[t];
-  uint32_t e = __ldg(list + start), g = __ldg(glist + start);
+  uint32_t g = __ldg(tile_g0 + t), nb = __ldg(offsets + g + 1);          // nb: first position past the current bucket
+  uint32_t e = __ldg(list + start);
   ge_niels q; ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu));
   ge acc = ge_from_niels(niels_cneg(q, (e >> 31) != 0));
   if (cnt > 1) { e = __ldg(list + start + 1); ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu)); }
   for (uint32_t j = 1; j < cnt; j++) {
-    uint32_t gj = __ldg(glist + start + j);
+    const uint32_t pos = (uint32_t)start + j;
     ge_niels cur = niels_cneg(q, (e >> 31) != 0);
     if (j + 1 < cnt) { e = __ldg(list + start + j + 1); ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu)); }
-    if (gj != g) {   // bucket boundary: flush the finished run, restart from this point
-      st_ge(part + 32 * (size_t)slot, acc); part_g[slot] = g; slot++; g = gj;
+    if (pos == nb) {   // bucket boundary: flush the finished run, restart from this point
+      st_ge(part + 32 * (size_t)slot, acc); part_g[slot] = g; slot++;
+      g = next_bucket(offsets, m, pos, g); nb = __ldg(offsets + g + 1);
       acc = ge_from_niels(cur);
     } else {
       acc = ge_madd(acc, cur);
@@ -352,13 +366,13 @@ extern "C" int32_t xhe_msm_plan(size_t n, int* c, int* W) { MsmPlan p = make_pla
 //   xhe_msm_finish -- steps 5-9: needs the points; d_out_ext (optional) = the un-normalised extended result (128 B)
 namespace {
 struct MsmPtrs {
-  uint32_t *counts, *offsets, *cursor, *blocksums, *list, *glist, *runs, *run_off, *part, *part_g, *pstart, *pcount, *heavy, *nodes_a, *nodes_b, *flag;
+  uint32_t *counts, *offsets, *cursor, *blocksums, *list, *tile_g0, *runs, *run_off, *part, *part_g, *pstart, *pcount, *heavy, *nodes_a, *nodes_b, *flag;
 };
 inline MsmPtrs msm_ptrs(const MsmPlan& p, void* d_ws, void* d_bad_flag) {
   uint8_t* ws = (uint8_t*)d_ws;
   MsmPtrs q;
   q.counts = (uint32_t*)(ws + p.off_counts); q.offsets = (uint32_t*)(ws + p.off_offsets); q.cursor = (uint32_t*)(ws + p.off_cursor);
-  q.blocksums = (uint32_t*)(ws + p.off_blocksums); q.list = (uint32_t*)(ws + p.off_list); q.glist = (uint32_t*)(ws + p.off_glist);
+  q.blocksums = (uint32_t*)(ws + p.off_blocksums); q.list = (uint32_t*)(ws + p.off_list); q.tile_g0 = (uint32_t*)(ws + p.off_tileg0);
   q.runs = (uint32_t*)(ws + p.off_runs); q.run_off = (uint32_t*)(ws + p.off_runoff); q.part = (uint32_t*)(ws + p.off_part); q.part_g = (uint32_t*)(ws + p.off_partg);
   q.pstart = (uint32_t*)(ws + p.off_pstart); q.pcount = (uint32_t*)(ws + p.off_pcount); q.heavy = (uint32_t*)(ws + p.off_heavy);
   q.nodes_a = (uint32_t*)(ws + p.off_nodes_a); q.nodes_b = (uint32_t*)(ws + p.off_nodes_b);
@@ -387,9 +401,9 @@ int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, 
   k_scan_blocks<<<nb, SCAN_THREADS, 0, st>>>(q.counts, m, q.offsets, q.blocksums); XHE_LAUNCHED(ctx);
   k_scan_totals<<<1, 1024, 0, st>>>(q.blocksums, (int)nb, q.offsets + m); XHE_LAUNCHED(ctx);
   k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(q.offsets, m, q.blocksums, q.cursor); XHE_LAUNCHED(ctx);
-  k_msm_scatter<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, q.cursor, q.list, q.glist); XHE_LAUNCHED(ctx);
+  k_msm_scatter<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, q.cursor, q.list); XHE_LAUNCHED(ctx);
   // offsets[m] = total number of non-zero digits (device-side); tiles beyond it are empty
-  k_msm_tile_runs<<<nblk(p.n_tiles + 1, 256), 256, 0, st>>>(q.glist, q.offsets + m, p.n_tiles, q.runs); XHE_LAUNCHED(ctx);
+  k_msm_tile_runs<<<nblk(p.n_tiles + 1, 256), 256, 0, st>>>(q.offsets, (uint32_t)m, p.n_tiles, q.runs, q.tile_g0); XHE_LAUNCHED(ctx);
   unsigned nbt = nblk(p.n_tiles + 1, SCAN_THREADS * SCAN_ITEMS);
   if (nbt > 4096) { ctx->err = "msm: too many tiles"; return XHE_E_ARG; }
   k_scan_blocks<<<nbt, SCAN_THREADS, 0, st>>>(q.runs, p.n_tiles + 1, q.run_off, q.blocksums); XHE_LAUNCHED(ctx);
@@ -410,9 +424,9 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
   const size_t m = p.total_buckets;
   { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
   switch (g_accum_variant) {
-    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.glist, q.offsets + m, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
   } }
   XHE_LAUNCHED(ctx);
   k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(q.part_g, q.run_off + p.n_tiles, p.max_runs, q.pstart, q.pcount); XHE_LAUNCHED(ctx);
