@@ -320,7 +320,11 @@ def main():
         streams.append(torch.cuda.Stream()); c.set_stream(streams[-1].cuda_stream)
     # sharded + pipelined: the cross-rank decisions (ordered NCCL all-gathers, sum of the partial encodings, commit of the
     # held-back balance updates) run on one thread per process, off the verification threads
-    decider = xd.AsyncDecider(xhe.Ctx(local, party_capacity=2), None, torch.device("cuda", local)) if (dist and pipelined) else None
+    decider = None
+    if dist and pipelined:
+        dec_ctx = xhe.Ctx(local, party_capacity=2)
+        streams_keep = torch.cuda.Stream(priority=-1); dec_ctx.set_stream(streams_keep.cuda_stream)      # its tiny kernels must not queue behind the batches
+        decider = xd.AsyncDecider(dec_ctx, None, torch.device("cuda", local))
     wthreads = max(1, host_threads // nfl)
 
     def worker(widx, nsteps, out, ledgers=None):
@@ -340,6 +344,7 @@ def main():
                 pipe_phases.append(tmw)
             out.append((code, idx))
     seq_base = [0]
+    decider_stats = None
     pipe_phases = []
     if pipelined:
         # warm-up of the extra contexts: every slot runs one batch (same sequence numbering on all ranks)
@@ -368,6 +373,7 @@ def main():
         flat = [o for oo in outs for o in oo]
         if decider:
             assert len(flat) == args.steps and all(verdicts[q] == (0, -1) for q in flat)
+            decider_stats = {kk: round(vv / max(1, decider.stats["n"]), 3) if kk.endswith("_ms") else vv for kk, vv in decider.stats.items()}
             decider.close()
         else:
             assert all(o == (0, -1) for o in flat) and len(flat) == args.steps
@@ -438,7 +444,7 @@ def main():
                     "single_call": {"value": args.txs * args.steps / single_s, "ms_per_step": 1e3 * single_s / args.steps},
                     "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": phases.get("keccak_f", 0) / args.txs,
                     "phases_ms_pipelined_mean": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None,
-                    "fiat_shamir": args.fiat_shamir, "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
+                    "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir, "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
             "value_batches_in_flight": {"value_this_rank": concurrent_value, "unit": "TX/s", "contexts": nfl, "note": "device-resident batches of all contexts in flight at once (no L2 flush); the GPU-side ceiling of the pipelined e2e"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_ms_per_step_isolated": {n: round(v["ms_per_step"], 4) for n, v in kernels.items()},
             "timeline_ms_one_step": timeline, "mint_seconds": round(t_mint, 1), "host_cores": ncpu}

@@ -140,6 +140,9 @@ int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t
  * results of the sigma or range MSM (src/proofs.rs:49-67 decides on the identity of the total) -- as one 32-thread
  * kernel with no allocation.  *all_valid = 0 if an encoding does not decode (such inputs are left out of the sum). */
 int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t out_enc[32], int32_t* is_identity, int32_t* all_valid);
+/* copy nbytes (<= 1 MiB) between device-accessible addresses (device memory or pinned host memory) with a kernel on the
+ * ctx stream -- for small control messages that must not queue behind bulk transfers on the copy engines */
+int32_t xhe_copy_small(xhe_ctx* ctx, void* dst, const void* src, size_t nbytes);
 
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns

@@ -49,6 +49,7 @@ def load_library():
         "xhe_msm_dev": (i32, [vp, vp, vp, sz, vp, sz, vp, vp]),
         "xhe_msm_vartime": (i32, [vp, u8p, u8p, sz, vp, C.POINTER(C.c_int32)]),
         "xhe_sum_encodings": (i32, [vp, u8p, sz, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "xhe_copy_small": (i32, [vp, vp, vp, sz]),
         "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
         "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),
@@ -70,6 +71,7 @@ class Ctx:
         if rc != 0:
             raise XheError(rc, "xhe_ctx_create failed (a CUDA device is required; there is no CPU fallback)")
         self.p = p
+        self.stream_ptr = None
 
     def close(self):
         if getattr(self, "p", None):
@@ -85,6 +87,7 @@ class Ctx:
 
     def set_stream(self, stream_ptr):
         self._chk(self.lib.xhe_ctx_set_stream(self.p, C.c_void_p(stream_ptr)))
+        self.stream_ptr = stream_ptr
 
     def sync(self):
         self._chk(self.lib.xhe_ctx_sync(self.p))
@@ -138,6 +141,10 @@ class Ctx:
         ident, valid = C.c_int32(0), C.c_int32(0)
         self._chk(self.lib.xhe_sum_encodings(self.p, encodings, n, out, C.byref(ident), C.byref(valid)))
         return out.raw, bool(ident.value) and bool(valid.value)
+
+    def copy_small(self, dst_ptr, src_ptr, nbytes):
+        """kernel-based copy on this context's stream between device-accessible addresses (device or pinned host memory)"""
+        self._chk(self.lib.xhe_copy_small(self.p, dst_ptr, src_ptr, nbytes))
 
     def msm_plan(self, n):
         c, w = C.c_int(), C.c_int()

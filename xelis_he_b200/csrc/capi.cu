@@ -62,9 +62,9 @@ extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_gens_niels) cudaFree(ctx->d_gens_niels);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-  if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->h_res) cudaFreeHost(ctx->h_res);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (auto& st : ctx->aux) if (st) cudaStreamDestroy(st);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

@@ -453,16 +453,31 @@ extern "C" int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t
   return XHE_OK;
 }
 
+// Byte copy by a kernel on the ctx stream between any two device-accessible addresses (device memory, or pinned host memory
+// under unified addressing).  For the few-hundred-byte control messages of the sharded path: a cudaMemcpyAsync of that size
+// queues behind the megabyte uploads of the batches in flight on the copy engines, a 1-block kernel does not.
+__global__ void k_copy_bytes(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+extern "C" int32_t xhe_copy_small(xhe_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  if (!ctx || (nbytes && (!dst || !src)) || nbytes > (1u << 20)) return XHE_E_ARG;
+  if (!nbytes) return XHE_OK;
+  k_copy_bytes<<<1, 256, 0, ctx->stream>>>((const uint8_t*)src, (uint8_t*)dst, (uint32_t)nbytes); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+
 // Sum of n <= 224 canonical Ristretto encodings (the per-rank partial MSM results of a sharded batch): encoding of the sum,
 // whether it is the identity, whether all inputs decoded.  No allocation, one 32-thread kernel, synchronous.
 extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t out_enc[32], int32_t* is_identity, int32_t* all_valid) {
   if (!ctx || !is_identity || (n && !enc) || n > 224) return XHE_E_ARG;
-  if (!ctx->d_small) XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_small, 8192));
-  uint8_t* d = (uint8_t*)ctx->d_small; uint8_t* dout = d + 7168;
-  if (n) XHE_CUDA_OK(ctx, cudaMemcpyAsync(d, enc, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
-  k_sum_encodings<<<1, 32, 0, ctx->stream>>>(d, (uint32_t)n, dout); XHE_LAUNCHED(ctx);
-  uint8_t h[40];
-  XHE_CUDA_OK(ctx, cudaMemcpyAsync(h, dout, 40, cudaMemcpyDeviceToHost, ctx->stream));
+  // input and result live in pinned host memory the kernel addresses directly (unified addressing): no copy-engine
+  // transfers, which would queue behind the uploads of the batches in flight; the host waits on a blocking-sync event
+  if (!ctx->h_small) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_small, 7168, cudaHostAllocMapped));
+  if (!ctx->h_res) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_res, 512, cudaHostAllocMapped));
+  uint8_t* h = (uint8_t*)ctx->h_res;
+  if (n) memcpy(ctx->h_small, enc, 32 * n);
+  k_sum_encodings<<<1, 32, 0, ctx->stream>>>((const uint8_t*)ctx->h_small, (uint32_t)n, h); XHE_LAUNCHED(ctx);
   XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, ctx->stream));
   if (out_enc) memcpy(out_enc, h, 32);
   uint32_t f, v; memcpy(&f, h + 32, 4); memcpy(&v, h + 36, 4); *is_identity = (int32_t)f; if (all_valid) *all_valid = (int32_t)v;
@@ -733,7 +748,7 @@ extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (!ctx || !ctx->resident || !v) return XHE_E_ARG;
   DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h; cudaStream_t st = ctx->stream;
   // pinned landing zone: a device-to-pageable copy would block (spinning) inside cudaMemcpyAsync until the batch is done
-  if (!ctx->h_res) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_res, 512, cudaHostAllocDefault));
+  if (!ctx->h_res) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_res, 512, cudaHostAllocMapped));
   uint32_t* h_res = ctx->h_res;
   XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, D.d_results, 512, cudaMemcpyDeviceToHost, st));
   if (v->point_ok) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->point_ok, D.d_ok, b->n_points, cudaMemcpyDeviceToHost, st));

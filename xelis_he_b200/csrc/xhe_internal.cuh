@@ -36,7 +36,7 @@ struct xhe_ctx {
   std::vector<Span> timeline;
   cudaEvent_t sync_ev = nullptr;                              // blocking-sync event: host waits yield the core instead of spinning
   uint32_t* h_res = nullptr;                                  // pinned 512-byte landing zone of a batch's result block
-  void* d_small = nullptr;                                    // 8 KiB device scratch for the tiny cross-rank combination (xhe_sum_encodings)
+  void* h_small = nullptr;                                    // pinned (device-mapped) 7 KiB input block of xhe_sum_encodings
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; // side streams for the independent pipelines of xhe_batch_run
   cudaEvent_t ev[12] = {nullptr};

@@ -38,10 +38,21 @@ def decide(records, sum_is_identity):
 _pinned = {}
 
 
-def all_gather_records(local_record, group=None, device=None):
+def sum_is_identity(ctx, encodings):
+    """is the sum of the ranks' partial results the identity?  Honest shards each report the identity encoding (32 zero
+    bytes) -- the common case needs no device work; anything else is decoded and added on the device (xhe_sum_encodings)."""
+    zero = bytes(32)
+    if all(e == zero for e in encodings):
+        return True
+    return ctx.sum_encodings(b"".join(encodings))[1]
+
+
+def all_gather_records(local_record, group=None, device=None, ctx=None):
     """One all-gather of the fixed-size per-rank records.  On CUDA the record travels through pinned host buffers and the
     host waits on a blocking-sync event: a synchronous copy to pageable memory would sit inside the driver for as long as
-    the slowest rank takes to arrive, and other threads' kernel launches (further batches in flight) queue up behind it."""
+    the slowest rank takes to arrive, and other threads' kernel launches (further batches in flight) queue up behind it.
+    With `ctx` (a context that owns a stream) the two tiny host<->device hops are kernel copies on that stream instead of
+    copy-engine transfers, which would wait behind the megabyte uploads of the batches in flight."""
     import threading
     import torch
     import torch.distributed as dist
@@ -53,18 +64,26 @@ def all_gather_records(local_record, group=None, device=None):
         dist.all_gather_into_tensor(out, t, group=group)
         raw = bytes(out.numpy())
         return [raw[i * n:(i + 1) * n] for i in range(world)]
-    key = (threading.get_ident(), n, world, device.index)
+    own_stream = ctx is not None and getattr(ctx, "stream_ptr", None)
+    key = (threading.get_ident(), n, world, device.index, bool(own_stream))
     buf = _pinned.get(key)
     if buf is None:
+        stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=device) if own_stream else torch.cuda.Stream(device=device)
         buf = _pinned[key] = (torch.empty(n, dtype=torch.uint8, pin_memory=True), torch.empty(world * n, dtype=torch.uint8, pin_memory=True),
                               torch.empty(n, dtype=torch.uint8, device=device), torch.empty(world * n, dtype=torch.uint8, device=device),
-                              torch.cuda.Event(blocking=True), torch.cuda.Stream(device=device))
+                              torch.cuda.Event(blocking=True), stream)
     h_in, h_out, d_in, d_out, ev, stream = buf
     h_in.copy_(torch.frombuffer(bytearray(local_record), dtype=torch.uint8))
     with torch.cuda.stream(stream):
-        d_in.copy_(h_in, non_blocking=True)
+        if own_stream:
+            ctx.copy_small(d_in.data_ptr(), h_in.data_ptr(), n)
+        else:
+            d_in.copy_(h_in, non_blocking=True)
         dist.all_gather_into_tensor(d_out, d_in, group=group)
-        h_out.copy_(d_out, non_blocking=True)
+        if own_stream:
+            ctx.copy_small(h_out.data_ptr(), d_out.data_ptr(), world * n)
+        else:
+            h_out.copy_(d_out, non_blocking=True)
         ev.record(stream)
     ev.synchronize()
     raw = bytes(h_out.numpy())
@@ -127,10 +146,14 @@ class AsyncDecider:
         self.ctx, self.group, self.device = ctx, group, device
         self.cv = threading.Condition()
         self.pending, self.verdicts, self.next_seq, self.submitted, self.stop, self.error = {}, {}, 0, 0, False, None
+        self.stats = {"n": 0, "exchanges": 0, "exchange_ms": 0.0, "decide_ms": 0.0, "commit_ms": 0.0}      # time spent by the decision thread
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
+    SLOTS = 8          # decisions per exchange at most: a backlog is cleared with one all-gather instead of one each
+
     def _run(self):
+        import time
         import torch
         from . import verifier
         try:
@@ -142,21 +165,37 @@ class AsyncDecider:
                         self.cv.wait(0.05)
                     if self.next_seq not in self.pending:
                         return
-                    rec, handle, ledger = self.pending.pop(self.next_seq)
-                if os.environ.get("XHE_DIAG_LOCAL_DECISION"):      # diagnostics: skip the exchange, decide on this rank's record alone
-                    records = [rec]
+                    mine = []
+                    while len(mine) < self.SLOTS and self.next_seq + len(mine) in self.pending:
+                        mine.append(self.pending[self.next_seq + len(mine)])
+                # message: how many consecutive decisions this rank is ready for, then that many records (fixed size)
+                rec_len = len(mine[0][0])
+                msg = struct.pack("<I", len(mine)) + b"".join(m[0] for m in mine) + bytes(rec_len * (self.SLOTS - len(mine)))
+                t0 = time.perf_counter()
+                if os.environ.get("XHE_DIAG_LOCAL_DECISION"):      # diagnostics: skip the exchange, decide on this rank's records alone
+                    msgs = [msg]
                 else:
-                    records = all_gather_records(rec, self.group, self.device)
-                verdict = decide(records, lambda encs: self.ctx.sum_encodings(b"".join(encs))[1])
-                if handle:
-                    if verdict[0] == OK and ledger is not None:
-                        verifier.commit_taken(handle, ledger)
-                    else:
-                        verifier.drop_taken(handle)
-                with self.cv:
-                    self.verdicts[self.next_seq] = verdict
-                    self.next_seq += 1
-                    self.cv.notify_all()
+                    msgs = all_gather_records(msg, self.group, self.device, self.ctx)
+                t1 = time.perf_counter()
+                ready = min(struct.unpack("<I", m[:4])[0] for m in msgs)      # every rank computes the same number (>= 1)
+                for j in range(ready):
+                    t2 = time.perf_counter()
+                    records = [m[4 + rec_len * j:4 + rec_len * (j + 1)] for m in msgs]
+                    verdict = decide(records, lambda encs: sum_is_identity(self.ctx, encs))
+                    t3 = time.perf_counter()
+                    _, handle, ledger = mine[j]
+                    if handle:
+                        if verdict[0] == OK and ledger is not None:
+                            verifier.commit_taken(handle, ledger)
+                        else:
+                            verifier.drop_taken(handle)
+                    self.stats["decide_ms"] += 1e3 * (t3 - t2); self.stats["commit_ms"] += 1e3 * (time.perf_counter() - t3)
+                    with self.cv:
+                        del self.pending[self.next_seq]
+                        self.verdicts[self.next_seq] = verdict
+                        self.next_seq += 1
+                        self.cv.notify_all()
+                self.stats["n"] += ready; self.stats["exchanges"] += 1; self.stats["exchange_ms"] += 1e3 * (t1 - t0)
         except Exception as e:          # surface the failure to drain() instead of hanging the workers
             with self.cv:
                 self.error = e
@@ -200,7 +239,7 @@ def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None,
     rec = pack_local(code, idx, shard_offset, s_enc, r_enc)
     records = gather(rec) if gather else all_gather_records(rec, group, torch.device("cuda", torch.cuda.current_device()))
     t1 = time.perf_counter()
-    verdict = decide(records, lambda encs: ctx.sum_encodings(b"".join(encs))[1])
+    verdict = decide(records, lambda encs: sum_is_identity(ctx, encs))
     t2 = time.perf_counter()
     if verdict[0] == OK and commit:
         verifier.commit_pending(ctx, ledger)
