@@ -119,12 +119,20 @@ __global__ void k_selftest_fe(int op, const uint32_t* __restrict__ a, const uint
   st_fe(out + 8 * i, r);
 }
 
-// integer-pipe microbenchmarks: 8 independent dependency chains per thread, ITER x 8 instructions of one kind
+// integer-pipe microbenchmarks: 8 independent dependency chains per thread, ITER x 8 x 8 instructions of one kind.
+// Every multiplicand changes from one instruction to the next use: ptxas hoists loop-invariant products and replaces a
+// `mad.wide` whose product is invariant by IADD3 pairs (an earlier version of WHICH == 2 measured exactly that, 18.4 T/s
+// of additions).  SASS of each variant is checked in tools/imad_probe.cu / DESIGN.md 4.1.
+//   0: IMAD (32-bit low product)        1: IMAD.HI.U32
+//   2: IMAD.WIDE.U32 Rd64, Ra, Rb, RZ  (two vector multiplicands, both result words live: the plain 32x32->64 product)
+//   3: IMAD.WIDE.U32 / IMAD.WIDE.U32.X carry chains (what the radix-2^32 field multiply issues)
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, int iters) {
   uint32_t a = seed + threadIdx.x, b = seed * 3 + 1;
   uint32_t x0 = a, x1 = a + 1, x2 = a + 2, x3 = a + 3, x4 = a + 4, x5 = a + 5, x6 = a + 6, x7 = a + 7;
-  unsigned long long w0 = a, w1 = a + 1, w2 = a + 2, w3 = a + 3, w4 = a + 4, w5 = a + 5, w6 = a + 6, w7 = a + 7;
+  unsigned long long w[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) w[k] = ((unsigned long long)(a * 2654435761u + k) << 32) | (a + k);
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -141,19 +149,15 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, 
         asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.u32 %3, %8, %9, %3;"
                      "mad.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
                      : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(b), "r"(a));
-      } else if (WHICH == 3) {
-        // carry-chained wide mads (what the radix-2^32 field multiply issues): 4 chains of 2 slots
-        asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.u32 %3, %8, %9, %3;"
-                     "mad.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
-                     : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(b), "r"(a));
       } else {
-        asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %9, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %9, %3;"
-                     "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %9, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %9, %7;"
-                     : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3), "+l"(w4), "+l"(w5), "+l"(w6), "+l"(w7) : "r"(b), "r"(a));
+        // w_k <- lo(w_k) * hi(w_{k+1}): 8 independent 64-bit products per round, every result word feeds a later multiply
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[k]) : "r"((uint32_t)w[k]), "r"((uint32_t)(w[(k + 1) & 7] >> 32)));
       }
     }
   }
-  uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7) ^ (uint32_t)((w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7) >> 32);
+  unsigned long long f = w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7];
+  uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)f ^ (uint32_t)(f >> 32);
   if (r == 0x12345678u) out[0] = r;   // practically never: keeps the chains alive
 }
 
@@ -226,7 +230,6 @@ extern "C" int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate) {
     cudaEventRecord(e0, ctx->stream);
     if (which == 0) k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else if (which == 1) k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
-    else if (which == 3) k_int_peak<3><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else if (which == 3) k_int_peak<3><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     else k_int_peak<2><<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
     XHE_LAUNCHED(ctx);
