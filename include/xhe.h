@@ -37,6 +37,9 @@ typedef struct xhe_ctx xhe_ctx;
  * src/proofs.rs:19-22): builds G/H tables and the 2*64*party_capacity generator table on `device`. */
 int32_t xhe_ctx_create(int device, uint32_t party_capacity, xhe_ctx** out);
 void xhe_ctx_destroy(xhe_ctx* ctx);
+/* the party capacity the context was created with: aggregated range proofs with m <= this many parties verify
+ * (the reference's BP_GENS holds 512, src/proofs.rs:20; a transaction with a assets and k transfers has m = next_pow2(a + k)) */
+uint32_t xhe_ctx_party_capacity(const xhe_ctx* ctx);
 const char* xhe_last_error(const xhe_ctx* ctx);
 /* stream all subsequent *_dev calls are launched on (a cudaStream_t passed as void*; NULL = default stream) */
 int32_t xhe_ctx_set_stream(xhe_ctx* ctx, void* cuda_stream);

@@ -76,6 +76,34 @@ def test_mixed_party_sizes_in_one_batch(ctx):
     assert hl.dump() == sorted(ol.dump())
 
 
+def test_255_transfer_transaction_m256():
+    """benches/tx.rs:109 `n_tx_bench(c, 255)`: one sender, 255 transfers, a 256-party aggregated range proof (lg = 14),
+    alone and inside a batch with small transactions (mixed m in one range MSM); a re-signed bad range proof is rejected
+    with RangeProof on both sides; a context created for fewer parties refuses loudly instead of mis-verifying."""
+    import xelis_he_b200 as xhe
+    from xelis_he_b200 import verifier
+    w = scenarios.World(b"m256")
+    bob = w.account(b"bob", [(NATIVE, 10000000)]); alice = w.account(b"alice", [(NATIVE, 0)]); carol = w.account(b"carol", [(NATIVE, 500)])
+    big = oracle.build_tx(bob, w.ledger, w.rng, fee=3, transfers=[(NATIVE, alice.pk, 1)] * 255, balances=[(NATIVE, 10000000)])
+    small = oracle.build_tx(carol, w.ledger, w.rng, fee=1, transfers=[(NATIVE, alice.pk, 7)], balances=[(NATIVE, 500)])
+    c = xhe.Ctx(0, party_capacity=256)
+    try:
+        assert both(c, w, [big]) == (OK, -1)
+        assert both(c, w, [small, big]) == (OK, -1)
+        rp0 = 64 + 324 * 255
+        bad = oracle.resign(_mut(big, rp0 + 128), bob, w.rng)              # range proof t_x
+        assert both(c, w, [bad]) == (RANGE, -1)
+        assert both(c, w, [small, bad]) == (RANGE, -1)
+    finally:
+        c.close()
+    c8 = xhe.Ctx(0, party_capacity=8)
+    try:
+        with pytest.raises(Exception):
+            verifier.verify_batch(c8, [big], w.host_ledger(), seed=SEED)
+    finally:
+        c8.close()
+
+
 def test_single_sender_chain(ctx):   # benches/tx.rs:129-186 shape: balances chained through one account
     from xelis_he_b200 import verifier
     b = oracle.mint_chain(5, 24, 1)

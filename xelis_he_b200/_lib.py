@@ -32,6 +32,7 @@ def load_library():
     sigs = {
         "xhe_ctx_create": (i32, [C.c_int, C.c_uint32, C.POINTER(vp)]),
         "xhe_ctx_destroy": (None, [vp]),
+        "xhe_ctx_party_capacity": (C.c_uint32, [vp]),
         "xhe_last_error": (C.c_char_p, [vp]),
         "xhe_ctx_set_stream": (i32, [vp, vp]),
         "xhe_ctx_sync": (i32, [vp]),

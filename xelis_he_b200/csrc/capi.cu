@@ -57,6 +57,7 @@ extern "C" int32_t xhe_ctx_create(int device, uint32_t party_capacity, xhe_ctx**
   *out = ctx;
   return XHE_OK;
 }
+extern "C" uint32_t xhe_ctx_party_capacity(const xhe_ctx* ctx) { return ctx ? ctx->party_capacity : 0; }
 extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) k_sigma_weights(const uint32_t* __restric
 // sum mod l of `count` scalars with stride (in scalars) -> one scalar per (blockIdx.y) column; two-stage by repeated launch
 __global__ void __launch_bounds__(256) k_reduce_scalars(const uint32_t* __restrict__ in, uint32_t count, uint32_t stride, uint32_t col_stride, uint32_t* __restrict__ out, uint32_t out_stride) {
   __shared__ uint32_t sm[256 * 8];
-  uint32_t col = blockIdx.y;
+  uint32_t col = blockIdx.z * gridDim.y + blockIdx.y;      // more than 65535 columns are split over grid.z (2 * 64 * 512 generator columns)
   sc acc = sc_zero();
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
     sc v; ld_sc_rw(v, in + 8 * ((size_t)k * stride + (size_t)col * col_stride));
@@ -233,17 +233,16 @@ __global__ void __launch_bounds__(256) k_reduce_scalars(const uint32_t* __restri
 }
 
 // ---- range proofs ----------------------------------------------------------------------------------------------------
-// per-proof derived scalars written by k_rp_prep, RP_DER scalars per proof.  M = Montgomery form, P = plain form: a
+// per-proof derived scalars written by k_rp_prep, der_stride scalars per proof.  M = Montgomery form, P = plain form: a
 // Montgomery product of a P and an M operand is the plain product, which lets k_rp_gens emit plain weights directly.
 enum { D_ALLINV = 0 /* M */, D_YINV /* M */, D_RZ /* P rho z */, D_RA /* P rho a */, D_RB /* P rho b */, D_RZZ /* unused */, D_Z /* M */, D_USQ /* M, lg entries */ };
-#define RP_MAX_LG 16
-#define RP_MAX_M 32
+#define RP_MAX_LG 16                     // lg = 6 + log2(m) <= 15 for m <= 512 = BP_GENS' party capacity (src/proofs.rs:20)
 #define D_YPW (D_USQ + RP_MAX_LG)        // M: y_inv^(2^j), lg entries
 #define D_RZZJ (D_USQ + 2 * RP_MAX_LG)   // P: rho z^2 z^j, m entries
-#define RP_DER (7 + 2 * RP_MAX_LG + RP_MAX_M)
+#define RP_DER_FIXED (7 + 2 * RP_MAX_LG) // a proof's record is der_stride = RP_DER_FIXED + m_max(batch) scalars
 
 __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ sc_in /* 7 per proof */, const uint32_t* __restrict__ chal_off,
-                                                const uint32_t* __restrict__ chal, const uint32_t* __restrict__ dyn_off /* term offset per proof */, uint32_t n_rp,
+                                                const uint32_t* __restrict__ chal, const uint32_t* __restrict__ dyn_off /* term offset per proof */, uint32_t n_rp, uint32_t der_stride,
                                                 uint32_t* __restrict__ der, uint32_t* __restrict__ dyn_sc, uint32_t* __restrict__ gh /* 2 per proof: G (B) and H (B_blinding) */) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_rp) return;
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_a
   sc allinv = onem;
   for (int j = 0; j < lg; j++) allinv = mmul_call(allinv, uinv[j]);
   sc yinv = uinv[lg], ym1inv = uinv[lg + 1];
-  uint32_t* d = der + 8 * (size_t)RP_DER * p;
+  uint32_t* d = der + 8 * (size_t)der_stride * p;
   sc zzm = mmul_call(zm, zm);
   st_sc(d + 8 * D_ALLINV, allinv); st_sc(d + 8 * D_YINV, yinv);
   st_sc(d + 8 * D_RZ, mmul_call(rho, zm)); st_sc(d + 8 * D_RA, mmul_call(rho, am)); st_sc(d + 8 * D_RB, mmul_call(rho, bm)); st_sc(d + 8 * D_Z, zm);
@@ -310,7 +309,7 @@ __global__ void k_pow2_table(uint32_t* __restrict__ tab) {
 #define RPG_WARPS 4
 #define RPG_THREADS (32 * RPG_WARPS)
 #define RPG_CHUNK 128
-__global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
+__global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, uint32_t der_stride, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
                                                          uint32_t Nmax, uint32_t n_rows, uint32_t* __restrict__ part) {
   extern __shared__ uint32_t sm[];           // per warp: t[128] then yl[128], 8 words each (Montgomery form)
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, row = blockIdx.x * RPG_WARPS + wib;
@@ -320,7 +319,7 @@ __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restr
   for (uint32_t i = lane; i < 2 * Nmax; i += 32) st_sc(my + 8 * i, sc_zero());
   for (uint32_t p = row; p < n_rp; p += n_rows) {
     const uint32_t m = m_arr[p]; const int lg = 6 + (31 - __clz(m)), lgc = lg < 7 ? lg : 7; const uint32_t N = 64u * m, Cn = 1u << lgc, Q = N >> lgc;
-    const uint32_t* d = der + 8 * (size_t)RP_DER * p;
+    const uint32_t* d = der + 8 * (size_t)der_stride * p;
     sc allinv; ld_sc(allinv, d + 8 * D_ALLINV);
     __syncwarp();
     if (lane == 0) { st_sc(t, Q == 1 ? allinv : mont_one()); st_sc(yl, mont_one()); }
@@ -487,7 +486,7 @@ extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n,
 // device-side image of one batch: every pointer lives in the ctx arena
 struct DeviceBatch {
   xhe_batch h;                       // scalar fields (counts) copied from the host description; pointers unused
-  uint32_t Nmax = 64, rp_grid = 0; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
+  uint32_t Nmax = 64, rp_grid = 0, der_stride = RP_DER_FIXED + 1; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
   uint8_t *d_enc, *d_ok, *d_sig_r, *d_op_out, *d_ws1, *d_ws2, *d_ws3; uint32_t* d_rparts; size_t ws_static = 0;
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
@@ -507,11 +506,11 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   uint32_t m_max = 1;
   for (uint32_t p = 0; p < b->n_rp; p++) {
     uint32_t m = b->rp_m[p];
-    if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity || 64u * m > 2048u) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs a power of two <= min(party_capacity, 32))"; return XHE_E_ARG; }
+    if (m == 0 || (m & (m - 1)) || m > ctx->party_capacity) { ctx->err = "verify_batch: unsupported range-proof party count m=" + std::to_string(m) + " (needs a power of two <= the context's party_capacity " + std::to_string(ctx->party_capacity) + ")"; return XHE_E_ARG; }
     if (m > m_max) m_max = m;
     D.sum_m += m;
   }
-  D.Nmax = 64 * m_max;
+  D.Nmax = 64 * m_max; D.der_stride = RP_DER_FIXED + m_max;
   D.n_pts_total = (size_t)b->n_points + b->n_ops;
   D.n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val; D.n_sigma = D.n_sigma_terms + 2;
   D.n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0; D.n_range = D.n_dyn + (b->n_rp ? 2 * (size_t)D.Nmax + 2 : 0);
@@ -532,7 +531,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
               + (size_t)b->n_ops * (8 + 8 + 8 + 8 + 128 * 2 + 32) + 4 * ((size_t)b->n_ops + 1) + 4 * n_terms
               + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
-              + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * RP_DER + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
+              + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * (size_t)D.der_stride + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
               + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + D.ws_static + 8192 + 512 * 64
               + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs;
   if (ctx->scratch_bytes < need) {
@@ -553,7 +552,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   TAKE(uint32_t, d_sigma_sc, 8 * n_sigma); TAKE(uint32_t, d_sigma_niels, 24 * n_sigma); TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
   TAKE(uint32_t, d_results, 128); TAKE(uint8_t, d_ws1, D.ws_sigma);
   TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
-  TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)RP_DER * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
+  TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)D.der_stride * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
   TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range); TAKE(uint8_t, d_ws3, D.ws_static); TAKE(uint32_t, d_rparts, 64);
   TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs);
   if (D.fs) { UP(D.d_blobs, b->fs_blobs, D.blob_bytes); UP(D.d_blob_off, b->fs_blob_off, 8 * ((size_t)b->n_tx + 1)); UP(D.d_fs_plan, b->fs_plan, 4 * (size_t)D.plan_stride * b->n_tx); UP(D.d_seed, b->fs_seed, 32); }
@@ -695,7 +694,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     ctx->stream = s_rp;
     { cudaStream_t st = s_rp;
       XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
-      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
+      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.der_stride, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_prep, s_rp));
     // s_dyn
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_prep, 0));
@@ -711,8 +710,9 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     { cudaStream_t st = s_rp;
       const size_t smem = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32;
       { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // 6 mod-l products per generator index, 64*m indices per proof
-        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
-      k_reduce_scalars<<<dim3(1, 2 * Nmax), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx);
+        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, D.der_stride, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
+      { const uint32_t cols = 2 * Nmax, gy = cols > 32768u ? 32768u : cols;     // cols = 128 * m_max, a power of two
+        k_reduce_scalars<<<dim3(1, gy, cols / gy), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx); }
       k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
       k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
       k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);

@@ -297,6 +297,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   for (size_t i = 0; i < n; i++) if (parse_rc[i]) return 0;
   double t1 = now_ms();
   FastCache& F = fast_cache_for(ctx);
+  const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
   F.off.resize(n + 1); F.plan.resize(8 * n); F.rp_m.resize(n); F.rp_pt_off.resize(n + 1); F.rp_ch_off.resize(n + 1);
   F.region_b.clear(); F.terms.clear(); F.term_off.clear(); F.prev.clear(); F.amount.clear();
   F.term_off.push_back(0);
@@ -326,7 +327,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     { uint8_t th; bool present = false; if (!state.get_multisig_for_account(tx.source, &signers, &th, &present) || present) return 0; }
     const uint32_t k = tx.n_transfers(), a = tx.n_sc, lg = (tx.rp_len / 32 - 9) / 2;
     uint32_t m = 1, lg_need = 6; while (m < a + k) { m <<= 1; lg_need++; }
-    if (lg != lg_need || m > 32) return 0;
+    if (lg != lg_need || m > party_capacity) return 0;            // larger proofs: the exact path reports the unsupported party count
     uint32_t* P = &F.plan[8 * i];
     P[0] = n_eq; P[1] = n_val; P[2] = (uint32_t)i; P[3] = F.rp_ch_off[i]; P[4] = (uint32_t)i; P[5] = 1; P[6] = pt; P[7] = (uint32_t)F.prev.size();
     F.rp_m[i] = m; F.rp_pt_off[i + 1] = F.rp_pt_off[i] + 4 + 2 * lg + m; F.rp_ch_off[i + 1] = F.rp_ch_off[i] + 4 + lg;
