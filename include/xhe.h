@@ -81,6 +81,7 @@ int32_t xhe_msm_dev(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, si
  * All pointers are HOST memory; indices refer to the point table.  Point index 0 MUST be the identity encoding (used
  * for the dud commitments of src/tx/verify.rs:466-475).  Indices >= n_points address balance-chain outputs
  * (n_points + j = output of op j). ----------------------------------------------------------------------------------- */
+#define XHE_OP_PLUS_AMOUNT (1LL << 50)
 typedef struct xhe_batch {
   uint32_t n_tx;
   uint32_t n_points; const uint8_t* points;              /* n_points x 32 compressed ristretto255 */
@@ -88,7 +89,10 @@ typedef struct xhe_batch {
   uint32_t n_sigs; const uint8_t* sig_s; const uint8_t* sig_e; const uint32_t* sig_pk;
   /* balance chains (src/tx/verify.rs:301-336,354-374; src/elgamal.rs:322-377): op j yields point n_points+j =
    * prev_j + sum(+-P[term]) - amount_j*G, where prev_j >= 0 is an earlier op of the same (account, asset, half) chain
-   * and prev_j < 0 encodes the initial balance point -(1+index).  One op per ciphertext half (commitment / handle). */
+   * and prev_j < 0 encodes the initial balance point -(1+index).  One op per ciphertext half (commitment / handle).
+   * prev_j = -(1+index) - XHE_OP_PLUS_AMOUNT makes the op ADD amount_j*G instead: with index 0 (the identity) and
+   * unsigned terms that is one half of get_sender_output_ct (src/tx/verify.rs:107-144), the ciphertext the reference
+   * hands to BlockchainVerificationState::set_output_ciphertext (src/tx/verify.rs:339-340, 582). */
   uint32_t n_ops; const int64_t* op_prev; const uint32_t* op_term_off /* n_ops+1 */; const uint32_t* op_terms /* bit 31 = subtract */;
   const uint64_t* op_amount; uint32_t max_chain /* longest chain length (>= 1) */;
   /* CommitmentEqProof::pre_verify (src/proofs.rs:134-211): points P_src,Y0,D_src,C_src,Y1,C_dst,Y2; scalars z_s,z_x,z_r,c,w,bf */

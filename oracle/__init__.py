@@ -153,6 +153,15 @@ class Ledger:
         raw = bytes(out)[: 128 * n]
         return [(raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128)]
 
+    def dump_outputs(self):
+        """(pk, asset, compressed output ciphertext) of the last set_output_ciphertext call per key (src/tx/verify.rs:339-340)."""
+        lib.xo_ledger_dump_outputs.restype = C.c_size_t
+        n = lib.xo_ledger_dump_outputs(self.ptr, None, C.c_size_t(0))
+        out = (C.c_uint8 * (128 * max(n, 1)))()
+        lib.xo_ledger_dump_outputs(self.ptr, out, C.c_size_t(128 * n))
+        raw = bytes(out)[: 128 * n]
+        return [(raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128)]
+
     def __del__(self):
         try:
             lib.xo_ledger_free(self.ptr)

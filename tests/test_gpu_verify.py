@@ -198,6 +198,41 @@ def test_apply_without_verify_matches_oracle(ctx):
     assert hl.dump() == sorted(ol.dump())
 
 
+def test_output_ciphertexts_match_oracle(ctx):
+    """BlockchainVerificationState::set_output_ciphertext (src/tx/verify.rs:60-66; called at 339-340 and 582): a state that
+    asks for them receives get_sender_output_ct(source, asset) per transaction, byte-identical (compressed) to the oracle's,
+    through every placement of the host/device split and through apply_without_verify; balances are unaffected."""
+    from xelis_he_b200 import verifier
+    worlds = [scenarios.realistic_world()[:2], scenarios.burn_world()[:2], (lambda r: (r[0], r[1]))(scenarios.mixed_types_world(12))]
+    for w, txs in worlds:
+        ol = w.ledger.clone()
+        assert oracle.verify_batch(txs, ol) == (OK, -1)
+        want_out, want_bal = sorted(ol.dump_outputs()), sorted(ol.dump())
+        assert want_out, "scenario produced no output ciphertexts"
+        for mode in ("host", "device", "fast"):
+            hl = w.host_ledger(); hl.record_outputs()
+            assert verifier.verify_batch(ctx, txs, hl, seed=SEED, threads=4, fiat_shamir=mode)[:2] == (OK, -1)
+            assert hl.dump_outputs() == want_out, mode
+            assert hl.dump() == want_bal, mode
+        quiet = w.host_ledger()                        # a state that does not ask gets none (and the same balances)
+        assert verifier.verify_batch(ctx, txs, quiet, seed=SEED, threads=4, fiat_shamir="fast")[:2] == (OK, -1)
+        assert quiet.dump_outputs() == [] and quiet.dump() == want_bal
+    # minted a2k6 batch through the fast path, and apply_without_verify
+    b = oracle.mint_transfers(77, 6, 2, 6, threads=8)
+    ol = b.ledger(); assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
+    hl = verifier.Ledger(); hl.import_records(b.ledger().dump()); hl.record_outputs()
+    code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir="fast")
+    assert (code, idx) == (OK, -1) and tm["fast_path"]
+    assert hl.dump_outputs() == sorted(ol.dump_outputs()) and hl.dump() == sorted(ol.dump())
+    w, txs, _ = scenarios.realistic_world()
+    ol = w.ledger.clone()
+    for t in txs:
+        assert oracle.apply_without_verify(t, ol) == 0
+    hl = w.host_ledger(); hl.record_outputs()
+    assert verifier.apply_without_verify(ctx, txs, hl) == 0
+    assert hl.dump_outputs() == sorted(ol.dump_outputs()) and hl.dump() == sorted(ol.dump())
+
+
 def test_device_fiat_shamir_matches_host(ctx):
     """both modes derive the same challenges and batch factors: the partial MSM encodings of a (deliberately invalid) shard
     are byte-identical, not just the verdicts"""

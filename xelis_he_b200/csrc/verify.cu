@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in,
 }
 
 // ---- balance chains -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_op_delta(const uint32_t* __restrict__ term_off, const uint32_t* __restrict__ terms, const uint64_t* __restrict__ amount,
+__global__ void __launch_bounds__(128) k_op_delta(const uint32_t* __restrict__ term_off, const uint32_t* __restrict__ terms, const uint64_t* __restrict__ amount, const long long* __restrict__ prev,
                                                   const uint32_t* __restrict__ pt_niels, const uint32_t* __restrict__ tabG, uint32_t n_ops, uint32_t* __restrict__ delta) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_ops) return;
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(128) k_op_delta(const uint32_t* __restrict__ t
     uint8_t b[8];
     for (int k = 0; k < 8; k++) b[k] = (uint8_t)(a >> (8 * k));
     ge ag = fixed_base_mul(tabG, b, 8);
-    acc = ge_add(acc, ge_neg(ag));      // balance - amount*G
+    const long long p = prev[j];
+    const bool plus = p < 0 && (((unsigned long long)(-(p + 1))) & (unsigned long long)XHE_OP_PLUS_AMOUNT) != 0;   // output-ciphertext op (xhe.h)
+    acc = ge_add(acc, plus ? ag : ge_neg(ag));      // balance - amount*G, or output + amount*G
   }
   st_ge(delta + 32 * (size_t)j, acc);
 }
@@ -676,7 +678,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     cudaStream_t st = main_st;
     XheTimed t(ctx, "balance_chain", (504.0 * 2 + 12688.0) * b->n_ops);
     XHE_CUDA_OK(ctx, cudaMemcpyAsync(D.d_ptr_a, D.d_ptr_init, 8 * (size_t)b->n_ops, cudaMemcpyDeviceToDevice, st));
-    k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(D.d_term_off, D.d_terms, D.d_amount, D.d_niels, T->tabG, b->n_ops, D.d_acc_a); XHE_LAUNCHED(ctx);
+    k_op_delta<<<nblk(b->n_ops, 128), 128, 0, st>>>(D.d_term_off, D.d_terms, D.d_amount, D.d_ptr_init, D.d_niels, T->tabG, b->n_ops, D.d_acc_a); XHE_LAUNCHED(ctx);
     uint32_t *acc_cur = D.d_acc_a, *acc_nxt = D.d_acc_b; long long *ptr_cur = D.d_ptr_a, *ptr_nxt = D.d_ptr_b;
     for (uint32_t span = 1; span < b->max_chain; span <<= 1) {
       k_op_jump<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, acc_nxt, ptr_nxt); XHE_LAUNCHED(ctx);

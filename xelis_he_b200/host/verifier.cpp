@@ -132,7 +132,11 @@ enum CheckKind : uint8_t { CK_HOST = 0, CK_POINT = 1, CK_SIG = 2 };
 struct Check { CheckKind kind; int32_t err; uint32_t a; };
 
 struct SigEntry { uint32_t tx; bool is_multisig; const uint8_t* sig; uint32_t pk; const uint8_t* pk_enc; };
-struct StateUpdate { Bytes32 account, asset; Role role; uint32_t op_c, op_d; };
+struct StateUpdate { Bytes32 account, asset; Role role; uint32_t op_c, op_d; bool output = false; /* set_output_ciphertext instead of update_account_balance */ };
+inline bool apply_update(VerificationState& state, const uint8_t* account, const uint8_t* asset, Role role, bool output, const uint8_t ct[64]) {
+  return output ? state.set_output_ciphertext(account, asset, ct) : state.update_account_balance(account, asset, ct, role);
+}
+const long long OUT_PREV_C = -1 - XHE_OP_PLUS_AMOUNT, OUT_PREV_D = -1;   // output-ciphertext ops start from the identity (point 0); the commitment half ADDS amount*G
 struct Chain { long last_c = -1, last_d = -1; uint32_t length = 0; };
 
 struct TxPlan {
@@ -231,6 +235,18 @@ inline void advance_chain(Builder& B, Chain* c, uint32_t op_c, uint32_t op_d) {
   if (c->length > B.max_chain) B.max_chain = c->length;
 }
 
+// the two ops of get_sender_output_ct(asset) (src/tx/verify.rs:107-144) and the state call that hands the result over
+template <typename Idx>
+inline void push_output_ops(Builder& B, const TxView& tx, const uint8_t* asset, const Idx& iC, const Idx& iDs, uint32_t k) {
+  uint32_t oc = B.add_op(OUT_PREV_C, plain_output_amount(tx, asset));
+  for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t]);
+  B.close_op();
+  uint32_t od = B.add_op(OUT_PREV_D, 0);
+  for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t]);
+  B.close_op();
+  StateUpdate u; memcpy(u.account.data(), tx.source, 32); memcpy(u.asset.data(), asset, 32); u.role = Sender; u.op_c = oc; u.op_d = od; u.output = true; B.updates.push_back(u);
+}
+
 }  // namespace
 
 // shard-mode state updates waiting for the cross-rank decision (one slot per ctx)
@@ -246,7 +262,7 @@ static int apply_pending(const Pending& P, VerificationState& state) {
     const StateUpdate& u = P.updates[j];
     if (j + 8 < n) state.prefetch_balance(P.updates[j + 8].account.data(), P.updates[j + 8].asset.data());
     uint8_t ct[64]; memcpy(ct, &P.op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &P.op_out[32 * (size_t)u.op_d], 32);
-    if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
+    if (!apply_update(state, u.account.data(), u.asset.data(), u.role, u.output, ct)) return XHE_ERR_STATE;
   }
   return XHE_OK;
 }
@@ -302,8 +318,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   F.region_b.clear(); F.terms.clear(); F.term_off.clear(); F.prev.clear(); F.amount.clear();
   F.term_off.push_back(0);
   FlatTable<64, Chain>& chains = F.chains; chains.clear(); chains.reserve(4 * n);
-  struct Upd { const uint8_t *account, *asset; Role role; uint32_t op_c; };
+  struct Upd { const uint8_t *account, *asset; Role role; uint32_t op_c; bool output; };
   std::vector<Upd> updates; updates.reserve(3 * n);
+  const bool want_out = state.wants_output_ciphertexts(); std::vector<size_t> out_slots;
   const long long RB = (long long)1 << 40;     // marks "region B slot j" until the region-A size is known
   uint32_t pt = 1, n_eq = 0, n_val = 0, max_chain = 1; uint64_t off = 0;
   F.rp_pt_off[0] = 0; F.rp_ch_off[0] = 0;
@@ -355,7 +372,8 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
       for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) F.terms.push_back((iT + 3 * t + 1) | 0x80000000u);
       F.term_off.push_back((uint32_t)F.terms.size());
       ch->last_c = oc; ch->last_d = od; if (++ch->length > max_chain) max_chain = ch->length;
-      updates.push_back({tx.source, asset, Sender, oc});
+      updates.push_back({tx.source, asset, Sender, oc, false});
+      if (want_out) { out_slots.push_back(updates.size()); updates.push_back({tx.source, asset, Sender, 0, true}); }   // reference order: update, then set_output (339-340)
     }
     for (uint32_t t = 0; t < k; t++) {
       const TransferView& tr = tx.transfers[t]; long long pc, pd;
@@ -363,14 +381,27 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
       uint32_t oc = push_op(pc, 0); F.terms.push_back(iT + 3 * t); F.term_off.push_back((uint32_t)F.terms.size());
       uint32_t od = push_op(pd, 0); F.terms.push_back(iT + 3 * t + 2); F.term_off.push_back((uint32_t)F.terms.size());
       ch->last_c = oc; ch->last_d = od; if (++ch->length > max_chain) max_chain = ch->length;
-      updates.push_back({tr.dest, tr.asset, Receiver, oc});
+      updates.push_back({tr.dest, tr.asset, Receiver, oc, false});
+    }
+    if (want_out) {   // output ciphertexts: appended after the ops k_layout indexes (P[7] + 2q are the sender ops)
+      for (uint32_t q = 0; q < a; q++) {
+        const uint8_t* asset = tx.sc + 256 * q;
+        uint32_t oc = push_op(OUT_PREV_C, plain_output_amount(tx, asset));
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) F.terms.push_back(iT + 3 * t);
+        F.term_off.push_back((uint32_t)F.terms.size());
+        push_op(OUT_PREV_D, 0);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) F.terms.push_back(iT + 3 * t + 1);
+        F.term_off.push_back((uint32_t)F.terms.size());
+        updates[out_slots[q]].op_c = oc;
+      }
+      out_slots.clear();
     }
     pt += 1 + 3 * k + a + 3 * a + k + 3 * k + 4 + 2 * lg;
     n_eq += a; n_val += k;
   }
   F.off[n] = off;
   const uint32_t n_a_end = pt, n_rb = (uint32_t)(F.region_b.size() / 32), n_points = n_a_end + n_rb;
-  for (size_t j = 0; j < F.prev.size(); j++) if (F.prev[j] <= -RB) F.prev[j] = -(1 + (long long)n_a_end + (-F.prev[j] - RB));
+  for (size_t j = 0; j < F.prev.size(); j++) if (F.prev[j] <= -RB && F.prev[j] > -XHE_OP_PLUS_AMOUNT) F.prev[j] = -(1 + (long long)n_a_end + (-F.prev[j] - RB));
   double t2 = now_ms();
   F.blob.resize(off);
   parallel_for(n, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) memcpy(&F.blob[F.off[i]], blobs[i], lens[i]); });
@@ -393,7 +424,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   if (shard) {
     memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32);
     Pending Pn; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.updates.reserve(updates.size());
-    for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; Pn.updates.push_back(su); }
+    for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; su.output = u.output; Pn.updates.push_back(su); }
     std::lock_guard<std::mutex> g(g_pending_mu);
     g_pending[ctx] = std::move(Pn);
   } else if (opt.apply_state) {
@@ -401,7 +432,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
       const Upd& u = updates[j];
       if (j + 8 < updates.size()) state.prefetch_balance(updates[j + 8].account, updates[j + 8].asset);
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 64);       // commitment op and handle op are adjacent
-      if (!state.update_account_balance(u.account, u.asset, ct, u.role)) { *rc_out = XHE_ERR_STATE; return 0; }
+      if (!apply_update(state, u.account, u.asset, u.role, u.output, ct)) { *rc_out = XHE_ERR_STATE; return 0; }
     }
   }
   double t5 = now_ms();
@@ -423,6 +454,7 @@ int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, 
 static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
   double t0 = now_ms();
   if (fail_index) *fail_index = -1;
+  const bool want_out = state.wants_output_ciphertexts();
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
   uint8_t seed[32];
   if (opt.rng_seed && opt.rng_seed_len) { uint8_t h[64]; sha3_512(opt.rng_seed, opt.rng_seed_len, h); memcpy(seed, h, 32); }
@@ -511,6 +543,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
         B.close_op();
         advance_chain(B, ch, oc, od);
         StateUpdate u; memcpy(u.account.data(), tx.source, 32); memcpy(u.asset.data(), asset, 32); u.role = Sender; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+        if (want_out) push_output_ops(B, tx, asset, iC, iDs, k);
         // eq proof: Y identity check (src/transcript.rs:73-84) then Y decompression (src/proofs.rs:168-179)
         if (is_zero32(proof) || is_zero32(proof + 32) || is_zero32(proof + 64)) { host_fail(XHE_ERR_TRANSCRIPT); stop = true; break; }
         uint32_t y0 = B.add_point(proof), y1 = B.add_point(proof + 32), y2 = B.add_point(proof + 64);
@@ -726,7 +759,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   } else if (verdict == XHE_OK && opt.apply_state) {
     for (const StateUpdate& u : B.updates) {
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
-      if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) { verdict = XHE_ERR_STATE; break; }
+      if (!apply_update(state, u.account.data(), u.asset.data(), u.role, u.output, ct)) { verdict = XHE_ERR_STATE; break; }
     }
   }
   if (fail_index) *fail_index = bad_tx;
@@ -742,6 +775,7 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
   std::vector<TxView> txs(n);
   for (size_t i = 0; i < n; i++) { int rc = txs[i].parse(blobs[i], lens[i]); if (rc) return rc; }
   Builder B(cache_for(ctx)); std::vector<uint32_t> need_ok;
+  const bool want_out = state.wants_output_ciphertexts();
   for (size_t i = 0; i < n; i++) {
     const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
     std::vector<uint32_t> iC(k), iDs(k), iDr(k);
@@ -758,6 +792,7 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
       B.close_op();
       advance_chain(B, ch, oc, od);
       StateUpdate u; memcpy(u.account.data(), tx.source, 32); memcpy(u.asset.data(), asset, 32); u.role = Sender; u.op_c = oc; u.op_d = od; B.updates.push_back(u);
+      if (want_out) push_output_ops(B, tx, asset, iC, iDs, k);
     }
     for (uint32_t t = 0; t < k; t++) {
       const TransferView& tr = tx.transfers[t]; long long pc, pd; int64_t loaded;
@@ -781,7 +816,7 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
   for (uint32_t p : need_ok) if (!point_ok[p]) return XHE_ERR_DECOMPRESSION;   // "ill-formed ciphertext" (the reference panics)
   for (const StateUpdate& u : B.updates) {
     uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
-    if (!state.update_account_balance(u.account.data(), u.asset.data(), ct, u.role)) return XHE_ERR_STATE;
+    if (!apply_update(state, u.account.data(), u.asset.data(), u.role, u.output, ct)) return XHE_ERR_STATE;
   }
   return XHE_OK;
 }
@@ -802,6 +837,10 @@ void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { ((MockL
 void xheh_ledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { ((MockLedger*)l)->set_multisig_for_account(pk, signers, n, threshold); }
 int xheh_ledger_has_multisig(void* l, const uint8_t* pk) { std::vector<Bytes32> s; uint8_t t; bool p; ((MockLedger*)l)->get_multisig_for_account(pk, &s, &t, &p); return p ? 1 : 0; }
 size_t xheh_ledger_size(void* l) { return ((MockLedger*)l)->balances.size(); }
+// output ciphertexts (set_output_ciphertext, src/tx/verify.rs:60-66): off by default like the reference mock, which drops them
+void xheh_ledger_record_outputs(void* l, int on) { ((MockLedger*)l)->record_outputs = on != 0; }
+size_t xheh_ledger_outputs_size(void* l) { return ((MockLedger*)l)->outputs.size(); }
+size_t xheh_ledger_export_outputs(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; L->outputs.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
 // bulk import of records (pk[32] asset[32] ct[64]) and nonce-0 accounts
 void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; L->balances.reserve(L->balances.size() + n); L->nonces.reserve(L->nonces.size() + n);
   for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; L->set_balance(r, r + 32, r + 64); bool fresh = false; uint64_t* v = L->nonces.insert(r, &fresh); if (fresh) *v = 0; } }

@@ -36,6 +36,11 @@ struct VerificationState {               // src/tx/verify.rs:25-77; every call r
   virtual bool update_account_nonce(const uint8_t account[32], uint64_t nonce) = 0;
   virtual bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) = 0;
   virtual bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) = 0;
+  // set_output_ciphertext (src/tx/verify.rs:60-66, called at 339-340 and 582): the ciphertext get_sender_output_ct
+  // produced for (source, asset), handed over COMPRESSED (64 B; dalek's RistrettoPoint is opaque to a C ABI).  It costs
+  // two extra encodings per (tx, asset) on the device, so it is computed only for states that ask for it.
+  virtual bool wants_output_ciphertexts() const { return false; }
+  virtual bool set_output_ciphertext(const uint8_t /*account*/[32], const uint8_t /*asset*/[32], const uint8_t /*ct*/[64]) { return true; }
   // optional hints (not part of the reference trait): the batch front end announces the lookups it is about to make
   virtual void prefetch_account(const uint8_t[32]) const {}
   virtual void prefetch_balance(const uint8_t[32], const uint8_t[32]) const {}
@@ -99,6 +104,10 @@ class MockLedger : public VerificationState {   // src/lib.rs:106-201
   FlatTable<64, Ct64> balances;                 // key = account || asset
   FlatTable<32, uint64_t> nonces;
   std::unordered_map<Bytes32, std::pair<std::vector<Bytes32>, uint8_t>, Key32Hash> multisig;
+  bool record_outputs = false;                  // the reference mock drops output ciphertexts (src/lib.rs:166-175); tests keep the last one per key
+  FlatTable<64, Ct64> outputs;
+  bool wants_output_ciphertexts() const override { return record_outputs; }
+  bool set_output_ciphertext(const uint8_t account[32], const uint8_t asset[32], const uint8_t ct[64]) override { memcpy(outputs.insert(key(account, asset).data())->data(), ct, 64); return true; }
   static Ct64 key(const uint8_t a[32], const uint8_t b[32]) { Ct64 k; memcpy(k.data(), a, 32); memcpy(k.data() + 32, b, 32); return k; }
   void set_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t ct[64]) { memcpy(balances.insert(key(account, asset).data())->data(), ct, 64); }
   void set_nonce(const uint8_t account[32], uint64_t nonce) { *nonces.insert(account) = nonce; }

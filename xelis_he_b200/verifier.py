@@ -27,6 +27,9 @@ def _lib():
     lib.xheh_ledger_size.restype = sz; lib.xheh_ledger_size.argtypes = [vp]
     lib.xheh_ledger_import.argtypes = [vp, C.c_char_p, sz]
     lib.xheh_ledger_export.restype = sz; lib.xheh_ledger_export.argtypes = [vp, vp, sz]
+    lib.xheh_ledger_record_outputs.argtypes = [vp, C.c_int]
+    lib.xheh_ledger_outputs_size.restype = sz; lib.xheh_ledger_outputs_size.argtypes = [vp]
+    lib.xheh_ledger_export_outputs.restype = sz; lib.xheh_ledger_export_outputs.argtypes = [vp, vp, sz]
     lib.xheh_verify_batch.restype = C.c_int32
     lib.xheh_verify_batch.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double)]
     lib.xheh_verify_batch_partial.restype = C.c_int32
@@ -76,6 +79,18 @@ class Ledger:
         n = self.lib.xheh_ledger_size(self.ptr)
         buf = C.create_string_buffer(128 * max(n, 1))
         self.lib.xheh_ledger_export(self.ptr, buf, 128 * n)
+        raw = buf.raw[:128 * n]
+        return sorted((raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128))
+
+    def record_outputs(self, on=True):
+        """keep the ciphertext of every set_output_ciphertext call (src/tx/verify.rs:339-340, 582); the reference mock drops
+        them, and a state that does not ask for them saves the device two encodings per (tx, asset)"""
+        self.lib.xheh_ledger_record_outputs(self.ptr, 1 if on else 0)
+
+    def dump_outputs(self):
+        n = self.lib.xheh_ledger_outputs_size(self.ptr)
+        buf = C.create_string_buffer(128 * max(n, 1))
+        self.lib.xheh_ledger_export_outputs(self.ptr, buf, 128 * n)
         raw = buf.raw[:128 * n]
         return sorted((raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128))
 
