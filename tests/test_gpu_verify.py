@@ -233,6 +233,24 @@ def test_output_ciphertexts_match_oracle(ctx):
     assert hl.dump_outputs() == sorted(ol.dump_outputs()) and hl.dump() == sorted(ol.dump())
 
 
+def test_plain_amounts_add_as_scalars_not_u64(ctx):
+    """get_sender_output_ct adds fee and burn / contract amounts as Scalars (src/tx/verify.rs:107-144, src/elgamal.rs:353-377):
+    fee = 2^64 - 1 plus a burn of 5 is 2^64 + 4, not 4.  A prover who wraps the sum gets a transaction the reference rejects;
+    verdict, balances (apply_without_verify) and output ciphertext must follow the reference, not the wrapped value."""
+    from xelis_he_b200 import verifier
+    w = scenarios.World(b"amount-overflow")
+    alice = w.account(b"alice", [(NATIVE, 100)])
+    tx = oracle.build_tx(alice, w.ledger, w.rng, fee=2**64 - 1, burn=(NATIVE, 5), balances=[(NATIVE, 100)])
+    code, _ = both(ctx, w, [tx])
+    assert code != OK
+    ol = w.ledger.clone()
+    assert oracle.apply_without_verify(tx, ol) == 0
+    hl = w.host_ledger(); hl.record_outputs()
+    assert verifier.apply_without_verify(ctx, [tx], hl) == 0
+    assert hl.dump() == sorted(ol.dump())
+    assert hl.dump_outputs() == sorted(ol.dump_outputs())
+
+
 def test_device_fiat_shamir_matches_host(ctx):
     """both modes derive the same challenges and batch factors: the partial MSM encodings of a (deliberately invalid) shard
     are byte-identical, not just the verdicts"""

@@ -71,6 +71,16 @@ def test_host_wide_reduction(lib):
         assert o.raw == oracle.sc_reduce_wide(x)
 
 
+def test_constant_2_64_G(lib):
+    """the encoding the host adds as a term when fee + amount reaches 2^64 (get_sender_output_ct adds Scalars)"""
+    import ctypes as C
+    import oracle
+    out = C.create_string_buffer(32)
+    lib.xheh_const_g_2_64(out)
+    G = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")      # RFC 9496 generator
+    assert out.raw == oracle.msm((2 ** 64).to_bytes(32, "little"), G)
+
+
 def test_host_to_bytes_matches_oracle(lib):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))

@@ -163,6 +163,9 @@ HostCache& cache_for(xhe_ctx* ctx) {
   return *c;
 }
 
+// 2^64 * G as a ristretto255 encoding (checked against the oracle and libsodium in tests/test_host_cpu.py)
+const uint8_t ENC_G_2_64[32] = {0xc8, 0x93, 0xf5, 0x39, 0x19, 0x0e, 0xa3, 0x9d, 0x3b, 0x95, 0x98, 0x4c, 0x6e, 0xcf, 0x75, 0x51,
+                                0xbb, 0xd9, 0x2b, 0x3b, 0x7a, 0x63, 0x51, 0x26, 0x14, 0xd6, 0x08, 0x40, 0xea, 0x02, 0x0d, 0x2d};
 struct Builder {
   PinnedVec<uint8_t>& points;           // 32 B each; index 0 = identity
   std::vector<Check> checks;
@@ -179,6 +182,7 @@ struct Builder {
     op_term_off.push_back(0); rp_point_off.push_back(0); rp_chal_off.push_back(0);
   }
   uint32_t add_point(const uint8_t* enc) { uint32_t i = (uint32_t)(points.size() / 32); points.append(enc, 32); return i; }
+  uint32_t g64 = 0; uint32_t g_2_64() { if (!g64) g64 = add_point(ENC_G_2_64); return g64; }   // term for plain amounts that reach 2^64
   uint32_t add_op(long long prev, uint64_t amount) { op_prev.push_back(prev); op_amount.push_back(amount); op_term_off.push_back((uint32_t)op_terms.size()); return (uint32_t)op_prev.size() - 1; }
   void close_op() { op_term_off.back() = (uint32_t)op_terms.size(); }
 };
@@ -205,12 +209,17 @@ bool verify_commitment_assets(const TxView& tx) {   // src/tx/verify.rs:161-199
   else if (tx.type == 2) { for (uint32_t i = 0; i < tx.count; i++) if (!has_commitment_for(tx, tx.body + 32 + 40 * i)) return false; }
   return true;
 }
-uint64_t plain_output_amount(const TxView& tx, const uint8_t* asset) {   // the `Scalar::from(..)` parts of get_sender_output_ct, src/tx/verify.rs:107-144
-  uint64_t a = 0;
-  if (is_zero32(asset)) a += tx.fee;
-  if (tx.type == 1) { if (!memcmp(asset, tx.body, 32)) a += rd64(tx.body + 32); }
-  else if (tx.type == 2) { const uint8_t* hit = nullptr; for (uint32_t i = 0; i < tx.count; i++) if (!memcmp(asset, tx.body + 32 + 40 * i, 32)) hit = tx.body + 32 + 40 * i; if (hit) a += rd64(hit + 32); }
-  return a;   // u64 wrap-around cannot occur for honest inputs; the reference adds Scalars (mod l) -- see DESIGN.md
+// the `Scalar::from(..)` parts of get_sender_output_ct, src/tx/verify.rs:107-144.  The reference adds them as Scalars, so
+// fee + amount can reach 2^64: the low 64 bits are returned and *carry says whether one 2^64 * G term has to be added
+// (at most two u64 summands per asset, so the carry is 0 or 1).
+uint64_t plain_output_amount(const TxView& tx, const uint8_t* asset, bool* carry) {
+  uint64_t a = 0, b = 0;
+  if (is_zero32(asset)) a = tx.fee;
+  if (tx.type == 1) { if (!memcmp(asset, tx.body, 32)) b = rd64(tx.body + 32); }
+  else if (tx.type == 2) { const uint8_t* hit = nullptr; for (uint32_t i = 0; i < tx.count; i++) if (!memcmp(asset, tx.body + 32 + 40 * i, 32)) hit = tx.body + 32 + 40 * i; if (hit) b = rd64(hit + 32); }
+  uint64_t s = a + b;
+  *carry = s < a;
+  return s;
 }
 
 // resolve the (account, asset) balance chain: returns prev references for the commitment / handle ops, registering the
@@ -238,8 +247,10 @@ inline void advance_chain(Builder& B, Chain* c, uint32_t op_c, uint32_t op_d) {
 // the two ops of get_sender_output_ct(asset) (src/tx/verify.rs:107-144) and the state call that hands the result over
 template <typename Idx>
 inline void push_output_ops(Builder& B, const TxView& tx, const uint8_t* asset, const Idx& iC, const Idx& iDs, uint32_t k) {
-  uint32_t oc = B.add_op(OUT_PREV_C, plain_output_amount(tx, asset));
+  bool carry; uint64_t amount = plain_output_amount(tx, asset, &carry);
+  uint32_t oc = B.add_op(OUT_PREV_C, amount);
   for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t]);
+  if (carry) B.op_terms.push_back(B.g_2_64());
   B.close_op();
   uint32_t od = B.add_op(OUT_PREV_D, 0);
   for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t]);
@@ -365,7 +376,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     for (uint32_t q = 0; q < a; q++) {
       const uint8_t* asset = tx.sc + 256 * q; long long pc, pd;
       Chain* ch = touch(tx.source, asset, Sender, &pc, &pd); if (!ch) return 0;
-      uint32_t oc = push_op(pc, plain_output_amount(tx, asset));
+      bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry);
+      if (carry) return 0;                                                      // fee + amount >= 2^64: exact path (adds the 2^64 * G term)
+      uint32_t oc = push_op(pc, amount);
       for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) F.terms.push_back((iT + 3 * t) | 0x80000000u);
       F.term_off.push_back((uint32_t)F.terms.size());
       uint32_t od = push_op(pd, 0);
@@ -386,7 +399,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     if (want_out) {   // output ciphertexts: appended after the ops k_layout indexes (P[7] + 2q are the sender ops)
       for (uint32_t q = 0; q < a; q++) {
         const uint8_t* asset = tx.sc + 256 * q;
-        uint32_t oc = push_op(OUT_PREV_C, plain_output_amount(tx, asset));
+        bool carry; uint32_t oc = push_op(OUT_PREV_C, plain_output_amount(tx, asset, &carry));   // carry == false: checked at the sender op above
         for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) F.terms.push_back(iT + 3 * t);
         F.term_off.push_back((uint32_t)F.terms.size());
         push_op(OUT_PREV_D, 0);
@@ -535,8 +548,10 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
         Chain* ch = resolve_chain(B, state, tx.source, asset, Sender, &pc, &pd, &loaded);
         if (!ch) { host_fail(XHE_ERR_STATE); stop = true; break; }
         if (loaded >= 0) { B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded}); B.checks.push_back({CK_POINT, XHE_ERR_DECOMPRESSION, (uint32_t)loaded + 1}); }
-        uint32_t oc = B.add_op(pc, plain_output_amount(tx, asset));
+        bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry);
+        uint32_t oc = B.add_op(pc, amount);
         for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t] | 0x80000000u);
+        if (carry) B.op_terms.push_back(B.g_2_64() | 0x80000000u);
         B.close_op();
         uint32_t od = B.add_op(pd, 0);
         for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t] | 0x80000000u);
@@ -784,8 +799,10 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
       const uint8_t* asset = tx.sc + 256 * q; long long pc, pd; int64_t loaded;
       Chain* ch = resolve_chain(B, state, tx.source, asset, Sender, &pc, &pd, &loaded); if (!ch) return XHE_ERR_STATE;
       if (loaded >= 0) { need_ok.push_back((uint32_t)loaded); need_ok.push_back((uint32_t)loaded + 1); }
-      uint32_t oc = B.add_op(pc, plain_output_amount(tx, asset));
+      bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry);
+      uint32_t oc = B.add_op(pc, amount);
       for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iC[t] | 0x80000000u);
+      if (carry) B.op_terms.push_back(B.g_2_64() | 0x80000000u);
       B.close_op();
       uint32_t od = B.add_op(pd, 0);
       for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) B.op_terms.push_back(iDs[t] | 0x80000000u);
@@ -880,6 +897,7 @@ void xheh_sha3_512(const uint8_t* m, size_t n, uint8_t* out) { sha3_512(m, n, ou
 void xheh_shake256(const uint8_t* m, size_t n, uint8_t* out, size_t outlen) { shake256(m, n, out, outlen); }
 void xheh_blake3(const uint8_t* m, size_t n, uint8_t* out) { blake3(m, n, out); }
 void xheh_reduce_wide(const uint8_t* in, uint8_t* out) { ScalarL::reduce_wide(in, out); }
+void xheh_const_g_2_64(uint8_t* out32) { memcpy(out32, xhe_host::ENC_G_2_64, 32); }
 int32_t xheh_tx_to_bytes(const uint8_t* blob, size_t len, uint8_t* out, size_t cap, size_t* out_len, size_t* ms_index) {
   TxView tx; int rc = tx.parse(blob, len); if (rc) return rc; std::vector<uint8_t> b; tx.to_bytes(b, ms_index); *out_len = b.size(); if (b.size() <= cap) memcpy(out, b.data(), b.size()); return XHE_OK; }
 }
