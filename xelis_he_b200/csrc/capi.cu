@@ -63,6 +63,9 @@ extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_gens_niels) cudaFree(ctx->d_gens_niels);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_fb_tab) cudaFree(ctx->d_fb_tab);
+  if (ctx->d_fb_dig) cudaFree(ctx->d_fb_dig);
+  if (ctx->d_fb_bsum) cudaFree(ctx->d_fb_bsum);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->h_res) cudaFreeHost(ctx->h_res);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);

@@ -1,6 +1,7 @@
 // kernels_point.cu -- per-point kernels: ristretto255 decode / encode / one-way map, ciphertext add/sub, selftest and
 // the integer-pipe microbenchmarks.  One thread per point; these kernels are bound by the integer-multiply pipe
 // (one invsqrt = 254 S + 11 M ~ 12k limb products per point against 32-128 B of traffic).
+#include <stdlib.h>
 #include "xhe_internal.cuh"
 #include "quad.cuh"
 using namespace xhe;
@@ -167,7 +168,9 @@ static inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n +
 extern "C" int32_t xhe_decompress_dev(xhe_ctx* ctx, const void* d_enc, size_t n, void* d_affine, void* d_niels, void* d_ok) {
   if (!ctx || (n && (!d_enc || !d_ok))) return XHE_E_ARG;
   if (!n) return XHE_OK;
-  k_decompress<<<blocks_for(n, XHE_PT_THREADS), XHE_PT_THREADS, 0, ctx->stream>>>((const uint8_t*)d_enc, n, (uint32_t*)d_affine, (uint32_t*)d_niels, (uint8_t*)d_ok);
+  static const size_t dec_smem = []() { const char* e = getenv("XHE_DEC_SMEM"); size_t v = e ? (size_t)atol(e) : 0;     // residency limiter, see k_msm_accum_tiles
+    if (v > 48 * 1024) cudaFuncSetAttribute(k_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); return v; }();
+  k_decompress<<<blocks_for(n, XHE_PT_THREADS), XHE_PT_THREADS, dec_smem, ctx->stream>>>((const uint8_t*)d_enc, n, (uint32_t*)d_affine, (uint32_t*)d_niels, (uint8_t*)d_ok);
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
 }
 extern "C" int32_t xhe_compress_dev(xhe_ctx* ctx, const void* d_ext, size_t n, void* d_enc) {

@@ -27,6 +27,7 @@ using namespace xhe;
 namespace {
 
 #define MSM_TILE 32   // entries per accumulation work item
+#define XHE_ACCUM_SMEM_DEFAULT 0
 
 struct MsmPlan {
   int c, W;             // window bits, windows
@@ -413,22 +414,31 @@ int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, 
   return XHE_OK;
 }
 
-int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext) {
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum) {
   if (!ctx) return XHE_E_ARG;
   cudaStream_t st = ctx->stream;
-  if (n == 0) { k_msm_empty<<<1, 1, 0, st>>>((uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK; }
+  if (n == 0) { k_msm_empty<<<1, 1, 0, st>>>((uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx); if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st)); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK; }
   if (!d_niels || !d_ws) return XHE_E_ARG;
   MsmPlan p = make_plan(n);
   if (ws_bytes < p.total) { ctx->err = "msm workspace too small"; return XHE_E_ARG; }
   MsmPtrs q = msm_ptrs(p, d_ws, nullptr);
   const size_t m = p.total_buckets;
+  // Residency limiter: the hot kernel takes the whole register file at 4 blocks of 128 threads x 128 registers per SM, so no
+  // block of a concurrently running latency-bound kernel (signatures, reduction tails of the other MSM) can start on an SM
+  // while a wave is resident.  The field multiply saturates the multiplier pipe from 2 warps per sub-partition, so a
+  // dynamic shared-memory request that caps residency at 3 blocks per SM costs the kernel little and leaves a quarter of
+  // the registers to the other streams (XHE_ACCUM_SMEM overrides; 0 = no cap).
+  static const size_t accum_smem = []() { const char* e = getenv("XHE_ACCUM_SMEM"); size_t v = e ? (size_t)atol(e) : (size_t)XHE_ACCUM_SMEM_DEFAULT;
+    if (v > 48 * 1024) { cudaFuncSetAttribute(k_msm_accum_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); }
+    return v; }();
   { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
   switch (g_accum_variant) {
-    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
+    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
   } }
   XHE_LAUNCHED(ctx);
+  if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st));      // the throughput-bound part of this MSM is over: what follows is latency-bound
   k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(q.part_g, q.run_off + p.n_tiles, p.max_runs, q.pstart, q.pcount); XHE_LAUNCHED(ctx);
   k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(q.pcount, m, q.heavy); XHE_LAUNCHED(ctx);
   k_msm_fold_heavy<<<std::min<size_t>(m, 2048), FOLD_THREADS, 0, st>>>(q.part, q.pstart, q.pcount, q.heavy); XHE_LAUNCHED(ctx);
@@ -450,7 +460,7 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
 int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag) {
   if (n && (!d_scalars || !d_niels || !d_ws)) return XHE_E_ARG;
   int32_t rc = xhe_msm_sort(ctx, d_scalars, n, d_ws, ws_bytes, d_bad_flag); if (rc) return rc;
-  return xhe_msm_finish(ctx, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, d_out_ext);
+  return xhe_msm_finish(ctx, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, d_out_ext, nullptr);
 }
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id) {
   return xhe_launch_msm_ex(ctx, d_scalars, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, nullptr, nullptr);

@@ -311,6 +311,7 @@ __global__ void k_pow2_table(uint32_t* __restrict__ tab) {
 #define RPG_WARPS 4
 #define RPG_THREADS (32 * RPG_WARPS)
 #define RPG_CHUNK 128
+#define XHE_RPG_SMEM_EXTRA_DEFAULT 0
 __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, uint32_t der_stride, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
                                                          uint32_t Nmax, uint32_t n_rows, uint32_t* __restrict__ part) {
   extern __shared__ uint32_t sm[];           // per warp: t[128] then yl[128], 8 words each (Montgomery form)
@@ -357,6 +358,104 @@ __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restr
         st_sc(my + 8 * i, sc_add(g0, gi)); st_sc(my + 8 * (Nmax + i), sc_add(h0, hi));
       }
     }
+  }
+}
+
+// ---- fixed-base MSM over the static range-proof generators -------------------------------------------------------------
+// The 2 * 64 * m_max + 2 generators of the range-proof mega-check (G_vec, H_vec, B, B_blinding; bulletproofs' BP_GENS /
+// PC_GENS, src/proofs.rs:19-22) never change, so their MSM needs no doublings: with T[g][j] = 2^(8j) * P_g precomputed
+// (affine Niels, 32 entries per generator), sum s_g P_g = sum_{g,j} d_{g,j} T[g][j] for the signed base-256 digits d of
+// s_g -- ONE 8-bit Pippenger window over 32 n entries: 128 buckets, no Horner chain.  The generic pipeline spent 0.6 ms
+// here on a 10 k batch (258 points: 13 latency-bound launches, 248 dependent doublings); this one is three small kernels.
+#define XHE_FB_MAX_PARTIES 64      // table = (2 + 128 * parties) * 32 * 96 B = 25 MB at 64 parties; larger contexts keep the generic MSM
+#define FB_CHUNK 4096
+__global__ void __launch_bounds__(64) k_fb_build(const uint32_t* __restrict__ gens_niels, uint32_t n_gens, uint32_t* __restrict__ tab) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_gens) return;
+  ge_niels q; ld_niels(q, gens_niels + 24 * (size_t)g);
+  ge p = ge_from_niels(q);
+  for (int j = 0; j < 32; j++) {
+    fe zi = fe_invert(p.Z);
+    ge_aff a; a.x = fe_mul(p.X, zi); a.y = fe_mul(p.Y, zi);
+    st_niels(tab + 24 * ((size_t)g * 32 + j), niels_from_affine(a));
+    if (j < 31) for (int k = 0; k < 8; k++) p = ge_double(p);
+  }
+}
+// signed base-256 digits in [-127, 128] of n canonical scalars (< l < 2^253, so the top digit absorbs the last carry)
+__global__ void __launch_bounds__(128) k_fb_digits(const uint32_t* __restrict__ sc_in, uint32_t n, int16_t* __restrict__ dig) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sc s; ld_sc_rw(s, sc_in + 8 * (size_t)i);
+  uint32_t carry = 0;
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    uint32_t v = ((s.v[j >> 2] >> ((j & 3) * 8)) & 0xffu) + carry;
+    carry = v > 128u ? 1u : 0u;
+    dig[32 * (size_t)i + j] = (int16_t)(carry ? (int)v - 256 : (int)v);
+  }
+}
+// static scalar index -> row of the generator table: [0, Nmax) G_vec, [Nmax, 2 Nmax) H_vec, then B (= G) and B_blinding (= H)
+__device__ __forceinline__ uint32_t fb_gen_row(uint32_t i, uint32_t Nmax, uint32_t cap) {
+  return i < Nmax ? 2u + i : (i < 2u * Nmax ? 2u + 64u * cap + (i - Nmax) : i - 2u * Nmax);
+}
+// one block per bucket b (entries whose |digit| is b + 1): the threads scan the digit array a chunk at a time and queue the
+// matches in shared memory, so that every queued entry costs exactly one mixed addition on one lane (no lane idles through
+// another lane's addition); the 128 per-thread sums are then folded by a shared-memory tree.
+__global__ void __launch_bounds__(128) k_fb_buckets(const int16_t* __restrict__ dig, uint32_t n_entries, const uint32_t* __restrict__ tab, uint32_t Nmax, uint32_t cap, uint32_t* __restrict__ bsum) {
+  __shared__ __align__(16) uint32_t red[128 * 32]; __shared__ uint32_t queue[FB_CHUNK]; __shared__ uint32_t qn;   // red: 128-bit accesses
+  const int want = (int)blockIdx.x + 1;
+  ge acc = ge_identity();
+  for (uint32_t base = 0; base < n_entries; base += FB_CHUNK) {
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+    const uint32_t end = min(base + FB_CHUNK, n_entries);
+    for (uint32_t e = base + threadIdx.x; e < end; e += 128) {
+      const int d = dig[e];
+      if ((d < 0 ? -d : d) == want) queue[atomicAdd(&qn, 1u)] = e | (d < 0 ? 0x80000000u : 0u);
+    }
+    __syncthreads();
+    const uint32_t cnt = qn;
+    for (uint32_t qi = threadIdx.x; qi < cnt; qi += 128) {
+      const uint32_t v = queue[qi], e = v & 0x7fffffffu;
+      ge_niels t; ld_niels(t, tab + 24 * ((size_t)fb_gen_row(e >> 5, Nmax, cap) * 32 + (e & 31u)));
+      acc = ge_madd(acc, niels_cneg(t, (v >> 31) != 0));
+    }
+    __syncthreads();
+  }
+  st_ge(red + 32 * threadIdx.x, acc);
+  __syncthreads();
+  for (int stride = 64; stride >= 1; stride >>= 1) {
+    if ((int)threadIdx.x < stride) { ge a, b; ld_ge(a, red + 32 * threadIdx.x); ld_ge(b, red + 32 * (threadIdx.x + stride)); st_ge(red + 32 * threadIdx.x, ge_add(a, b)); }
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) bsum[32 * (size_t)blockIdx.x + threadIdx.x] = red[threadIdx.x];
+}
+__device__ __forceinline__ ge fb_shfl_down(const ge& p, int d) {
+  ge r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], d); r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], d);
+    r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], d); r.T.v[i] = __shfl_down_sync(0xffffffffu, p.T.v[i], d);
+  }
+  return r;
+}
+// sum_b (b + 1) S_b over the 128 bucket sums by one warp: lane l folds buckets 4l..4l+3 into (run, wsum), a warp-shuffle
+// suffix scan gives sum_l l * run_l (the combination k_msm_nodes uses), out = 4 * that + sum wsum + sum run
+__global__ void __launch_bounds__(32) k_fb_reduce(const uint32_t* __restrict__ bsum, uint32_t* __restrict__ out_ext) {
+  const uint32_t lane = threadIdx.x;
+  ge run = ge_identity(), wsum = ge_identity(), s;
+  for (int t = 3; t >= 0; t--) { ld_ge(s, bsum + 32 * (size_t)(4 * lane + t)); run = ge_add(run, s); if (t >= 1) wsum = ge_add(wsum, run); }
+  ge suf = run;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) { ge t = fb_shfl_down(suf, d); ge a = ge_add(suf, t); bool take = lane + d < 32; suf.X = fe_select(suf.X, a.X, take); suf.Y = fe_select(suf.Y, a.Y, take); suf.Z = fe_select(suf.Z, a.Z, take); suf.T = fe_select(suf.T, a.T, take); }
+  ge A = suf;
+  if (lane == 0) A = ge_identity();
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) { A = ge_add(A, fb_shfl_down(A, d)); wsum = ge_add(wsum, fb_shfl_down(wsum, d)); }
+  if (lane == 0) {
+    A = ge_double(ge_double(A));
+    ge r = ge_add(ge_add(wsum, A), suf);
+    st_fe(out_ext, fe_freeze(r.X)); st_fe(out_ext + 8, fe_freeze(r.Y)); st_fe(out_ext + 16, fe_freeze(r.Z)); st_fe(out_ext + 24, fe_freeze(r.T));
   }
 }
 
@@ -485,6 +584,9 @@ extern "C" int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n,
   return XHE_OK;
 }
 
+// dynamic shared memory of k_rp_gens: its tables, plus XHE_RPG_SMEM_EXTRA bytes that only cap how many of its blocks an SM holds
+static size_t rpg_smem() { static const size_t v = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32 + (getenv("XHE_RPG_SMEM_EXTRA") ? (size_t)atol(getenv("XHE_RPG_SMEM_EXTRA")) : (size_t)XHE_RPG_SMEM_EXTRA_DEFAULT); return v; }
+
 // device-side image of one batch: every pointer lives in the ctx arena
 struct DeviceBatch {
   xhe_batch h;                       // scalar fields (counts) copied from the host description; pointers unused
@@ -519,7 +621,8 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   D.n_chal = b->n_rp ? b->rp_chal_off[b->n_rp] : 0;
   // rows of per-warp partial sums for k_rp_gens: one resident wave of warps, capped so the partial buffer stays within 64 MiB
   static int gens_blocks_per_sm = 0;
-  if (!gens_blocks_per_sm) { int nb = 0; XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32)); gens_blocks_per_sm = nb > 0 ? nb : 1; }
+  if (!gens_blocks_per_sm) { int nb = 0; if (rpg_smem() > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rpg_smem()));
+    XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, rpg_smem())); gens_blocks_per_sm = nb > 0 ? nb : 1; }
   D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS), std::max<size_t>(64, ((size_t)64 << 20) / (64 * (size_t)D.Nmax))) : 0;
   D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_dyn); D.ws_static = xhe_msm_workspace_bytes(ctx, D.n_range - D.n_dyn);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
@@ -622,7 +725,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   //   s_rp : [transcripts] range scalars -> static-generator weights -> MSM over the static generators -> [s_dyn] combine
   //   s_dyn: [range scalars] sort -> [decompress] gather -> MSM over the proofs' own points
   cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2], s_dyn = serial ? main_st : ctx->aux[3];
-  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8];
+  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8], e_acc_sigma = ctx->ev[9], e_acc_dyn = ctx->ev[10];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
   const uint32_t np = b->n_eq + b->n_val;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
@@ -705,27 +808,8 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
       rc = xhe_msm_sort(ctx, D.d_range_sc, n_dyn, D.d_ws2, D.ws_range, D.d_results + 97); if (rc) return rc;
       XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_dec, 0));
       k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, s_dyn>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
-      rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts); if (rc) return rc; }
+      rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts, e_acc_dyn); if (rc) return rc; }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_dyn, s_dyn));
-    // s_rp
-    ctx->stream = s_rp;
-    { cudaStream_t st = s_rp;
-      const size_t smem = (size_t)RPG_WARPS * 2 * RPG_CHUNK * 32;
-      { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // 6 mod-l products per generator index, 64*m indices per proof
-        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, D.der_stride, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
-      { const uint32_t cols = 2 * Nmax, gy = cols > 32768u ? 32768u : cols;     // cols = 128 * m_max, a power of two
-        k_reduce_scalars<<<dim3(1, gy, cols / gy), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx); }
-      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
-      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
-      k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
-      k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
-      k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
-      { XheTimed t(ctx, "msm_range_static", 0);
-        rc = xhe_launch_msm_ex(ctx, D.d_range_sc + 8 * n_dyn, D.d_range_niels + 24 * n_dyn, n_static, D.d_ws3, D.ws_static, nullptr, nullptr, D.d_rparts + 32, D.d_results + 97); if (rc) return rc; }
-      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dyn, 0));
-      k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
-    }
-    XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
   }
   // ---- main: sigma MSM over the gathered operands (inputs and balance-chain outputs)
   ctx->stream = main_st;
@@ -735,8 +819,50 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     if (np) { k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx); }
     k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, D.d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
     XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
-    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16); if (rc) return rc;
+    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, e_acc_sigma); if (rc) return rc;
   }
+  // ---- s_rp: weights of the static generators and their fixed-base MSM.  Nothing needs the result before the final
+  // combination, and k_rp_gens is a one-warp-per-proof kernel whose resident blocks take most of the register file: issued
+  // early it keeps the blocks of both MSM accumulations off the SMs until it has drained (timeline in DESIGN.md 4.5).  It
+  // therefore waits until the two accumulations have been issued and runs beside their latency-bound reduction tails.
+  if (b->n_rp) {
+    const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
+    static const bool defer_gens = getenv("XHE_GENS_EARLY") == nullptr;
+    if (defer_gens && !serial) { XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_sigma, 0)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_dyn, 0)); }
+    // s_rp
+    ctx->stream = s_rp;
+    { cudaStream_t st = s_rp;
+      const size_t smem = rpg_smem();
+      { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // 6 mod-l products per generator index, 64*m indices per proof
+        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, D.der_stride, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
+      { const uint32_t cols = 2 * Nmax, gy = cols > 32768u ? 32768u : cols;     // cols = 128 * m_max, a power of two
+        k_reduce_scalars<<<dim3(1, gy, cols / gy), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx); }
+      k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);
+      k_reduce_scalars<<<dim3(1, 2), 256, 0, st>>>(D.d_rgh_part, 32, 2, 1, D.d_range_sc + 8 * (n_dyn + 2 * (size_t)Nmax), 2); XHE_LAUNCHED(ctx);
+      static const bool fb_off = getenv("XHE_NO_FIXED_BASE") != nullptr;          // diagnostics: force the generic MSM
+      if (ctx->party_capacity <= XHE_FB_MAX_PARTIES && !fb_off) {
+        XheTimed t(ctx, "msm_range_static", 0);
+        if (!ctx->d_fb_tab) {        // first batch with range proofs on this context: build the table (about 1.5 ms, once)
+          const size_t ng = ctx->n_gens;
+          XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_tab, 96 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_dig, 2 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_bsum, 128 * 128));
+          k_fb_build<<<nblk(ng, 64), 64, 0, st>>>(gens, (uint32_t)ng, (uint32_t*)ctx->d_fb_tab); XHE_LAUNCHED(ctx);
+        }
+        k_fb_digits<<<nblk(n_static, 128), 128, 0, st>>>(D.d_range_sc + 8 * n_dyn, (uint32_t)n_static, (int16_t*)ctx->d_fb_dig); XHE_LAUNCHED(ctx);
+        k_fb_buckets<<<128, 128, 0, st>>>((const int16_t*)ctx->d_fb_dig, (uint32_t)(32 * n_static), (const uint32_t*)ctx->d_fb_tab, Nmax, ctx->party_capacity, (uint32_t*)ctx->d_fb_bsum); XHE_LAUNCHED(ctx);
+        k_fb_reduce<<<1, 32, 0, st>>>((const uint32_t*)ctx->d_fb_bsum, D.d_rparts + 32); XHE_LAUNCHED(ctx);
+      } else {
+        k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * 2, 24 * Nmax, D.d_range_niels + 24 * n_dyn); XHE_LAUNCHED(ctx);
+        k_copy_words<<<nblk(24 * (size_t)Nmax, 256), 256, 0, st>>>(gens + 24 * (2 + 64 * (size_t)ctx->party_capacity), 24 * Nmax, D.d_range_niels + 24 * (n_dyn + Nmax)); XHE_LAUNCHED(ctx);
+        k_copy_words<<<1, 64, 0, st>>>(gens, 48, D.d_range_niels + 24 * (n_dyn + 2 * (size_t)Nmax)); XHE_LAUNCHED(ctx);
+        XheTimed t(ctx, "msm_range_static", 0);
+        rc = xhe_launch_msm_ex(ctx, D.d_range_sc + 8 * n_dyn, D.d_range_niels + 24 * n_dyn, n_static, D.d_ws3, D.ws_static, nullptr, nullptr, D.d_rparts + 32, D.d_results + 97); if (rc) return rc;
+      }
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dyn, 0));
+      k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
+    }
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
+  }
+  ctx->stream = main_st;
   // ---- join
   if (b->n_sigs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sig, 0));
   if (b->n_rp) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_rp, 0));

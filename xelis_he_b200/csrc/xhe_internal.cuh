@@ -20,6 +20,9 @@ struct xhe_ctx {
   // generator tables (device): affine Niels, index 0 = G, 1 = H, then G_vec[party][64], H_vec[party][64]
   void* d_gens_niels = nullptr;   // (2 + 128 * party_capacity) * 96 B
   size_t n_gens = 0;
+  // fixed-base table of the range-proof generators (verify.cu, k_fb_*): entry (g, j) = 2^(8j) * gens[g], affine Niels;
+  // built on the first batch with range proofs when party_capacity <= XHE_FB_MAX_PARTIES, else the generic MSM is used
+  void* d_fb_tab = nullptr; void* d_fb_dig = nullptr; void* d_fb_bsum = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;       // grow-only device scratch for host-buffer entry points
   void* h_pinned = nullptr; size_t pinned_bytes = 0;         // grow-only pinned staging
   // optional CUDA-event timing of the main kernels (bench.py roofline): accumulated since the last reset
@@ -124,5 +127,5 @@ __device__ __forceinline__ void st_ge(uint32_t* p, const ge& g) { st_fe(p, g.X);
 
 // kernel launchers implemented across the .cu files
 int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, size_t ws_bytes, void* d_bad_flag);
-int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext);
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum = nullptr);
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id);
