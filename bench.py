@@ -435,7 +435,7 @@ def main():
             for n, v in leaf.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
     roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide, "share_of_step_work": leaf[dom]["alg_lp_per_step"] / max(1.0, sum(v["alg_lp_per_step"] for n, v in leaf.items())),
                 "peak_source": "measured live: IMAD.WIDE.U32 Rd64, Ra, Rb, RZ microkernel (two vector multiplicands, both result words live; SASS checked: IMAD.WIDE only)", "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": ach / peak_chain,
-                "traffic": 14.9e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress launch of this workload (profiles/r01_ncu_full_top_kernels.md); algorithmic bytes are 65.6 MB (32 B in, 160 B out per point): the outputs stay in the 126 MB L2",
+                "traffic": 13.39e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress launch of this workload (ncu --set full, profiles/r01_ncu_full_v3.md); algorithmic bytes are 65.6 MB (32 B in, 160 B out per point): the outputs stay in the 126 MB L2",
                 "per_kernel_isolated": work, "note": "every 32x32->64 form (IMAD.WIDE, IMAD.WIDE.X carry chains, IMAD.HI) issues at 4 cycles per warp instruction per SM sub-partition on sm_100a, half the rate of the 32-bit IMAD; bench lines before r01 v5 divided by an 18.4 T/s figure that turned out to measure IADD3 pairs (DESIGN.md 4.1)"}
     line = {"metric": "verified TX/s (10k-transfer batch)", "value": value, "unit": "TX/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
