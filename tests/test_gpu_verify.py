@@ -284,6 +284,37 @@ def test_verdict_partials_combine(ctx):
     assert flag.value == 1 and bytes(out) == bytes(32)
 
 
+def test_fixed_base_and_generic_static_msm_agree(ctx):
+    """The MSM over the static range-proof generators runs from a fixed-base table on contexts of up to 64 parties and
+    through the generic Pippenger pipeline above: for the same shard (same seed, so the same batch factors) the partial
+    range / sigma encodings must be byte-identical -- including a shard whose range sum is NOT the identity."""
+    import xelis_he_b200 as xhe
+    from xelis_he_b200 import verifier
+    b = oracle.mint_transfers(91, 12, 2, 6, threads=8)               # m = 8
+    big = xhe.Ctx(0, party_capacity=128)                              # > 64: generic pipeline
+    try:
+        for blobs in (list(b.blobs), list(b.blobs[:5])):
+            outs = []
+            for c in (ctx, big):
+                for mode in ("host", "fast"):
+                    hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+                    code, idx, sig, rng, _ = verifier.verify_batch_partial(c, blobs, hl, seed=SEED, fiat_shamir=mode)
+                    assert (code, idx) == (OK, -1)
+                    outs.append((sig, rng))
+            assert outs[0] == outs[2] and outs[1] == outs[3], "fixed-base and generic static MSM disagree"
+        # a deliberately broken range proof (re-signing is not needed for the partial sums: signatures are checked apart)
+        bad = list(b.blobs[:3]); raw = bytearray(bad[1])
+        k, rp0 = 6, 64 + 324 * 6
+        raw[rp0 + 128] ^= 1; bad[1] = bytes(raw)
+        res = []
+        for c in (ctx, big):
+            hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
+            res.append(verifier.verify_batch_partial(c, bad, hl, seed=SEED, fiat_shamir="host")[:4])
+        assert res[0] == res[1] and res[0][3] != bytes(32)
+    finally:
+        big.close()
+
+
 def test_large_batch_size_independent_properties(ctx):
     """2,000-transfer batch (the bench workload's shape at a size the oracle still checks in seconds): accept through the
     fast path, every updated ciphertext equal to the oracle's apply_without_verify, and a tampered transaction deep inside

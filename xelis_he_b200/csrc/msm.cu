@@ -58,7 +58,8 @@ MsmPlan make_plan(size_t n) {
   }
   if (n <= 4096 && bc < 8) bc = 8;   // tiny inputs are pure latency: fewer windows shorten the per-window stages and the Horner chain
   p.c = bc; p.W = (254 + bc - 1) / bc; p.B = 1u << (bc - 1); p.total_buckets = (size_t)p.W * p.B;
-  p.seg_log = std::min(3, bc - 1);
+  static const int seg_env = getenv("XHE_MSM_SEG_LOG") ? atoi(getenv("XHE_MSM_SEG_LOG")) : 3;   // buckets per running-sum thread = 2^seg_log
+  p.seg_log = std::min(seg_env, bc - 1);
   size_t o = 0;
   p.off_counts = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
   p.off_offsets = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
