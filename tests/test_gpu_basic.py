@@ -114,6 +114,72 @@ def test_ct_update_parity(ctx):
     assert got[64:128] == bytes(64)   # P - P = identity encoding
 
 
+def _dev_points(ctx, torch, n, seed):
+    """n pseudo-random valid ristretto255 encodings on the device (one-way map of seeded bytes)"""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    uni = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=g)
+    enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    assert ctx.lib.xhe_from_uniform_dev(ctx.p, uni.data_ptr(), n, enc.data_ptr()) == 0
+    return enc
+
+
+def test_ct_update_resident_parity(ctx):
+    """config 4, resident layout (the HBM-bound kernel): planar extended balances +/- planar affine-Niels deltas, updated
+    in place; re-encoded results must equal the compressed-I/O kernel and the CPU oracle byte for byte."""
+    import torch
+    import oracle
+    lib = ctx.lib
+    n = 2048; npts = 2 * n
+    bal_enc = _dev_points(ctx, torch, npts, 11); del_enc = _dev_points(ctx, torch, npts, 12)
+    sub = (torch.arange(n, device="cuda") % 3 == 0).to(torch.uint8)
+    aff = torch.empty((npts, 16), dtype=torch.int32, device="cuda"); ok = torch.empty((npts,), dtype=torch.uint8, device="cuda")
+    niels = torch.empty((npts, 24), dtype=torch.int32, device="cuda"); aff_d = torch.empty((npts, 16), dtype=torch.int32, device="cuda")
+    assert lib.xhe_decompress_dev(ctx.p, bal_enc.data_ptr(), npts, aff.data_ptr(), None, ok.data_ptr()) == 0
+    assert lib.xhe_decompress_dev(ctx.p, del_enc.data_ptr(), npts, aff_d.data_ptr(), niels.data_ptr(), ok.data_ptr()) == 0
+    torch.cuda.synchronize()
+    a = aff.cpu().numpy().view(np.uint32)
+    xs, ys = _ints(a[:, :8]), _ints(a[:, 8:])
+    T = _words([x * y % P for x, y in zip(xs, ys)])
+    one = np.zeros((npts, 8), dtype=np.uint32); one[:, 0] = 1
+    planar = np.stack([a[:, :8], a[:, 8:], one, T])                                  # [X|Y|Z|T][2n][8]
+    bal = torch.from_numpy(planar.view(np.int32).copy()).cuda()
+    dn = niels.view(npts, 3, 8).permute(1, 0, 2).contiguous()                        # [ypx|ymx|t2d][2n][8]
+    assert lib.xhe_ct_update_resident_dev(ctx.p, bal.data_ptr(), dn.data_ptr(), sub.data_ptr(), n) == 0
+    ext = bal.permute(1, 0, 2).contiguous()                                           # back to X,Y,Z,T per point
+    got = torch.empty((npts, 32), dtype=torch.uint8, device="cuda")
+    assert lib.xhe_compress_dev(ctx.p, ext.data_ptr(), npts, got.data_ptr()) == 0
+    out = torch.empty((n, 64), dtype=torch.uint8, device="cuda"); okb = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    assert lib.xhe_ct_update_dev(ctx.p, bal_enc.data_ptr(), del_enc.data_ptr(), sub.data_ptr(), n, out.data_ptr(), okb.data_ptr()) == 0
+    torch.cuda.synchronize()
+    got_b = bytes(got.cpu().numpy().tobytes()); out_b = bytes(out.cpu().numpy().tobytes())
+    assert int(okb.sum()) == n and got_b == out_b
+    want, ok_ref = oracle.ct_update(bytes(bal_enc.cpu().numpy().tobytes()), bytes(del_enc.cpu().numpy().tobytes()), bytes(sub.cpu().numpy().tobytes()))
+    assert all(ok_ref) and got_b == want
+
+
+def test_ct_update_full_size_round_trip(ctx):
+    """config 4 at BASELINE's size (1,048,576 accounts, compressed I/O): (bal +/- delta) -/+ delta == bal byte for byte
+    (encodings are canonical), every account valid, and a 1,024-account sample equals the oracle."""
+    import torch
+    import oracle
+    lib = ctx.lib
+    n = 1 << 20
+    bal = _dev_points(ctx, torch, 2 * n, 21).view(n, 64); delta = _dev_points(ctx, torch, 2 * n, 22).view(n, 64)
+    g = torch.Generator(device="cuda"); g.manual_seed(23)
+    sub = torch.randint(0, 2, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    out = torch.empty((n, 64), dtype=torch.uint8, device="cuda"); back = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    ok = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    assert lib.xhe_ct_update_dev(ctx.p, bal.data_ptr(), delta.data_ptr(), sub.data_ptr(), n, out.data_ptr(), ok.data_ptr()) == 0
+    torch.cuda.synchronize(); assert int(ok.sum()) == n
+    inv = 1 - sub
+    assert lib.xhe_ct_update_dev(ctx.p, out.data_ptr(), delta.data_ptr(), inv.data_ptr(), n, back.data_ptr(), ok.data_ptr()) == 0
+    torch.cuda.synchronize(); assert int(ok.sum()) == n
+    assert torch.equal(back, bal) and not torch.equal(out, bal)
+    idx = torch.arange(0, n, n // 1024, device="cuda")[:1024]
+    want, ok_ref = oracle.ct_update(bytes(bal[idx].cpu().numpy().tobytes()), bytes(delta[idx].cpu().numpy().tobytes()), bytes(sub[idx].cpu().numpy().tobytes()))
+    assert all(ok_ref) and bytes(out[idx].cpu().numpy().tobytes()) == want
+
+
 def test_int_peak_reports(ctx):
     rates = [ctx.int_peak(w) for w in range(3)]
     print("int peak (inst/s): IMAD.lo %.3e IMAD.HI %.3e IMAD.WIDE %.3e" % tuple(rates))
