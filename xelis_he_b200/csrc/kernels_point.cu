@@ -94,7 +94,8 @@ __global__ void k_and_pairs(const uint8_t* __restrict__ ok_pt, size_t n, uint8_t
 // [X | Y | Z | T][2n points][8 limbs]; deltas as affine Niels planar [ypx | ymx | t2d][2n][8].  One thread per point:
 // 7 loads + 4 stores of 32 B, fully coalesced (adjacent lanes touch adjacent 32-byte sectors).  HBM-bound:
 // 128 B read + 128 B written + 96 B read = 352 B per point = 704 B per account.
-__global__ void __launch_bounds__(256) k_ct_update_resident(uint32_t* __restrict__ bal, const uint32_t* __restrict__ delta, const uint8_t* __restrict__ sub, size_t n_points) {
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_ct_update_resident(uint32_t* __restrict__ bal, const uint32_t* __restrict__ delta, const uint8_t* __restrict__ sub, size_t n_points) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   ge p; ge_niels q;
@@ -210,7 +211,10 @@ extern "C" int32_t xhe_ct_update_dev(xhe_ctx* ctx, const void* d_bal, const void
 extern "C" int32_t xhe_ct_update_resident_dev(xhe_ctx* ctx, void* d_bal_ext, const void* d_delta_niels, const void* d_sub, size_t n) {
   if (!ctx || (n && (!d_bal_ext || !d_delta_niels || !d_sub))) return XHE_E_ARG;
   if (!n) return XHE_OK;
-  k_ct_update_resident<<<blocks_for(2 * n, 256), 256, 0, ctx->stream>>>((uint32_t*)d_bal_ext, (const uint32_t*)d_delta_niels, (const uint8_t*)d_sub, 2 * n);
+  static const int tpb = getenv("XHE_CTRES_TPB") ? atoi(getenv("XHE_CTRES_TPB")) : 128;     // experiment knob: threads per block (x10 + min blocks/SM for the capped variants).  Measured on B200, 1 M accounts, L2 flushed (tools/ct_resident_bench.py): 256 -> 0.161 ms, 128 -> 0.156, 64 -> 0.155, 128 capped at 80 registers -> 0.163, at 64 registers -> 0.199
+#define XHE_CTRES(T, M) k_ct_update_resident<T, M><<<blocks_for(2 * n, T), T, 0, ctx->stream>>>((uint32_t*)d_bal_ext, (const uint32_t*)d_delta_niels, (const uint8_t*)d_sub, 2 * n)
+  if (tpb == 64) XHE_CTRES(64, 1); else if (tpb == 128) XHE_CTRES(128, 1); else if (tpb == 1286) XHE_CTRES(128, 6); else if (tpb == 1288) XHE_CTRES(128, 8); else XHE_CTRES(256, 1);
+#undef XHE_CTRES
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
 }
 extern "C" int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {

@@ -442,7 +442,7 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
   if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st));      // the throughput-bound part of this MSM is over: what follows is latency-bound
   k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(q.part_g, q.run_off + p.n_tiles, p.max_runs, q.pstart, q.pcount); XHE_LAUNCHED(ctx);
   k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(q.pcount, m, q.heavy); XHE_LAUNCHED(ctx);
-  k_msm_fold_heavy<<<std::min<size_t>(m, 2048), FOLD_THREADS, 0, st>>>(q.part, q.pstart, q.pcount, q.heavy); XHE_LAUNCHED(ctx);
+  k_msm_fold_heavy<<<std::min<size_t>(m, 2 * (size_t)ctx->sm_count), FOLD_THREADS, 0, st>>>(q.part, q.pstart, q.pcount, q.heavy); XHE_LAUNCHED(ctx);
   size_t n_nodes = m >> p.seg_log;
   k_msm_seg<<<nblk(n_nodes, 128), 128, 0, st>>>(q.part, q.pstart, q.pcount, n_nodes, p.seg_log, q.nodes_a); XHE_LAUNCHED(ctx);
   uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;
