@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) k_raw(uint32_t* out, const uint32_t* in, 
   uint32_t av[8], bv[8];
   unsigned long long w[8];
   uint32_t lo[8], hi[8];
+  const double dA = 1.0 + (double)(in[1] & 0xff) * 1e-9, dB = (double)(in[2] & 0xff) * 1e-3;
 #pragma unroll
   for (int k = 0; k < 8; k++) { av[k] = in[(threadIdx.x + k) & 63] | 1u; bv[k] = in[(threadIdx.x + 3 * k + 1) & 63] | 1u; w[k] = a + k; lo[k] = a + k; hi[k] = k; }
   for (int it = 0; it < iters; it++) {
@@ -70,6 +71,9 @@ __global__ void __launch_bounds__(256) k_raw(uint32_t* out, const uint32_t* in, 
                      "addc.cc.u32 %4, %4, %12; addc.cc.u32 %5, %5, %13; addc.cc.u32 %6, %6, %14; addc.u32 %7, %7, %15;"
                      : "+r"(hi[0]), "+r"(hi[1]), "+r"(hi[2]), "+r"(hi[3]), "+r"(hi[4]), "+r"(hi[5]), "+r"(hi[6]), "+r"(hi[7])
                      : "r"(av[0]), "r"(av[1]), "r"(av[2]), "r"(av[3]), "r"(av[4]), "r"(av[5]), "r"(av[6]), "r"(av[7]));
+      } else if (WHICH == 10) {  // DFMA (FP64 pipe), 8 dependent chains: the instruction a 52-bit-limb multiply would use (not taken: north_star)
+#pragma unroll
+        for (int k = 0; k < 8; k++) { double x = __longlong_as_double((long long)w[k]); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(dA), "d"(dB)); w[k] = (unsigned long long)__double_as_longlong(x); }
       } else if (WHICH == 9) {   // accumulate form written in C (ptxas keeps IMAD.WIDE Rd, Ra, Rb, Rc64 here)
 #pragma unroll
         for (int k = 0; k < 8; k++) w[k] += (unsigned long long)(uint32_t)w[(k + 1) & 7] * bv[k];
@@ -153,10 +157,10 @@ int main() {
   uint32_t *d_in, *d_out; CK(cudaMalloc(&d_in, sizeof h)); CK(cudaMalloc(&d_out, (size_t)sms * 8 * 256 * 32)); CK(cudaMemcpy(d_in, h, sizeof h, cudaMemcpyHostToDevice));
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_mhz\": %.0f,\n \"raw_T_per_s\": {", prop.name, sms, g_clock_hz / 1e6);
   const int iters = 2048, blocks = sms * 8, threads = 256;
-  const char* names[10] = {"acc_uniform_b", "acc_two_vector", "acc_shared_a", "prod_rz_two_vector", "prod_rz_plus_2_iadd3", "carry_chain", "iadd3_chain", "prod_rz_shared_a", "carry_chain_plus_iadd3", "acc_c_code"};
+  const char* names[11] = {"acc_uniform_b", "acc_two_vector", "acc_shared_a", "prod_rz_two_vector", "prod_rz_plus_2_iadd3", "carry_chain", "iadd3_chain", "prod_rz_shared_a", "carry_chain_plus_iadd3", "acc_c_code", "dfma_f64"};
   // multiply (or add) instructions per thread per iteration
-  const double per_iter[10] = {32, 32, 32, 32, 32, 32, 64, 32, 16, 32};
-  for (int w = 0; w < 10; w++) {
+  const double per_iter[11] = {32, 32, 32, 32, 32, 32, 64, 32, 16, 32, 32};
+  for (int w = 0; w < 11; w++) {
     float ms = 0;
     switch (w) {
       case 0: ms = time_kernel([&] { k_raw<0><<<blocks, threads>>>(d_out, d_in, iters); }); break;
@@ -169,6 +173,7 @@ int main() {
       case 7: ms = time_kernel([&] { k_raw<7><<<blocks, threads>>>(d_out, d_in, iters); }); break;
       case 8: ms = time_kernel([&] { k_raw<8><<<blocks, threads>>>(d_out, d_in, iters); }); break;
       case 9: ms = time_kernel([&] { k_raw<9><<<blocks, threads>>>(d_out, d_in, iters); }); break;
+      case 10: ms = time_kernel([&] { k_raw<10><<<blocks, threads>>>(d_out, d_in, iters); }); break;
     }
     double rate = (double)blocks * threads * iters * per_iter[w] / (ms * 1e-3);
     double cyc = ms * 1e-3 * g_clock_hz / ((double)blocks * (threads / 32) / (sms * 4.0) * iters * per_iter[w]);   // cycles per warp instruction per SMSP
