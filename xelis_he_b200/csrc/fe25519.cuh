@@ -198,200 +198,6 @@ XHE_HD void mul4w(uint32_t* out, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t
 #endif
 }
 
-// chain with one (a_k, b_k) product per slot: acc[2k], acc[2k+1] += a_k * b_k for k < N, carry chained across the slots and
-// the carry out of the last slot ADDED to `co`.  The squaring uses these so that one chain covers a whole diagonal layer
-// of partial products (7 chains instead of 13: every chain end costs a carry-catch instruction on the ALU pipe).
-#if !XHE_ASM
-inline uint32_t emu_madp(uint32_t* acc, const uint32_t* a, const uint32_t* b, int n) {
-  uint64_t c = 0;
-  for (int k = 0; k < n; k++) {
-    uint64_t p = (uint64_t)a[k] * b[k];
-    uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
-    acc[2 * k] = (uint32_t)lo;
-    uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
-    acc[2 * k + 1] = (uint32_t)hi;
-    c = hi >> 32;
-  }
-  return (uint32_t)c;
-}
-#endif
-XHE_HD void madp1(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(co)
-      : "r"(a0), "r"(b0));
-#else
-  const uint32_t a[1] = {a0}, b[1] = {b0};
-  co += emu_madp(acc, a, b, 1);
-#endif
-}
-XHE_HD void madp2(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
-      "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
-      "madc.lo.cc.u32 %2, %7, %8, %2;\n\t"
-      "madc.hi.cc.u32 %3, %7, %8, %3;\n\t"
-      "addc.u32 %4, %4, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1));
-#else
-  const uint32_t a[2] = {a0, a1}, b[2] = {b0, b1};
-  co += emu_madp(acc, a, b, 2);
-#endif
-}
-XHE_HD void madp3(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
-      "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
-      "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
-      "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
-      "madc.lo.cc.u32 %4, %11, %12, %4;\n\t"
-      "madc.hi.cc.u32 %5, %11, %12, %5;\n\t"
-      "addc.u32 %6, %6, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(a2), "r"(b2));
-#else
-  const uint32_t a[3] = {a0, a1, a2}, b[3] = {b0, b1, b2};
-  co += emu_madp(acc, a, b, 3);
-#endif
-}
-XHE_HD void madp4(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
-      "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
-      "madc.lo.cc.u32 %2, %11, %12, %2;\n\t"
-      "madc.hi.cc.u32 %3, %11, %12, %3;\n\t"
-      "madc.lo.cc.u32 %4, %13, %14, %4;\n\t"
-      "madc.hi.cc.u32 %5, %13, %14, %5;\n\t"
-      "madc.lo.cc.u32 %6, %15, %16, %6;\n\t"
-      "madc.hi.cc.u32 %7, %15, %16, %7;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(a2), "r"(b2), "r"(a3), "r"(b3));
-#else
-  const uint32_t a[4] = {a0, a1, a2, a3}, b[4] = {b0, b1, b2, b3};
-  co += emu_madp(acc, a, b, 4);
-#endif
-}
-XHE_HD void madp5(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3, uint32_t a4, uint32_t b4) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %11, %12, %0;\n\t"
-      "madc.hi.cc.u32 %1, %11, %12, %1;\n\t"
-      "madc.lo.cc.u32 %2, %13, %14, %2;\n\t"
-      "madc.hi.cc.u32 %3, %13, %14, %3;\n\t"
-      "madc.lo.cc.u32 %4, %15, %16, %4;\n\t"
-      "madc.hi.cc.u32 %5, %15, %16, %5;\n\t"
-      "madc.lo.cc.u32 %6, %17, %18, %6;\n\t"
-      "madc.hi.cc.u32 %7, %17, %18, %7;\n\t"
-      "madc.lo.cc.u32 %8, %19, %20, %8;\n\t"
-      "madc.hi.cc.u32 %9, %19, %20, %9;\n\t"
-      "addc.u32 %10, %10, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(a2), "r"(b2), "r"(a3), "r"(b3), "r"(a4), "r"(b4));
-#else
-  const uint32_t a[5] = {a0, a1, a2, a3, a4}, b[5] = {b0, b1, b2, b3, b4};
-  co += emu_madp(acc, a, b, 5);
-#endif
-}
-XHE_HD void madp6(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3, uint32_t a4, uint32_t b4, uint32_t a5, uint32_t b5) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %13, %14, %0;\n\t"
-      "madc.hi.cc.u32 %1, %13, %14, %1;\n\t"
-      "madc.lo.cc.u32 %2, %15, %16, %2;\n\t"
-      "madc.hi.cc.u32 %3, %15, %16, %3;\n\t"
-      "madc.lo.cc.u32 %4, %17, %18, %4;\n\t"
-      "madc.hi.cc.u32 %5, %17, %18, %5;\n\t"
-      "madc.lo.cc.u32 %6, %19, %20, %6;\n\t"
-      "madc.hi.cc.u32 %7, %19, %20, %7;\n\t"
-      "madc.lo.cc.u32 %8, %21, %22, %8;\n\t"
-      "madc.hi.cc.u32 %9, %21, %22, %9;\n\t"
-      "madc.lo.cc.u32 %10, %23, %24, %10;\n\t"
-      "madc.hi.cc.u32 %11, %23, %24, %11;\n\t"
-      "addc.u32 %12, %12, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(a2), "r"(b2), "r"(a3), "r"(b3), "r"(a4), "r"(b4), "r"(a5), "r"(b5));
-#else
-  const uint32_t a[6] = {a0, a1, a2, a3, a4, a5}, b[6] = {b0, b1, b2, b3, b4, b5};
-  co += emu_madp(acc, a, b, 6);
-#endif
-}
-XHE_HD void madp7(uint32_t* acc, uint32_t& co, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3, uint32_t a4, uint32_t b4, uint32_t a5, uint32_t b5, uint32_t a6, uint32_t b6) {
-#if XHE_ASM
-  asm("mad.lo.cc.u32 %0, %15, %16, %0;\n\t"
-      "madc.hi.cc.u32 %1, %15, %16, %1;\n\t"
-      "madc.lo.cc.u32 %2, %17, %18, %2;\n\t"
-      "madc.hi.cc.u32 %3, %17, %18, %3;\n\t"
-      "madc.lo.cc.u32 %4, %19, %20, %4;\n\t"
-      "madc.hi.cc.u32 %5, %19, %20, %5;\n\t"
-      "madc.lo.cc.u32 %6, %21, %22, %6;\n\t"
-      "madc.hi.cc.u32 %7, %21, %22, %7;\n\t"
-      "madc.lo.cc.u32 %8, %23, %24, %8;\n\t"
-      "madc.hi.cc.u32 %9, %23, %24, %9;\n\t"
-      "madc.lo.cc.u32 %10, %25, %26, %10;\n\t"
-      "madc.hi.cc.u32 %11, %25, %26, %11;\n\t"
-      "madc.lo.cc.u32 %12, %27, %28, %12;\n\t"
-      "madc.hi.cc.u32 %13, %27, %28, %13;\n\t"
-      "addc.u32 %14, %14, 0;"
-      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(co)
-      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(a2), "r"(b2), "r"(a3), "r"(b3), "r"(a4), "r"(b4), "r"(a5), "r"(b5), "r"(a6), "r"(b6));
-#else
-  const uint32_t a[7] = {a0, a1, a2, a3, a4, a5, a6}, b[7] = {b0, b1, b2, b3, b4, b5, b6};
-  co += emu_madp(acc, a, b, 7);
-#endif
-}
-// r[0..14] += y[0..14] (one carry chain; the caller proves there is no carry out)
-XHE_HD void addto15_nc(uint32_t* r, const uint32_t* y) {
-#if XHE_ASM
-  asm("add.cc.u32 %0, %0, %15;\n\t"
-      "addc.cc.u32 %1, %1, %16;\n\t"
-      "addc.cc.u32 %2, %2, %17;\n\t"
-      "addc.cc.u32 %3, %3, %18;\n\t"
-      "addc.cc.u32 %4, %4, %19;\n\t"
-      "addc.cc.u32 %5, %5, %20;\n\t"
-      "addc.cc.u32 %6, %6, %21;\n\t"
-      "addc.cc.u32 %7, %7, %22;\n\t"
-      "addc.cc.u32 %8, %8, %23;\n\t"
-      "addc.cc.u32 %9, %9, %24;\n\t"
-      "addc.cc.u32 %10, %10, %25;\n\t"
-      "addc.cc.u32 %11, %11, %26;\n\t"
-      "addc.cc.u32 %12, %12, %27;\n\t"
-      "addc.cc.u32 %13, %13, %28;\n\t"
-      "addc.u32 %14, %14, %29;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14])
-      : "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]), "r"(y[8]), "r"(y[9]), "r"(y[10]), "r"(y[11]), "r"(y[12]), "r"(y[13]), "r"(y[14]));
-#else
-  uint64_t c = 0;
-  for (int i = 0; i < 15; i++) { c += (uint64_t)r[i] + y[i]; r[i] = (uint32_t)c; c >>= 32; }
-#endif
-}
-// r[0..15] = 2 * r[0..15] (one carry chain; r < 2^511)
-XHE_HD void dbl16_nc(uint32_t* r) {
-#if XHE_ASM
-  asm("add.cc.u32 %0, %0, %0;\n\t"
-      "addc.cc.u32 %1, %1, %1;\n\t"
-      "addc.cc.u32 %2, %2, %2;\n\t"
-      "addc.cc.u32 %3, %3, %3;\n\t"
-      "addc.cc.u32 %4, %4, %4;\n\t"
-      "addc.cc.u32 %5, %5, %5;\n\t"
-      "addc.cc.u32 %6, %6, %6;\n\t"
-      "addc.cc.u32 %7, %7, %7;\n\t"
-      "addc.cc.u32 %8, %8, %8;\n\t"
-      "addc.cc.u32 %9, %9, %9;\n\t"
-      "addc.cc.u32 %10, %10, %10;\n\t"
-      "addc.cc.u32 %11, %11, %11;\n\t"
-      "addc.cc.u32 %12, %12, %12;\n\t"
-      "addc.cc.u32 %13, %13, %13;\n\t"
-      "addc.cc.u32 %14, %14, %14;\n\t"
-      "addc.u32 %15, %15, %15;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
-#else
-  uint64_t c = 0;
-  for (int i = 0; i < 16; i++) { c += 2 * (uint64_t)r[i]; r[i] = (uint32_t)c; c >>= 32; }
-#endif
-}
-
 // r = x + y + cin (8 limbs), returns carry-out.  cin in {0,1}.
 XHE_HD uint32_t add8c(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin) {
 #if XHE_ASM
@@ -534,11 +340,17 @@ XHE_HD fe fe_sub(const fe& a, const fe& b) {
 XHE_HD fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
 XHE_HD fe fe_dbl(const fe& a) { return fe_add(a, a); }
 
-// t[0..15] = ev[0..15] + (od[0..14] << 32)   (one 15-limb carry chain; the sum is a product < 2^512, so no carry out)
+// t[0..15] = ev[0..15] + (od[0..14] << 32)
 XHE_HD void merge16(uint32_t* t, const uint32_t* ev, const uint32_t* od) {
+  t[0] = ev[0];
+  uint32_t c = add8(t + 1, ev + 1, od);  // limbs 1..8
+  uint32_t e2[8], o2[8], hi[8];
 #pragma unroll
-  for (int i = 0; i < 16; i++) t[i] = ev[i];
-  addto15_nc(t + 1, od);
+  for (int i = 0; i < 7; i++) { e2[i] = ev[9 + i]; o2[i] = od[8 + i]; }
+  e2[7] = 0; o2[7] = 0;
+  add8c(hi, e2, o2, c);
+#pragma unroll
+  for (int i = 0; i < 7; i++) t[9 + i] = hi[i];
 }
 
 // 16-limb product t -> fe: lo + 38*hi (nine limbs), then fold the ninth limb twice
@@ -585,24 +397,33 @@ XHE_HD fe fe_mul(const fe& a, const fe& b) {
 
 // t[0..15] = x[0..7]^2
 XHE_HD void sq512(uint32_t* t, const uint32_t* x) {
-  // 28 cross products x[i]*x[j] (i<j), doubled, plus the 8 squares: 36 IMAD.WIDE.  A chain may take a different product
-  // in every slot, so the cross products are laid out as diagonal LAYERS: limb position p = i+j holds up to four products,
-  // and layer k takes the k-th product of every position it covers.  Seven chains (3 even, 4 odd) instead of
-  // one chain per (multiplier, parity) pair = 13: each chain end is a carry-catch instruction on the ALU pipe.  Inner
-  // layers go first, so every carry-out lands in a word that no chain has touched yet (it cannot overflow that word).
+  // 28 cross products x[i]*x[j] (i<j) in even/odd chains, doubled, plus the 8 squares: 36 IMAD.WIDE.
   uint32_t ev[16], od[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
   // limb position p = i+j; p even -> slot ev[p], p odd -> slot od[p-1]
-  madp1(od + 6, od[8], x[3], x[4]);                                                                        // p = 7
-  madp3(od + 4, od[10], x[2], x[3], x[2], x[5], x[4], x[5]);                                               // p = 5,7,9
-  madp5(od + 2, od[12], x[1], x[2], x[1], x[4], x[1], x[6], x[3], x[6], x[5], x[6]);                       // p = 3..11
-  madp7(od + 0, od[14], x[0], x[1], x[0], x[3], x[0], x[5], x[0], x[7], x[2], x[7], x[4], x[7], x[6], x[7]);   // p = 1..13
-  madp2(ev + 6, ev[10], x[2], x[4], x[3], x[5]);                                                           // p = 6,8
-  madp4(ev + 4, ev[12], x[1], x[3], x[1], x[5], x[2], x[6], x[4], x[6]);                                   // p = 4..10
-  madp6(ev + 2, ev[14], x[0], x[2], x[0], x[4], x[0], x[6], x[1], x[7], x[3], x[7], x[5], x[7]);           // p = 2..12
+  mad4w(od + 0, od[8], x[1], x[3], x[5], x[7], x[0]);   // p = 1,3,5,7
+  mad3w(ev + 2, ev[8], x[2], x[4], x[6], x[0]);         // p = 2,4,6
+  mad3w(od + 2, od[8], x[2], x[4], x[6], x[1]);         // p = 3,5,7
+  mad3w(ev + 4, ev[10], x[3], x[5], x[7], x[1]);        // p = 4,6,8
+  mad3w(od + 4, od[10], x[3], x[5], x[7], x[2]);        // p = 5,7,9
+  mad2w(ev + 6, ev[10], x[4], x[6], x[2]);              // p = 6,8
+  mad2w(od + 6, od[10], x[4], x[6], x[3]);              // p = 7,9
+  mad2w(ev + 8, ev[12], x[5], x[7], x[3]);              // p = 8,10
+  mad2w(od + 8, od[12], x[5], x[7], x[4]);              // p = 9,11
+  mad1w(ev + 10, ev[12], x[6], x[4]);                   // p = 10
+  mad1w(od + 10, od[12], x[6], x[5]);                   // p = 11
+  mad1w(ev + 12, ev[14], x[7], x[5]);                   // p = 12
+  mad1w_nc(od + 12, x[7], x[6]);                        // p = 13
   merge16(t, ev, od);
-  dbl16_nc(t);     // t = 2t (t < 2^511)
+  // t = 2t (t < 2^511)
+  {
+    uint32_t lo[8], hi[8];
+    uint32_t c = add8(lo, t, t);
+    add8c(hi, t + 8, t + 8, c);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t[i] = lo[i]; t[8 + i] = hi[i]; }
+  }
   // + squares x[i]^2 at limb 2i
 #if XHE_ASM
   asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
