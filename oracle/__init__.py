@@ -153,6 +153,11 @@ class Ledger:
         raw = bytes(out)[: 128 * n]
         return [(raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128)]
 
+    def record_outputs(self, on=True):
+        """keep (compressed) what set_output_ciphertext receives; off by default like the reference mock, which drops it"""
+        lib.xo_ledger_record_outputs(self.ptr, 1 if on else 0)
+        return self
+
     def dump_outputs(self):
         """(pk, asset, compressed output ciphertext) of the last set_output_ciphertext call per key (src/tx/verify.rs:339-340)."""
         lib.xo_ledger_dump_outputs.restype = C.c_size_t

@@ -76,7 +76,7 @@ size_t xo_tx_to_bytes(const xo_tx *tx, uint8_t **out, size_t *multisig_index) {
 /* ---------------------------------------------------------------- mock ledger: open-addressing tables */
 typedef struct { uint8_t key[64]; uint8_t val[64]; uint8_t *ext; int ext_n; uint8_t used; } slot;
 typedef struct { slot *s; size_t cap, n; } tbl;
-struct xo_ledger { tbl bal, nonce, ms, out; /* out: last set_output_ciphertext per (account, asset), src/tx/verify.rs:339-340 */ };
+struct xo_ledger { tbl bal, nonce, ms, out; int record_out; /* out: last set_output_ciphertext per (account, asset), src/tx/verify.rs:339-340 -- kept only on request: the reference hands the ciphertext over uncompressed and its mock drops it, so the CPU baseline must not pay two encodings for it */ };
 static uint64_t khash(const uint8_t k[64]) { uint64_t h = 1469598103934665603ULL; for (int i = 0; i < 64; i++) { h ^= k[i]; h *= 1099511628211ULL; } return h; }
 static slot *tbl_find(const tbl *t, const uint8_t k[64]) { if (!t->cap) return NULL; size_t i = khash(k) & (t->cap - 1); while (t->s[i].used) { if (!memcmp(t->s[i].key, k, 64)) return &t->s[i]; i = (i + 1) & (t->cap - 1); } return NULL; }
 static slot *tbl_put(tbl *t, const uint8_t k[64]) {
@@ -88,7 +88,7 @@ static slot *tbl_put(tbl *t, const uint8_t k[64]) {
 static void mk(uint8_t k[64], const uint8_t a[32], const uint8_t b[32]) { memcpy(k, a, 32); if (b) memcpy(k + 32, b, 32); else memset(k + 32, 0, 32); }
 xo_ledger *xo_ledger_new(void) { return calloc(1, sizeof(xo_ledger)); }
 static void tbl_clone(tbl *d, const tbl *s) { *d = *s; if (s->cap) { d->s = malloc(s->cap * sizeof(slot)); memcpy(d->s, s->s, s->cap * sizeof(slot)); for (size_t i = 0; i < s->cap; i++) if (s->s[i].used && s->s[i].ext) { d->s[i].ext = malloc(s->s[i].ext_n * 32); memcpy(d->s[i].ext, s->s[i].ext, s->s[i].ext_n * 32); } } }
-xo_ledger *xo_ledger_clone(const xo_ledger *l) { xo_ledger *c = calloc(1, sizeof *c); tbl_clone(&c->bal, &l->bal); tbl_clone(&c->nonce, &l->nonce); tbl_clone(&c->ms, &l->ms); tbl_clone(&c->out, &l->out); return c; }
+xo_ledger *xo_ledger_clone(const xo_ledger *l) { xo_ledger *c = calloc(1, sizeof *c); tbl_clone(&c->bal, &l->bal); tbl_clone(&c->nonce, &l->nonce); tbl_clone(&c->ms, &l->ms); tbl_clone(&c->out, &l->out); c->record_out = l->record_out; return c; }
 void xo_ledger_free(xo_ledger *l) { if (!l) return; for (size_t i = 0; i < l->ms.cap; i++) if (l->ms.s[i].used) free(l->ms.s[i].ext); free(l->bal.s); free(l->nonce.s); free(l->ms.s); free(l->out.s); free(l); }
 void xo_ledger_set_balance(xo_ledger *l, const uint8_t pk[32], const uint8_t asset[32], const uint8_t ct[64]) { uint8_t k[64]; mk(k, pk, asset); memcpy(tbl_put(&l->bal, k)->val, ct, 64); }
 int xo_ledger_get_balance(const xo_ledger *l, const uint8_t pk[32], const uint8_t asset[32], uint8_t ct[64]) { uint8_t k[64]; mk(k, pk, asset); slot *s = tbl_find(&l->bal, k); if (!s) return 0; memcpy(ct, s->val, 64); return 1; }
@@ -104,6 +104,7 @@ int xo_ledger_get_multisig(const xo_ledger *l, const uint8_t pk[32], const uint8
 static int cmp128(const void *a, const void *b) { return memcmp(a, b, 64); }
 /* set_output_ciphertext (src/tx/verify.rs:60-66): the mock of the reference ignores it (src/lib.rs:166-175); recorded here
  * (compressed) so that the CUDA path's output ciphertexts can be checked byte for byte */
+void xo_ledger_record_outputs(xo_ledger *l, int on) { l->record_out = on; }
 void xo_ledger_set_output(xo_ledger *l, const uint8_t pk[32], const uint8_t asset[32], const uint8_t ct[64]) { uint8_t k[64]; mk(k, pk, asset); memcpy(tbl_put(&l->out, k)->val, ct, 64); }
 size_t xo_ledger_dump_outputs(const xo_ledger *l, uint8_t *out, size_t cap) {
   size_t n = 0; for (size_t i = 0; i < l->out.cap; i++) if (l->out.s[i].used) { if ((n + 1) * 128 <= cap) { memcpy(out + n * 128, l->out.s[i].key, 64); memcpy(out + n * 128 + 64, l->out.s[i].val, 64); } n++; }
@@ -178,7 +179,7 @@ static int pre_verify(const xo_tx *tx, xo_ledger *st, xo_collector *col, xo_rng 
     xo_transcript_append(&out->t, "dom-sep", "new-commitment-proof", 20); xo_transcript_append(&out->t, "new_source_commitment_asset", asset, 32); xo_transcript_append(&out->t, "new_source_commitment", asset + 32, 32);
     rc = xo_eq_proof_pre_verify(asset + 64, &src, &n.C, &n.D, &nsc[i], &out->t, col, rng); if (rc) goto done;
     ct_encode(enc, &n); xo_ledger_set_balance(st, tx->source, asset, enc);
-    ct_encode(enc, &o); xo_ledger_set_output(st, tx->source, asset, enc);
+    if (st->record_out) { ct_encode(enc, &o); xo_ledger_set_output(st, tx->source, asset, enc); }
   }
   if (tx->type == XO_TX_TRANSFERS) {
     for (uint32_t i = 0; i < k; i++) {
@@ -235,7 +236,7 @@ int xo_apply_without_verify(const uint8_t *blob, size_t len, xo_ledger *st) { /*
       !ristretto_decode(&dt[i].receiver_handle, tx.transfers[i].receiver_handle)) { rc = XO_ERR_DECOMPRESSION; goto done; }
   for (int i = 0; i < tx.n_sc; i++) { const uint8_t *asset = tx.sc + 256 * i; uint8_t cur[64], enc[64]; ct_t c, o, n;
     if (!xo_ledger_get_balance(st, tx.source, asset, cur)) { rc = XO_ERR_STATE; goto done; } if (!ct_decode(&c, cur)) { rc = XO_ERR_DECOMPRESSION; goto done; }
-    sender_output_ct(&o, &tx, asset, dt); ge_sub(&n.C, &c.C, &o.C); ge_sub(&n.D, &c.D, &o.D); ct_encode(enc, &n); xo_ledger_set_balance(st, tx.source, asset, enc); ct_encode(enc, &o); xo_ledger_set_output(st, tx.source, asset, enc); }
+    sender_output_ct(&o, &tx, asset, dt); ge_sub(&n.C, &c.C, &o.C); ge_sub(&n.D, &c.D, &o.D); ct_encode(enc, &n); xo_ledger_set_balance(st, tx.source, asset, enc); if (st->record_out) { ct_encode(enc, &o); xo_ledger_set_output(st, tx.source, asset, enc); } }
   for (uint32_t i = 0; i < k; i++) { const xo_transfer *t = &tx.transfers[i]; uint8_t cur[64], enc[64]; ct_t c;
     if (!xo_ledger_get_balance(st, t->dest, t->asset, cur)) { rc = XO_ERR_STATE; goto done; } if (!ct_decode(&c, cur)) { rc = XO_ERR_DECOMPRESSION; goto done; }
     ge_add(&c.C, &c.C, &dt[i].commitment); ge_add(&c.D, &c.D, &dt[i].receiver_handle); ct_encode(enc, &c); xo_ledger_set_balance(st, t->dest, t->asset, enc); }

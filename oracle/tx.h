@@ -37,6 +37,7 @@ int  xo_ledger_get_nonce(const xo_ledger *l, const uint8_t pk[32], uint64_t *non
 void xo_ledger_set_multisig(xo_ledger *l, const uint8_t pk[32], const uint8_t *signers, int n, uint8_t threshold);
 int  xo_ledger_get_multisig(const xo_ledger *l, const uint8_t pk[32], const uint8_t **signers, int *n, uint8_t *threshold);
 size_t xo_ledger_dump(const xo_ledger *l, uint8_t *out, size_t cap); /* sorted (pk,asset,ct) records, 128 B each */
+void xo_ledger_record_outputs(xo_ledger *l, int on);   /* default off */
 void xo_ledger_set_output(xo_ledger *l, const uint8_t pk[32], const uint8_t asset[32], const uint8_t ct[64]);   /* set_output_ciphertext, compressed */
 size_t xo_ledger_dump_outputs(const xo_ledger *l, uint8_t *out, size_t cap); /* sorted (pk,asset,output ct) records */
 /* entry points; *fail_index = index of the first failing tx (or -1 for the batch-level MSM checks) */

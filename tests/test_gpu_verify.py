@@ -205,7 +205,7 @@ def test_output_ciphertexts_match_oracle(ctx):
     from xelis_he_b200 import verifier
     worlds = [scenarios.realistic_world()[:2], scenarios.burn_world()[:2], (lambda r: (r[0], r[1]))(scenarios.mixed_types_world(12))]
     for w, txs in worlds:
-        ol = w.ledger.clone()
+        ol = w.ledger.clone().record_outputs()
         assert oracle.verify_batch(txs, ol) == (OK, -1)
         want_out, want_bal = sorted(ol.dump_outputs()), sorted(ol.dump())
         assert want_out, "scenario produced no output ciphertexts"
@@ -219,13 +219,13 @@ def test_output_ciphertexts_match_oracle(ctx):
         assert quiet.dump_outputs() == [] and quiet.dump() == want_bal
     # minted a2k6 batch through the fast path, and apply_without_verify
     b = oracle.mint_transfers(77, 6, 2, 6, threads=8)
-    ol = b.ledger(); assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
+    ol = b.ledger().record_outputs(); assert oracle.verify_batch(b.blobs, ol) == (OK, -1)
     hl = verifier.Ledger(); hl.import_records(b.ledger().dump()); hl.record_outputs()
     code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir="fast")
     assert (code, idx) == (OK, -1) and tm["fast_path"]
     assert hl.dump_outputs() == sorted(ol.dump_outputs()) and hl.dump() == sorted(ol.dump())
     w, txs, _ = scenarios.realistic_world()
-    ol = w.ledger.clone()
+    ol = w.ledger.clone().record_outputs()
     for t in txs:
         assert oracle.apply_without_verify(t, ol) == 0
     hl = w.host_ledger(); hl.record_outputs()
@@ -243,7 +243,7 @@ def test_plain_amounts_add_as_scalars_not_u64(ctx):
     tx = oracle.build_tx(alice, w.ledger, w.rng, fee=2**64 - 1, burn=(NATIVE, 5), balances=[(NATIVE, 100)])
     code, _ = both(ctx, w, [tx])
     assert code != OK
-    ol = w.ledger.clone()
+    ol = w.ledger.clone().record_outputs()
     assert oracle.apply_without_verify(tx, ol) == 0
     hl = w.host_ledger(); hl.record_outputs()
     assert verifier.apply_without_verify(ctx, [tx], hl) == 0
