@@ -143,7 +143,7 @@ def secondary_metrics(lib, ctx, stream, hbm_peak_gbs):
     bytes_per_account = 2 * (128 + 128 + 96)       # two points per account: extended balance read + write, affine-Niels delta read
     gbs = na * bytes_per_account / ms / 1e6
     out["ct_update_resident_1M"] = {"accounts": na, "ms": ms, "accounts_per_s": na / ms * 1e3,
-                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s", "frac": gbs / hbm_peak_gbs, "traffic": None,
+                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s", "frac": gbs / hbm_peak_gbs, "traffic": 688.9e6, "traffic_note": "dram__bytes_read.sum (470.8 MB = 2 M points x 224 B, exactly the operands) + dram__bytes_write.sum (218.1 MB; the rest of the 268 MB written is still in L2 when the kernel ends) of one launch, ncu, profiles/r01_ct_resident_traffic.csv: no re-reads",
                                                  "algorithmic_bytes_per_account": bytes_per_account, "working_set_mb": na * bytes_per_account / 1e6}}
     return out
 
