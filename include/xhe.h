@@ -28,7 +28,9 @@ enum {
   XHE_ERR_INVALID_NONCE = 9,        /* VerificationError::InvalidNonce                 src/tx/verify.rs:19 */
   XHE_ERR_STATE = 10,               /* VerificationError::State(..)                    src/tx/verify.rs:18 */
   XHE_ERR_PARSE = 11,               /* wire-format / serde-level rejection (before verify is reachable) */
-  XHE_E_ARG = -1, XHE_E_CUDA = -2, XHE_E_NOMEM = -3, XHE_E_NCCL = -4
+  XHE_E_ARG = -1, XHE_E_CUDA = -2, XHE_E_NOMEM = -3, XHE_E_NCCL = -4,
+  XHE_E_CAPACITY = -5               /* a transaction's range proof needs more parties than the context was created for
+                                       (party_capacity < m <= 512); nothing was verified or applied, *fail_index names the tx */
 };
 
 typedef struct xhe_ctx xhe_ctx;
@@ -83,6 +85,7 @@ int32_t xhe_msm_dev(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, si
  * (n_points + j = output of op j). ----------------------------------------------------------------------------------- */
 #define XHE_OP_PLUS_AMOUNT (1LL << 50)
 typedef struct xhe_batch {
+  uint32_t struct_size;            /* = sizeof(xhe_batch): a caller compiled against another layout is refused with XHE_E_ARG */
   uint32_t n_tx;
   uint32_t n_points; const uint8_t* points;              /* n_points x 32 compressed ristretto255 */
   /* Signature::verify (src/elgamal.rs:38-42): r_i = s_i*H - e_i*P[sig_pk_i]; the SHA3-512 compare stays with the caller */
@@ -110,6 +113,10 @@ typedef struct xhe_batch {
    * rp_challenges are then ignored (may be zero).  fs_plan: 6 words per tx = eq_begin, val_begin, rp slot (0xffffffff none),
    * rp challenge offset, main-signature slot (0xffffffff none), flags (bit 0: sigma / range stage reached). */
   const uint8_t* fs_blobs; const uint64_t* fs_blob_off /* n_tx+1 */; const uint32_t* fs_plan; uint8_t fs_seed[32];
+  /* index of this batch's first transaction inside the whole (possibly sharded) batch: transaction i draws its factors from
+   * SHAKE256("xhe-batch-factors" || fs_seed || fs_index_base + i), so two shards never share a factor stream.  fs_seed must
+   * be unpredictable to whoever produced the proofs (the host layer folds OS entropy into it). */
+  uint64_t fs_index_base;
   /* OPTIONAL device-side layout (fast path; requires fs_blobs; SURVEY.md 8 f.2 in spirit).  When layout_on_device != 0 the
    * library also builds the point table and every per-proof / signature array from the blobs (kernel k_layout), so
    * points / sig_* / eq_* / val_* / rp_points / rp_scalars may be NULL.  The host supplies counts (n_points, n_sigs, n_eq, n_val,
@@ -120,6 +127,7 @@ typedef struct xhe_batch {
 } xhe_batch;
 
 typedef struct xhe_verdict {
+  uint32_t struct_size;          /* = sizeof(xhe_verdict) */
   int32_t sigma_is_identity;     /* BatchCollector::verify (src/proofs.rs:49-67) */
   int32_t range_is_identity;     /* RangeProof::verify_batch mega-check */
   uint8_t sigma_enc[32], range_enc[32];
@@ -128,7 +136,10 @@ typedef struct xhe_verdict {
   uint8_t* sig_r;                /* n_sigs x 32: compressed r_i (caller-allocated) */
   uint8_t* op_out;               /* n_ops x 32: compressed chain outputs = updated balance halves (caller-allocated) */
   uint8_t* sig_ok;               /* n_sigs: filled only in device Fiat-Shamir mode, for the main-signature slots (caller-allocated, optional) */
-  uint32_t device_flags;         /* device-layout mode: bit 0 identity-encoded Y/A/S/T/L/R, bit 1 some point failed to decompress, bit 2 some signature mismatched */
+  uint32_t device_flags;         /* device-layout mode: bit 0 identity-encoded sigma-proof Y, bit 1 some point failed to decompress, bit 2 some signature
+                                    mismatched, bit 3 a state-derived point (region_b) failed to decompress, bit 4 identity-encoded A/S/T/L/R of a range proof */
+  uint8_t* tx_flags;             /* n_tx (caller-allocated, optional, device-layout mode): per transaction bits 0-2 as above and bit 3 = its range proof has
+                                    an identity-encoded point; copied back only when device_flags != 0 -- lets the host re-decide ONE transaction, not the batch */
 } xhe_verdict;
 
 /* returns XHE_OK when the device work completed (verdict fields filled) -- the accept/reject decision and its error
@@ -147,6 +158,15 @@ int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t
  * results of the sigma or range MSM (src/proofs.rs:49-67 decides on the identity of the total) -- as one 32-thread
  * kernel with no allocation.  *all_valid = 0 if an encoding does not decode (such inputs are left out of the sum). */
 int32_t xhe_sum_encodings(xhe_ctx* ctx, const uint8_t* enc, size_t n, uint8_t out_enc[32], int32_t* is_identity, int32_t* all_valid);
+/* The same decision with everything on the device (asynchronous on the ctx stream), so that a sharded step -- kernels, exchange,
+ * decision -- can be timed with CUDA events: xhe_batch_record_dev writes this rank's 80-byte record (int32 code, int64 first
+ * failing tx at offset 4, sigma partial at 12, range partial at 44) of the batch that xhe_batch_run just processed; after an
+ * all-gather of the records (ncclAllGather on the same stream), xhe_shard_decide_dev writes int32 code and, at offset 8, int64
+ * index: first failing transaction of the whole batch, else GenericProof if the summed sigma partials are not the identity, else
+ * RangeProof (structural failure in a shard, or the summed range partials), else 0.  Code 0xFF in a record = that shard saw a
+ * per-transaction anomaly its host has to name. */
+int32_t xhe_batch_record_dev(xhe_ctx* ctx, void* d_record80);
+int32_t xhe_shard_decide_dev(xhe_ctx* ctx, const void* d_records, uint32_t world, void* d_out16);
 /* copy nbytes (<= 1 MiB) between device-accessible addresses (device memory or pinned host memory) with a kernel on the
  * ctx stream -- for small control messages that must not queue behind bulk transfers on the copy engines */
 int32_t xhe_copy_small(xhe_ctx* ctx, void* dst, const void* src, size_t nbytes);

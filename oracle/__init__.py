@@ -28,6 +28,9 @@ def _load():
     lib.xo_msm_timed.restype = C.c_double
     lib.xo_mint_transfers.restype = C.c_void_p
     lib.xo_mint_chain.restype = C.c_void_p
+    lib.xo_mint_chain_par.restype = C.c_void_p
+    lib.xo_mint_mixed.restype = C.c_void_p
+    lib.xo_ledger_dump_multisig.restype = C.c_size_t
     lib.xo_batch_slice.restype = C.c_void_p
     lib.xo_ledger_new.restype = C.c_void_p
     lib.xo_ledger_clone.restype = C.c_void_p
@@ -153,6 +156,17 @@ class Ledger:
         raw = bytes(out)[: 128 * n]
         return [(raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128)]
 
+    def dump_multisig(self):
+        """[(pk, [signers], threshold)] of every account with a multisig setting"""
+        n = lib.xo_ledger_dump_multisig(self.ptr, None, C.c_size_t(0))
+        out = (C.c_uint8 * max(n, 1))()
+        lib.xo_ledger_dump_multisig(self.ptr, out, C.c_size_t(n))
+        raw, o, res = bytes(out)[:n], 0, []
+        while o < len(raw):
+            k, th = raw[o + 32], raw[o + 33]
+            res.append((raw[o:o + 32], [raw[o + 34 + 32 * i:o + 66 + 32 * i] for i in range(k)], th)); o += 34 + 32 * k
+        return res
+
     def record_outputs(self, on=True):
         """keep (compressed) what set_output_ciphertext receives; off by default like the reference mock, which drops it"""
         lib.xo_ledger_record_outputs(self.ptr, 1 if on else 0)
@@ -210,8 +224,16 @@ def mint_transfers(seed, T, a=1, k=1, threads=8):
     return Batch(lib.xo_mint_transfers(C.c_uint64(seed), C.c_size_t(T), a, k, threads))
 
 
-def mint_chain(seed, T, k=1):
+def mint_chain(seed, T, k=1, threads=1):
+    """one sender, T transactions chained through its balance (benches/tx.rs:153-186); threads > 1 mints in two parallel passes"""
+    if threads > 1:
+        return Batch(lib.xo_mint_chain_par(C.c_uint64(seed), C.c_size_t(T), k, threads))
     return Batch(lib.xo_mint_chain(C.c_uint64(seed), C.c_size_t(T), k))
+
+
+def mint_mixed(seed, T, threads=8):
+    """config 5: transfers (k 1..4, a 1..2), burns, contract calls, multisig set-ups and transfers from threshold-2 multisig accounts"""
+    return Batch(lib.xo_mint_mixed(C.c_uint64(seed), C.c_size_t(T), threads))
 
 
 def verify_batch(blobs, ledger: Ledger, rng_seed=1):

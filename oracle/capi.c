@@ -94,6 +94,96 @@ xo_batch *xo_mint_chain(uint64_t seed, size_t T, int k) {
   }
   xo_ledger_free(prover); return b;
 }
+/* The same one-sender chain (benches/tx.rs:153-186) minted in PARALLEL, for 10k-transaction chains: every transaction draws its
+ * randomness from its own stream (seed, i), so its transfer ciphertexts do not depend on the prover's state.  Pass 1 builds all
+ * transactions against the initial ledger (their ciphertexts are final, their eq proofs are not); the running sender balance after
+ * each of them follows by apply_without_verify (cheap, sequential); pass 2 rebuilds every transaction with the same randomness
+ * against the balance it really meets. */
+typedef struct { uint64_t seed; size_t lo, hi; int k; const sc *sk; const uint8_t *pk, *rpk; const uint8_t *pre_ct /* T x 64 or NULL */; const uint8_t *init_ct; uint8_t **blob; size_t *len; } chain_job;
+static void *chain_worker(void *arg) { chain_job *j = arg; uint8_t native[32] = {0};
+  for (size_t i = j->lo; i < j->hi; i++) {
+    uint8_t sd[24]; memcpy(sd, "chain-tx", 8); memcpy(sd + 8, &j->seed, 8); uint64_t ii = i; memcpy(sd + 16, &ii, 8); xo_rng rng; xo_rng_init(&rng, sd, 24);
+    xo_ledger *tmp = xo_ledger_new(); xo_ledger_set_balance(tmp, j->pk, native, j->pre_ct ? j->pre_ct + 64 * i : j->init_ct); xo_ledger_set_nonce(tmp, j->pk, 0);
+    xo_transfer_spec *ts = calloc(j->k ? j->k : 1, sizeof *ts); for (int q = 0; q < j->k; q++) { memcpy(ts[q].dest, j->rpk, 32); ts[q].amount = 1; }
+    uint64_t bal = 100000 - (uint64_t)i * (3 + (uint64_t)j->k);
+    xo_tx_spec sp; memset(&sp, 0, sizeof sp); sp.version = 1; sp.type = XO_TX_TRANSFERS; sp.fee = 3; sp.transfers = ts; sp.n_transfers = j->k; sp.assets = native; sp.balances = &bal; sp.n_assets = 1;
+    if (j->blob[i]) { free(j->blob[i]); j->blob[i] = NULL; }
+    j->len[i] = xo_tx_build(&j->blob[i], &sp, j->sk, tmp, &rng, NULL, NULL, 0); free(ts); xo_ledger_free(tmp);
+  } return NULL; }
+xo_batch *xo_mint_chain_par(uint64_t seed, size_t T, int k, int threads) {
+  if (threads < 1) threads = 1; if (threads > 64) threads = 64; if ((uint64_t)T * (3 + (uint64_t)k) > 100000) return NULL;
+  size_t m = 1; while (m < (size_t)(1 + k)) m <<= 1; xo_init((int)m);
+  uint8_t sd[16]; memcpy(sd, "mintchp", 8); memcpy(sd + 8, &seed, 8); xo_rng rng; xo_rng_init(&rng, sd, 16);
+  sc sk, rsk; uint8_t pk[32], rpk[32]; ge P, RP; derive_key(seed, "S", 0, &sk); derive_key(seed, "R", 0, &rsk); xo_pubkey_from_secret(&sk, pk, &P); xo_pubkey_from_secret(&rsk, rpk, &RP);
+  xo_batch *b = calloc(1, sizeof *b); b->n = T; b->offsets = calloc(T + 1, sizeof(size_t)); b->ledger = xo_ledger_new(); uint8_t native[32] = {0}, ct0[64], ct[64]; sc op;
+  xo_rng_scalar(&rng, &op); xo_encrypt(ct0, &P, 100000, &op); xo_ledger_set_balance(b->ledger, pk, native, ct0); xo_rng_scalar(&rng, &op); xo_encrypt(ct, &RP, 0, &op); xo_ledger_set_balance(b->ledger, rpk, native, ct);
+  xo_ledger_set_nonce(b->ledger, pk, 0); xo_ledger_set_nonce(b->ledger, rpk, 0);
+  uint8_t **blob = calloc(T, sizeof *blob); size_t *len = calloc(T, sizeof *len); uint8_t *pre = malloc(64 * T + 64);
+  pthread_t th[64]; chain_job jobs[64];
+  for (int pass = 0; pass < 2; pass++) {
+    for (int t = 0; t < threads; t++) { jobs[t] = (chain_job){ seed, T * t / threads, T * (t + 1) / threads, k, &sk, pk, rpk, pass ? pre : NULL, ct0, blob, len }; pthread_create(&th[t], NULL, chain_worker, &jobs[t]); }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    if (pass == 0) {   /* the sender balance each transaction meets */
+      xo_ledger *run = xo_ledger_clone(b->ledger);
+      for (size_t i = 0; i < T; i++) { if (!len[i]) return NULL; xo_ledger_get_balance(run, pk, native, pre + 64 * i); xo_apply_without_verify(blob[i], len[i], run); }
+      xo_ledger_free(run);
+    }
+  }
+  for (size_t i = 0; i < T; i++) { if (!len[i]) return NULL; b->offsets[i + 1] = b->offsets[i] + len[i]; }
+  b->blobs = malloc(b->offsets[T] + 1);
+  for (size_t i = 0; i < T; i++) { memcpy(b->blobs + b->offsets[i], blob[i], len[i]); free(blob[i]); }
+  free(blob); free(len); free(pre); return b;
+}
+/* Config 5: a mixed batch -- 60 % Transfers (k in 1..4, a in 1..2), 15 % Burn, 15 % CallContract (one asset, one
+ * parameter), 5 % MultiSig set-ups, 5 % transfers from threshold-2 multisig accounts -- every transaction from its own fresh
+ * sender, so the batch mints in parallel.  party_capacity 8 covers it (a + k <= 6). */
+typedef struct { uint64_t seed; size_t lo, hi; uint8_t **blob; size_t *len; uint8_t *spk, *sct, *rpk, *rct, *ms /* T x (1 + 2 x 32): flag, two signer keys */; } mixed_job;
+static int mixed_kind(size_t i) { unsigned r = (unsigned)((i * 2654435761u) >> 7) % 100; return r < 60 ? 0 : r < 75 ? 1 : r < 90 ? 2 : r < 95 ? 4 : 5; }   /* 5 = transfer from a multisig account */
+static void *mixed_worker(void *arg) { mixed_job *j = arg;
+  for (size_t i = j->lo; i < j->hi; i++) {
+    uint8_t sd[24]; memcpy(sd, "mixed-tx", 8); memcpy(sd + 8, &j->seed, 8); uint64_t ii = i; memcpy(sd + 16, &ii, 8); xo_rng rng; xo_rng_init(&rng, sd, 24);
+    sc sk, rsk, c1, c2; derive_key(j->seed, "s", i, &sk); ge P; uint8_t pk[32]; xo_pubkey_from_secret(&sk, pk, &P); memcpy(j->spk + 32 * i, pk, 32);
+    derive_key(j->seed, "r", i, &rsk); ge RP; uint8_t rpk[32]; xo_pubkey_from_secret(&rsk, rpk, &RP); memcpy(j->rpk + 32 * i, rpk, 32);
+    const int kind = mixed_kind(i); uint32_t rnd; xo_rng_bytes(&rng, &rnd, 4);
+    const int a = (kind == 0 || kind == 5) ? 1 + (int)(rnd & 1) : 1, k = (kind == 0 || kind == 5) ? 1 + (int)((rnd >> 1) & 3) : 0;
+    xo_ledger *tmp = xo_ledger_new(); uint8_t assets[2 * 32]; uint64_t bals[2];
+    for (int q = 0; q < 2; q++) { asset_id(assets + 32 * q, q); bals[q] = XO_BAL; sc op; xo_rng_scalar(&rng, &op); uint8_t ct[64]; xo_encrypt(ct, &P, XO_BAL, &op); memcpy(j->sct + (i * 2 + q) * 64, ct, 64); xo_ledger_set_balance(tmp, pk, assets + 32 * q, ct);
+      sc op2; xo_rng_scalar(&rng, &op2); xo_encrypt(ct, &RP, 0, &op2); memcpy(j->rct + (i * 2 + q) * 64, ct, 64); }
+    xo_tx_spec sp; memset(&sp, 0, sizeof sp); sp.version = 1; sp.fee = 3; sp.assets = assets; sp.balances = bals; sp.n_assets = (uint32_t)a;
+    xo_transfer_spec ts[4]; memset(ts, 0, sizeof ts); uint64_t amt = 0; uint8_t tail[32]; uint8_t signers[64], msidx[2] = {0, 1}; sc mssk[2];
+    j->ms[65 * i] = 0;
+    if (kind == 0 || kind == 5) {
+      sp.type = XO_TX_TRANSFERS; sp.transfers = ts; sp.n_transfers = (uint32_t)k;
+      for (int q = 0; q < k; q++) { asset_id(ts[q].asset, q % a); memcpy(ts[q].dest, rpk, 32); uint32_t v; xo_rng_bytes(&rng, &v, 4); ts[q].amount = v; }
+    } else if (kind == 1) { sp.type = XO_TX_BURN; memcpy(sp.burn_asset, assets, 32); sp.burn_amount = 1000 + (rnd & 0xffff);
+    } else if (kind == 2) { sp.type = XO_TX_CALL; memset(sp.contract, 9, 32); amt = 40 + (rnd & 0xff); sp.call_assets = assets; sp.call_amounts = &amt; sp.n_call_assets = 1;
+      uint32_t kl = 6, vl = 4; memcpy(tail, &kl, 4); memcpy(tail + 4, "method", 6); memcpy(tail + 10, &vl, 4); memcpy(tail + 14, "swap", 4); sp.raw_tail = tail; sp.raw_tail_len = 18; sp.n_params = 1;
+    } else if (kind == 4) { sp.type = XO_TX_MULTISIG; derive_key(j->seed, "c", 2 * i, &c1); derive_key(j->seed, "c", 2 * i + 1, &c2); xo_pubkey_from_secret(&c1, signers, NULL); xo_pubkey_from_secret(&c2, signers + 32, NULL);
+      sp.signers = signers; sp.n_signers = 2; sp.threshold = 1; }
+    if (kind == 5) {   /* the account already has a threshold-2 multisig setting in the ledger: both co-signers sign */
+      derive_key(j->seed, "c", 2 * i, &c1); derive_key(j->seed, "c", 2 * i + 1, &c2); xo_pubkey_from_secret(&c1, signers, NULL); xo_pubkey_from_secret(&c2, signers + 32, NULL);
+      j->ms[65 * i] = 1; memcpy(j->ms + 65 * i + 1, signers, 64); mssk[0] = c1; mssk[1] = c2;
+      xo_ledger_set_multisig(tmp, pk, signers, 2, 2);
+      j->len[i] = xo_tx_build(&j->blob[i], &sp, &sk, tmp, &rng, msidx, mssk, 2);
+    } else j->len[i] = xo_tx_build(&j->blob[i], &sp, &sk, tmp, &rng, NULL, NULL, 0);
+    xo_ledger_free(tmp);
+  } return NULL; }
+xo_batch *xo_mint_mixed(uint64_t seed, size_t T, int threads) {
+  if (threads < 1) threads = 1; if (threads > 64) threads = 64; xo_init(8);
+  uint8_t **blob = calloc(T, sizeof *blob); size_t *len = calloc(T, sizeof *len); uint8_t *spk = malloc(32 * T + 1), *sct = malloc(128 * T + 1), *rpk = malloc(32 * T + 1), *rct = malloc(128 * T + 1), *ms = calloc(65 * T + 1, 1);
+  pthread_t th[64]; mixed_job jobs[64];
+  for (int t = 0; t < threads; t++) { jobs[t] = (mixed_job){ seed, T * t / threads, T * (t + 1) / threads, blob, len, spk, sct, rpk, rct, ms }; pthread_create(&th[t], NULL, mixed_worker, &jobs[t]); }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  xo_batch *b = calloc(1, sizeof *b); b->n = T; b->offsets = calloc(T + 1, sizeof(size_t)); b->ledger = xo_ledger_new();
+  for (size_t i = 0; i < T; i++) { if (!len[i]) return NULL; b->offsets[i + 1] = b->offsets[i] + len[i]; }
+  b->blobs = malloc(b->offsets[T] + 1);
+  for (size_t i = 0; i < T; i++) { memcpy(b->blobs + b->offsets[i], blob[i], len[i]); free(blob[i]); xo_ledger_set_nonce(b->ledger, spk + 32 * i, 0); xo_ledger_set_nonce(b->ledger, rpk + 32 * i, 0);
+    for (int q = 0; q < 2; q++) { uint8_t as[32]; asset_id(as, q); xo_ledger_set_balance(b->ledger, spk + 32 * i, as, sct + (i * 2 + q) * 64); xo_ledger_set_balance(b->ledger, rpk + 32 * i, as, rct + (i * 2 + q) * 64); }
+    if (ms[65 * i]) xo_ledger_set_multisig(b->ledger, spk + 32 * i, ms + 65 * i + 1, 2, 2); }
+  free(blob); free(len); free(spk); free(sct); free(rpk); free(rct); free(ms); return b;
+}
+/* the multisig settings of a batch's initial ledger as records pk[32] n[1] threshold[1] signers[n x 32] (for importing into another ledger) */
+size_t xo_ledger_dump_multisig(const xo_ledger *l, uint8_t *out, size_t cap);
 void xo_batch_free(xo_batch *b) { if (!b) return; free(b->blobs); free(b->offsets); xo_ledger_free(b->ledger); free(b); }
 /* verify a whole batch against a clone of its ledger; returns verdict */
 int xo_batch_verify(const xo_batch *b, uint64_t rng_seed, long *fail_index, xo_ledger **final_state) {

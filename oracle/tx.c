@@ -101,6 +101,12 @@ void xo_ledger_set_multisig(xo_ledger *l, const uint8_t pk[32], const uint8_t *s
 int xo_ledger_get_multisig(const xo_ledger *l, const uint8_t pk[32], const uint8_t **signers, int *n, uint8_t *threshold) {
   uint8_t k[64]; mk(k, pk, NULL); slot *s = tbl_find(&l->ms, k); if (!s || !s->val[1]) return 0; *signers = s->ext; *n = s->ext_n; *threshold = s->val[0]; return 1;
 }
+/* multisig settings as records pk[32] n[1] threshold[1] signers[n x 32] (test plumbing: copy a minted batch's settings into another ledger) */
+size_t xo_ledger_dump_multisig(const xo_ledger *l, uint8_t *out, size_t cap) {
+  size_t o = 0; for (size_t i = 0; i < l->ms.cap; i++) if (l->ms.s[i].used && l->ms.s[i].val[1]) { size_t need = 34 + 32 * (size_t)l->ms.s[i].ext_n;
+    if (o + need <= cap) { memcpy(out + o, l->ms.s[i].key, 32); out[o + 32] = (uint8_t)l->ms.s[i].ext_n; out[o + 33] = l->ms.s[i].val[0]; memcpy(out + o + 34, l->ms.s[i].ext, 32 * (size_t)l->ms.s[i].ext_n); } o += need; }
+  return o;
+}
 static int cmp128(const void *a, const void *b) { return memcmp(a, b, 64); }
 /* set_output_ciphertext (src/tx/verify.rs:60-66): the mock of the reference ignores it (src/lib.rs:166-175); recorded here
  * (compressed) so that the CUDA path's output ciphertexts can be checked byte for byte */

@@ -113,3 +113,18 @@ def transfer_with_extra_data_world():   # src/lib.rs:951-1029: memo bytes are co
     memo = b"\x01\x02\x03 encrypted memo bytes" + bytes(64)   # cipher || sender_handle || receiver_handle (opaque to the verifier)
     tx = oracle.build_tx(bob, w.ledger, w.rng, fee=1, transfers=[(NATIVE, alice.pk, 5, memo)], balances=[(NATIVE, 100)])
     return w, [tx], (bob, alice)
+
+
+def shared_receiver_world(n=6):   # several senders (in different shards) credit ONE receiver, which then spends the lot
+    w = World(b"shared-rcv")
+    senders = [w.account(b"snd%d" % i, [(NATIVE, 1000)]) for i in range(n - 1)]
+    rcv = w.account(b"rcv", [(NATIVE, 10)])
+    sink = w.account(b"sink", [(NATIVE, 0)])
+    txs, state, total = [], w.ledger.clone(), 10
+    for i, kp in enumerate(senders):
+        tx = oracle.build_tx(kp, w.ledger, w.rng, fee=1, transfers=[(NATIVE, rcv.pk, 20 + i)], balances=[(NATIVE, 1000)])
+        assert oracle.apply_without_verify(tx, state) == 0
+        txs.append(tx); total += 20 + i
+    # the receiver spends everything it has by now: valid only against the balance AFTER all the credits
+    txs.append(oracle.build_tx(rcv, state, w.rng, fee=2, transfers=[(NATIVE, sink.pk, total - 2)], balances=[(NATIVE, total)]))
+    return w, txs

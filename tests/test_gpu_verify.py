@@ -20,6 +20,12 @@ def ctx():
     c.close()
 
 
+def _fresh(batch):
+    from xelis_he_b200 import verifier
+    hl = verifier.Ledger(); hl.import_records(batch.ledger().dump())
+    return hl
+
+
 def both(ctx, world, txs, expect=None):
     """run oracle and device on clones of the same ledger; assert identical verdicts (+ states on accept)"""
     from xelis_he_b200 import verifier
@@ -38,8 +44,6 @@ def both(ctx, world, txs, expect=None):
     assert hl_fast.dump() == hl.dump()
     if code == OK and txs and not any(t[1] == 4 or t[3] != 0xFF for t in txs) and not world.multisig:
         assert tm_f["fast_path"], "an honest non-multisig batch must be decided by the fast path"
-    if code != OK:
-        assert not tm_f["fast_path"]
     if expect is not None:
         assert code == expect
     if code == OK:
@@ -261,8 +265,12 @@ def test_device_fiat_shamir_matches_host(ctx):
     outs = []
     for mode in ("host", "device"):
         hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
-        outs.append(verifier.verify_batch_partial(ctx, blobs, hl, seed=SEED, threads=3, fiat_shamir=mode)[:4])
+        outs.append(verifier.verify_batch_partial(ctx, blobs, hl, seed=SEED, threads=3, fiat_shamir=mode, deterministic=True)[:4])
     assert outs[0] == outs[1] and outs[0][0] == SIG and outs[0][1] == 4 and outs[0][2] != bytes(32)
+    # outside the replay flag the factors are unpredictable -- the same call twice gives different partial sums
+    a1 = verifier.verify_batch_partial(ctx, blobs, _fresh(b), seed=SEED, fiat_shamir="device")[2]
+    a2 = verifier.verify_batch_partial(ctx, blobs, _fresh(b), seed=SEED, fiat_shamir="device")[2]
+    assert a1 != a2 and a1 != outs[0][2]
     swapped = [b.blobs[1], b.blobs[0]] + b.blobs[2:]          # valid txs: partials are the identity in both modes
     for mode in ("host", "device", "fast"):
         hl = verifier.Ledger(); hl.import_records(b.ledger().dump())
@@ -318,7 +326,7 @@ def test_fixed_base_and_generic_static_msm_agree(ctx):
 def test_large_batch_size_independent_properties(ctx):
     """2,000-transfer batch (the bench workload's shape at a size the oracle still checks in seconds): accept through the
     fast path, every updated ciphertext equal to the oracle's apply_without_verify, and a tampered transaction deep inside
-    the batch rejected at the index and with the code the oracle reports (exact-path fallback)."""
+    the batch rejected at the index and with the code the oracle reports."""
     from xelis_he_b200 import verifier
     T = 2000
     b = oracle.mint_transfers(91, T, 1, 1, threads=16)
@@ -338,7 +346,7 @@ def test_large_batch_size_independent_properties(ctx):
     hl3 = verifier.Ledger(); hl3.import_records(b.ledger().dump())
     got = verifier.verify_batch(ctx, bad, hl3, seed=SEED, fiat_shamir="fast")
     assert got[:2] == oracle.verify_batch(bad[:victim + 1], b.slice(victim + 1).ledger()) == (1, victim)
-    assert not got[2]["fast_path"]
+    assert got[2]["fast_path"]       # decided by the fast path + the exact verdict of that ONE transaction, not by a re-run of the batch
 
 
 def test_long_single_sender_chain(ctx):

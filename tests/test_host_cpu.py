@@ -20,11 +20,51 @@ def lib():
 
 
 def test_library_exports_every_declared_symbol(lib):
+    for header, pattern, least in (("xhe.h", r"\b(xhe_[a-z0-9_]+)\s*\(", 20), ("xhe_host.h", r"\b(xheh_[a-z0-9_]+)\s*\(", 20)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        names = sorted(set(re.findall(pattern, hdr)))
+        assert len(names) >= least, header
+        missing = [n for n in names if not hasattr(lib, n)]
+        assert not missing, (header, missing)
+
+
+def test_rust_sys_crate_matches_the_header(tmp_path):
+    """xhe-sys/ is source-only here (no Rust toolchain): pin what can be pinned without one -- every extern it declares is
+    in include/xhe.h, and the struct sizes its layout test asserts are the C compiler's sizes for the header's structs."""
+    import subprocess
+    rs = open(os.path.join(ROOT, "xhe-sys", "src", "lib.rs")).read()
     hdr = open(os.path.join(ROOT, "include", "xhe.h")).read()
-    names = sorted(set(re.findall(r"\b(xhe_[a-z0-9_]+)\s*\(", hdr)))
-    assert len(names) >= 20
-    missing = [n for n in names if not hasattr(lib, n)]
-    assert not missing, missing
+    declared = set(re.findall(r"\b(xhe_[a-z0-9_]+)\s*\(", hdr))
+    fns = set(re.findall(r"pub fn (xhe_[a-z0-9_]+)\(", rs))
+    assert len(fns) >= 20 and not (fns - declared), fns - declared
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "xhe.h"\nint main(void){printf("%zu %zu\\n", sizeof(xhe_batch), sizeof(xhe_verdict));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    c_batch, c_verdict = subprocess.check_output([str(exe)]).split()
+    assert re.search(r"size_of::<xhe_batch>\(\), (\d+)\)", rs).group(1) == c_batch.decode()
+    assert re.search(r"size_of::<xhe_verdict>\(\), (\d+)\)", rs).group(1) == c_verdict.decode()
+    # field order of the Rust structs = field order of the C structs
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            for part in decl.split(","):
+                m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(\[\d+\])?\s*$", part.strip())
+                if m and part.strip():
+                    out.append(m.group(1))
+        return out
+    def rs_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, re.S).group(1)
+        return re.findall(r"pub ([a-z0-9_]+):", body)
+    for name in ("xhe_batch", "xhe_verdict"):
+        assert c_fields(name) == rs_fields(name), name
+
+
+def test_build_is_keyed_on_a_source_hash():
+    from xelis_he_b200 import build
+    assert not build.needs_build() and open(build.HASH_FILE).read().strip() == build.source_hash()
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -7,7 +7,7 @@ _lib = None
 
 ERR_NAMES = {0: "Ok", 1: "Signature", 2: "Decompression", 3: "CommitmentEqProof", 4: "CiphertextValidityProof", 5: "GenericProof",
              6: "RangeProof", 7: "Transcript", 8: "Format", 9: "InvalidNonce", 10: "State", 11: "Parse",
-             -1: "E_ARG", -2: "E_CUDA", -3: "E_NOMEM", -4: "E_NCCL"}
+             -1: "E_ARG", -2: "E_CUDA", -3: "E_NOMEM", -4: "E_NCCL", -5: "E_CAPACITY"}
 
 
 class XheError(RuntimeError):
@@ -51,6 +51,8 @@ def load_library():
         "xhe_msm_vartime": (i32, [vp, u8p, u8p, sz, vp, C.POINTER(C.c_int32)]),
         "xhe_sum_encodings": (i32, [vp, u8p, sz, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "xhe_copy_small": (i32, [vp, vp, vp, sz]),
+        "xhe_batch_record_dev": (i32, [vp, vp]),
+        "xhe_shard_decide_dev": (i32, [vp, vp, C.c_uint32, vp]),
         "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
         "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),

@@ -1,4 +1,9 @@
-"""Build libxhe_cuda.so (sm_100a only) in-tree with nvcc.  Called by __graft_entry__.build()."""
+"""Build libxhe_cuda.so (sm_100a only) in-tree with nvcc.  Called by __graft_entry__.build().
+
+The library is rebuilt whenever the SHA-256 of its sources (csrc/, host/, include/ and the compiler flags) differs from the
+hash recorded beside the last build (build/libxhe_cuda.srchash): a prebuilt .so that travels with the tree is only reused
+if it was built from exactly these sources, whatever the file times say."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -16,18 +21,31 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")) + sorted(os.path.join(host, f) for f in os.listdir(host) if f.endswith(".cpp"))
 
 
+def _dep_files():
+    return sorted(os.path.join(r, f) for d in (CSRC, os.path.join(HERE, "host"), os.path.join(HERE, "..", "include"))
+                  for r, _, fs in os.walk(d) for f in fs if f.endswith((".cu", ".cuh", ".hpp", ".h", ".cpp")) and "experimental" not in r)
+
+
+def source_hash():
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in _dep_files():
+        h.update(os.path.relpath(p, HERE).encode()); h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+HASH_FILE = os.path.join(HERE, "build", "libxhe_cuda.srchash")
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HASH_FILE):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(r, f) for d in (CSRC, os.path.join(HERE, "host"), os.path.join(HERE, "..", "include"))
-            for r, _, fs in os.walk(d) for f in fs if f.endswith((".cu", ".cuh", ".hpp", ".h", ".cpp"))]
-    return any(os.path.getmtime(p) > t for p in deps)
+    return open(HASH_FILE).read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    want = source_hash()
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
@@ -48,6 +66,8 @@ def build(force=False, verbose=False):
         if rc != 0:
             raise RuntimeError(f"nvcc failed on {src}")
     subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"])
+    with open(HASH_FILE, "w") as f:
+        f.write(want + "\n")
     return LIB
 
 

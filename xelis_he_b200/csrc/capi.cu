@@ -2,8 +2,10 @@
 #include "xhe_internal.cuh"
 #include "../host/keccak.hpp"
 #include <vector>
+#include <algorithm>
 
 int32_t xhe_from_uniform_niels_dev(xhe_ctx* ctx, const void* d_u, size_t n, void* d_niels);
+size_t xhe_preload_msm(); size_t xhe_preload_verify(); size_t xhe_preload_fs(); size_t xhe_preload_point();
 int32_t xhe_compress_xy_bytes_dev(xhe_ctx* ctx, const void* d_xy, size_t n, void* d_enc);
 int32_t xhe_affine_to_bytes_dev(xhe_ctx* ctx, const void* d_aff, size_t n, void* d_xy);
 
@@ -20,6 +22,17 @@ extern "C" int32_t xhe_ctx_create(int device, uint32_t party_capacity, xhe_ctx**
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return XHE_E_CUDA;   // no GPU: fail loudly, there is no fallback
   if (cudaSetDevice(device) != cudaSuccess) return XHE_E_CUDA;
+  // Two things CUDA does lazily would make the first launch of a kernel wait for every RUNNING kernel -- fatal while the
+  // polling chain kernel of msm.cu is in flight (it waits for exactly those launches; measured: the first batch of a context
+  // timed out): loading the kernel (CUDA_MODULE_LOADING=LAZY), and growing the context's local-memory pool when a kernel needs
+  // a larger per-thread stack than any before it (k_rp_prep: 3.5 KB against the 1 KB default).  Both happen here instead.
+  { static bool loaded[64] = {false};
+    if (device < 64 && !loaded[device]) {
+      size_t frame = std::max(std::max(xhe_preload_msm(), xhe_preload_verify()), std::max(xhe_preload_fs(), xhe_preload_point()));
+      size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+      size_t want = std::max<size_t>(4096, frame + 512);       // (the pool is this many bytes x the resident threads of the device: ~1.2 GB at 4 KB)
+      if (cur < want) cudaDeviceSetLimit(cudaLimitStackSize, want);
+      cudaGetLastError(); loaded[device] = true; } }
   xhe_ctx* ctx = new xhe_ctx();
   ctx->device = device; ctx->party_capacity = party_capacity;
   cudaDeviceProp prop;
@@ -72,6 +85,9 @@ extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (auto& st : ctx->aux) if (st) cudaStreamDestroy(st);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto& l : ctx->msm_side) for (auto& st : l) if (st) cudaStreamDestroy(st);
+  for (auto& l : ctx->msm_ev) for (auto& e : l) if (e) cudaEventDestroy(e);
   delete ctx;
 }
 extern "C" const char* xhe_last_error(const xhe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
@@ -81,8 +97,9 @@ extern "C" uint64_t xhe_ctx_launch_count(const xhe_ctx* ctx) { return ctx ? ctx-
 extern "C" int32_t xhe_ctx_set_serial(xhe_ctx* ctx, int serial) { if (!ctx) return XHE_E_ARG; ctx->serial = serial != 0; return XHE_OK; }
 extern "C" int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable) {
   if (!ctx) return XHE_E_ARG;
-  for (auto& p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  for (auto& p : ctx->pending) { ctx->ev_pool.push_back(p.e0); ctx->ev_pool.push_back(p.e1); }
   ctx->pending.clear(); ctx->n_timers = 0; ctx->timing = enable != 0;
+  if (enable) while (ctx->ev_pool.size() < 2048) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; ctx->ev_pool.push_back(e); }
   for (auto& t : ctx->timers) t = xhe_ctx::KernelTimer();
   return XHE_OK;
 }
@@ -99,7 +116,7 @@ extern "C" int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double*
       float a = 0, b = 0;
       if (cudaEventElapsedTime(&a, ctx->tl_base, p.e0) == cudaSuccess && cudaEventElapsedTime(&b, ctx->tl_base, p.e1) == cudaSuccess) ctx->timeline.push_back({ctx->timers[p.timer].name, a, b});
     }
-    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+    ctx->ev_pool.push_back(p.e0); ctx->ev_pool.push_back(p.e1);
   }
   (void)cudaGetLastError();
   ctx->pending.clear(); ctx->tl_mark = 0;

@@ -152,7 +152,7 @@ __device__ __forceinline__ uint64_t rd64(const uint8_t* p) { return (uint64_t)rd
 
 // plan words per tx: 0 eq_begin, 1 val_begin, 2 rp_slot (0xffffffff none), 3 rp_chal_begin, 4 main signature slot (0xffffffff none), 5 flags (bit0: proofs stage reached)
 __global__ void __launch_bounds__(64) k_fiat_shamir(const uint8_t* __restrict__ blobs, const unsigned long long* __restrict__ blob_off, const uint32_t* __restrict__ plan, uint32_t plan_stride, uint32_t n_tx,
-                                                    const uint8_t* __restrict__ seed32, uint32_t* __restrict__ eq_sc, uint32_t* __restrict__ val_sc, uint32_t* __restrict__ rp_sc,
+                                                    const uint8_t* __restrict__ seed32, unsigned long long index_base, uint32_t* __restrict__ eq_sc, uint32_t* __restrict__ val_sc, uint32_t* __restrict__ rp_sc,
                                                     uint32_t* __restrict__ rp_chal, const uint32_t* __restrict__ rp_m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tx) return;
@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(64) k_fiat_shamir(const uint8_t* __restrict__ 
   else if (type == 3) p += aux;
   else p += 32 * (size_t)count;
   const uint8_t* rp = p; const uint8_t* scs = rp + rp_len;
-  // per-proof random batch factors: SHAKE256("xhe-batch-factors" || seed || tx index), 32 bytes each, top nibble cleared
+  // per-proof random batch factors: SHAKE256("xhe-batch-factors" || seed || index of the tx in the whole batch), 32 bytes each, top nibble cleared
   Sponge rng; rng.init(136);
-  { const char tag[] = "xhe-batch-factors"; rng.absorb((const uint8_t*)tag, 17); rng.absorb(seed32, 32); unsigned long long idx = i; rng.absorb((const uint8_t*)&idx, 8); rng.finish(0x1f); }
+  { const char tag[] = "xhe-batch-factors"; rng.absorb((const uint8_t*)tag, 17); rng.absorb(seed32, 32); unsigned long long idx = index_base + i; rng.absorb((const uint8_t*)&idx, 8); rng.finish(0x1f); }
   auto rnd_scalar = [&](uint32_t* out8) { uint8_t r[32]; rng.squeeze(r, 32); r[31] &= 0x0f; sc v = sc_frombytes(r); for (int q = 0; q < 8; q++) out8[q] = v.v[q]; };
   Merlin T; T.init("transaction-proof", 17);
   T.append_u64(LBL("version"), version); T.append(LBL("source_pubkey"), source, 32); T.append_u64(LBL("fee"), fee); T.append_u64(LBL("nonce"), nonce);
@@ -226,8 +226,11 @@ __global__ void __launch_bounds__(64) k_fiat_shamir(const uint8_t* __restrict__ 
 }
 
 // main signature check: e' = SHA3-512(pk || to_bytes(tx) || r) mod l ; ok = (e' == e)    (src/elgamal.rs:38-42,53-65; to_bytes: src/tx/verify.rs:623-688)
-__global__ void __launch_bounds__(64) k_sig_hash(const uint8_t* __restrict__ blobs, const unsigned long long* __restrict__ blob_off, const uint32_t* __restrict__ plan, uint32_t plan_stride, uint32_t n_tx,
-                                                 const uint8_t* __restrict__ sig_r, const uint32_t* __restrict__ sig_e, uint8_t* __restrict__ sig_ok) {
+// r is the LAST thing absorbed, so the check is split: k_sig_hash_prefix absorbs pk || to_bytes(tx) (about 19 of the 20
+// permutations of a one-transfer transaction) as soon as the blobs are on the device, beside the signature group operations;
+// k_sig_hash_final only absorbs r, pads and compares.  state = 25 lanes + the byte position, 26 x 8 bytes per signature slot.
+__global__ void __launch_bounds__(64) k_sig_hash_prefix(const uint8_t* __restrict__ blobs, const unsigned long long* __restrict__ blob_off, const uint32_t* __restrict__ plan, uint32_t plan_stride, uint32_t n_tx,
+                                                        unsigned long long* __restrict__ state) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tx) return;
   uint32_t slot = plan[plan_stride * (size_t)i + 4];
@@ -249,6 +252,20 @@ __global__ void __launch_bounds__(64) k_sig_hash(const uint8_t* __restrict__ blo
   h.absorb(p, rp_len); p += rp_len;
   h.absorb(p, 256 * (uint32_t)n_sc); p += 256 * (size_t)n_sc;
   if (n_ms > 0) h.absorb(p, 65 * (uint32_t)n_ms);
+  unsigned long long* o = state + 26 * (size_t)slot;
+  for (int q = 0; q < 25; q++) o[q] = h.st[q];
+  o[25] = h.pos;
+}
+__global__ void __launch_bounds__(64) k_sig_hash_final(const uint32_t* __restrict__ plan, uint32_t plan_stride, uint32_t n_tx, const unsigned long long* __restrict__ state,
+                                                       const uint8_t* __restrict__ sig_r, const uint32_t* __restrict__ sig_e, uint8_t* __restrict__ sig_ok) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tx) return;
+  uint32_t slot = plan[plan_stride * (size_t)i + 4];
+  if (slot == 0xFFFFFFFFu) return;
+  Sponge h; h.rate = 72;
+  const unsigned long long* in = state + 26 * (size_t)slot;
+  for (int q = 0; q < 25; q++) h.st[q] = in[q];
+  h.pos = (uint32_t)in[25];
   h.absorb(sig_r + 32 * (size_t)slot, 32);
   h.finish(0x06);
   uint8_t d[64]; h.squeeze(d, 64);
@@ -260,17 +277,23 @@ __global__ void __launch_bounds__(64) k_sig_hash(const uint8_t* __restrict__ blo
 
 }  // namespace
 
-int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed,
+int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed, unsigned long long index_base,
                                uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_rp_chal, const uint32_t* d_rp_m) {
   if (!n_tx) return XHE_OK;
   XheTimed t(ctx, "k_fiat_shamir", 0);
-  k_fiat_shamir<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, plan_stride, n_tx, d_seed, d_eq_sc, d_val_sc, d_rp_sc, d_rp_chal, d_rp_m);
+  k_fiat_shamir<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, plan_stride, n_tx, d_seed, index_base, d_eq_sc, d_val_sc, d_rp_sc, d_rp_chal, d_rp_m);
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
 }
-int32_t xhe_launch_sig_hash(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_sig_r, const uint32_t* d_sig_e, uint8_t* d_sig_ok) {
+int32_t xhe_launch_sig_hash_prefix(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, unsigned long long* d_state) {
+  if (!n_tx) return XHE_OK;
+  XheTimed t(ctx, "k_sig_hash_prefix", 0);
+  k_sig_hash_prefix<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, plan_stride, n_tx, d_state);
+  XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
+}
+int32_t xhe_launch_sig_hash_final(xhe_ctx* ctx, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const unsigned long long* d_state, const uint8_t* d_sig_r, const uint32_t* d_sig_e, uint8_t* d_sig_ok) {
   if (!n_tx) return XHE_OK;
   XheTimed t(ctx, "k_sig_hash", 0);
-  k_sig_hash<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, plan_stride, n_tx, d_sig_r, d_sig_e, d_sig_ok);
+  k_sig_hash_final<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_plan, plan_stride, n_tx, d_state, d_sig_r, d_sig_e, d_sig_ok);
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
 }
 
@@ -280,7 +303,8 @@ int32_t xhe_launch_sig_hash(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned
 // from the blob bytes, so the host never touches proof bytes.  Per-tx point layout (region A, starting at plan[6]):
 //   [source] [k x (C, D_sender, D_receiver)] [a x new commitment] [a x (Y0,Y1,Y2)] [k x dest] [k x (Y0,Y1,Y2)] [A,S,T1,T2] [L x lg] [R x lg]
 // plan words: 0 eq_begin, 1 val_begin, 2 rp slot, 3 rp challenge offset, 4 signature slot, 5 flags, 6 point base, 7 first balance-op index
-// An all-zero Y / A / S / T / L / R encoding (TranscriptError::IdentityPoint, src/transcript.rs:73-84) raises bit 0 of *viol.
+// An all-zero Y encoding (TranscriptError::IdentityPoint, src/transcript.rs:73-84) raises bit 0 of *viol and of the transaction's
+// flag byte; an all-zero A / S / T / L / R (rejected inside bulletproofs' verifier) raises bit 4 of *viol / bit 3 of the flag byte.
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ bool copy32_is_zero(uint8_t* dst, const uint8_t* src) {
@@ -302,7 +326,7 @@ __global__ void __launch_bounds__(64) k_layout(const uint8_t* __restrict__ blobs
                                                uint32_t n_points, uint8_t* __restrict__ enc, uint32_t* __restrict__ sig_idx /* eq then val point indices */, uint32_t n_eq_total,
                                                uint32_t* __restrict__ eq_sc, uint32_t* __restrict__ val_sc, uint32_t* __restrict__ rp_sc, uint32_t* __restrict__ range_idx,
                                                const uint32_t* __restrict__ rp_pt_off, uint32_t* __restrict__ sig_s, uint32_t* __restrict__ sig_e, uint32_t* __restrict__ sig_pk,
-                                               uint32_t* __restrict__ viol) {
+                                               uint32_t* __restrict__ viol, uint8_t* __restrict__ tx_flags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tx) return;
   const uint32_t* P = plan + 8 * (size_t)i;
@@ -343,9 +367,10 @@ __global__ void __launch_bounds__(64) k_layout(const uint8_t* __restrict__ blobs
     ei[0] = iSrc; ei[1] = iEqY + 3 * q; ei[2] = n_points + op + 1; ei[3] = n_points + op; ei[4] = iEqY + 3 * q + 1; ei[5] = iN + q; ei[6] = iEqY + 3 * q + 2;
     copy_words(eq_sc + 48 * (size_t)(P[0] + q), proof + 96, 24);
   }
+  bool bad_rp = false;   // an identity-encoded A / S / T / L / R fails inside the range-proof batch (RangeProof, after the sigma check), not at this transaction
   { // range proof: points A,S,T1,T2,L[lg],R[lg],V[m]; scalars t_x,t_x_blinding,e_blinding,a,b
-    for (int q = 0; q < 4; q++) bad |= copy32_is_zero(enc + 32 * (size_t)(iRp + q), rp + 32 * q);
-    for (uint32_t q = 0; q < lg; q++) { bad |= copy32_is_zero(enc + 32 * (size_t)(iRp + 4 + q), rp + 224 + 64 * (size_t)q); bad |= copy32_is_zero(enc + 32 * (size_t)(iRp + 4 + lg + q), rp + 224 + 64 * (size_t)q + 32); }
+    for (int q = 0; q < 4; q++) bad_rp |= copy32_is_zero(enc + 32 * (size_t)(iRp + q), rp + 32 * q);
+    for (uint32_t q = 0; q < lg; q++) { bad_rp |= copy32_is_zero(enc + 32 * (size_t)(iRp + 4 + q), rp + 224 + 64 * (size_t)q); bad_rp |= copy32_is_zero(enc + 32 * (size_t)(iRp + 4 + lg + q), rp + 224 + 64 * (size_t)q + 32); }
     uint32_t* ri = range_idx + rp_pt_off[P[2]]; uint32_t m = 1; while (m < a + k) m <<= 1;
     for (uint32_t q = 0; q < 4 + 2 * lg; q++) ri[q] = iRp + q;
     for (uint32_t q = 0; q < a; q++) ri[4 + 2 * lg + q] = iN + q;
@@ -355,9 +380,22 @@ __global__ void __launch_bounds__(64) k_layout(const uint8_t* __restrict__ blobs
     copy_words(rs, rp + 128, 24); copy_words(rs + 24, rp + rp_len - 64, 16);
   }
   copy_words(sig_s + 8 * (size_t)P[4], sig, 8); copy_words(sig_e + 8 * (size_t)P[4], sig + 32, 8); sig_pk[P[4]] = iSrc;
+  tx_flags[i] = (bad ? 1 : 0) | (bad_rp ? 8 : 0);
   if (bad) atomicOr(viol, 1u);
+  if (bad_rp) atomicOr(viol, 16u);
 }
 
+// per-transaction anomaly bits of the device-layout path (same meaning as xhe_verdict.device_flags bits 0-2): bit 0 was set by
+// k_layout; bit 1 = one of the transaction's own points (region A) failed to decompress; bit 2 = its signature hash mismatched
+__global__ void __launch_bounds__(128) k_tx_flags(const uint32_t* __restrict__ plan, uint32_t n_tx, uint32_t n_a_end, const uint8_t* __restrict__ pt_ok, const uint8_t* __restrict__ sig_ok, uint8_t* __restrict__ tx_flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tx) return;
+  const uint32_t lo = plan[8 * (size_t)i + 6], hi = i + 1 < n_tx ? plan[8 * (size_t)(i + 1) + 6] : n_a_end;
+  uint8_t f = tx_flags[i];
+  for (uint32_t p = lo; p < hi; p++) if (!pt_ok[p]) { f |= 2; break; }
+  if (!sig_ok[plan[8 * (size_t)i + 4]]) f |= 4;
+  tx_flags[i] = f;
+}
 // OR of (flag byte == 0) over n bytes into bit `bit` of *viol
 __global__ void __launch_bounds__(256) k_any_zero(const uint8_t* __restrict__ flags, uint32_t n, uint32_t bit, uint32_t* __restrict__ viol) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,14 +406,29 @@ __global__ void __launch_bounds__(256) k_any_zero(const uint8_t* __restrict__ fl
 
 int32_t xhe_launch_layout(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t n_tx, uint32_t n_points, uint8_t* d_enc,
                           uint32_t* d_sig_idx, uint32_t n_eq, uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_range_idx, const uint32_t* d_rp_pt_off,
-                          uint32_t* d_sig_s, uint32_t* d_sig_e, uint32_t* d_sig_pk, uint32_t* d_viol) {
+                          uint32_t* d_sig_s, uint32_t* d_sig_e, uint32_t* d_sig_pk, uint32_t* d_viol, uint8_t* d_tx_flags) {
   if (!n_tx) return XHE_OK;
   XheTimed t(ctx, "k_layout", 0);
-  k_layout<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, n_tx, n_points, d_enc, d_sig_idx, n_eq, d_eq_sc, d_val_sc, d_rp_sc, d_range_idx, d_rp_pt_off, d_sig_s, d_sig_e, d_sig_pk, d_viol);
+  k_layout<<<(n_tx + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_off, d_plan, n_tx, n_points, d_enc, d_sig_idx, n_eq, d_eq_sc, d_val_sc, d_rp_sc, d_range_idx, d_rp_pt_off, d_sig_s, d_sig_e, d_sig_pk, d_viol, d_tx_flags);
+  XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
+}
+int32_t xhe_launch_tx_flags(xhe_ctx* ctx, const uint32_t* d_plan, uint32_t n_tx, uint32_t n_a_end, const uint8_t* d_pt_ok, const uint8_t* d_sig_ok, uint8_t* d_tx_flags) {
+  if (!n_tx) return XHE_OK;
+  k_tx_flags<<<(n_tx + 127) / 128, 128, 0, ctx->stream>>>(d_plan, n_tx, n_a_end, d_pt_ok, d_sig_ok, d_tx_flags);
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
 }
 int32_t xhe_launch_any_zero(xhe_ctx* ctx, const uint8_t* d_flags, uint32_t n, uint32_t bit, uint32_t* d_viol) {
   if (!n) return XHE_OK;
   k_any_zero<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_flags, n, bit, d_viol);
   XHE_LAUNCHED(ctx); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK;
+}
+
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2), and loading one may need every running kernel
+// to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
+// kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
+size_t xhe_preload_fs() {      // returns the largest per-thread local-memory frame among them
+  const void* ks[] = {(const void*)k_fiat_shamir, (const void*)k_sig_hash_prefix, (const void*)k_sig_hash_final, (const void*)k_layout, (const void*)k_tx_flags, (const void*)k_any_zero};
+  cudaFuncAttributes a; size_t mx = 0;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
+  return mx;
 }

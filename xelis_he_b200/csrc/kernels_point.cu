@@ -306,3 +306,12 @@ extern "C" int32_t xhe_bench_op(xhe_ctx* ctx, int op, int threads_per_block, int
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_c); return XHE_OK;
 }
+
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2), and loading one may need every running kernel
+// to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
+// kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
+void xhe_preload_point() {
+  const void* ks[] = {(const void*)k_decompress, (const void*)k_compress_ext, (const void*)k_compress_aff, (const void*)k_compress_xy_bytes, (const void*)k_affine_to_bytes, (const void*)k_from_uniform, (const void*)k_ct_update, (const void*)k_and_pairs, (const void*)k_ct_update_resident<128, 1>, (const void*)k_selftest_fe};      // (the microbenchmark kernels never run beside a batch)
+  cudaFuncAttributes a;
+  for (const void* k : ks) cudaFuncGetAttributes(&a, k);
+}

@@ -5,15 +5,22 @@
 // Not a port of dalek's w <= 8 column loop: the whole scalar is recoded into W = ceil(254/c) signed c-bit digits
 // (c chosen per n, up to 16+), every (window, bucket) pair is an independent work item, and the pipeline is
 //
-//   k_msm_count     thread/point : recode scalar -> W signed digits, histogram (window,bucket) sizes      [L2 atomics]
-//   scan            3 kernels    : exclusive prefix sum over the W*2^(c-1) bucket sizes
-//   k_msm_scatter   thread/point : counting-sort point indices (sign in bit 31) into bucket order          [L2 atomics]
-//   k_msm_sizeperm  thread/bucket: order buckets by size (descending) so the 32 lanes of a warp loop equally
-//   k_msm_accum     thread/bucket: gather 96-byte affine-Niels points (6 x LDG.128, next point prefetched),
-//                                  7 M mixed additions into a register-resident extended accumulator        [HOT: IMAD pipe]
-//   k_msm_seg       thread/8 buckets: running-sum reduction of 8 consecutive buckets -> (run, wsum) node
-//   k_msm_nodes     warp/32 nodes: warp-shuffle suffix-scan + tree reduction of nodes (repeated until 1 node/window)
-//   k_msm_horner    1 thread     : sum_w 2^(c w) S_w by Horner, ristretto encode, identity flag
+//   k_msm_count       thread/point : recode scalar -> W signed digits, histogram (window,bucket) sizes      [L2 atomics]
+//   scan              3 kernels    : exclusive prefix sum over the W*2^(c-1) bucket sizes
+//   k_msm_scatter     thread/point : counting-sort point indices (sign in bit 31) into bucket order          [L2 atomics, 8 in flight]
+//   k_msm_tile_runs   thread/tile  : the sorted list is cut into fixed tiles of 32 entries; count the bucket runs per tile
+//   k_msm_accum_tiles thread/tile  : gather 96-byte affine-Niels points (6 x LDG.128, next point prefetched),
+//                                    7 M mixed additions into a register-resident extended accumulator      [HOT: IMAD pipe]
+//                                    -- also records where each bucket's partial sums start / how many there are
+//   k_msm_fold_heavy  block/bucket : buckets with many partials (under-filled top window, skewed scalars)
+//   k_msm_bucket_seg  CTA/256 buckets: thread/bucket merge of the partials, then quad/4 buckets running sum -> (run, wsum) node
+//   k_msm_nodes32     CTA/32 nodes : shared-memory suffix scan + tree with quad-cooperative point arithmetic (quad.cuh),
+//                                    repeated until one node per window
+//   k_msm_horner_g    1 warp       : Horner over the windows of one window GROUP, chained through a 128-byte accumulator
+//
+// Windows are sorted most-significant first and processed in G groups: group g's accumulation runs on the caller's stream
+// while the latency-bound reduction + Horner segment of group g-1 (its c * windows dependent doublings) runs on a
+// high-priority side stream, so only the last group's tail is exposed.
 //
 // Algorithmic work: n*W mixed adds of 7 M = 504 limb products each dominate.
 #include <stdlib.h>
@@ -27,16 +34,19 @@ using namespace xhe;
 namespace {
 
 #define MSM_TILE 32   // entries per accumulation work item
+#define MSM_SEG 4     // buckets per level-1 running-sum segment (one quad)
+#define MSM_SEG_LOG 2
+#define MSM_MAX_GROUPS 8
 #define XHE_ACCUM_SMEM_DEFAULT 0
 
 struct MsmPlan {
   int c, W;             // window bits, windows
   uint32_t B;           // buckets per window = 2^(c-1)
   size_t total_buckets; // W * B
-  int seg_log;          // log2 of buckets per level-1 segment
+  int G, Wg;            // window groups (most significant first) and windows per group (the last group may be shorter)
   // workspace offsets (bytes)
   size_t n_tiles, max_runs;
-  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_tileg0, off_runs, off_runoff, off_part, off_partg, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_flag, total;
+  size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_tileg0, off_runs, off_runoff, off_part, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_hnodes, off_hacc, off_ready, off_flag, total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -58,8 +68,14 @@ MsmPlan make_plan(size_t n) {
   }
   if (n <= 4096 && bc < 8) bc = 8;   // tiny inputs are pure latency: fewer windows shorten the per-window stages and the Horner chain
   p.c = bc; p.W = (254 + bc - 1) / bc; p.B = 1u << (bc - 1); p.total_buckets = (size_t)p.W * p.B;
-  static const int seg_env = getenv("XHE_MSM_SEG_LOG") ? atoi(getenv("XHE_MSM_SEG_LOG")) : 3;   // buckets per running-sum thread = 2^seg_log
-  p.seg_log = std::min(seg_env, bc - 1);
+  // window groups: the reduction + Horner segment of a group overlaps the accumulation of the next one.  Small inputs are
+  // pure latency (one launch wave per group at best): no split.
+  // A group's accumulation launch must still fill the machine for a few waves (measured: four launches of 183 blocks each
+  // took 2.2x the time of one launch of 732), so a group gets at least ~5 M list entries; 4 groups from 2^20 points up.
+  static const int g_env = getenv("XHE_MSM_GROUPS") ? atoi(getenv("XHE_MSM_GROUPS")) : 0;
+  int G = g_env > 0 ? g_env : (int)std::min<size_t>(4, std::max<size_t>(1, n * (size_t)p.W / ((size_t)5 << 20)));
+  G = std::max(1, std::min(G, MSM_MAX_GROUPS));
+  p.Wg = (p.W + G - 1) / G; p.G = (p.W + p.Wg - 1) / p.Wg;
   size_t o = 0;
   p.off_counts = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
   p.off_offsets = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
@@ -73,13 +89,15 @@ MsmPlan make_plan(size_t n) {
   p.off_runs = o; o = align_up(o + 4 * (p.n_tiles + 1), 256);
   p.off_runoff = o; o = align_up(o + 4 * (p.n_tiles + 1), 256);
   p.off_part = o; o = align_up(o + 128 * p.max_runs, 256);
-  p.off_partg = o; o = align_up(o + 4 * p.max_runs, 256);
   p.off_pstart = o; o = align_up(o + 4 * p.total_buckets, 256);
   p.off_pcount = o; o = align_up(o + 4 * p.total_buckets, 256);
-  p.off_heavy = o; o = align_up(o + 4 * (p.total_buckets + 4), 256);
-  size_t nodes1 = p.total_buckets >> p.seg_log;
+  p.off_heavy = o; o = align_up(o + 4 * (p.total_buckets + 8 * (MSM_MAX_GROUPS + 1)), 256);      // per group: [count, bucket ids...]
+  size_t nodes1 = (p.total_buckets + MSM_SEG - 1) / MSM_SEG + 64;
   p.off_nodes_a = o; o = align_up(o + 256 * nodes1, 256);
-  p.off_nodes_b = o; o = align_up(o + 256 * ((nodes1 + 31) / 32 + (size_t)p.W), 256);
+  p.off_nodes_b = o; o = align_up(o + 256 * ((nodes1 + 31) / 32 + (size_t)p.W + 64), 256);
+  p.off_hnodes = o; o = align_up(o + 256 * ((size_t)p.W + 1), 256);      // one final node per window: input of the Horner stream
+  p.off_hacc = o; o = align_up(o + 128 * (MSM_MAX_GROUPS + 1), 256);
+  p.off_ready = o; o = align_up(o + 64, 256);          // ready[g]: final nodes of group g written; ready[8]: chain status
   p.off_flag = o; o = align_up(o + 64, 256);
   p.total = o;
   return p;
@@ -87,51 +105,68 @@ MsmPlan make_plan(size_t n) {
 
 // ---- digit recoding ----------------------------------------------------------------------------------------------
 // signed radix-2^c digits d_w in [-2^(c-1), 2^(c-1)], sum d_w 2^(c w) = s, for s < 2^253 and c*W >= 254 (the top digit
-// absorbs the final carry without overflow).
-template <typename F>
-__device__ __forceinline__ void for_each_digit(const uint32_t s[8], int c, int W, F&& f) {
-  uint32_t carry = 0;
+// absorbs the final carry without overflow).  The sort key of digit d of window w is (W-1-w) * B + |d| - 1: windows are
+// laid out MOST SIGNIFICANT FIRST, so the reduction / Horner pipeline can start on the top windows while the lower ones
+// are still being accumulated.
+__device__ __forceinline__ uint32_t limb_of(const uint32_t s[8], int limb) {      // s[limb] without dynamic register indexing
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r = (limb == k) ? s[k] : r;
+  return r;
+}
+__device__ __forceinline__ int32_t next_digit(const uint32_t s[8], int w, int c, uint32_t& carry) {
   const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
-  for (int w = 0; w < W; w++) {
-    int bit = w * c, limb = bit >> 5, sh = bit & 31;
-    uint32_t v = 0;
-    if (limb < 8) {
-      v = s[limb] >> sh;
-      if (sh + c > 32 && limb + 1 < 8) v |= s[limb + 1] << (32 - sh);
-    }
-    v = (v & mask) + carry;
-    carry = v > half ? 1u : 0u;          // v in [0, 2^c]; digits above half become negative with a carry
-    int32_t d = carry ? (int32_t)v - (int32_t)(1u << c) : (int32_t)v;
-    f(w, d);
+  int bit = w * c, limb = bit >> 5, sh = bit & 31;
+  uint32_t v = 0;
+  if (limb < 8) {
+    v = limb_of(s, limb) >> sh;
+    if (sh + c > 32 && limb + 1 < 8) v |= limb_of(s, limb + 1) << (32 - sh);
   }
+  v = (v & mask) + carry;
+  carry = v > half ? 1u : 0u;            // v in [0, 2^c]; digits above half become negative with a carry
+  return carry ? (int32_t)v - (int32_t)(1u << c) : (int32_t)v;
+}
+__device__ __forceinline__ void ld_scalar(uint32_t s[8], const uint32_t* __restrict__ scalars, size_t i) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i)), b = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i) + 1);
+  s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
 }
 
 __global__ void __launch_bounds__(256) k_msm_count(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ bad_flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t s[8];
-  { uint4 a = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i)), b = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i) + 1);
-    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w; }
+  uint32_t s[8]; ld_scalar(s, scalars, i);
   if (sc_geq_l(s)) { atomicOr(bad_flag, 1u); return; }   // non-canonical scalar: reported as a bad argument, contributes nothing
-  for_each_digit(s, c, W, [&](int w, int32_t d) {
-    if (d != 0) atomicAdd(&counts[(size_t)w * B + (uint32_t)((d < 0 ? -d : d) - 1)], 1u);
-  });
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    int32_t d = next_digit(s, w, c, carry);
+    if (d != 0) atomicAdd(&counts[(size_t)(W - 1 - w) * B + (uint32_t)((d < 0 ? -d : d) - 1)], 1u);
+  }
 }
 
+// counting-sort scatter.  The position of an entry is a RETURNING atomic on its bucket's cursor; eight of them are issued
+// before the first dependent store, so a thread has eight L2 round trips in flight instead of one.
+#define SCAT_CH 8
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t s[8];
-  { uint4 a = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i)), b = __ldg(reinterpret_cast<const uint4*>(scalars + 8 * i) + 1);
-    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w; }
+  uint32_t s[8]; ld_scalar(s, scalars, i);
   if (sc_geq_l(s)) return;
-  for_each_digit(s, c, W, [&](int w, int32_t d) {
-    if (d != 0) {
-      uint32_t g = (uint32_t)w * B + (uint32_t)((d < 0 ? -d : d) - 1);
-      uint32_t pos = atomicAdd(&cursor[g], 1u);
-      list[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);     // the bucket of a position follows from the offsets: no second array
+  uint32_t carry = 0;
+  for (int w0 = 0; w0 < W; w0 += SCAT_CH) {
+    uint32_t key[SCAT_CH], val[SCAT_CH], pos[SCAT_CH];
+#pragma unroll
+    for (int j = 0; j < SCAT_CH; j++) {
+      key[j] = 0xffffffffu; val[j] = 0;
+      if (w0 + j < W) {
+        int32_t d = next_digit(s, w0 + j, c, carry);
+        if (d != 0) { key[j] = (uint32_t)(W - 1 - (w0 + j)) * B + (uint32_t)((d < 0 ? -d : d) - 1); val[j] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u); }
+      }
     }
-  });
+#pragma unroll
+    for (int j = 0; j < SCAT_CH; j++) pos[j] = key[j] != 0xffffffffu ? atomicAdd(&cursor[key[j]], 1u) : 0u;
+#pragma unroll
+    for (int j = 0; j < SCAT_CH; j++) if (key[j] != 0xffffffffu) list[pos[j]] = val[j];     // the bucket of a position follows from the offsets: no second array
+  }
 }
 
 // ---- exclusive scan over m uint32 (m up to 4096 * 2048) --------------------------------------------------------------
@@ -208,18 +243,33 @@ __global__ void __launch_bounds__(256) k_msm_tile_runs(const uint32_t* __restric
 // HOT: each thread walks MSM_TILE consecutive entries, gathers the 96-byte affine-Niels points (6 x LDG.128, the next
 // point prefetched under the current addition) and accumulates 7 M mixed additions in registers; a partial sum is
 // flushed whenever the bucket id changes.  Every lane does the same number of additions: no divergence on bucket size.
+// One launch per window group: a thread works only if its tile STARTS in a bucket of [klo, khi).  The partial sums of a
+// bucket occupy consecutive slots in bucket order; the run that contains the bucket's first entry records the first slot
+// (pstart), every flush counts (pcount), and the flush that makes a bucket "heavy" appends it to its group's list.
+#define HEAVY_PARTIALS 12
+struct AccumOut { uint32_t *part, *pstart, *pcount, *heavy; uint32_t keys_per_group; };
+__device__ __forceinline__ void flush_run(const AccumOut& o, uint32_t slot, uint32_t g, const ge& acc) {
+  st_ge(o.part + 32 * (size_t)slot, acc);
+  if (atomicAdd(&o.pcount[g], 1u) == HEAVY_PARTIALS) {
+    uint32_t grp = g / o.keys_per_group; uint32_t* h = o.heavy + (size_t)grp * o.keys_per_group + 8 * grp;
+    h[1 + atomicAdd(&h[0], 1u)] = g;
+  }
+}
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* __restrict__ niels, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offsets, uint32_t m,
                                                               const uint32_t* __restrict__ tile_g0, const uint32_t* __restrict__ run_off, size_t n_tiles,
-                                                              uint32_t* __restrict__ part, uint32_t* __restrict__ part_g) {
+                                                              uint32_t klo, uint32_t khi, AccumOut out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
   uint32_t N = __ldg(offsets + m);
   size_t start = t * MSM_TILE;
   if (start >= N) return;
+  uint32_t g = __ldg(tile_g0 + t);
+  if (g < klo || g >= khi) return;
   uint32_t cnt = (uint32_t)(min((size_t)N, start + MSM_TILE) - start);
   uint32_t slot = run_off[t];
-  uint32_t g = __ldg(tile_g0 + t), nb = __ldg(offsets + g + 1);          // nb: first position past the current bucket
+  uint32_t nb = __ldg(offsets + g + 1);          // nb: first position past the current bucket
+  if (__ldg(offsets + g) == (uint32_t)start) out.pstart[g] = slot;
   uint32_t e = __ldg(list + start);
   ge_niels q; ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu));
   ge acc = ge_from_niels(niels_cneg(q, (e >> 31) != 0));
@@ -229,73 +279,26 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* _
     ge_niels cur = niels_cneg(q, (e >> 31) != 0);
     if (j + 1 < cnt) { e = __ldg(list + start + j + 1); ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu)); }
     if (pos == nb) {   // bucket boundary: flush the finished run, restart from this point
-      st_ge(part + 32 * (size_t)slot, acc); part_g[slot] = g; slot++;
+      flush_run(out, slot, g, acc); slot++;
       g = next_bucket(offsets, m, pos, g); nb = __ldg(offsets + g + 1);
+      out.pstart[g] = slot;                       // pos is this bucket's first entry
       acc = ge_from_niels(cur);
     } else {
       acc = ge_madd(acc, cur);
     }
   }
-  st_ge(part + 32 * (size_t)slot, acc); part_g[slot] = g;
+  flush_run(out, slot, g, acc);
 }
 
-// partial sums are in bucket order; record where each bucket's partials start and how many there are
-__global__ void __launch_bounds__(256) k_msm_bucket_index(const uint32_t* __restrict__ part_g, const uint32_t* __restrict__ total_runs, size_t max_runs, uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount) {
-  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= max_runs || s >= *total_runs) return;
-  uint32_t g = part_g[s];
-  atomicAdd(&pcount[g], 1u);
-  if (s == 0 || part_g[s - 1] != g) pstart[g] = (uint32_t)s;
+__global__ void k_msm_zero_heads(uint32_t* __restrict__ heavy, uint32_t keys_per_group, int G, uint32_t* __restrict__ ready) {
+  if ((int)threadIdx.x < G) heavy[(size_t)threadIdx.x * keys_per_group + 8 * threadIdx.x] = 0;
+  if (threadIdx.x < 16) ready[threadIdx.x] = 0;
 }
 
-// buckets whose partial list is long (under-filled top window, skewed scalars) are folded by a whole block first
-#define HEAVY_PARTIALS 6
-__global__ void __launch_bounds__(256) k_msm_find_heavy(const uint32_t* __restrict__ pcount, size_t m, uint32_t* __restrict__ heavy /* [0] = count, [1..] = bucket ids */) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < m && pcount[g] > HEAVY_PARTIALS) heavy[1 + atomicAdd(&heavy[0], 1u)] = (uint32_t)g;
-}
+// buckets whose partial list is long (under-filled top window, skewed scalars) are folded first, one WARP per bucket: the
+// lanes stride over the partial sums, then a shuffle tree.  (Round 1 used a block per bucket with a 7-round shared-memory
+// tree: at 2^22 points the top window alone has 8,192 buckets of ~17 partials, and that fold took 0.19 ms at 2^20.)
 #define FOLD_THREADS 128
-__global__ void __launch_bounds__(FOLD_THREADS) k_msm_fold_heavy(uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount, const uint32_t* __restrict__ heavy) {
-  __shared__ uint32_t sm[FOLD_THREADS * 32];
-  uint32_t nh = heavy[0];
-  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
-    uint32_t g = heavy[1 + h], ps = pstart[g], pc = pcount[g];
-    ge acc = ge_identity(), s;
-    for (uint32_t j = threadIdx.x; j < pc; j += FOLD_THREADS) { ld_ge(s, part + 32 * (size_t)(ps + j)); acc = ge_add(acc, s); }
-    st_ge(sm + 32 * threadIdx.x, acc);
-    __syncthreads();
-    for (int stride = FOLD_THREADS / 2; stride >= 1; stride >>= 1) {
-      if ((int)threadIdx.x < stride && threadIdx.x + stride < min(pc, (uint32_t)FOLD_THREADS)) {
-        ge a, b; ld_ge(a, sm + 32 * threadIdx.x); ld_ge(b, sm + 32 * (threadIdx.x + stride));
-        st_ge(sm + 32 * threadIdx.x, ge_add(a, b));
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { ge r; ld_ge(r, sm); st_ge(part + 32 * (size_t)ps, r); pcount[g] = 1; }
-    __syncthreads();
-  }
-}
-
-// ---- bucket reduction -----------------------------------------------------------------------------------------------
-// node = (run, wsum): run = sum of the bucket sums in its range, wsum = sum (b - lo) * S_b (weights relative to the range)
-__global__ void __launch_bounds__(128) k_msm_seg(const uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
-                                                 size_t n_nodes, int seg_log, uint32_t* __restrict__ nodes) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_nodes) return;
-  const int L = 1 << seg_log;
-  size_t b0 = t << seg_log;
-  ge run = ge_identity(), wsum = ge_identity(), s;
-  for (int r = L - 1; r >= 0; r--) {
-    uint32_t pc = pcount[b0 + r];
-    if (pc) {
-      uint32_t ps = pstart[b0 + r];
-      for (uint32_t j = 0; j < pc; j++) { ld_ge(s, part + 32 * (size_t)(ps + j)); run = ge_add(run, s); }
-    }
-    if (r >= 1) wsum = ge_add(wsum, run);
-  }
-  st_ge(nodes + 64 * t, run); st_ge(nodes + 64 * t + 32, wsum);
-}
-
 __device__ __forceinline__ ge shfl_down_ge(const ge& p, int d) {
   ge r;
 #pragma unroll
@@ -305,48 +308,189 @@ __device__ __forceinline__ ge shfl_down_ge(const ge& p, int d) {
   }
   return r;
 }
-// one warp folds 32 consecutive child nodes (each of width 2^child_log buckets) of ONE window into a parent node.
-// nodes_per_window_in children per window; parents per window = ceil(children / 32).
-__global__ void __launch_bounds__(128) k_msm_nodes(const uint32_t* __restrict__ in, uint32_t children_per_window, uint32_t parents_per_window, int W, int child_log, uint32_t* __restrict__ out) {
-  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= parents_per_window * (uint32_t)W) return;
-  uint32_t w = warp / parents_per_window, pidx = warp % parents_per_window;
-  uint32_t child = pidx * 32 + lane;
-  ge run, wsum;
-  if (child < children_per_window) { const uint32_t* p = in + 64 * ((size_t)w * children_per_window + child); ld_ge(run, p); ld_ge(wsum, p + 32); }
-  else { run = ge_identity(); wsum = ge_identity(); }
-  // suffix sums of run: suf_c = sum_{j >= c} run_j
-  ge suf = run;
+__global__ void __launch_bounds__(FOLD_THREADS) k_msm_fold_heavy(uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, uint32_t* __restrict__ pcount, const uint32_t* __restrict__ heavy) {
+  const uint32_t nh = heavy[0], lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t h = warp; h < nh; h += n_warps) {
+    const uint32_t g = heavy[1 + h], ps = pstart[g], pc = pcount[g];
+    ge acc = ge_identity(), s;
+    for (uint32_t j = lane; j < pc; j += 32) { ld_ge(s, part + 32 * (size_t)(ps + j)); acc = ge_add(acc, s); }
 #pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) { ge t = shfl_down_ge(suf, d); ge a = ge_add(suf, t); bool take = lane + d < 32; suf.X = fe_select(suf.X, a.X, take); suf.Y = fe_select(suf.Y, a.Y, take); suf.Z = fe_select(suf.Z, a.Z, take); suf.T = fe_select(suf.T, a.T, take); }
-  // A = sum_{c >= 1} suf_c = sum_c c * run_c ;  Ws = sum_c wsum_c  (both by tree reduction towards lane 0)
-  ge A = suf;
-  if (lane == 0) A = ge_identity();
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) { A = ge_add(A, shfl_down_ge(A, d)); wsum = ge_add(wsum, shfl_down_ge(wsum, d)); }
-  if (lane == 0) {
-    for (int k = 0; k < child_log; k++) A = ge_double(A);
-    wsum = ge_add(wsum, A);
-    uint32_t* o = out + 64 * ((size_t)w * parents_per_window + pidx);
-    st_ge(o, suf); st_ge(o + 32, wsum);
+    for (int d = 16; d >= 1; d >>= 1) acc = ge_add(acc, shfl_down_ge(acc, d));
+    if (lane == 0) { st_ge(part + 32 * (size_t)ps, acc); pcount[g] = 1; }
   }
 }
 
-// final: one node per window.  S_w = wsum + run (bucket b carries multiplier b+1); result = sum_w 2^(c w) S_w by Horner.
-// 254 sequential doublings: a pure latency chain, so one quad (4 lanes) shares every point operation (quad.cuh).
-__global__ void __launch_bounds__(32) k_msm_horner(const uint32_t* __restrict__ nodes, int W, int c, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
+// ---- bucket reduction -----------------------------------------------------------------------------------------------
+// node = (run, wsum): run = sum of the bucket sums in its range, wsum = sum (b - lo) * S_b (weights relative to the range).
+// These stages have few work items and long dependent chains, so every point operation is shared by the four lanes of a
+// quad (quad.cuh); each lane of a quad holds the same point.
+__device__ __forceinline__ void st_ge_quad(uint32_t* p, const ge& g) {       // lane ql of the quad stores coordinate ql
+  const int ql = threadIdx.x & 3;
+  st_fe(p + 8 * ql, quad_pick(g.X, g.Y, g.Z, g.T, ql));
+}
+// level 1: one CTA per 256 consecutive bucket keys.  Phase 1: thread/bucket adds up the bucket's partial sums (at most
+// HEAVY_PARTIALS after the fold).  Phase 2: quad/4 buckets running sum -> node of width 4.
+__global__ void __launch_bounds__(256) k_msm_bucket_seg(const uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
+                                                        uint32_t klo, uint32_t khi, uint32_t* __restrict__ nodes) {
+  __shared__ __align__(16) uint32_t sm[256 * 32];
+  const uint32_t k = klo + blockIdx.x * 256 + threadIdx.x;
+  ge v = ge_identity();
+  if (k < khi) {
+    const uint32_t pc = pcount[k];
+    if (pc) {
+      const uint32_t ps = pstart[k];
+      ld_ge(v, part + 32 * (size_t)ps);
+      for (uint32_t j = 1; j < pc; j++) { ge s; ld_ge(s, part + 32 * (size_t)(ps + j)); v = ge_add(v, s); }
+    }
+  }
+  st_ge(sm + 32 * threadIdx.x, v);
+  __syncthreads();
+  const uint32_t q = threadIdx.x >> 2;
+  ge run, wsum, s;
+  ld_ge(run, sm + 32 * (4 * q + 3)); wsum = run;
+  ld_ge(s, sm + 32 * (4 * q + 2)); run = quad_add(run, s); wsum = quad_add(wsum, run);
+  ld_ge(s, sm + 32 * (4 * q + 1)); run = quad_add(run, s); wsum = quad_add(wsum, run);
+  ld_ge(s, sm + 32 * (4 * q + 0)); run = quad_add(run, s);
+  const uint32_t kq = klo + blockIdx.x * 256 + 4 * q;
+  if (kq < khi) { uint32_t* o = nodes + 64 * (size_t)((kq - klo) >> MSM_SEG_LOG); st_ge_quad(o, run); st_ge_quad(o + 32, wsum); }
+}
+
+// one CTA (32 quads) folds 32 consecutive child nodes (each of width 2^child_log buckets) of ONE window into a parent:
+//   run' = sum run_c ; wsum' = sum wsum_c + 2^child_log * sum_c c * run_c , and sum_c c * run_c = sum_{c >= 1} suffix_c.
+// Suffix sums by a Hillis-Steele scan through shared memory (5 rounds), then the 31 suffixes and the 32 wsums are summed by
+// two trees that run side by side on quads 0-15 / 16-31 (5 rounds).
+__global__ void __launch_bounds__(128) k_msm_nodes32(const uint32_t* __restrict__ in, uint32_t children_per_window, uint32_t parents_per_window, int child_log, uint32_t* __restrict__ out,
+                                                     uint32_t* __restrict__ ready /* NULL, or the counter of finished final nodes the chain kernel polls */) {
+  __shared__ __align__(16) uint32_t sA[32 * 32], sW[32 * 32];
+  const uint32_t w = blockIdx.x / parents_per_window, pidx = blockIdx.x % parents_per_window;
+  const uint32_t q = threadIdx.x >> 2, child = pidx * 32 + q;
+  ge run, wsum;
+  if (child < children_per_window) { const uint32_t* p = in + 64 * ((size_t)w * children_per_window + child); ld_ge(run, p); ld_ge(wsum, p + 32); }
+  else { run = ge_identity(); wsum = ge_identity(); }
+  ge suf = run;
+#pragma unroll 1
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    st_ge_quad(sA + 32 * q, suf);
+    __syncthreads();
+    ge t = ge_identity();
+    if (q + d < 32) ld_ge(t, sA + 32 * (q + d));
+    __syncthreads();
+    suf = quad_add(suf, t);
+  }
+  { ge A = suf; if (q == 0) A = ge_identity(); st_ge_quad(sA + 32 * q, A); st_ge_quad(sW + 32 * q, wsum); }
+  __syncthreads();
+  uint32_t* arr = q < 16 ? sA : sW; const uint32_t i = q & 15;
+#pragma unroll 1
+  for (uint32_t st = 16; st >= 1; st >>= 1) {
+    ge a = ge_identity(), b = ge_identity();
+    if (i < st) { ld_ge(a, arr + 32 * i); ld_ge(b, arr + 32 * (i + st)); }
+    ge r = quad_add(a, b);
+    __syncthreads();
+    if (i < st) st_ge_quad(arr + 32 * i, r);
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) {     // warp 0 (its eight quads compute the same thing; quad 0 stores)
+    ge At, Wt; ld_ge(At, sA); ld_ge(Wt, sW);
+    for (int k = 0; k < child_log; k++) At = quad_double(At);
+    Wt = quad_add(Wt, At);
+    if (q == 0) { uint32_t* o = out + 64 * ((size_t)w * parents_per_window + pidx); st_ge_quad(o, suf); st_ge_quad(o + 32, Wt); if (ready) __threadfence(); }
+    __syncwarp();
+    if (ready && threadIdx.x == 0) atomicAdd(ready, 1u);      // release: the four lanes' stores are fenced before the count moves
+  }
+}
+
+// Horner segment over the n_w windows of one group (most significant first): acc = 2^c * acc + S_w, S_w = wsum + run
+// (bucket b carries multiplier b+1).  acc_in = the accumulator the previous group left (NULL for the first group, whose
+// first window needs no doublings).  c * n_w sequential doublings: a pure latency chain, so one quad shares every point
+// operation (the eight quads of the warp first form the S_w in parallel).  The last group also encodes the result.
+__global__ void __launch_bounds__(32) k_msm_horner_g(const uint32_t* __restrict__ nodes, int n_w, int c, const uint32_t* __restrict__ acc_in, uint32_t* __restrict__ acc_out, int last,
+                                                    uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
+  __shared__ __align__(16) uint32_t sS[32 * 32];
+  const int q = threadIdx.x >> 2;
+  for (int base = 0; base < n_w; base += 8) {
+    const int j = base + q;
+    ge run = ge_identity(), wsum = ge_identity();
+    if (j < n_w) { ld_ge(run, nodes + 64 * (size_t)j); ld_ge(wsum, nodes + 64 * (size_t)j + 32); }
+    ge S = quad_add(run, wsum);
+    if (j < n_w) st_ge_quad(sS + 32 * j, S);
+  }
+  __syncwarp();
   ge acc = ge_identity();
-  for (int w = W - 1; w >= 0; w--) {
-    if (w != W - 1) for (int k = 0; k < c; k++) acc = quad_double(acc);
-    ge run, wsum; ld_ge(run, nodes + 64 * (size_t)w); ld_ge(wsum, nodes + 64 * (size_t)w + 32);
-    acc = quad_add(acc, quad_add(run, wsum));
+  if (acc_in) ld_ge(acc, acc_in);
+  for (int w = 0; w < n_w; w++) {
+    if (acc_in || w) for (int k = 0; k < c; k++) acc = quad_double(acc);
+    ge S; ld_ge(S, sS + 32 * w);
+    acc = quad_add(acc, S);
   }
   if (threadIdx.x != 0) return;
+  if (acc_out) st_ge(acc_out, acc);
+  if (!last) return;
   if (out_ext) {   // canonical coordinates so any consumer (other ranks, the CPU oracle) can read them
     st_fe(out_ext, fe_freeze(acc.X)); st_fe(out_ext + 8, fe_freeze(acc.Y)); st_fe(out_ext + 16, fe_freeze(acc.Z)); st_fe(out_ext + 24, fe_freeze(acc.T));
   }
   if (out_enc) encode_words(out_enc, acc);
   if (is_identity) *is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
+}
+// The same chain as ONE kernel that is launched BEFORE its inputs exist and polls for them (experiment, XHE_MSM_CHAIN=1):
+// a latency-bound chain that shares a sub-partition with the warps of a throughput-bound kernel gets 1/(N+1) of the
+// multiplier pipe and stretches N-fold (measured: the per-group Horner kernels above gained nothing beside the
+// accumulation).  This CTA is sized to own its SM (512 threads x 128 registers = the whole register file; 14 warps park
+// at the final barrier), so the one or two chains it serves (warp 0 / warp 1 sit on different sub-partitions) run at their
+// isolated speed.  The producers (last level of k_msm_nodes32) count finished nodes in ready[g]; the polling is bounded
+// (2 s): on a timeout the status word is raised and the caller reports XHE_E_CUDA instead of hanging.
+struct ChainJob {
+  const uint32_t* hnodes; uint32_t* ready; int G, Wg, W, c;
+  uint8_t* out_enc; uint32_t* is_identity; uint32_t* out_ext; uint32_t* status;
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void chain_run(const ChainJob& J, uint32_t* sS, int wait) {
+  const int lane = threadIdx.x & 31, q = lane >> 2;
+  ge acc = ge_identity();
+  bool ok = true; uint32_t diag = 0;
+  for (int g = 0; g < J.G && ok; g++) {
+    const int w0 = g * J.Wg, nw = min(J.Wg, J.W - w0);
+    if (wait) {
+      const unsigned long long t0 = globaltimer_ns();
+      for (;;) {
+        uint32_t st = 0;
+        if (lane == 0) { uint32_t seen = *(volatile uint32_t*)(J.ready + g); st = seen >= (uint32_t)nw ? 1u : (globaltimer_ns() - t0 > 2000000000ull ? 2u : 0u);
+                         if (st == 2u) diag = 0x80000000u | ((uint32_t)(threadIdx.x >> 5) << 28) | ((uint32_t)g << 24) | ((uint32_t)nw << 12) | (seen & 0xfffu); }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st == 1u) break;
+        if (st == 2u) { ok = false; break; }
+        __nanosleep(200);
+      }
+      if (!ok) break;
+      __threadfence();
+    }
+    for (int base = 0; base < nw; base += 8) {
+      const int j = base + q;
+      ge run = ge_identity(), wsum = ge_identity();
+      if (j < nw) { ld_ge(run, J.hnodes + 64 * (size_t)(w0 + j)); ld_ge(wsum, J.hnodes + 64 * (size_t)(w0 + j) + 32); }
+      ge S = quad_add(run, wsum);
+      if (j < nw) st_ge_quad(sS + 32 * j, S);
+    }
+    __syncwarp();
+    for (int w = 0; w < nw; w++) {
+      if (g || w) for (int k = 0; k < J.c; k++) acc = quad_double(acc);
+      ge S; ld_ge(S, sS + 32 * w);
+      acc = quad_add(acc, S);
+    }
+    __syncwarp();
+  }
+  if (lane != 0) return;
+  if (!ok) { *J.status = diag; if (J.is_identity) *J.is_identity = 2u; return; }      // status: which chain, which group, expected and seen node counts
+  if (J.out_ext) { st_fe(J.out_ext, fe_freeze(acc.X)); st_fe(J.out_ext + 8, fe_freeze(acc.Y)); st_fe(J.out_ext + 16, fe_freeze(acc.Z)); st_fe(J.out_ext + 24, fe_freeze(acc.T)); }
+  if (J.out_enc) encode_words(J.out_enc, acc);
+  if (J.is_identity) *J.is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(512, 1) k_msm_chain(ChainJob j0, ChainJob j1, int wait) {
+  __shared__ __align__(16) uint32_t sS[2][32 * 32];
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && j0.W > 0) chain_run(j0, sS[0], wait);
+  if (warp == 1 && j1.W > 0) chain_run(j1, sS[1], wait);
+  __syncthreads();
 }
 __global__ void k_msm_empty(uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
   if (out_enc) { reinterpret_cast<uint4*>(out_enc)[0] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(out_enc)[1] = make_uint4(0, 0, 0, 0); }
@@ -365,19 +509,20 @@ extern "C" int32_t xhe_msm_plan(size_t n, int* c, int* W) { MsmPlan p = make_pla
 
 // The pipeline in two phases, so that a caller whose scalars are ready before its points (xhe_batch_run) can overlap them:
 //   xhe_msm_sort   -- steps 1-4: needs only the scalars (digit recoding, counting sort into bucket order, tile runs)
-//   xhe_msm_finish -- steps 5-9: needs the points; d_out_ext (optional) = the un-normalised extended result (128 B)
+//   xhe_msm_finish -- accumulation + reduction + Horner: needs the points; d_out_ext (optional) = the un-normalised
+//                     extended result (128 B)
 namespace {
 struct MsmPtrs {
-  uint32_t *counts, *offsets, *cursor, *blocksums, *list, *tile_g0, *runs, *run_off, *part, *part_g, *pstart, *pcount, *heavy, *nodes_a, *nodes_b, *flag;
+  uint32_t *counts, *offsets, *cursor, *blocksums, *list, *tile_g0, *runs, *run_off, *part, *pstart, *pcount, *heavy, *nodes_a, *nodes_b, *hnodes, *hacc, *ready, *flag;
 };
 inline MsmPtrs msm_ptrs(const MsmPlan& p, void* d_ws, void* d_bad_flag) {
   uint8_t* ws = (uint8_t*)d_ws;
   MsmPtrs q;
   q.counts = (uint32_t*)(ws + p.off_counts); q.offsets = (uint32_t*)(ws + p.off_offsets); q.cursor = (uint32_t*)(ws + p.off_cursor);
   q.blocksums = (uint32_t*)(ws + p.off_blocksums); q.list = (uint32_t*)(ws + p.off_list); q.tile_g0 = (uint32_t*)(ws + p.off_tileg0);
-  q.runs = (uint32_t*)(ws + p.off_runs); q.run_off = (uint32_t*)(ws + p.off_runoff); q.part = (uint32_t*)(ws + p.off_part); q.part_g = (uint32_t*)(ws + p.off_partg);
+  q.runs = (uint32_t*)(ws + p.off_runs); q.run_off = (uint32_t*)(ws + p.off_runoff); q.part = (uint32_t*)(ws + p.off_part);
   q.pstart = (uint32_t*)(ws + p.off_pstart); q.pcount = (uint32_t*)(ws + p.off_pcount); q.heavy = (uint32_t*)(ws + p.off_heavy);
-  q.nodes_a = (uint32_t*)(ws + p.off_nodes_a); q.nodes_b = (uint32_t*)(ws + p.off_nodes_b);
+  q.nodes_a = (uint32_t*)(ws + p.off_nodes_a); q.nodes_b = (uint32_t*)(ws + p.off_nodes_b); q.hnodes = (uint32_t*)(ws + p.off_hnodes); q.hacc = (uint32_t*)(ws + p.off_hacc); q.ready = (uint32_t*)(ws + p.off_ready);
   q.flag = d_bad_flag ? (uint32_t*)d_bad_flag : (uint32_t*)(ws + p.off_flag);
   return q;
 }
@@ -395,8 +540,8 @@ int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, 
   const size_t m = p.total_buckets;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(q.counts, 0, 4 * (m + 1), st));
   XHE_CUDA_OK(ctx, cudaMemsetAsync(q.pcount, 0, 4 * m, st));
-  XHE_CUDA_OK(ctx, cudaMemsetAsync(q.heavy, 0, 4, st));
   if (!d_bad_flag) XHE_CUDA_OK(ctx, cudaMemsetAsync(q.flag, 0, 4, st));
+  k_msm_zero_heads<<<1, 32, 0, st>>>(q.heavy, (uint32_t)(p.Wg * p.B), p.G, q.ready); XHE_LAUNCHED(ctx);
   k_msm_count<<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)d_scalars, n, p.c, p.W, p.B, q.counts, q.flag); XHE_LAUNCHED(ctx);
   unsigned nb = nblk(m, SCAN_THREADS * SCAN_ITEMS);
   if (nb > 4096) { ctx->err = "msm: too many buckets"; return XHE_E_ARG; }
@@ -415,15 +560,59 @@ int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, 
   return XHE_OK;
 }
 
-int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum) {
-  if (!ctx) return XHE_E_ARG;
+// side streams / events of the grouped tail (lane 0: the caller's first MSM in flight, lane 1: a second one, as in
+// xhe_batch_run where the sigma and the range MSM run side by side)
+int32_t xhe_msm_side_init(xhe_ctx* ctx, int lane) {
+  if (ctx->msm_side[lane][0]) return XHE_OK;
+  int lo_pri = 0, hi_pri = 0; XHE_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+  for (int i = 0; i < 2; i++) XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->msm_side[lane][i], cudaStreamNonBlocking, hi_pri));   // latency chains first
+  for (auto& e : ctx->msm_ev[lane]) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return XHE_OK;
+}
+
+static XheChainJob to_job(const ChainJob& j) { XheChainJob o; o.hnodes = j.hnodes; o.ready = j.ready; o.G = j.G; o.Wg = j.Wg; o.W = j.W; o.c = j.c; o.out_enc = j.out_enc; o.is_identity = j.is_identity; o.out_ext = j.out_ext; o.status = j.status; return o; }
+static ChainJob from_job(const XheChainJob& j) { ChainJob o; o.hnodes = j.hnodes; o.ready = j.ready; o.G = j.G; o.Wg = j.Wg; o.W = j.W; o.c = j.c; o.out_enc = j.out_enc; o.is_identity = j.is_identity; o.out_ext = j.out_ext; o.status = j.status; return o; }
+// the chain job of the MSM over n points whose workspace is d_ws (W = 0: nothing to do)
+XheChainJob xhe_msm_chain_job(size_t n, void* d_ws, void* d_out_enc, void* d_is_id, void* d_out_ext) {
+  ChainJob j; memset(&j, 0, sizeof j);
+  if (n && d_ws) {
+    MsmPlan p = make_plan(n); MsmPtrs q = msm_ptrs(p, d_ws, nullptr);
+    j.hnodes = q.hnodes; j.ready = q.ready; j.G = p.G; j.Wg = p.Wg; j.W = p.W; j.c = p.c; j.status = q.ready + 8;
+    j.out_enc = (uint8_t*)d_out_enc; j.is_identity = (uint32_t*)d_is_id; j.out_ext = (uint32_t*)d_out_ext;
+  }
+  return to_job(j);
+}
+int32_t xhe_msm_chain_reset(xhe_ctx* ctx, cudaStream_t st, const XheChainJob& j) {
+  if (j.W > 0) XHE_CUDA_OK(ctx, cudaMemsetAsync(j.ready, 0, 64, st));
+  return XHE_OK;
+}
+int32_t xhe_msm_chain_launch(xhe_ctx* ctx, cudaStream_t st, const XheChainJob& a, const XheChainJob& b, int wait) {
+  if (a.W <= 0 && b.W <= 0) return XHE_OK;
+  k_msm_chain<<<1, 512, 0, st>>>(from_job(a), from_job(b), wait); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+// OFF by default (XHE_MSM_CHAIN=1 switches it on).  Measured on B200, 10 k a1k1 batch: the chain itself runs at its isolated
+// speed, but the step did not get faster (3.49 ms against 3.32 ms: the reduction kernels that feed it are what the contention
+// stretches), and a polling kernel makes every implicit device synchronisation elsewhere in the process (cudaMalloc, pinned
+// allocations, a kernel that grows the local-memory pool) a 2-second stall -- DESIGN.md 4.4 has the numbers.
+bool xhe_msm_chain_enabled() { static const bool on = getenv("XHE_MSM_CHAIN") && atoi(getenv("XHE_MSM_CHAIN")) != 0; return on; }
+
+// chain_mode: 0 = per-group Horner kernels behind events (also what the serial diagnostics mode uses);
+//             1 = this call launches its own polling chain kernel first;
+//             2 = the caller has launched a chain kernel that serves this MSM (xhe_batch_run: one kernel for both MSMs) and joins it
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum, int lane, int chain_mode) {
+  if (!ctx || lane < 0 || lane > 1) return XHE_E_ARG;
   cudaStream_t st = ctx->stream;
   if (n == 0) { k_msm_empty<<<1, 1, 0, st>>>((uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx); if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st)); XHE_CUDA_OK(ctx, cudaGetLastError()); return XHE_OK; }
   if (!d_niels || !d_ws) return XHE_E_ARG;
   MsmPlan p = make_plan(n);
   if (ws_bytes < p.total) { ctx->err = "msm workspace too small"; return XHE_E_ARG; }
+  if (p.Wg > 32) { ctx->err = "msm: window group too large"; return XHE_E_ARG; }
   MsmPtrs q = msm_ptrs(p, d_ws, nullptr);
   const size_t m = p.total_buckets;
+  if (chain_mode < 0) chain_mode = xhe_msm_chain_enabled() ? 1 : 0;
+  if (ctx->serial) chain_mode = 0;
   // Residency limiter: the hot kernel takes the whole register file at 4 blocks of 128 threads x 128 registers per SM, so no
   // block of a concurrently running latency-bound kernel (signatures, reduction tails of the other MSM) can start on an SM
   // while a wave is resident.  The field multiply saturates the multiplier pipe from 2 warps per sub-partition, so a
@@ -432,28 +621,59 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
   static const size_t accum_smem = []() { const char* e = getenv("XHE_ACCUM_SMEM"); size_t v = e ? (size_t)atol(e) : (size_t)XHE_ACCUM_SMEM_DEFAULT;
     if (v > 48 * 1024) { cudaFuncSetAttribute(k_msm_accum_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); }
     return v; }();
-  { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
-  switch (g_accum_variant) {
-    case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
-    default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, q.part, q.part_g); break;
-  } }
-  XHE_LAUNCHED(ctx);
-  if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st));      // the throughput-bound part of this MSM is over: what follows is latency-bound
-  k_msm_bucket_index<<<nblk(p.max_runs, 256), 256, 0, st>>>(q.part_g, q.run_off + p.n_tiles, p.max_runs, q.pstart, q.pcount); XHE_LAUNCHED(ctx);
-  k_msm_find_heavy<<<nblk(m, 256), 256, 0, st>>>(q.pcount, m, q.heavy); XHE_LAUNCHED(ctx);
-  k_msm_fold_heavy<<<std::min<size_t>(m, 2 * (size_t)ctx->sm_count), FOLD_THREADS, 0, st>>>(q.part, q.pstart, q.pcount, q.heavy); XHE_LAUNCHED(ctx);
-  size_t n_nodes = m >> p.seg_log;
-  k_msm_seg<<<nblk(n_nodes, 128), 128, 0, st>>>(q.part, q.pstart, q.pcount, n_nodes, p.seg_log, q.nodes_a); XHE_LAUNCHED(ctx);
-  uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;
-  uint32_t *cur = q.nodes_a, *nxt = q.nodes_b;
-  while (per_window > 1) {
-    uint32_t parents = (per_window + 31) / 32;
-    size_t warps = (size_t)parents * p.W;
-    k_msm_nodes<<<nblk(warps * 32, 128), 128, 0, st>>>(cur, per_window, parents, p.W, child_log, nxt); XHE_LAUNCHED(ctx);
-    std::swap(cur, nxt); per_window = parents; child_log += 5;
+  // The grouped tail: accumulation launches of the window groups back to back on the caller's stream; behind each, on a
+  // high-priority side stream, the group's reduction (s_red); the Horner chain on s_hor (chain_mode 0 / 1) or in the
+  // caller's chain kernel (chain_mode 2).
+  const bool split = !ctx->serial && (p.G > 1 || chain_mode == 1);
+  cudaStream_t s_red = st, s_hor = st;
+  cudaEvent_t* ev = nullptr;
+  if (split || chain_mode == 2) { int32_t rc = xhe_msm_side_init(ctx, lane); if (rc) return rc; ev = ctx->msm_ev[lane]; }
+  if (split) { s_red = ctx->msm_side[lane][0]; s_hor = ctx->msm_side[lane][1]; }
+  if (chain_mode == 1) {      // the polling chain goes first: it must own an SM before the accumulation fills the machine
+    XheChainJob job = xhe_msm_chain_job(n, d_ws, d_out_enc, d_is_id, d_out_ext), none; memset(&none, 0, sizeof none);
+    XHE_CUDA_OK(ctx, cudaEventRecord(ev[2 * MSM_MAX_GROUPS], st)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_hor, ev[2 * MSM_MAX_GROUPS], 0));      // after the sort (which zeroed ready[])
+    int32_t rc = xhe_msm_chain_launch(ctx, s_hor, job, none, 1); if (rc) return rc;
   }
-  k_msm_horner<<<1, 32, 0, st>>>(cur, p.W, p.c, (uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx);
+  const uint32_t kpg = (uint32_t)(p.Wg * p.B);
+  AccumOut ao{q.part, q.pstart, q.pcount, q.heavy, kpg};
+  { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
+    for (int g = 0; g < p.G; g++) {
+      const uint32_t klo = (uint32_t)g * kpg, khi = (uint32_t)std::min<size_t>(m, (size_t)(g + 1) * kpg);
+      switch (g_accum_variant) {
+        case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+        case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+        default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+      }
+      XHE_LAUNCHED(ctx);
+      if (s_red != st) XHE_CUDA_OK(ctx, cudaEventRecord(ev[g], st));
+    } }
+  if (after_accum) XHE_CUDA_OK(ctx, cudaEventRecord(after_accum, st));      // the throughput-bound part of this MSM is over: what follows is latency-bound
+  for (int g = 0; g < p.G; g++) {
+    const uint32_t klo = (uint32_t)g * kpg, khi = (uint32_t)std::min<size_t>(m, (size_t)(g + 1) * kpg);
+    const uint32_t nw = (khi - klo) / p.B;
+    if (s_red != st) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_red, ev[g], 0));
+    const uint32_t* heavy_g = q.heavy + (size_t)g * kpg + 8 * g;
+    k_msm_fold_heavy<<<(unsigned)std::min<size_t>((khi - klo + 3) / 4, 8 * (size_t)ctx->sm_count), FOLD_THREADS, 0, s_red>>>(q.part, q.pstart, q.pcount, heavy_g); XHE_LAUNCHED(ctx);
+    k_msm_bucket_seg<<<nblk(khi - klo, 256), 256, 0, s_red>>>(q.part, q.pstart, q.pcount, klo, khi, q.nodes_a); XHE_LAUNCHED(ctx);
+    uint32_t per_window = (uint32_t)(p.B >> MSM_SEG_LOG); int child_log = MSM_SEG_LOG;
+    uint32_t *cur = q.nodes_a, *nxt = q.nodes_b;
+    uint32_t* hn = q.hnodes + 64 * (size_t)(klo / p.B);
+    while (per_window > 1) {
+      const uint32_t parents = (per_window + 31) / 32;
+      uint32_t* dst = parents == 1 ? hn : nxt;
+      k_msm_nodes32<<<parents * nw, 128, 0, s_red>>>(cur, per_window, parents, child_log, dst, (parents == 1 && chain_mode) ? q.ready + g : nullptr); XHE_LAUNCHED(ctx);
+      std::swap(cur, nxt); per_window = parents; child_log += 5;
+    }
+    if (chain_mode == 0) {
+      if (s_hor != s_red) { XHE_CUDA_OK(ctx, cudaEventRecord(ev[MSM_MAX_GROUPS + g], s_red)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_hor, ev[MSM_MAX_GROUPS + g], 0)); }
+      const bool last = g == p.G - 1;
+      k_msm_horner_g<<<1, 32, 0, s_hor>>>(hn, (int)nw, p.c, g ? q.hacc + 32 * (size_t)(g - 1) : nullptr, q.hacc + 32 * (size_t)g, last ? 1 : 0,
+                                          (uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx);
+    }
+  }
+  // joins come LAST: every producer is already queued when a wait on the chain kernel enters a hardware queue
+  if (s_red != st && chain_mode != 0) { XHE_CUDA_OK(ctx, cudaEventRecord(ev[2 * MSM_MAX_GROUPS - 1], s_red)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(st, ev[2 * MSM_MAX_GROUPS - 1], 0)); }
+  if (s_hor != st && chain_mode != 2) { XHE_CUDA_OK(ctx, cudaEventRecord(ev[2 * MSM_MAX_GROUPS], s_hor)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(st, ev[2 * MSM_MAX_GROUPS], 0)); }
   XHE_CUDA_OK(ctx, cudaGetLastError());
   return XHE_OK;
 }
@@ -461,7 +681,7 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
 int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag) {
   if (n && (!d_scalars || !d_niels || !d_ws)) return XHE_E_ARG;
   int32_t rc = xhe_msm_sort(ctx, d_scalars, n, d_ws, ws_bytes, d_bad_flag); if (rc) return rc;
-  return xhe_msm_finish(ctx, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, d_out_ext, nullptr);
+  return xhe_msm_finish(ctx, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, d_out_ext, nullptr, 0, -1);
 }
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id) {
   return xhe_launch_msm_ex(ctx, d_scalars, d_niels, n, d_ws, ws_bytes, d_out_enc, d_is_id, nullptr, nullptr);
@@ -491,6 +711,16 @@ extern "C" int32_t xhe_msm_vartime(xhe_ctx* ctx, const uint8_t* scalars, const u
   if (bad) { ctx->err = "msm: non-canonical scalar"; return XHE_E_ARG; }
   for (size_t i = 0; i < n; i++) if (!ok[i]) { ctx->err = "msm: invalid point encoding at index " + std::to_string(i); return XHE_E_ARG; }
   memcpy(out_enc, host, 32);
-  if (is_identity) { uint32_t f; memcpy(&f, host + 32, 4); *is_identity = (int32_t)f; }
+  { uint32_t f; memcpy(&f, host + 32, 4); if (f == 2u) { ctx->err = "msm: the Horner chain kernel timed out waiting for its inputs"; return XHE_E_CUDA; } if (is_identity) *is_identity = (int32_t)f; }
   return XHE_OK;
+}
+
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2), and loading one may need every running kernel
+// to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
+// kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
+size_t xhe_preload_msm() {      // returns the largest per-thread local-memory frame among them
+  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4>, (const void*)k_msm_accum_tiles<6>, (const void*)k_msm_accum_tiles<8>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_chain, (const void*)k_msm_empty};
+  cudaFuncAttributes a; size_t mx = 0;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
+  return mx;
 }

@@ -21,12 +21,14 @@ using namespace xhe;
 
 int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag);
 extern "C" size_t xhe_msm_workspace_bytes(const xhe_ctx*, size_t n);
-int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed,
+int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed, unsigned long long index_base,
                                uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_rp_chal, const uint32_t* d_rp_m);
-int32_t xhe_launch_sig_hash(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_sig_r, const uint32_t* d_sig_e, uint8_t* d_sig_ok);
+int32_t xhe_launch_sig_hash_prefix(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, unsigned long long* d_state);
+int32_t xhe_launch_sig_hash_final(xhe_ctx* ctx, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const unsigned long long* d_state, const uint8_t* d_sig_r, const uint32_t* d_sig_e, uint8_t* d_sig_ok);
 int32_t xhe_launch_layout(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t n_tx, uint32_t n_points, uint8_t* d_enc,
                           uint32_t* d_sig_idx, uint32_t n_eq, uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_range_idx, const uint32_t* d_rp_pt_off,
-                          uint32_t* d_sig_s, uint32_t* d_sig_e, uint32_t* d_sig_pk, uint32_t* d_viol);
+                          uint32_t* d_sig_s, uint32_t* d_sig_e, uint32_t* d_sig_pk, uint32_t* d_viol, uint8_t* d_tx_flags);
+int32_t xhe_launch_tx_flags(xhe_ctx* ctx, const uint32_t* d_plan, uint32_t n_tx, uint32_t n_a_end, const uint8_t* d_pt_ok, const uint8_t* d_sig_ok, uint8_t* d_tx_flags);
 int32_t xhe_launch_any_zero(xhe_ctx* ctx, const uint8_t* d_flags, uint32_t n, uint32_t bit, uint32_t* d_viol);
 
 namespace {
@@ -81,8 +83,12 @@ __device__ __forceinline__ ge fixed_base_mul(const uint32_t* __restrict__ tab, c
 // (a quad-cooperative variant was measured: 0.96 ms vs 0.82 ms for 10k signatures -- four times the warps contend for the
 // multiplier pipe -- so one thread per signature stays; the Horner tail of the MSM is where quads pay off)
 // r = s*H - e*P.  s*H from the 32-window fixed-base table of H; (-e)*P by 4-bit fixed-window double-and-add.
+// The kernel decodes P from its ENCODING itself (one more inverse square root, +8 % work) instead of waiting for the batch-wide
+// decompression: the signatures are a 250-doubling latency chain per thread, and started right after the upload they are off
+// the critical path of the step.  An invalid P decodes to the identity here; its decompression flag (k_decompress) carries
+// the verdict, as for every other point.
 __global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in, const uint32_t* __restrict__ e_in, const uint32_t* __restrict__ pk_idx,
-                                              const uint32_t* __restrict__ pt_aff, const uint8_t* __restrict__ pt_ok, const uint32_t* __restrict__ tabH,
+                                              const uint8_t* __restrict__ pt_enc, const uint32_t* __restrict__ tabH,
                                               uint32_t n, uint8_t* __restrict__ r_enc, uint32_t* __restrict__ scratch /* n x 16 x 32 words */) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in,
   ge acc_h = fixed_base_mul(tabH, sb, 32);
   // table of 0..15 multiples of P in global scratch (extended coordinates)
   uint32_t pi = pk_idx[i];
-  ge_aff pa; ld_fe(pa.x, pt_aff + 16 * (size_t)pi); ld_fe(pa.y, pt_aff + 16 * (size_t)pi + 8);
+  ge_aff pa;
+  if (!decode_words(pa, pt_enc + 32 * (size_t)pi)) pa = ge_aff_identity();
   ge P = ge_from_affine(pa);
   uint32_t* tab = scratch + (size_t)i * 16 * 32;
   ge cur = ge_identity();
@@ -104,7 +111,6 @@ __global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in,
     if (d) { ge t; ld_ge(t, tab + 32 * d); acc = ge_add(acc, t); }
   }
   acc = ge_add(acc, acc_h);
-  (void)pt_ok;
   encode_words(r_enc + 32 * (size_t)i, acc);
 }
 
@@ -512,6 +518,55 @@ __global__ void __launch_bounds__(32) k_sum_encodings(const uint8_t* __restrict_
   if (threadIdx.x == 0) { encode_words(out, acc); ((uint32_t*)out)[8] = ge_ristretto_is_identity(acc) ? 1u : 0u; ((uint32_t*)out)[9] = all_ok; }
 }
 
+// ---- sharded batches: record + joint decision on the device (what bench.py times inside `value` at N > 1) ---------------
+// record of one rank, 80 bytes: int32 code, int64 first failing tx (index into the whole batch, -1 none) at offset 4, sigma
+// partial encoding at 12, range partial encoding at 44, 4 bytes padding -- the layout distributed.pack_local produces
+__global__ void k_make_record(const uint32_t* __restrict__ results, uint8_t* __restrict__ rec) {
+  const uint32_t t = threadIdx.x;
+  if (t >= 32) return;
+  const uint32_t flags = results[98];
+  // per-transaction anomalies are the host's to name (it re-decides that transaction): code 0xFF = "this shard needs its host"
+  if (t == 0) { int32_t code = (flags & 15u) ? 0xFF : ((flags & 16u) ? XHE_ERR_RANGE_PROOF : XHE_OK); long long idx = -1; memcpy(rec, &code, 4); memcpy(rec + 4, &idx, 8); rec[76] = rec[77] = rec[78] = rec[79] = 0; }
+  if (t < 8) { uint32_t w = results[t]; memcpy(rec + 12 + 4 * t, &w, 4); }
+  else if (t < 16) { uint32_t w = results[48 + (t - 8)]; memcpy(rec + 44 + 4 * (t - 8), &w, 4); }
+}
+// joint decision over the gathered records of all ranks, in the reference's order (distributed.decide): the first failing
+// transaction of the whole batch, then the sigma check on the SUM of the partials (src/proofs.rs:49-67), then a shard's
+// structural range-proof failure, then the range check on the sum.  out: int32 code, int64 index (at offset 8).
+__global__ void __launch_bounds__(32) k_shard_decide(const uint8_t* __restrict__ recs, uint32_t world, uint8_t* __restrict__ out) {
+  __shared__ uint32_t pts[32 * 16]; __shared__ uint32_t okw[32];
+  int32_t code_out = XHE_OK; long long idx_out = -1; bool per_tx = false, other = false, rp_struct = false;
+  for (uint32_t r = 0; r < world; r++) {
+    int32_t code; long long idx; memcpy(&code, recs + 80 * (size_t)r, 4); memcpy(&idx, recs + 80 * (size_t)r + 4, 8);
+    if (code != XHE_OK && idx >= 0) { if (!per_tx || idx < idx_out) { idx_out = idx; code_out = code; } per_tx = true; }
+    else if (code == XHE_ERR_RANGE_PROOF) rp_struct = true;
+    else if (code != XHE_OK && code != XHE_ERR_GENERIC_PROOF && !other && !per_tx) { other = true; code_out = code; idx_out = idx; }
+  }
+  bool ident[2] = {true, true};
+  for (int which = 0; which < 2; which++) {
+    ge acc = ge_identity(); bool all_ok = true;
+    for (uint32_t base = 0; base < world; base += 32) {
+      uint32_t i = base + threadIdx.x; ge_aff a; bool ok = true;
+      if (i < world) { ok = decode_words(a, recs + 80 * (size_t)i + 12 + 32 * which); for (int q = 0; q < 8; q++) { pts[16 * threadIdx.x + q] = a.x.v[q]; pts[16 * threadIdx.x + 8 + q] = a.y.v[q]; } }
+      okw[threadIdx.x] = ok ? 1u : 0u;
+      __syncwarp();
+      if (threadIdx.x == 0) for (uint32_t k = 0; k < 32 && base + k < world; k++) {
+        if (!okw[k]) { all_ok = false; continue; }
+        ge_aff b; for (int q = 0; q < 8; q++) { b.x.v[q] = pts[16 * k + q]; b.y.v[q] = pts[16 * k + 8 + q]; }
+        acc = ge_add(acc, ge_from_affine(b));
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x == 0) ident[which] = all_ok && ge_ristretto_is_identity(acc);
+  }
+  if (threadIdx.x != 0) return;
+  if (!per_tx && !other) {
+    if (!ident[0]) { code_out = XHE_ERR_GENERIC_PROOF; idx_out = -1; }
+    else if (rp_struct || !ident[1]) { code_out = XHE_ERR_RANGE_PROOF; idx_out = -1; }
+  }
+  memcpy(out, &code_out, 4); memset(out + 4, 0, 4); memcpy(out + 8, &idx_out, 8);
+}
+
 inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 struct Arena {   // bump allocator over one cudaMalloc'd block (grow-only, owned by the ctx)
@@ -595,12 +650,28 @@ struct DeviceBatch {
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
   long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
-  double sum_m = 0; bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok; unsigned long long* d_blob_off; uint32_t* d_fs_plan; size_t blob_bytes = 0;
+  double sum_m = 0; bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok, *d_tx_flags; unsigned long long *d_blob_off, *d_sig_state; uint32_t* d_fs_plan; size_t blob_bytes = 0;
 };
+
+// this rank's 80-byte record of the batch that is resident on ctx (after xhe_batch_run, same stream, asynchronous), and the joint
+// decision over the all-gathered records of `world` ranks -- both on the device, so a sharded step can be timed with CUDA events
+extern "C" int32_t xhe_batch_record_dev(xhe_ctx* ctx, void* d_rec80) {
+  if (!ctx || !ctx->resident || !d_rec80) return XHE_E_ARG;
+  k_make_record<<<1, 32, 0, ctx->stream>>>(((DeviceBatch*)ctx->resident)->d_results, (uint8_t*)d_rec80); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+extern "C" int32_t xhe_shard_decide_dev(xhe_ctx* ctx, const void* d_records, uint32_t world, void* d_out16) {
+  if (!ctx || !d_records || !d_out16 || world == 0 || world > 1024) return XHE_E_ARG;
+  k_shard_decide<<<1, 32, 0, ctx->stream>>>((const uint8_t*)d_records, world, (uint8_t*)d_out16); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
 
 // stage 1: allocate from the ctx arena and upload the host description
 extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   if (!ctx || !b) return XHE_E_ARG;
+  if (b->struct_size != sizeof(xhe_batch)) { ctx->err = "verify_batch: xhe_batch.struct_size does not match this library (caller compiled against another include/xhe.h)"; return XHE_E_ARG; }
   if (b->n_points == 0 || (!b->points && !(b->layout_on_device && b->fs_blobs))) { ctx->err = "verify_batch: point table must contain the identity at index 0"; return XHE_E_ARG; }
   int32_t rc = ensure_tables(ctx); if (rc) return rc;
   cudaStream_t st = ctx->stream;
@@ -615,6 +686,13 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
     D.sum_m += m;
   }
   D.Nmax = 64 * m_max; D.der_stride = RP_DER_FIXED + m_max;
+  if (b->n_rp && ctx->party_capacity <= XHE_FB_MAX_PARTIES && !ctx->d_fb_tab && !getenv("XHE_NO_FIXED_BASE")) {
+    // first batch with range proofs on this context: build the fixed-base table of the static generators (about 1.5 ms, once).
+    // Done here and not inside xhe_batch_run: no allocation may happen while the polling chain kernel is in flight.
+    const size_t ng = ctx->n_gens;
+    XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_tab, 96 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_dig, 2 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_bsum, 128 * 128));
+    k_fb_build<<<nblk(ng, 64), 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, (uint32_t)ng, (uint32_t*)ctx->d_fb_tab); XHE_LAUNCHED(ctx);
+  }
   D.n_pts_total = (size_t)b->n_points + b->n_ops;
   D.n_sigma_terms = 7 * (size_t)b->n_eq + 8 * (size_t)b->n_val; D.n_sigma = D.n_sigma_terms + 2;
   D.n_dyn = b->n_rp ? b->rp_point_off[b->n_rp] : 0; D.n_range = D.n_dyn + (b->n_rp ? 2 * (size_t)D.Nmax + 2 : 0);
@@ -638,7 +716,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
               + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * (size_t)D.der_stride + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
               + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + D.ws_static + 8192 + 512 * 64
-              + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs;
+              + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs + b->n_tx + 512 + 208 * (size_t)b->n_sigs + 256;
   if (ctx->scratch_bytes < need) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
@@ -659,7 +737,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
   TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)D.der_stride * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
   TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range); TAKE(uint8_t, d_ws3, D.ws_static); TAKE(uint32_t, d_rparts, 64);
-  TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs);
+  TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs); TAKE(uint8_t, d_tx_flags, b->n_tx); TAKE(unsigned long long, d_sig_state, 26 * (size_t)b->n_sigs);
   if (D.fs) { UP(D.d_blobs, b->fs_blobs, D.blob_bytes); UP(D.d_blob_off, b->fs_blob_off, 8 * ((size_t)b->n_tx + 1)); UP(D.d_fs_plan, b->fs_plan, 4 * (size_t)D.plan_stride * b->n_tx); UP(D.d_seed, b->fs_seed, 32); }
   if (!D.layout) {
     UP(D.d_enc, b->points, 32 * (size_t)b->n_points);
@@ -712,9 +790,15 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     // the transcript and range pipelines form the longest dependency chain of a step: give their blocks priority
     int lo_pri = 0, hi_pri = 0; XHE_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     // (measured: priorities move the step time by < 2 % either way; kept because they cost nothing)
-    const int pri[4] = {hi_pri, lo_pri, hi_pri, hi_pri};
-    for (int i = 0; i < 4; i++) XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, pri[i]));
+    const int pri[5] = {hi_pri, lo_pri, hi_pri, hi_pri, lo_pri};
+    for (int i = 0; i < 5; i++) XHE_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, pri[i]));
     for (auto& e : ctx->ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // every stream and event of the step exists before its first chain kernel starts polling: creating one later can wait for
+    // the running kernels (measured: the first batch of a context timed out in exactly that way)
+    rc = xhe_msm_side_init(ctx, 0); if (rc) return rc;
+    rc = xhe_msm_side_init(ctx, 1); if (rc) return rc;
+    if (!ctx->tl_base) XHE_CUDA_OK(ctx, cudaEventCreate(&ctx->tl_base));
+    if (!ctx->sync_ev) XHE_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   }
   static const bool serial_env = getenv("XHE_SERIAL") != nullptr;
   const bool serial = serial_env || ctx->serial;                   // diagnostics / isolated kernel timing: one stream, back to back
@@ -724,25 +808,59 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   //   s_sig: [decompress] signatures -> signature hashes
   //   s_rp : [transcripts] range scalars -> static-generator weights -> MSM over the static generators -> [s_dyn] combine
   //   s_dyn: [range scalars] sort -> [decompress] gather -> MSM over the proofs' own points
-  cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2], s_dyn = serial ? main_st : ctx->aux[3];
-  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8], e_acc_sigma = ctx->ev[9], e_acc_dyn = ctx->ev[10];
+  cudaStream_t main_st = ctx->stream, s_fs = serial ? main_st : ctx->aux[0], s_sig = serial ? main_st : ctx->aux[1], s_rp = serial ? main_st : ctx->aux[2], s_dyn = serial ? main_st : ctx->aux[3], s_pre = serial ? main_st : ctx->aux[4];
+  cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8], e_acc_sigma = ctx->ev[9], e_acc_dyn = ctx->ev[10], e_pre = ctx->ev[12];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
   const uint32_t np = b->n_eq + b->n_val;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
-  if (ctx->timing) { if (!ctx->tl_base) XHE_CUDA_OK(ctx, cudaEventCreate(&ctx->tl_base)); XHE_CUDA_OK(ctx, cudaEventRecord(ctx->tl_base, main_st)); ctx->tl_mark = ctx->pending.size(); }
+  // The Horner chains of both MSMs are served by ONE polling kernel that is launched now, while the machine is empty, and owns
+  // an SM for the whole step (msm.cu, k_msm_chain): the sigma chain on warp 0, the range chain on warp 1.
+  const bool ext_chain = !serial && xhe_msm_chain_enabled();
+  XheChainJob job_sigma = xhe_msm_chain_job(n_sigma, D.d_ws1, D.d_results, D.d_results + 8, D.d_results + 16);
+  XheChainJob job_range = xhe_msm_chain_job(b->n_rp ? n_dyn : 0, D.d_ws2, nullptr, nullptr, D.d_rparts);
+  job_sigma.status = D.d_results + 99; if (job_range.W > 0) job_range.status = D.d_results + 99;
+  if (ext_chain) { rc = xhe_msm_chain_reset(ctx, main_st, job_sigma); if (rc) return rc; rc = xhe_msm_chain_reset(ctx, main_st, job_range); if (rc) return rc; }
+  if (ctx->timing) { XHE_CUDA_OK(ctx, cudaEventRecord(ctx->tl_base, main_st)); ctx->tl_mark = ctx->pending.size(); }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_start, main_st));
+  cudaStream_t s_chain = nullptr;
+  if (ext_chain) {
+    s_chain = ctx->msm_side[0][1];
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_chain, e_start, 0));
+    rc = xhe_msm_chain_launch(ctx, s_chain, job_sigma, job_range, 1); if (rc) return rc;
+  }
+  // ---- s_pre: signature hash of everything but r
+  if (D.fs && b->n_sigs) {
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_pre, e_start, 0));
+    ctx->stream = s_pre;
+    rc = xhe_launch_sig_hash_prefix(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_sig_state); if (rc) return rc;
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_pre, s_pre));
+    ctx->stream = main_st;
+  }
   // ---- s_fs: transcripts
   XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_fs, e_start, 0));
   if (D.fs) {
     ctx->stream = s_fs;
-    rc = xhe_launch_fiat_shamir(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_seed, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_chal, D.d_m); if (rc) return rc;
+    rc = xhe_launch_fiat_shamir(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_seed, b->fs_index_base, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_chal, D.d_m); if (rc) return rc;
     XHE_CUDA_OK(ctx, cudaEventRecord(e_fs, s_fs));
   }
   // ---- main: (fast path) build the tables from the blobs
   ctx->stream = main_st;
   if (D.layout) { rc = xhe_launch_layout(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, b->n_tx, b->n_points, D.d_enc, D.d_sig_idx, b->n_eq, D.d_eq_sc, D.d_val_sc, D.d_rp_sc, D.d_range_idx, D.d_pt_off,
-                                         D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_results + 98); if (rc) return rc; }
+                                         D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_results + 98, D.d_tx_flags); if (rc) return rc; }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_lay, main_st));               // results cleared, per-proof tables in place
+  // ---- s_sig: signatures.  They need only the encodings of the public keys (k_sig_r decodes them itself), so they start
+  // now, beside the decompression; the hash of everything but r was started with the step (s_pre).
+  if (b->n_sigs) {
+    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_lay, 0));
+    ctx->stream = s_sig;
+    { XheTimed t(ctx, "k_sig_r", 160000.0 * b->n_sigs);
+      k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, s_sig>>>(D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_enc, T->tabH, b->n_sigs, D.d_sig_r, D.d_sig_tab); XHE_LAUNCHED(ctx); }
+    if (D.fs) { XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sig_ok, 0, b->n_sigs, s_sig));
+                XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_pre, 0));
+                rc = xhe_launch_sig_hash_final(ctx, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_sig_state, D.d_sig_r, D.d_sig_e, D.d_sig_ok); if (rc) return rc;
+                if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_sig_ok, b->n_sigs, 2, D.d_results + 98); if (rc) return rc; } }
+    ctx->stream = main_st;
+  }
   // ---- s_fs: sigma-proof weights and the scalar half of their MSM
   {
     ctx->stream = s_fs; cudaStream_t st = s_fs;
@@ -763,16 +881,16 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   ctx->stream = main_st;
   { XheTimed t(ctx, "k_decompress", 12632.0 * b->n_points);
     rc = xhe_decompress_dev(ctx, D.d_enc, b->n_points, D.d_aff, D.d_niels, D.d_ok); if (rc) return rc; }
-  if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_ok, b->n_points, 1, D.d_results + 98); if (rc) return rc; }
+  if (D.layout) {   // bit 1: one of the transactions' own points; bit 3: a state-derived point (cannot be blamed on a transaction)
+    const uint32_t n_a = b->n_points - b->n_region_b;
+    rc = xhe_launch_any_zero(ctx, D.d_ok, n_a, 1, D.d_results + 98); if (rc) return rc;
+    rc = xhe_launch_any_zero(ctx, D.d_ok + n_a, b->n_region_b, 3, D.d_results + 98); if (rc) return rc;
+  }
   XHE_CUDA_OK(ctx, cudaEventRecord(e_dec, main_st));
-  // ---- s_sig: signatures
+  // ---- s_sig: per-transaction anomaly flags need the decompression flags
   if (b->n_sigs) {
-    XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_dec, 0));
-    ctx->stream = s_sig;
-    { XheTimed t(ctx, "k_sig_r", 160000.0 * b->n_sigs);
-      k_sig_r<<<nblk(b->n_sigs, 64), 64, 0, s_sig>>>(D.d_sig_s, D.d_sig_e, D.d_sig_pk, D.d_aff, D.d_ok, T->tabH, b->n_sigs, D.d_sig_r, D.d_sig_tab); XHE_LAUNCHED(ctx); }
-    if (D.fs) { XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sig_ok, 0, b->n_sigs, s_sig)); rc = xhe_launch_sig_hash(ctx, D.d_blobs, D.d_blob_off, D.d_fs_plan, D.plan_stride, b->n_tx, D.d_sig_r, D.d_sig_e, D.d_sig_ok); if (rc) return rc;
-                if (D.layout) { rc = xhe_launch_any_zero(ctx, D.d_sig_ok, b->n_sigs, 2, D.d_results + 98); if (rc) return rc; } }
+    if (D.layout && D.fs) { XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_sig, e_dec, 0)); ctx->stream = s_sig;
+                            rc = xhe_launch_tx_flags(ctx, D.d_fs_plan, b->n_tx, b->n_points - b->n_region_b, D.d_ok, D.d_sig_ok, D.d_tx_flags); if (rc) return rc; }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_sig, s_sig));
   }
   // ---- main: balance chains (their outputs are sigma MSM operands)
@@ -808,7 +926,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
       rc = xhe_msm_sort(ctx, D.d_range_sc, n_dyn, D.d_ws2, D.ws_range, D.d_results + 97); if (rc) return rc;
       XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_dec, 0));
       k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, s_dyn>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
-      rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts, e_acc_dyn); if (rc) return rc; }
+      rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts, e_acc_dyn, 1, ext_chain ? 2 : 0); if (rc) return rc; }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_dyn, s_dyn));
   }
   // ---- main: sigma MSM over the gathered operands (inputs and balance-chain outputs)
@@ -819,7 +937,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     if (np) { k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx); }
     k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, D.d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
     XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
-    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, e_acc_sigma); if (rc) return rc;
+    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, e_acc_sigma, 0, ext_chain ? 2 : 0); if (rc) return rc;
   }
   // ---- s_rp: weights of the static generators and their fixed-base MSM.  Nothing needs the result before the final
   // combination, and k_rp_gens is a one-warp-per-proof kernel whose resident blocks take most of the register file: issued
@@ -842,11 +960,6 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
       static const bool fb_off = getenv("XHE_NO_FIXED_BASE") != nullptr;          // diagnostics: force the generic MSM
       if (ctx->party_capacity <= XHE_FB_MAX_PARTIES && !fb_off) {
         XheTimed t(ctx, "msm_range_static", 0);
-        if (!ctx->d_fb_tab) {        // first batch with range proofs on this context: build the table (about 1.5 ms, once)
-          const size_t ng = ctx->n_gens;
-          XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_tab, 96 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_dig, 2 * 32 * ng)); XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_fb_bsum, 128 * 128));
-          k_fb_build<<<nblk(ng, 64), 64, 0, st>>>(gens, (uint32_t)ng, (uint32_t*)ctx->d_fb_tab); XHE_LAUNCHED(ctx);
-        }
         k_fb_digits<<<nblk(n_static, 128), 128, 0, st>>>(D.d_range_sc + 8 * n_dyn, (uint32_t)n_static, (int16_t*)ctx->d_fb_dig); XHE_LAUNCHED(ctx);
         k_fb_buckets<<<128, 128, 0, st>>>((const int16_t*)ctx->d_fb_dig, (uint32_t)(32 * n_static), (const uint32_t*)ctx->d_fb_tab, Nmax, ctx->party_capacity, (uint32_t*)ctx->d_fb_bsum); XHE_LAUNCHED(ctx);
         k_fb_reduce<<<1, 32, 0, st>>>((const uint32_t*)ctx->d_fb_bsum, D.d_rparts + 32); XHE_LAUNCHED(ctx);
@@ -858,12 +971,15 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
         rc = xhe_launch_msm_ex(ctx, D.d_range_sc + 8 * n_dyn, D.d_range_niels + 24 * n_dyn, n_static, D.d_ws3, D.ws_static, nullptr, nullptr, D.d_rparts + 32, D.d_results + 97); if (rc) return rc;
       }
       XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dyn, 0));
+      // (every producer of the chain kernel is queued by now: only here may a wait on it enter a hardware queue)
+      if (ext_chain) { XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], s_chain)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, ctx->ev[11], 0)); }
       k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
     }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
   }
   ctx->stream = main_st;
   // ---- join
+  if (ext_chain) { if (!b->n_rp) XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], s_chain)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, ctx->ev[11], 0)); }
   if (b->n_sigs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sig, 0));
   if (b->n_rp) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_rp, 0));
   if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_fs, 0));
@@ -874,6 +990,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
 // stage 3: read the results back (synchronises the stream)
 extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (!ctx || !ctx->resident || !v) return XHE_E_ARG;
+  if (v->struct_size != sizeof(xhe_verdict)) { ctx->err = "verify_batch: xhe_verdict.struct_size does not match this library"; return XHE_E_ARG; }
   DeviceBatch& D = *(DeviceBatch*)ctx->resident; const xhe_batch* b = &D.h; cudaStream_t st = ctx->stream;
   // pinned landing zone: a device-to-pageable copy would block (spinning) inside cudaMemcpyAsync until the batch is done
   if (!ctx->h_res) XHE_CUDA_OK(ctx, cudaHostAlloc((void**)&ctx->h_res, 512, cudaHostAllocMapped));
@@ -885,7 +1002,12 @@ extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (v->sig_ok && D.fs && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_ok, D.d_sig_ok, b->n_sigs, cudaMemcpyDeviceToHost, st));
   XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
   if (h_res[96] | h_res[97]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
+  if (h_res[99]) { char m[160]; snprintf(m, sizeof m, "verify_batch: the Horner chain kernel timed out waiting for its inputs (chain %u, group %u, %u of %u nodes)", (h_res[99] >> 28) & 7u, (h_res[99] >> 24) & 15u, h_res[99] & 0xfffu, (h_res[99] >> 12) & 0xfffu); ctx->err = m; return XHE_E_CUDA; }
   v->device_flags = h_res[98];
+  if (D.layout && v->tx_flags && v->device_flags) {      // reject path only: which transactions raised the flags
+    XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->tx_flags, D.d_tx_flags, b->n_tx, cudaMemcpyDeviceToHost, st));
+    XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
+  }
   memcpy(v->sigma_enc, h_res, 32); v->sigma_is_identity = (int32_t)h_res[8]; memcpy(v->sigma_ext, h_res + 16, 128);
   if (b->n_rp) { memcpy(v->range_enc, h_res + 48, 32); v->range_is_identity = (int32_t)h_res[56]; memcpy(v->range_ext, h_res + 64, 128); }
   else { memset(v->range_enc, 0, 32); v->range_is_identity = 1; memset(v->range_ext, 0, 128); ((uint32_t*)v->range_ext)[8] = 1; ((uint32_t*)v->range_ext)[16] = 1; }
@@ -894,6 +1016,7 @@ extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
 
 extern "C" int32_t xhe_verify_batch(xhe_ctx* ctx, const xhe_batch* b, xhe_verdict* v) {
   if (!ctx || !b || !v) return XHE_E_ARG;
+  if (v->struct_size != sizeof(xhe_verdict)) { ctx->err = "verify_batch: xhe_verdict.struct_size does not match this library"; return XHE_E_ARG; }
   int32_t rc = xhe_batch_prepare(ctx, b); if (rc) return rc;
   rc = xhe_batch_run(ctx); if (rc) return rc;
   return xhe_batch_fetch(ctx, v);
@@ -914,10 +1037,20 @@ extern "C" int32_t xhe_sig_r(xhe_ctx* ctx, const uint8_t* s, const uint8_t* e, c
   TRY(cudaMemcpyAsync(d_enc, pk_enc, 32 * n, cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_s, s, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
   TRY(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_idx, idx.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   rc = xhe_decompress_dev(ctx, d_enc, n, d_aff, nullptr, d_ok); if (rc) { cleanup(); return rc; }
-  k_sig_r<<<nblk(n, 64), 64, 0, ctx->stream>>>((const uint32_t*)d_s, (const uint32_t*)d_e, (const uint32_t*)d_idx, (const uint32_t*)d_aff, (const uint8_t*)d_ok, g_tables[ctx->device]->tabH, (uint32_t)n, (uint8_t*)d_r, (uint32_t*)d_tab); XHE_LAUNCHED(ctx);
+  k_sig_r<<<nblk(n, 64), 64, 0, ctx->stream>>>((const uint32_t*)d_s, (const uint32_t*)d_e, (const uint32_t*)d_idx, (const uint8_t*)d_enc, g_tables[ctx->device]->tabH, (uint32_t)n, (uint8_t*)d_r, (uint32_t*)d_tab); XHE_LAUNCHED(ctx);
   TRY(cudaMemcpyAsync(r_enc, d_r, 32 * n, cudaMemcpyDeviceToHost, ctx->stream)); TRY(cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
   TRY(cudaStreamSynchronize(ctx->stream));
 #undef TRY
   cleanup();
   return XHE_OK;
+}
+
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2), and loading one may need every running kernel
+// to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
+// kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
+size_t xhe_preload_verify() {      // returns the largest per-thread local-memory frame among them
+  const void* ks[] = {(const void*)k_build_tab8, (const void*)k_sig_r, (const void*)k_op_delta, (const void*)k_op_jump, (const void*)k_op_finish, (const void*)k_sigma_weights, (const void*)k_reduce_scalars, (const void*)k_rp_prep, (const void*)k_pow2_table, (const void*)k_rp_gens, (const void*)k_fb_build, (const void*)k_fb_digits, (const void*)k_fb_buckets, (const void*)k_fb_reduce, (const void*)k_gather_niels, (const void*)k_copy_words, (const void*)k_combine, (const void*)k_combine_out, (const void*)k_sum_encodings, (const void*)k_copy_bytes, (const void*)k_make_record, (const void*)k_shard_decide};
+  cudaFuncAttributes a; size_t mx = 0;
+  for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
+  return mx;
 }

@@ -33,6 +33,7 @@ struct xhe_ctx {
   int n_timers = 0;
   struct Pending { int timer; cudaEvent_t e0, e1; };
   std::vector<Pending> pending;
+  std::vector<cudaEvent_t> ev_pool;                           // timing events, created when timing is switched on: nothing may be created while a chain kernel polls (msm.cu)
   // timeline of the last timed xhe_batch_run (start/end of every timed kernel relative to the start of the run)
   cudaEvent_t tl_base = nullptr; size_t tl_mark = 0;
   struct Span { const char* name; float t0, t1; };
@@ -41,8 +42,11 @@ struct xhe_ctx {
   uint32_t* h_res = nullptr;                                  // pinned 512-byte landing zone of a batch's result block
   void* h_small = nullptr;                                    // pinned (device-mapped) 7 KiB input block of xhe_sum_encodings
   void* resident = nullptr;                                   // DeviceBatch of the batch currently resident (verify.cu)
-  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; // side streams for the independent pipelines of xhe_batch_run
-  cudaEvent_t ev[12] = {nullptr};
+  cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // side streams for the independent pipelines of xhe_batch_run
+  cudaEvent_t ev[14] = {nullptr};
+  // grouped MSM tail (msm.cu): per lane a reduction stream, a Horner stream and their events
+  cudaStream_t msm_side[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t msm_ev[2][17] = {{nullptr}, {nullptr}};
 };
 
 // scoped timing of one kernel launch on ctx->stream (no-op unless ctx->timing)
@@ -53,8 +57,10 @@ struct XheTimed {
     for (int i = 0; i < c->n_timers; i++) if (!strcmp(c->timers[i].name, name)) idx = i;
     if (idx < 0 && c->n_timers < 16) { idx = c->n_timers++; c->timers[idx].name = name; }
     if (idx < 0) return;
+    if (c->ev_pool.size() < 2) { idx = -1; return; }          // pool exhausted: this launch goes untimed
     c->timers[idx].launches++; c->timers[idx].units += units;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream);
+    e0 = c->ev_pool.back(); c->ev_pool.pop_back(); e1 = c->ev_pool.back(); c->ev_pool.pop_back();
+    cudaEventRecord(e0, c->stream);
   }
   ~XheTimed() { if (idx >= 0) { cudaEventRecord(e1, ctx->stream); ctx->pending.push_back({idx, e0, e1}); } }
 };
@@ -127,5 +133,12 @@ __device__ __forceinline__ void st_ge(uint32_t* p, const ge& g) { st_fe(p, g.X);
 
 // kernel launchers implemented across the .cu files
 int32_t xhe_msm_sort(xhe_ctx* ctx, const void* d_scalars, size_t n, void* d_ws, size_t ws_bytes, void* d_bad_flag);
-int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum = nullptr);
+int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, cudaEvent_t after_accum = nullptr, int lane = 0, int chain_mode = -1);
+// the Horner chain of an MSM as a job for the polling chain kernel (msm.cu): one kernel can serve two MSMs
+struct XheChainJob { const uint32_t* hnodes; uint32_t* ready; int G, Wg, W, c; uint8_t* out_enc; uint32_t* is_identity; uint32_t* out_ext; uint32_t* status; };
+XheChainJob xhe_msm_chain_job(size_t n, void* d_ws, void* d_out_enc, void* d_is_id, void* d_out_ext);
+int32_t xhe_msm_chain_reset(xhe_ctx* ctx, cudaStream_t st, const XheChainJob& j);
+int32_t xhe_msm_chain_launch(xhe_ctx* ctx, cudaStream_t st, const XheChainJob& a, const XheChainJob& b, int wait);
+bool xhe_msm_chain_enabled();
+int32_t xhe_msm_side_init(xhe_ctx* ctx, int lane);
 int32_t xhe_launch_msm(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id);

@@ -1,12 +1,22 @@
 """Multi-GPU batch verification: one process per GPU, transactions sharded across ranks.
 
-Every rank verifies its contiguous shard with its own GPU (`verifier.verify_batch_partial`): per-TX checks are local, and
-the two big multiscalar multiplications are computed as PARTIAL sums (each rank also folds its own share of the static
-Bulletproofs generator scalars into its partial, so no scalars are exchanged).  The only exchange is one small
-all-gather per batch: (local verdict, first failing tx, sigma partial encoding, range partial encoding) = 72 bytes per
-rank over NCCL (or gloo on CPU in the tests).  Ristretto encodings are canonical, so summing the decoded partials and
-testing the identity is exactly the reference's `mega_check.is_identity()` on the whole batch (src/proofs.rs:49-67).
-NCCL has no user-defined reduction, hence all-gather + local add rather than an all-reduce.
+Every rank holds the WHOLE batch (as every node of a network receives the whole block) and verifies one contiguous shard of
+it with its own GPU (`verifier.verify_batch_shard`): per-TX checks are local, and the two big multiscalar multiplications are
+computed as PARTIAL sums (each rank also folds its own share of the static Bulletproofs generator scalars into its partial,
+so no scalars are exchanged).  The only exchange on the verification path is one small all-gather per batch: (local verdict,
+first failing tx, sigma partial encoding, range partial encoding) = 80 bytes per rank over NCCL (or gloo on CPU in the
+tests).  Ristretto encodings are canonical, so summing the decoded partials and testing the identity is exactly the
+reference's `mega_check.is_identity()` on the whole batch (src/proofs.rs:49-67).  NCCL has no user-defined reduction, hence
+all-gather + local add rather than an all-reduce.
+
+Dependent transactions.  The reference threads `state` through the batch in order (src/tx/verify.rs:301-336,354-374): a
+transaction's source ciphertext is the initial balance moved by EVERY earlier transaction on that (account, asset) -- its own
+earlier spends and what it received (src/lib.rs:908-921).  A shard therefore follows the balance chains of its keys back
+through the earlier shards: the host layer replays the group operations of the earlier transactions that touch those keys
+(no proofs -- their own rank verifies them; no communication -- the bytes are in the batch), so verdicts and balances equal
+the single-process result however the batch is cut.  After an accepted batch a rank commits its own shard's updates; with
+`sync_state=True` the ranks also exchange their updates (one all-gather of 128 bytes per touched balance) and apply them in
+shard order, so every replica of the state ends up identical to the reference's.
 """
 import os
 import struct
@@ -23,8 +33,12 @@ def decide(records, sum_is_identity):
     """records: per-rank 80-byte records in rank (= shard) order; sum_is_identity(list of 32-byte encodings) -> bool.
     Mirrors the reference's order: first failing tx in batch order, then the sigma check, then the range check."""
     parsed = [struct.unpack("<iq", r[:12]) + (r[12:44], r[44:76]) for r in records]
-    for code, gidx, _, _ in parsed:          # shards are contiguous and in order: the lowest rank with a per-tx error wins
-        if code != OK and code not in (RANGE_PROOF,) or (code == RANGE_PROOF and gidx >= 0):
+    per_tx = [(gidx, code) for code, gidx, _, _ in parsed if code != OK and gidx >= 0]
+    if per_tx:                               # the first failing transaction of the whole batch (src/tx/verify.rs:492-498)
+        gidx, code = min(per_tx)
+        return code, gidx
+    for code, gidx, _, _ in parsed:          # a shard-level error without a transaction (state backend failure)
+        if code != OK and code not in (GENERIC_PROOF, RANGE_PROOF):
             return code, gidx
     if not sum_is_identity([p[2] for p in parsed]):
         return GENERIC_PROOF, -1
@@ -227,21 +241,78 @@ class AsyncDecider:
         self.thread.join(5)
 
 
-def verify_batch_distributed(ctx, shard_blobs, ledger, shard_offset, group=None, seed=None, threads=0, prepared=None, commit=True, fiat_shamir="host", gather=None):
-    """Transaction::verify_batch over a batch sharded across the ranks of `group`.  Returns (code, global first failing tx,
-    timings).  On accept every rank commits its own shard's balance updates to its ledger.  `gather` (record -> list of
-    records) replaces the direct all-gather when several batches are in flight (OrderedGatherer)."""
+def shard_bounds(n, rank, world):
+    """contiguous shard [lo, hi) of rank `rank` in a batch of n transactions"""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def all_gather_bytes(data: bytes, group=None, device=None):
+    """all-gather of one variable-length byte string per rank (lengths first, then the padded payloads)"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = device if device is not None and device.type == "cuda" else torch.device("cpu")
+    ln = torch.tensor([len(data)], dtype=torch.int64, device=dev)
+    lens = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens, ln, group=group)
+    lens = [int(x) for x in lens.cpu().tolist()]
+    cap = max(max(lens), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8)
+    if data:
+        buf[:len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, buf.to(dev), group=group)
+    raw = bytes(out.cpu().numpy())
+    return [raw[r * cap:r * cap + lens[r]] for r in range(world)]
+
+
+def sync_and_commit(ctx, ledger, group=None, device=None):
+    """After an accepted sharded batch: exchange the ranks' balance updates and apply them in shard order (a later shard's
+    value of a shared balance is the final one), so every rank's replica of the state equals the reference's final state."""
+    import torch.distributed as dist
+    from . import verifier
+    rank = dist.get_rank(group)
+    handle = verifier.take_pending(ctx)
+    mine = verifier.export_taken(handle) if handle else b""
+    parts = all_gather_bytes(mine, group, device)
+    rc = 0
+    for r, recs in enumerate(parts):
+        if r == rank:
+            if handle:
+                rc = rc or verifier.commit_taken(handle, ledger)      # own shard: nonces / multisig settings / output ciphertexts too
+        elif recs:
+            rc = rc or ledger.apply_records(recs)
+    return rc
+
+
+def verify_batch_distributed(ctx, blobs, ledger, group=None, seed=None, threads=0, prepared=None, commit=True, fiat_shamir="host", gather=None,
+                             sync_state=False, deterministic=False):
+    """Transaction::verify_batch over a batch sharded across the ranks of `group`; EVERY rank passes the whole batch.
+    Returns (code, first failing tx, timings) -- the same on every rank and equal to the single-process verdict, also when
+    transactions of different shards touch the same (account, asset).  On accept every rank commits its own shard's balance
+    updates to its ledger (`sync_state=True`: all shards' updates, see sync_and_commit).  `gather` (record -> list of records)
+    replaces the direct all-gather when several batches are in flight (OrderedGatherer)."""
     import time
     import torch
+    import torch.distributed as dist
     from . import verifier
-    code, idx, s_enc, r_enc, tm = verifier.verify_batch_partial(ctx, shard_blobs, ledger, seed=seed, threads=threads, prepared=prepared, fiat_shamir=fiat_shamir)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = prepared.n if prepared is not None else len(blobs)
+    lo, hi = shard_bounds(n, rank, world)
+    code, idx, s_enc, r_enc, tm = verifier.verify_batch_shard(ctx, blobs, ledger, lo, hi, seed=seed, threads=threads, prepared=prepared, fiat_shamir=fiat_shamir, deterministic=deterministic)
     t0 = time.perf_counter()
-    rec = pack_local(code, idx, shard_offset, s_enc, r_enc)
-    records = gather(rec) if gather else all_gather_records(rec, group, torch.device("cuda", torch.cuda.current_device()))
+    rec = pack_local(code, idx, 0, s_enc, r_enc)            # idx is already an index into the whole batch
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    records = gather(rec) if gather else all_gather_records(rec, group, dev)
     t1 = time.perf_counter()
     verdict = decide(records, lambda encs: sum_is_identity(ctx, encs))
     t2 = time.perf_counter()
     if verdict[0] == OK and commit:
-        verifier.commit_pending(ctx, ledger)
+        if sync_state:
+            sync_and_commit(ctx, ledger, group, dev)
+        else:
+            verifier.commit_pending(ctx, ledger)
+    elif verdict[0] != OK:
+        verifier.drop_taken(verifier.take_pending(ctx))
     tm = dict(tm); tm["exchange_ms"] = 1e3 * (t1 - t0); tm["decide_ms"] = 1e3 * (t2 - t1); tm["commit_ms"] = 1e3 * (time.perf_counter() - t2)
     return verdict[0], verdict[1], tm

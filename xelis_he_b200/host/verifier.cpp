@@ -260,14 +260,72 @@ inline void push_output_ops(Builder& B, const TxView& tx, const uint8_t* asset, 
 
 }  // namespace
 
-// shard-mode state updates waiting for the cross-rank decision (one slot per ctx)
+// Writes to the state that a batch wants to make besides balances: update_account_nonce (src/tx/verify.rs:219-221) and
+// set_multisig_for_account (src/tx/verify.rs:426).  They are STAGED while the batch is walked -- later transactions of the
+// batch read the multisig settings through the overlay -- and applied together with the balance updates once the batch is
+// accepted, so a rejected (or dropped) batch leaves the state untouched.  `foreign` entries come from earlier shards of a
+// sharded batch: visible to this shard's transactions, committed by the rank that owns them.
 namespace {
-struct Pending { std::vector<StateUpdate> updates; std::vector<uint8_t> op_out; };
+struct Staged {
+  struct Ms { Bytes32 account; std::vector<uint8_t> signers; uint8_t threshold; bool foreign; };
+  std::vector<std::pair<Bytes32, uint64_t>> nonces;
+  std::vector<Ms> multisig;
+  std::unordered_map<Bytes32, size_t, Key32Hash> ms_index;      // account -> latest entry of `multisig`
+  void set_nonce(const uint8_t* account, uint64_t nonce) { Bytes32 k; memcpy(k.data(), account, 32); nonces.emplace_back(k, nonce); }
+  void set_multisig(const uint8_t* account, const uint8_t* signers, size_t n, uint8_t threshold, bool foreign) {
+    Ms m; memcpy(m.account.data(), account, 32); m.signers.assign(signers, signers + 32 * n); m.threshold = threshold; m.foreign = foreign;
+    ms_index[m.account] = multisig.size(); multisig.push_back(std::move(m));
+  }
+  // get_multisig_for_account through the overlay
+  bool get_multisig(VerificationState& state, const uint8_t* account, std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) const {
+    if (!ms_index.empty()) {
+      Bytes32 k; memcpy(k.data(), account, 32);
+      auto it = ms_index.find(k);
+      if (it != ms_index.end()) {
+        const Ms& m = multisig[it->second]; const size_t n = m.signers.size() / 32;
+        *present = n != 0;                       // an empty signer list deletes the setting (src/lib.rs:186-193)
+        if (n) { signers->resize(n); for (size_t i = 0; i < n; i++) memcpy((*signers)[i].data(), &m.signers[32 * i], 32); *threshold = m.threshold; }
+        return true;
+      }
+    }
+    return state.get_multisig_for_account(account, signers, threshold, present);
+  }
+  int apply(VerificationState& state) const {
+    for (const auto& nn : nonces) if (!state.update_account_nonce(nn.first.data(), nn.second)) return XHE_ERR_STATE;
+    for (const Ms& m : multisig) if (!m.foreign && !state.set_multisig_for_account(m.account.data(), m.signers.data(), m.signers.size() / 32, m.threshold)) return XHE_ERR_STATE;
+    return XHE_OK;
+  }
+};
+// MultiSig payload rules (src/tx/verify.rs:401-418)
+bool multisig_payload_ok(const TxView& tx) {
+  const uint32_t ns = tx.count, th = tx.aux;
+  if (th > ns || (ns != 0 && th == 0)) return false;
+  for (uint32_t x = 0; x < ns; x++) for (uint32_t y = 0; y < ns; y++) if (x != y && !memcmp(tx.body + 32 * x, tx.body + 32 * y, 32)) return false;
+  for (uint32_t x = 0; x < ns; x++) if (!memcmp(tx.body + 32 * x, tx.source, 32)) return false;
+  return true;
+}
+// random seed of the batch factors: SHA3-512(personalisation || 32 bytes of OS entropy); the personalisation alone only when
+// the caller asked for a replayable run (tests)
+bool make_seed(const BatchOptions& opt, uint8_t seed[32]) {
+  Sponge sp(72);
+  if (opt.rng_seed && opt.rng_seed_len) sp.absorb(opt.rng_seed, opt.rng_seed_len);
+  if (!(opt.deterministic_seed && opt.rng_seed && opt.rng_seed_len)) {
+    uint8_t os[32]; FILE* f = fopen("/dev/urandom", "rb");
+    if (!f || fread(os, 1, 32, f) != 32) { if (f) fclose(f); return false; }
+    fclose(f); sp.absorb(os, 32);
+  }
+  sp.finish(0x06); uint8_t h[64]; sp.squeeze(h, 64); memcpy(seed, h, 32);
+  return true;
+}
+
+// shard-mode state updates waiting for the cross-rank decision (one slot per ctx)
+struct Pending { std::vector<StateUpdate> updates; std::vector<uint8_t> op_out; Staged staged; };
 std::mutex g_pending_mu;
 std::unordered_map<xhe_ctx*, Pending> g_pending;
 }  // namespace
 
 static int apply_pending(const Pending& P, VerificationState& state) {
+  int rc = P.staged.apply(state); if (rc) return rc;
   const size_t n = P.updates.size();
   for (size_t j = 0; j < n; j++) {
     const StateUpdate& u = P.updates[j];
@@ -293,6 +351,18 @@ int commit_pending(xhe_ctx* ctx, VerificationState& state) {
   delete P;
   return rc;
 }
+// the (key, new balance) pairs a shard-mode batch is holding back, as 128-byte records account || asset || ciphertext in
+// update order -- what a rank sends to its peers so that every replica of the state ends up identical (distributed.py)
+size_t export_pending(void* pending, uint8_t* out, size_t cap) {
+  Pending* P = (Pending*)pending; if (!P) return 0;
+  size_t k = 0;
+  for (const StateUpdate& u : P->updates) {
+    if (u.output) continue;
+    if ((k + 1) * 128 <= cap) { uint8_t* o = out + 128 * k; memcpy(o, u.account.data(), 32); memcpy(o + 32, u.asset.data(), 32); memcpy(o + 64, &P->op_out[32 * (size_t)u.op_c], 32); memcpy(o + 96, &P->op_out[32 * (size_t)u.op_d], 32); }
+    k++;
+  }
+  return k;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Transaction::verify_batch
@@ -305,23 +375,40 @@ int commit_pending(xhe_ctx* ctx, VerificationState& state) {
 // error precedence.  Multisig accounts / multisig transactions always take the exact path.
 // ------------------------------------------------------------------------------------------------------------------
 struct FastCache {
-  PinnedVec<uint8_t> blob, region_b, op_out; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
+  PinnedVec<uint8_t> blob, region_b, op_out, tx_flags; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
   FlatTable<64, Chain> chains;       // (account, asset) -> tail of its balance chain inside the batch
 };
 static std::unordered_map<xhe_ctx*, FastCache*> g_fast_cache;
 static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g_cache_mu); FastCache*& c = g_fast_cache[ctx]; if (!c) c = new FastCache(); return *c; }
 
-static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, BatchTimings* tm, int* rc_out) {
+static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm);
+
+// the reference's verdict for ONE transaction of the batch (it is known to be the first one that fails a per-transaction
+// check): the exact path over the one-transaction shard [i, i+1) -- earlier transactions only advance its balance chains
+static int exact_verdict_of(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, size_t i) {
+  BatchOptions o = opt; o.fast_path = false; o.shard_lo = i; o.shard_hi = i + 1; o.apply_state = false;
+  uint8_t partial[64]; o.partial_out = partial;
+  long fi = -1;
+  int code = verify_batch_exact(ctx, blobs, lens, n, state, o, &fi, nullptr);
+  delete take_pending(ctx);                                   // shard mode parks the updates: not wanted here
+  return code;
+}
+
+// returns 1: accepted (state applied, or partials / pending updates out in shard mode); 2: decided, *rc_out = verdict code and
+// *fail_out = failing transaction (index into the whole batch, -1 for the two batch-level checks); 0: not decided here, the
+// caller runs the exact path (*rc_out < 0: infrastructure error).
+static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n_total, VerificationState& state, const BatchOptions& opt, BatchTimings* tm, int* rc_out, long* fail_out) {
   double t0 = now_ms();
-  *rc_out = XHE_OK;
-  if (n == 0) return 0;
+  *rc_out = XHE_OK; *fail_out = -1;
+  const size_t lo = std::min(opt.shard_lo, n_total), hi = std::min(opt.shard_hi, n_total);
+  if (hi <= lo) return 0;
+  const size_t n = hi - lo;                                   // transactions of this shard; index j <-> batch index lo + j
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
   uint8_t seed[32];
-  if (opt.rng_seed && opt.rng_seed_len) { uint8_t h[64]; sha3_512(opt.rng_seed, opt.rng_seed_len, h); memcpy(seed, h, 32); }
-  else { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(seed, 1, 32, f) != 32) { if (f) fclose(f); return 0; } fclose(f); }
-  std::vector<TxView> txs(n); std::vector<int> parse_rc(n, 0);
-  parallel_for(n, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
-  for (size_t i = 0; i < n; i++) if (parse_rc[i]) return 0;
+  if (!make_seed(opt, seed)) return 0;
+  std::vector<TxView> txs(hi); std::vector<int> parse_rc(hi, 0);
+  parallel_for(hi, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
+  for (size_t i = lo; i < hi; i++) if (parse_rc[i]) return 0;
   double t1 = now_ms();
   FastCache& F = fast_cache_for(ctx);
   const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
@@ -331,11 +418,63 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   FlatTable<64, Chain>& chains = F.chains; chains.clear(); chains.reserve(4 * n);
   struct Upd { const uint8_t *account, *asset; Role role; uint32_t op_c; bool output; };
   std::vector<Upd> updates; updates.reserve(3 * n);
+  Staged staged; staged.nonces.reserve(n);
   const bool want_out = state.wants_output_ciphertexts(); std::vector<size_t> out_slots;
   const long long RB = (long long)1 << 40;     // marks "region B slot j" until the region-A size is known
   uint32_t pt = 1, n_eq = 0, n_val = 0, max_chain = 1; uint64_t off = 0;
   F.rp_pt_off[0] = 0; F.rp_ch_off[0] = 0;
   std::vector<Bytes32> signers;
+  std::vector<size_t> rb_terms;                // positions in F.terms that hold a region-B slot (foreign ciphertext points)
+  auto touch = [&](const uint8_t* account, const uint8_t* asset, Role role, long long* pc, long long* pd) -> Chain* {
+    Ct64 kk = MockLedger::key(account, asset); bool fresh = false;
+    Chain& c = *chains.insert(kk.data(), &fresh);
+    if (fresh) {
+      uint8_t ct[64];
+      if (!state.get_account_balance(account, asset, role, ct)) return nullptr;
+      long long j = (long long)(F.region_b.size() / 32); F.region_b.append(ct, 64);
+      c.last_c = -(RB + j); c.last_d = -(RB + j + 1); c.length = 0;
+    }
+    *pc = c.last_c; *pd = c.last_d; return &c;
+  };
+  auto push_op = [&](long long prev, uint64_t amount) { F.prev.push_back(prev); F.amount.push_back(amount); return (uint32_t)F.prev.size() - 1; };
+  auto rb_term = [&](const uint8_t* enc, bool neg) { uint32_t j = (uint32_t)(F.region_b.size() / 32); F.region_b.append(enc, 32); rb_terms.push_back(F.terms.size()); F.terms.push_back(j | (neg ? 0x80000000u : 0u)); };
+  // ---- earlier shards of a sharded batch: follow the balance chains (and multisig settings) this shard's transactions depend
+  // on.  The group operations of a foreign transaction on a shared (account, asset) are replayed here (no proofs: its own
+  // rank verifies them); its ciphertext points travel in region B.
+  if (lo > 0) {
+    FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * n); sources.reserve(n);
+    for (size_t i = lo; i < hi; i++) {
+      const TxView& tx = txs[i]; sources.insert(tx.source);
+      for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
+      for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
+    }
+    for (size_t i = 0; i < lo; i++) {
+      if (parse_rc[i]) continue;
+      const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
+      if (tx.type == 4 && sources.find(tx.source)) return 0;                    // multisig setting for one of our senders: exact path
+      for (uint32_t q = 0; q < tx.n_sc; q++) {
+        const uint8_t* asset = tx.sc + 256 * q;
+        if (!keys.find(MockLedger::key(tx.source, asset).data())) continue;
+        long long pc, pd; Chain* ch = touch(tx.source, asset, Sender, &pc, &pd); if (!ch) return 0;
+        bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry); if (carry) return 0;
+        uint32_t oc = push_op(pc, amount);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) rb_term(tx.transfers[t].commitment, true);
+        F.term_off.push_back((uint32_t)F.terms.size());
+        uint32_t od = push_op(pd, 0);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) rb_term(tx.transfers[t].sender_handle, true);
+        F.term_off.push_back((uint32_t)F.terms.size());
+        ch->last_c = oc; ch->last_d = od; if (++ch->length > max_chain) max_chain = ch->length;
+      }
+      for (uint32_t t = 0; t < k; t++) {
+        const TransferView& tr = tx.transfers[t];
+        if (!keys.find(MockLedger::key(tr.dest, tr.asset).data())) continue;
+        long long pc, pd; Chain* ch = touch(tr.dest, tr.asset, Receiver, &pc, &pd); if (!ch) return 0;
+        uint32_t oc = push_op(pc, 0); rb_term(tr.commitment, false); F.term_off.push_back((uint32_t)F.terms.size());
+        uint32_t od = push_op(pd, 0); rb_term(tr.receiver_handle, false); F.term_off.push_back((uint32_t)F.terms.size());
+        ch->last_c = oc; ch->last_d = od; if (++ch->length > max_chain) max_chain = ch->length;
+      }
+    }
+  }
   // the walk below is one dependent hash lookup after another: announce the lookups a few transactions ahead
   const size_t AHEAD = 6;
   auto announce = [&](const TxView& tx) {
@@ -343,39 +482,29 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); Ct64 kk = MockLedger::key(tx.source, tx.sc + 256 * q); chains.prefetch(kk.data()); }
     for (uint32_t t = 0; t < tx.n_transfers(); t++) { const TransferView& tr = tx.transfers[t]; state.prefetch_balance(tr.dest, tr.asset); Ct64 kk = MockLedger::key(tr.dest, tr.asset); chains.prefetch(kk.data()); }
   };
-  for (size_t i = 0; i < n && i < AHEAD; i++) announce(txs[i]);
-  for (size_t i = 0; i < n; i++) {
-    const TxView& tx = txs[i];
-    if (i + AHEAD < n) announce(txs[i + AHEAD]);
+  for (size_t j = 0; j < n && j < AHEAD; j++) announce(txs[lo + j]);
+  // A transaction that fails one of the HOST-side checks ends the walk (n_run transactions go to the device): the reference
+  // stops at the first failing transaction, so whatever comes after it cannot change the verdict.
+  size_t n_run = n; bool host_fail = false;
+  for (size_t j = 0; j < n; j++) {
+    const TxView& tx = txs[lo + j];
+    if (j + AHEAD < n) announce(txs[lo + j + AHEAD]);
     if (tx.type == 4 || tx.n_ms >= 0) return 0;                               // multisig: exact path
     uint64_t nonce;
-    if (!state.get_account_nonce(tx.source, &nonce) || nonce != tx.nonce) return 0;
-    state.update_account_nonce(tx.source, tx.nonce);
-    if (!verify_commitment_assets(tx)) return 0;
-    { uint8_t th; bool present = false; if (!state.get_multisig_for_account(tx.source, &signers, &th, &present) || present) return 0; }
+    if (!state.get_account_nonce(tx.source, &nonce) || nonce != tx.nonce || !verify_commitment_assets(tx)) { n_run = j; host_fail = true; break; }
+    { uint8_t th; bool present = false; if (!staged.get_multisig(state, tx.source, &signers, &th, &present) || present) return 0; }
     const uint32_t k = tx.n_transfers(), a = tx.n_sc, lg = (tx.rp_len / 32 - 9) / 2;
     uint32_t m = 1, lg_need = 6; while (m < a + k) { m <<= 1; lg_need++; }
-    if (lg != lg_need || m > party_capacity) return 0;            // larger proofs: the exact path reports the unsupported party count
-    uint32_t* P = &F.plan[8 * i];
-    P[0] = n_eq; P[1] = n_val; P[2] = (uint32_t)i; P[3] = F.rp_ch_off[i]; P[4] = (uint32_t)i; P[5] = 1; P[6] = pt; P[7] = (uint32_t)F.prev.size();
-    F.rp_m[i] = m; F.rp_pt_off[i + 1] = F.rp_pt_off[i] + 4 + 2 * lg + m; F.rp_ch_off[i + 1] = F.rp_ch_off[i] + 4 + lg;
-    F.off[i] = off; off += (lens[i] + 15) & ~(size_t)15;
+    if (lg != lg_need || m > party_capacity) return 0;            // structural range-proof failure / larger proofs: the exact path decides
+    const size_t n_prev0 = F.prev.size(), n_terms0 = F.terms.size(), n_rb0 = F.region_b.size(), n_upd0 = updates.size();
+    uint32_t* P = &F.plan[8 * j];
+    P[0] = n_eq; P[1] = n_val; P[2] = (uint32_t)j; P[3] = F.rp_ch_off[j]; P[4] = (uint32_t)j; P[5] = 1; P[6] = pt; P[7] = (uint32_t)F.prev.size();
+    F.rp_m[j] = m; F.rp_pt_off[j + 1] = F.rp_pt_off[j] + 4 + 2 * lg + m; F.rp_ch_off[j + 1] = F.rp_ch_off[j] + 4 + lg;
     const uint32_t iT = pt + 1;
-    auto touch = [&](const uint8_t* account, const uint8_t* asset, Role role, long long* pc, long long* pd) -> Chain* {
-      Ct64 kk = MockLedger::key(account, asset); bool fresh = false;
-      Chain& c = *chains.insert(kk.data(), &fresh);
-      if (fresh) {
-        uint8_t ct[64];
-        if (!state.get_account_balance(account, asset, role, ct)) return nullptr;
-        long long j = (long long)(F.region_b.size() / 32); F.region_b.append(ct, 64);
-        c.last_c = -(RB + j); c.last_d = -(RB + j + 1); c.length = 0;
-      }
-      *pc = c.last_c; *pd = c.last_d; return &c;
-    };
-    auto push_op = [&](long long prev, uint64_t amount) { F.prev.push_back(prev); F.amount.push_back(amount); return (uint32_t)F.prev.size() - 1; };
+    bool state_fail = false;
     for (uint32_t q = 0; q < a; q++) {
       const uint8_t* asset = tx.sc + 256 * q; long long pc, pd;
-      Chain* ch = touch(tx.source, asset, Sender, &pc, &pd); if (!ch) return 0;
+      Chain* ch = touch(tx.source, asset, Sender, &pc, &pd); if (!ch) { state_fail = true; break; }
       bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry);
       if (carry) return 0;                                                      // fee + amount >= 2^64: exact path (adds the 2^64 * G term)
       uint32_t oc = push_op(pc, amount);
@@ -388,13 +517,18 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
       updates.push_back({tx.source, asset, Sender, oc, false});
       if (want_out) { out_slots.push_back(updates.size()); updates.push_back({tx.source, asset, Sender, 0, true}); }   // reference order: update, then set_output (339-340)
     }
-    for (uint32_t t = 0; t < k; t++) {
+    for (uint32_t t = 0; t < k && !state_fail; t++) {
       const TransferView& tr = tx.transfers[t]; long long pc, pd;
-      Chain* ch = touch(tr.dest, tr.asset, Receiver, &pc, &pd); if (!ch) return 0;
+      Chain* ch = touch(tr.dest, tr.asset, Receiver, &pc, &pd); if (!ch) { state_fail = true; break; }
       uint32_t oc = push_op(pc, 0); F.terms.push_back(iT + 3 * t); F.term_off.push_back((uint32_t)F.terms.size());
       uint32_t od = push_op(pd, 0); F.terms.push_back(iT + 3 * t + 2); F.term_off.push_back((uint32_t)F.terms.size());
       ch->last_c = oc; ch->last_d = od; if (++ch->length > max_chain) max_chain = ch->length;
       updates.push_back({tr.dest, tr.asset, Receiver, oc, false});
+    }
+    if (state_fail) {   // a balance lookup failed: this transaction fails (the exact path names the error)
+      if (F.prev.size() != n_prev0 || updates.size() != n_upd0) return 0;      // ... but it had already advanced a chain: let the exact path sort it out
+      (void)n_terms0; (void)n_rb0;
+      n_run = j; host_fail = true; break;
     }
     if (want_out) {   // output ciphertexts: appended after the ops k_layout indexes (P[7] + 2q are the sender ops)
       for (uint32_t q = 0; q < a; q++) {
@@ -409,43 +543,75 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
       }
       out_slots.clear();
     }
+    staged.set_nonce(tx.source, tx.nonce);                                      // update_account_nonce(source, nonce), src/tx/verify.rs:219-221
+    F.off[j] = off; off += (lens[lo + j] + 15) & ~(size_t)15;
     pt += 1 + 3 * k + a + 3 * a + k + 3 * k + 4 + 2 * lg;
     n_eq += a; n_val += k;
   }
-  F.off[n] = off;
+  const bool shard = opt.partial_out != nullptr;
+  if (n_run == 0) {   // the first transaction of the shard already fails a host-side check
+    int code = exact_verdict_of(ctx, blobs, lens, n_total, state, opt, lo);
+    if (code <= 0) { *rc_out = code < 0 ? code : XHE_OK; return 0; }
+    if (shard) { memset(opt.partial_out, 0, 64); std::lock_guard<std::mutex> g(g_pending_mu); g_pending[ctx] = Pending(); }
+    *rc_out = code; *fail_out = (long)lo; return 2;
+  }
+  F.off[n_run] = off;
   const uint32_t n_a_end = pt, n_rb = (uint32_t)(F.region_b.size() / 32), n_points = n_a_end + n_rb;
-  for (size_t j = 0; j < F.prev.size(); j++) if (F.prev[j] <= -RB && F.prev[j] > -XHE_OP_PLUS_AMOUNT) F.prev[j] = -(1 + (long long)n_a_end + (-F.prev[j] - RB));
+  for (size_t q = 0; q < F.prev.size(); q++) if (F.prev[q] <= -RB && F.prev[q] > -XHE_OP_PLUS_AMOUNT) F.prev[q] = -(1 + (long long)n_a_end + (-F.prev[q] - RB));
+  for (size_t pos : rb_terms) F.terms[pos] = (F.terms[pos] & 0x80000000u) | (n_a_end + (F.terms[pos] & 0x7fffffffu));
   double t2 = now_ms();
   F.blob.resize(off);
-  parallel_for(n, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) memcpy(&F.blob[F.off[i]], blobs[i], lens[i]); });
+  parallel_for(n_run, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) memcpy(&F.blob[F.off[j]], blobs[lo + j], lens[lo + j]); });
   double t3 = now_ms();
-  xhe_batch xb; memset(&xb, 0, sizeof xb);
-  xb.n_tx = (uint32_t)n; xb.n_points = n_points; xb.n_sigs = (uint32_t)n;
+  xhe_batch xb; memset(&xb, 0, sizeof xb); xb.struct_size = (uint32_t)sizeof xb;
+  xb.n_tx = (uint32_t)n_run; xb.n_points = n_points; xb.n_sigs = (uint32_t)n_run;
   xb.n_ops = (uint32_t)F.prev.size(); xb.op_prev = (const int64_t*)F.prev.data(); xb.op_term_off = F.term_off.data(); xb.op_terms = F.terms.data(); xb.op_amount = F.amount.data(); xb.max_chain = max_chain;
-  xb.n_eq = n_eq; xb.n_val = n_val; xb.n_rp = (uint32_t)n; xb.rp_m = F.rp_m.data(); xb.rp_point_off = F.rp_pt_off.data(); xb.rp_chal_off = F.rp_ch_off.data();
-  xb.fs_blobs = F.blob.data(); xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32);
+  xb.n_eq = n_eq; xb.n_val = n_val; xb.n_rp = (uint32_t)n_run; xb.rp_m = F.rp_m.data(); xb.rp_point_off = F.rp_pt_off.data(); xb.rp_chal_off = F.rp_ch_off.data();
+  xb.fs_blobs = F.blob.data(); xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32); xb.fs_index_base = lo;
   xb.layout_on_device = 1; xb.n_region_b = n_rb; xb.region_b = F.region_b.data();
   PinnedVec<uint8_t>& op_out = F.op_out; op_out.n = 0; op_out.reserve(32 * (size_t)xb.n_ops + 64); op_out.n = 32 * (size_t)xb.n_ops;
-  xhe_verdict v; memset(&v, 0, sizeof v); v.op_out = op_out.data();
+  PinnedVec<uint8_t>& txf = F.tx_flags; txf.n = 0; txf.reserve(n_run + 64); txf.n = n_run;
+  xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.op_out = op_out.data(); v.tx_flags = txf.data();
   int32_t rc = xhe_verify_batch(ctx, &xb, &v);
   double t4 = now_ms();
   if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->total_ms = t4 - t0; }
   if (rc != XHE_OK) { *rc_out = rc; return 0; }
-  const bool shard = opt.partial_out != nullptr;
-  if (v.device_flags != 0) return 0;
-  if (!shard && (!v.sigma_is_identity || !v.range_is_identity)) return 0;
+  // ---- verdict.  Per-transaction anomalies first (the first failing transaction in batch order, src/tx/verify.rs:492-498),
+  // then the two batch-level checks.  The failing transaction's error is the exact path's verdict on that ONE transaction.
+  long first_bad = -1;
+  if (v.device_flags & 8u) return 0;                                            // a balance read from the state does not decode: exact path
+  if (v.device_flags & 7u) { for (size_t j = 0; j < n_run; j++) if (txf[j] & 7u) { first_bad = (long)j; break; } if (first_bad < 0) return 0; }
+  if (first_bad < 0 && host_fail) first_bad = (long)n_run;
+  if (first_bad >= 0) {
+    int code = exact_verdict_of(ctx, blobs, lens, n_total, state, opt, lo + (size_t)first_bad);
+    if (code <= 0) { *rc_out = code < 0 ? code : XHE_OK; return 0; }            // the exact path disagrees: let it decide the whole batch
+    if (shard) { memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32); std::lock_guard<std::mutex> g(g_pending_mu); g_pending[ctx] = Pending(); }
+    *rc_out = code; *fail_out = (long)lo + first_bad;
+    if (tm) { tm->used_fast_path = true; tm->finish_ms = now_ms() - t4; tm->total_ms = now_ms() - t0; }
+    return 2;
+  }
+  const bool rp_structural = (v.device_flags & 16u) != 0;      // an identity-encoded range-proof point: RangeProof, but only after the sigma check
+  if (!shard) {
+    int code = !v.sigma_is_identity ? XHE_ERR_GENERIC_PROOF : ((rp_structural || !v.range_is_identity) ? XHE_ERR_RANGE_PROOF : XHE_OK);      // src/tx/verify.rs:500-502, 504-514
+    if (code) { *rc_out = code; *fail_out = -1; if (tm) { tm->used_fast_path = true; tm->finish_ms = now_ms() - t4; tm->total_ms = now_ms() - t0; } return 2; }
+  } else if (rp_structural) {   // the joint decision (distributed.decide) places a shard's structural failure after the summed sigma check
+    memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32);
+    { std::lock_guard<std::mutex> g(g_pending_mu); g_pending[ctx] = Pending(); }
+    *rc_out = XHE_ERR_RANGE_PROOF; *fail_out = -1; return 2;
+  }
   if (shard) {
     memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32);
-    Pending Pn; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.updates.reserve(updates.size());
+    Pending Pn; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.updates.reserve(updates.size()); Pn.staged = std::move(staged);
     for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; su.output = u.output; Pn.updates.push_back(su); }
     std::lock_guard<std::mutex> g(g_pending_mu);
     g_pending[ctx] = std::move(Pn);
   } else if (opt.apply_state) {
+    if (staged.apply(state) != XHE_OK) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; }
     for (size_t j = 0; j < updates.size(); j++) {
       const Upd& u = updates[j];
       if (j + 8 < updates.size()) state.prefetch_balance(updates[j + 8].account, updates[j + 8].asset);
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 64);       // commitment op and handle op are adjacent
-      if (!apply_update(state, u.account, u.asset, u.role, u.output, ct)) { *rc_out = XHE_ERR_STATE; return 0; }
+      if (!apply_update(state, u.account, u.asset, u.role, u.output, ct)) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; }
     }
   }
   double t5 = now_ms();
@@ -453,50 +619,96 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   return 1;
 }
 
-static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm);
-
 int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
   if (opt.fast_path) {
-    int rc = XHE_OK;
-    if (verify_batch_fast(ctx, blobs, lens, n, state, opt, tm, &rc)) { if (fail_index) *fail_index = -1; return XHE_OK; }
-    if (rc < 0) return rc;                       // infrastructure error: report it
+    int rc = XHE_OK; long fi = -1;
+    int how = verify_batch_fast(ctx, blobs, lens, n, state, opt, tm, &rc, &fi);
+    if (how == 1) { if (fail_index) *fail_index = -1; return XHE_OK; }
+    if (how == 2) { if (fail_index) *fail_index = fi; return rc; }
+    if (rc != XHE_OK) { if (fail_index) *fail_index = -1; return rc; }       // infrastructure error: report it
   }
   return verify_batch_exact(ctx, blobs, lens, n, state, opt, fail_index, tm);
 }
 
-static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
+static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n_total, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
   double t0 = now_ms();
   if (fail_index) *fail_index = -1;
   const bool want_out = state.wants_output_ciphertexts();
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
   uint8_t seed[32];
-  if (opt.rng_seed && opt.rng_seed_len) { uint8_t h[64]; sha3_512(opt.rng_seed, opt.rng_seed_len, h); memcpy(seed, h, 32); }
-  else { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(seed, 1, 32, f) != 32) { if (f) fclose(f); return XHE_E_ARG; } fclose(f); }
+  if (!make_seed(opt, seed)) return XHE_E_ARG;
+  // this call verifies transactions [lo, hi) of the batch (everything unless shard_lo / shard_hi say otherwise); batch index
+  // i <-> local index i - lo in `plan` and in the device batch
+  const size_t lo = std::min(opt.shard_lo, n_total), hi = std::min(opt.shard_hi, n_total);
+  const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
 
   // ---- parse (parallel)
-  std::vector<TxView> txs(n); std::vector<int> parse_rc(n, 0);
-  parallel_for(n, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
-  size_t n_live = n; int parse_err = XHE_OK;
-  for (size_t i = 0; i < n; i++) if (parse_rc[i]) { n_live = i; parse_err = parse_rc[i]; break; }
+  std::vector<TxView> txs(hi); std::vector<int> parse_rc(hi, 0);
+  parallel_for(hi, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
+  size_t n_live = hi; int parse_err = XHE_OK;
+  for (size_t i = lo; i < hi; i++) if (parse_rc[i]) { n_live = i; parse_err = parse_rc[i]; break; }
   double t1 = now_ms();
 
   // ---- phase A: sequential state resolution and batch layout (mirrors pre_verify's order, src/tx/verify.rs:203-485)
   HostCache& HC = cache_for(ctx);
-  Builder B(HC); std::vector<TxPlan> plan(n_live);
+  Builder B(HC); std::vector<TxPlan> plan(n_live > lo ? n_live - lo : 0);
+  Staged staged;
   {
     size_t tk = 0, ta = 0, tlg = 0;
-    for (size_t i = 0; i < n_live; i++) { tk += txs[i].n_transfers(); ta += txs[i].n_sc; tlg += (txs[i].rp_len / 32 - 9) / 2; }
-    size_t npts = 1 + n_live * 5 + tk * 9 + ta * 6 + 2 * tlg + 8;
-    B.points.reserve(32 * npts); B.checks.reserve(npts + 2 * n_live); B.sigs.reserve(n_live + 8);
+    for (size_t i = lo; i < n_live; i++) { tk += txs[i].n_transfers(); ta += txs[i].n_sc; tlg += (txs[i].rp_len / 32 - 9) / 2; }
+    size_t nl = n_live - std::min(lo, n_live), npts = 1 + nl * 5 + tk * 9 + ta * 6 + 2 * tlg + 8;
+    B.points.reserve(32 * npts); B.checks.reserve(npts + 2 * nl); B.sigs.reserve(nl + 8);
     B.op_prev.reserve(2 * (ta + tk)); B.op_amount.reserve(2 * (ta + tk)); B.op_term_off.reserve(2 * (ta + tk) + 1); B.op_terms.reserve(2 * (ta + 2 * tk));
     B.eq_points.reserve(7 * ta); B.eq_scalars.reserve(192 * ta); B.val_points.reserve(8 * tk); B.val_scalars.reserve(160 * tk);
-    B.rp_m.reserve(n_live); B.rp_point_off.reserve(n_live + 1); B.rp_chal_off.reserve(n_live + 1); B.rp_points.reserve(4 * n_live + 2 * tlg + 2 * (ta + tk)); B.rp_scalars.reserve(224 * n_live);
-    B.rp_challenges.reserve(32 * (4 * n_live + tlg)); B.updates.reserve(ta + tk); B.chains.reserve(2 * (ta + tk));
+    B.rp_m.reserve(nl); B.rp_point_off.reserve(nl + 1); B.rp_chal_off.reserve(nl + 1); B.rp_points.reserve(4 * nl + 2 * tlg + 2 * (ta + tk)); B.rp_scalars.reserve(224 * nl);
+    B.rp_challenges.reserve(32 * (4 * nl + tlg)); B.updates.reserve(ta + tk); B.chains.reserve(2 * (ta + tk));
+  }
+  // ---- earlier shards of a sharded batch: an (account, asset) balance this shard reads may have been moved by
+  // transactions [0, lo) -- a sender with transactions in both shards, a receiver credited there and spending here
+  // (src/lib.rs:908-921), two shards crediting one receiver.  Their GROUP operations on the shared keys are replayed here in
+  // batch order as ordinary balance-chain ops (no proofs: the owning rank verifies those), so this shard's proofs meet the
+  // same ciphertexts as in the reference's sequential walk (src/tx/verify.rs:301-336,354-374).  MultiSig settings of earlier
+  // shards are visible through the overlay.  If a foreign transaction is invalid its own rank rejects the batch.
+  if (lo > 0 && n_live > lo) {
+    FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * (n_live - lo)); sources.reserve(n_live - lo);
+    for (size_t i = lo; i < n_live; i++) {
+      const TxView& tx = txs[i]; sources.insert(tx.source);
+      for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
+      for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
+    }
+    for (size_t i = 0; i < lo; i++) {
+      if (parse_rc[i]) continue;
+      const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
+      if (tx.type == 4 && sources.find(tx.source) && multisig_payload_ok(tx)) staged.set_multisig(tx.source, tx.body, tx.count, (uint8_t)tx.aux, true);
+      for (uint32_t q = 0; q < tx.n_sc; q++) {
+        const uint8_t* asset = tx.sc + 256 * q;
+        if (!keys.find(MockLedger::key(tx.source, asset).data())) continue;
+        long long pc, pd; int64_t loaded; Chain* ch = resolve_chain(B, state, tx.source, asset, Sender, &pc, &pd, &loaded); if (!ch) continue;
+        bool carry; const uint64_t amount = plain_output_amount(tx, asset, &carry);
+        uint32_t oc = B.add_op(pc, amount);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) { uint32_t ip = B.add_point(tx.transfers[t].commitment); B.op_terms.push_back(ip | 0x80000000u); }
+        if (carry) B.op_terms.push_back(B.g_2_64() | 0x80000000u);
+        B.close_op();
+        uint32_t od = B.add_op(pd, 0);
+        for (uint32_t t = 0; t < k; t++) if (!memcmp(asset, tx.transfers[t].asset, 32)) { uint32_t ip = B.add_point(tx.transfers[t].sender_handle); B.op_terms.push_back(ip | 0x80000000u); }
+        B.close_op();
+        advance_chain(B, ch, oc, od);
+      }
+      for (uint32_t t = 0; t < k; t++) {
+        const TransferView& tr = tx.transfers[t];
+        if (!keys.find(MockLedger::key(tr.dest, tr.asset).data())) continue;
+        long long pc, pd; int64_t loaded; Chain* ch = resolve_chain(B, state, tr.dest, tr.asset, Receiver, &pc, &pd, &loaded); if (!ch) continue;
+        uint32_t oc = B.add_op(pc, 0); { uint32_t ip = B.add_point(tr.commitment); B.op_terms.push_back(ip); } B.close_op();
+        uint32_t od = B.add_op(pd, 0); { uint32_t ip = B.add_point(tr.receiver_handle); B.op_terms.push_back(ip); } B.close_op();
+        advance_chain(B, ch, oc, od);
+      }
+    }
   }
   std::vector<uint32_t> iC, iDs, iDr, iN, Ls, Rs; std::vector<Bytes32> signers;
   size_t n_reached = n_live;    // txs after the first host-side hard error are never reached by the reference
-  for (size_t i = 0; i < n_live; i++) {
-    const TxView& tx = txs[i]; TxPlan& P = plan[i];
+  long capacity_fail = -1;
+  for (size_t i = lo; i < n_live; i++) {
+    const TxView& tx = txs[i]; TxPlan& P = plan[i - lo];
     P.check_begin = (uint32_t)B.checks.size(); P.sig_begin = (uint32_t)B.sigs.size();
     auto host_fail = [&](int err) { B.checks.push_back({CK_HOST, err, 0}); };
     auto finish = [&]() { P.check_end = (uint32_t)B.checks.size(); P.sig_end = (uint32_t)B.sigs.size(); };
@@ -505,7 +717,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
       uint64_t nonce;
       if (!state.get_account_nonce(tx.source, &nonce)) { host_fail(XHE_ERR_STATE); stop = true; break; }
       if (nonce != tx.nonce) { host_fail(XHE_ERR_INVALID_NONCE); stop = true; break; }
-      state.update_account_nonce(tx.source, tx.nonce);
+      staged.set_nonce(tx.source, tx.nonce);                     // update_account_nonce(source, nonce): applied with the batch (src/tx/verify.rs:219-221)
       if (!verify_commitment_assets(tx)) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
       const uint32_t k = tx.n_transfers(), a = tx.n_sc;
       iC.resize(k); iDs.resize(k); iDr.resize(k); iN.resize(a);
@@ -521,7 +733,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
       // multisig rules (259-292)
       {
         uint8_t threshold = 0; bool present = false;
-        if (!state.get_multisig_for_account(tx.source, &signers, &threshold, &present)) { host_fail(XHE_ERR_STATE); stop = true; break; }
+        if (!staged.get_multisig(state, tx.source, &signers, &threshold, &present)) { host_fail(XHE_ERR_STATE); stop = true; break; }
         if (present) {
           if (tx.n_ms < 0) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
           if (tx.n_ms == 0 || tx.n_ms != (int)threshold) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
@@ -593,17 +805,18 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
         }
         if (stop) break;
       } else if (tx.type == 4) {   // MultiSig setup (401-428)
-        uint32_t ns = tx.count, th = tx.aux; bool bad = th > ns || (ns != 0 && th == 0);
-        for (uint32_t x = 0; x < ns && !bad; x++) for (uint32_t y = 0; y < ns; y++) if (x != y && !memcmp(tx.body + 32 * x, tx.body + 32 * y, 32)) { bad = true; break; }
-        for (uint32_t x = 0; x < ns && !bad; x++) if (!memcmp(tx.body + 32 * x, tx.source, 32)) bad = true;
-        if (bad) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
-        state.set_multisig_for_account(tx.source, tx.body, ns, (uint8_t)th);
+        if (!multisig_payload_ok(tx)) { host_fail(XHE_ERR_FORMAT); stop = true; break; }
+        staged.set_multisig(tx.source, tx.body, tx.count, (uint8_t)tx.aux, false);      // set_multisig_for_account: applied with the batch (src/tx/verify.rs:426)
       }
       // 3. range proof view (434-478, 504-510): commitments = new source commitments ++ transfer commitments ++ identity duds
       {
         uint32_t nc = a + k, m = 1; while (m < nc) m <<= 1;
         uint32_t lg = (tx.rp_len / 32 - 9) / 2, lg_need = 6; { uint32_t mm = m; while (mm > 1) { mm >>= 1; lg_need++; } }
-        bool structural = (lg != lg_need);
+        // more parties than bulletproofs' BP_GENS holds (BulletproofGens::new(64, 512), src/proofs.rs:20): the reference's batch
+        // verifier answers with a RangeProof error, after the sigma check.  More than THIS context was created for is an
+        // operator error, reported as such with the transaction's index before anything runs on the device.
+        bool structural = (lg != lg_need) || m > 512;
+        if (!structural && m > party_capacity) { capacity_fail = (long)i; stop = true; break; }
         const uint8_t* rp = tx.rp;
         for (int q = 0; q < 4 && !structural; q++) if (is_zero32(rp + 32 * q)) structural = true;
         for (uint32_t q = 0; q < 2 * lg && !structural; q++) if (is_zero32(rp + 224 + 32 * q)) structural = true;
@@ -630,8 +843,13 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
       P.proofs = true;
     } while (false);
     finish();
-    if (stop) { n_reached = i + 1; plan.resize(n_reached); break; }
+    if (stop) { n_reached = i + 1; plan.resize(n_reached - lo); break; }
   }
+  if (capacity_fail >= 0) {
+    if (fail_index) *fail_index = capacity_fail;
+    return XHE_E_CAPACITY;
+  }
+  const size_t n_loc = n_reached > lo ? n_reached - lo : 0;      // transactions of this shard that reach the device
   double t2 = now_ms();
 
   // ---- phase B: Merlin transcripts / Fiat-Shamir challenges, message hashes, random batch factors (parallel over txs)
@@ -639,10 +857,11 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   const bool dev_fs = opt.device_fiat_shamir || opt.fast_path;
   std::vector<Sponge> sig_sponge(n_sigs, Sponge(72));
   std::vector<uint64_t> perms(threads > 0 ? threads : 1, 0);
-  parallel_for(n_reached, threads, [&](size_t lo, size_t hi, int tid) {
+  parallel_for(n_loc, threads, [&](size_t ja, size_t jb, int tid) {
     std::vector<uint8_t> bytes; uint64_t kf = 0;
-    for (size_t i = lo; i < hi; i++) {
-      const TxView& tx = txs[i]; const TxPlan& P = plan[i];
+    for (size_t j = ja; j < jb; j++) {
+      const size_t i = lo + j;
+      const TxView& tx = txs[i]; const TxPlan& P = plan[j];
       // signature message hashes: SHA3-512(pk || message || r) -- absorb everything but r now (src/elgamal.rs:53-65)
       // (device Fiat-Shamir mode: only multisig co-signatures, which need BLAKE3, are still hashed here)
       if (P.sig_end > P.sig_begin && (!dev_fs || P.sig_end - P.sig_begin > 1)) {
@@ -655,7 +874,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
         }
       }
       if (!P.proofs || dev_fs) continue;
-      Rng rng(seed, 32, i);
+      Rng rng(seed, 32, i);                 // i = index in the WHOLE batch: two shards never share a factor stream
       Transcript T("transaction-proof");    // prepare_transcript, src/tx/verify.rs:146-158
       T.append_u64("version", tx.version); T.append("source_pubkey", tx.source, 32); T.append_u64("fee", tx.fee); T.append_u64("nonce", tx.nonce);
       auto challenge = [&](const char* label, uint8_t out[32]) { uint8_t b64[64]; T.challenge(label, b64, 64); ScalarL::reduce_wide(b64, out); };
@@ -714,8 +933,8 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   for (size_t q = 0; q < B.eq_points.size(); q++) if (B.eq_points[q] & OPREF) B.eq_points[q] = n_points + (B.eq_points[q] & ~OPREF);
   PinnedVec<uint8_t>&sig_s = HC.sig_s, &sig_e = HC.sig_e; sig_s.resize(32 * n_sigs + 1); sig_e.resize(32 * n_sigs + 1); std::vector<uint32_t> sig_pk(n_sigs + 1);
   for (size_t s = 0; s < n_sigs; s++) { memcpy(&sig_s[32 * s], B.sigs[s].sig, 32); memcpy(&sig_e[32 * s], B.sigs[s].sig + 32, 32); sig_pk[s] = B.sigs[s].pk; }
-  xhe_batch xb; memset(&xb, 0, sizeof xb);
-  xb.n_tx = (uint32_t)n_reached; xb.n_points = n_points; xb.points = B.points.data();
+  xhe_batch xb; memset(&xb, 0, sizeof xb); xb.struct_size = (uint32_t)sizeof xb;
+  xb.n_tx = (uint32_t)n_loc; xb.n_points = n_points; xb.points = B.points.data();
   xb.n_sigs = (uint32_t)n_sigs; xb.sig_s = sig_s.data(); xb.sig_e = sig_e.data(); xb.sig_pk = sig_pk.data();
   xb.n_ops = (uint32_t)B.op_prev.size(); xb.op_prev = (const int64_t*)B.op_prev.data(); xb.op_term_off = B.op_term_off.data(); xb.op_terms = B.op_terms.data(); xb.op_amount = B.op_amount.data(); xb.max_chain = B.max_chain;
   xb.n_eq = (uint32_t)(B.eq_points.size() / 7); xb.eq_points = B.eq_points.data(); xb.eq_scalars = B.eq_scalars.data();
@@ -723,22 +942,22 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   xb.n_rp = (uint32_t)B.rp_m.size(); xb.rp_m = B.rp_m.data(); xb.rp_point_off = B.rp_point_off.data(); xb.rp_points = B.rp_points.data();
   xb.rp_scalars = B.rp_scalars.data(); xb.rp_chal_off = B.rp_chal_off.data(); xb.rp_challenges = B.rp_challenges.data();
   PinnedVec<uint8_t>& fs_blob = HC.fs_blob; PinnedVec<uint64_t>& fs_off = HC.fs_off; PinnedVec<uint32_t>& fs_plan = HC.fs_plan;
-  if (dev_fs && n_reached) {
-    fs_off.resize(n_reached + 1); fs_off[0] = 0;
-    for (size_t i = 0; i < n_reached; i++) fs_off[i + 1] = fs_off[i] + ((lens[i] + 15) & ~(size_t)15);
-    fs_blob.resize(fs_off[n_reached]); fs_plan.resize(6 * n_reached);
-    parallel_for(n_reached, threads, [&](size_t lo, size_t hi, int) {
-      for (size_t i = lo; i < hi; i++) {
-        memcpy(&fs_blob[fs_off[i]], blobs[i], lens[i]);
-        const TxPlan& P = plan[i]; uint32_t* w = &fs_plan[6 * i];
+  if (dev_fs && n_loc) {
+    fs_off.resize(n_loc + 1); fs_off[0] = 0;
+    for (size_t j = 0; j < n_loc; j++) fs_off[j + 1] = fs_off[j] + ((lens[lo + j] + 15) & ~(size_t)15);
+    fs_blob.resize(fs_off[n_loc]); fs_plan.resize(6 * n_loc);
+    parallel_for(n_loc, threads, [&](size_t ja, size_t jb, int) {
+      for (size_t j = ja; j < jb; j++) {
+        memcpy(&fs_blob[fs_off[j]], blobs[lo + j], lens[lo + j]);
+        const TxPlan& P = plan[j]; uint32_t* w = &fs_plan[6 * j];
         w[0] = P.eq_begin; w[1] = P.val_begin; w[2] = P.rp_slot >= 0 ? (uint32_t)P.rp_slot : 0xFFFFFFFFu; w[3] = P.rp_chal_begin;
         w[4] = P.sig_end > P.sig_begin ? P.sig_begin : 0xFFFFFFFFu; w[5] = P.proofs ? 1u : 0u;
       }
     });
-    xb.fs_blobs = fs_blob.data(); xb.fs_blob_off = fs_off.data(); xb.fs_plan = fs_plan.data(); memcpy(xb.fs_seed, seed, 32);
+    xb.fs_blobs = fs_blob.data(); xb.fs_blob_off = fs_off.data(); xb.fs_plan = fs_plan.data(); memcpy(xb.fs_seed, seed, 32); xb.fs_index_base = lo;
   }
   std::vector<uint8_t> point_ok(n_points + 1), sig_r(32 * n_sigs + 1), op_out(32 * (size_t)xb.n_ops + 1), sig_ok_dev(n_sigs + 1, 0);
-  xhe_verdict v; memset(&v, 0, sizeof v); v.point_ok = point_ok.data(); v.sig_r = sig_r.data(); v.op_out = op_out.data(); v.sig_ok = sig_ok_dev.data();
+  xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.point_ok = point_ok.data(); v.sig_r = sig_r.data(); v.op_out = op_out.data(); v.sig_ok = sig_ok_dev.data();
   int32_t rc = xhe_verify_batch(ctx, &xb, &v);
   double t4 = now_ms();
   if (rc != XHE_OK) { if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->total_ms = t4 - t0; } return rc; }
@@ -754,25 +973,26 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
     }
   });
   int verdict = XHE_OK; long bad_tx = -1;
-  for (size_t i = 0; i < n_reached && verdict == XHE_OK; i++) {
-    for (uint32_t c = plan[i].check_begin; c < plan[i].check_end; c++) {
+  for (size_t j = 0; j < n_loc && verdict == XHE_OK; j++) {
+    for (uint32_t c = plan[j].check_begin; c < plan[j].check_end; c++) {
       const Check& ck = B.checks[c]; bool fail = false;
       if (ck.kind == CK_HOST) fail = true; else if (ck.kind == CK_POINT) fail = !point_ok[ck.a]; else fail = !sig_ok[ck.a];
-      if (fail) { verdict = ck.err; bad_tx = (long)i; break; }
+      if (fail) { verdict = ck.err; bad_tx = (long)(lo + j); break; }
     }
   }
   if (verdict == XHE_OK && parse_err != XHE_OK) { verdict = parse_err; bad_tx = (long)n_live; }
   const bool shard = opt.partial_out != nullptr;
   if (shard) { memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32); }
   if (verdict == XHE_OK && !shard && !v.sigma_is_identity) verdict = XHE_ERR_GENERIC_PROOF;            // src/tx/verify.rs:500-502
-  if (verdict == XHE_OK) { for (size_t i = 0; i < n_reached; i++) if (plan[i].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
+  if (verdict == XHE_OK) { for (size_t j = 0; j < n_loc; j++) if (plan[j].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
   if (verdict == XHE_OK && !shard && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;               // src/tx/verify.rs:504-514
   if (shard) {
-    Pending Pn; Pn.updates = B.updates; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size());
+    Pending Pn; Pn.updates = B.updates; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.staged = std::move(staged);
     std::lock_guard<std::mutex> g(g_pending_mu);
     g_pending[ctx] = std::move(Pn);
   } else if (verdict == XHE_OK && opt.apply_state) {
-    for (const StateUpdate& u : B.updates) {
+    if (staged.apply(state) != XHE_OK) verdict = XHE_ERR_STATE;
+    if (verdict == XHE_OK) for (const StateUpdate& u : B.updates) {
       uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 32); memcpy(ct + 32, &op_out[32 * (size_t)u.op_d], 32);
       if (!apply_update(state, u.account.data(), u.asset.data(), u.role, u.output, ct)) { verdict = XHE_ERR_STATE; break; }
     }
@@ -823,12 +1043,12 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
     if (tx.type == 4) state.set_multisig_for_account(tx.source, tx.body, tx.count, (uint8_t)tx.aux);
   }
   const uint32_t n_points = (uint32_t)(B.points.size() / 32);
-  xhe_batch xb; memset(&xb, 0, sizeof xb);
+  xhe_batch xb; memset(&xb, 0, sizeof xb); xb.struct_size = (uint32_t)sizeof xb;
   xb.n_tx = (uint32_t)n; xb.n_points = n_points; xb.points = B.points.data();
   xb.n_ops = (uint32_t)B.op_prev.size(); xb.op_prev = (const int64_t*)B.op_prev.data(); xb.op_term_off = B.op_term_off.data(); xb.op_terms = B.op_terms.data(); xb.op_amount = B.op_amount.data(); xb.max_chain = B.max_chain;
   uint32_t zero_off = 0; xb.rp_point_off = &zero_off; xb.rp_chal_off = &zero_off;
   std::vector<uint8_t> point_ok(n_points + 1), op_out(32 * (size_t)xb.n_ops + 1);
-  xhe_verdict v; memset(&v, 0, sizeof v); v.point_ok = point_ok.data(); v.op_out = op_out.data();
+  xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.point_ok = point_ok.data(); v.op_out = op_out.data();
   int32_t rc = xhe_verify_batch(ctx, &xb, &v); if (rc) return rc;
   for (uint32_t p : need_ok) if (!point_ok[p]) return XHE_ERR_DECOMPRESSION;   // "ill-formed ciphertext" (the reference panics)
   for (const StateUpdate& u : B.updates) {
@@ -877,9 +1097,24 @@ int32_t xheh_verify_batch_partial(xhe_ctx* ctx, void* ledger, const uint8_t* con
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
   return rc;
 }
-// general entry: flags bit 0 = device-side Fiat-Shamir, bit 1 = shard mode (partial64 must be non-null)
+// general entry: flags bit 0 = device-side Fiat-Shamir, bit 1 = shard mode (partial64 must be non-null), bit 2 = fast path,
+// bit 3 = replayable batch factors (tests only: the seed is used without OS entropy)
 int32_t xheh_verify_batch_ex(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, uint32_t flags, long* fail_index, double* timings7, uint8_t* partial64) {
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = (flags & 2u) ? partial64 : nullptr; opt.fast_path = (flags & 4u) != 0;
+  opt.deterministic_seed = (flags & 8u) != 0;
+  BatchTimings tm;
+  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
+  return rc;
+}
+// one rank's share of a sharded batch: blobs = the WHOLE batch, this call verifies [lo, hi) and follows the
+// balance chains that start in [0, lo).  Always shard mode: partial64 receives the partial sigma / range encodings, the
+// state updates wait for xheh_commit_pending / xheh_take_pending, *fail_index is an index into the whole batch.
+int32_t xheh_verify_batch_shard(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi, const uint8_t* seed, size_t seed_len, int threads, uint32_t flags,
+                                long* fail_index, double* timings7, uint8_t* partial64) {
+  if (!partial64 || lo > hi) return XHE_E_ARG;
+  BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = partial64; opt.fast_path = (flags & 4u) != 0;
+  opt.deterministic_seed = (flags & 8u) != 0; opt.shard_lo = lo; opt.shard_hi = hi;
   BatchTimings tm;
   int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
@@ -890,6 +1125,10 @@ int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(
 void* xheh_take_pending(xhe_ctx* ctx) { return take_pending(ctx); }
 int32_t xheh_commit_taken(void* pending, void* ledger) { if (!pending) return XHE_E_ARG; Pending* P = (Pending*)pending; int rc = apply_pending(*P, *(MockLedger*)ledger); delete P; return rc; }
 void xheh_drop_taken(void* pending) { delete (Pending*)pending; }
+// the balance updates a detached shard-mode batch holds, as 128-byte records (account, asset, new ciphertext) in update order
+size_t xheh_export_taken(void* pending, uint8_t* out, size_t cap) { return export_pending(pending, out, cap); }
+// apply such records to a ledger (a peer rank's updates): update_account_balance per record, in order
+int32_t xheh_ledger_apply_records(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; if (!L->update_account_balance(r, r + 32, r + 64, Receiver)) return XHE_ERR_STATE; } return XHE_OK; }
 int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(MockLedger*)ledger); }
 // host-only helpers exposed for CPU tests of the host logic
 void xheh_merlin_test(const char* proto, const char* label, const uint8_t* msg, size_t n, const char* chal_label, uint8_t* out, size_t outlen) { Transcript t(proto); t.append(label, msg, n); t.challenge(chal_label, out, outlen); }

@@ -141,19 +141,31 @@ struct TxView {   // parsed xtx1 blob (pointers into the caller's buffer)
 };
 
 struct BatchTimings { bool used_fast_path = false; double parse_ms = 0, resolve_ms = 0, transcript_ms = 0, device_ms = 0, finish_ms = 0, total_ms = 0; uint64_t keccak_f = 0; };
-struct BatchOptions { int threads = 0; const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool apply_state = true;
+struct BatchOptions { int threads = 0;
+                      /* Personalisation of the per-proof random batch factors (reference: Scalar::random per proof, src/proofs.rs:181,326).
+                       * The factors MUST be unpredictable to whoever produced the proofs, so 32 bytes of OS entropy are always folded in;
+                       * deterministic_seed (tests only) uses rng_seed alone so that a run can be replayed. */
+                      const uint8_t* rng_seed = nullptr; size_t rng_seed_len = 0; bool deterministic_seed = false;
+                      bool apply_state = true;
                       uint8_t* partial_out = nullptr; /* 64 B: shard mode, see verify_batch */
+                      /* shard mode on the WHOLE batch: this rank verifies transactions [shard_lo, min(shard_hi, n)) of blobs[0..n) and reads
+                       * the earlier ones only to advance the balance chains (and multisig settings) its own transactions depend on */
+                      size_t shard_lo = 0, shard_hi = (size_t)-1;
                       bool device_fiat_shamir = false; /* transcripts, batch factors and main-signature hashes on the GPU */
                       bool fast_path = false; /* optimistic device-layout path first (implies device Fiat-Shamir); the exact path decides on any failure */ };
 
 // Transaction::verify_batch.  Returns XHE_OK or the verdict code; *fail_index = first failing tx (-1 for the two
 // batch-level MSM checks, as in the reference where those errors carry no tx).
+// Nothing is written to `state` before the verdict is known: nonce and multisig writes are staged like the balance updates
+// and applied together on accept (the reference mutates as it goes and tells callers to discard the state of a failed batch).
 // Shard mode (opt.partial_out != nullptr, multi-GPU): the two identity decisions are NOT taken here; the encodings of this
 // shard's partial sigma / range sums are returned (sigma || range) for the caller to combine across ranks, and the state
-// updates are held back until commit_pending().
+// updates are held back until commit_pending().  With shard_lo / shard_hi the call takes the WHOLE batch: *fail_index is
+// then an index into the whole batch, and balance chains that start in earlier shards are followed.
 int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* timings);
 // apply the balance updates a shard-mode verify_batch held back (after the cross-rank decision accepted the batch)
 int commit_pending(xhe_ctx* ctx, VerificationState& state);
+size_t export_pending(void* pending, uint8_t* out, size_t cap);
 // Transaction::apply_without_verify for a list of txs applied in order (balance updates only; config 4 shape)
 int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state);
 

@@ -36,6 +36,10 @@ def _lib():
     lib.xheh_verify_batch_partial.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
     lib.xheh_verify_batch_ex.restype = C.c_int32
     lib.xheh_verify_batch_ex.argtypes = [vp, vp, vp, vp, sz, C.c_char_p, sz, C.c_int, C.c_uint32, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
+    lib.xheh_verify_batch_shard.restype = C.c_int32
+    lib.xheh_verify_batch_shard.argtypes = [vp, vp, vp, vp, sz, sz, sz, C.c_char_p, sz, C.c_int, C.c_uint32, C.POINTER(C.c_long), C.POINTER(C.c_double), vp]
+    lib.xheh_export_taken.restype = sz; lib.xheh_export_taken.argtypes = [vp, vp, sz]
+    lib.xheh_ledger_apply_records.restype = C.c_int32; lib.xheh_ledger_apply_records.argtypes = [vp, C.c_char_p, sz]
     lib.xheh_commit_pending.restype = C.c_int32; lib.xheh_commit_pending.argtypes = [vp, vp]
     lib.xheh_apply_without_verify.restype = C.c_int32
     lib.xheh_apply_without_verify.argtypes = [vp, vp, vp, vp, sz]
@@ -44,6 +48,7 @@ def _lib():
 
 
 _MODE_FLAGS = {"host": 0, "device": 1, "fast": 5}
+_DETERMINISTIC = 8      # tests only: batch factors from the seed alone (a run can be replayed); otherwise OS entropy is always folded in
 
 
 class Ledger:
@@ -74,6 +79,11 @@ class Ledger:
         """records: iterable of (pk, asset, ct64); accounts get nonce 0."""
         blob = b"".join(pk + asset + ct for pk, asset, ct in records)
         self.lib.xheh_ledger_import(self.ptr, blob, len(blob) // 128)
+
+    def apply_records(self, records: bytes):
+        """update_account_balance for each 128-byte record (account, asset, new ciphertext), in order -- the balance updates a
+        peer rank exported with export_taken()"""
+        return self.lib.xheh_ledger_apply_records(self.ptr, records, len(records) // 128)
 
     def dump(self):
         n = self.lib.xheh_ledger_size(self.ptr)
@@ -110,7 +120,7 @@ class _Blobs:
         self.n = n
 
 
-def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host"):
+def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False):
     """Transaction::verify_batch.  Returns (code, first_failing_tx, timings dict); code 0 = Ok, >0 = verdicts (ERR_NAMES).
     fiat_shamir = "host" (Merlin transcripts on host threads, north_star's split), "device"  or "fast"
     (device transcripts + device-side batch layout, optimistic; any failure is re-decided by the exact path)."""
@@ -118,7 +128,10 @@ def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_s
     bl = prepared or _Blobs(blobs)
     fi = C.c_long(-1)
     tm = (C.c_double * 7)()
-    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, _MODE_FLAGS[fiat_shamir], C.byref(fi), tm, None)
+    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, _MODE_FLAGS[fiat_shamir] | (_DETERMINISTIC if deterministic else 0), C.byref(fi), tm, None)
+    if rc == -5:      # XHE_E_CAPACITY: nothing was verified or applied; the index names the transaction
+        e = XheError(rc, f"transaction {fi.value} needs more range-proof parties than this context's party_capacity"); e.index = fi.value
+        raise e
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
@@ -126,7 +139,7 @@ def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_s
     return rc, fi.value, d
 
 
-def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host"):
+def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False):
     """Shard mode for multi-GPU batches: (local code, first failing local tx, sigma partial enc, range partial enc, timings).
     The sigma / range identity decisions are left to the caller (xelis_he_b200.distributed); balance updates are held back
     until commit_pending()."""
@@ -135,7 +148,27 @@ def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None
     fi = C.c_long(-1)
     tm = (C.c_double * 7)()
     part = C.create_string_buffer(64)
-    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, 2 | _MODE_FLAGS[fiat_shamir], C.byref(fi), tm, part)
+    rc = lib.xheh_verify_batch_ex(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, seed, len(seed) if seed else 0, threads, 2 | _MODE_FLAGS[fiat_shamir] | (_DETERMINISTIC if deterministic else 0), C.byref(fi), tm, part)
+    if rc < 0:
+        raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
+    keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
+    d = dict(zip(keys, tm)); d["fast_path"] = d["keccak_f"] < 0
+    return rc, fi.value, part.raw[:32], part.raw[32:], d
+
+
+def verify_batch_shard(ctx, blobs, ledger, lo, hi, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False):
+    """One rank's share of a sharded batch.  `blobs` is the WHOLE batch (every rank holds it); this call
+    verifies transactions [lo, hi) and reads the earlier ones only to follow the (account, asset) balance chains -- and the
+    multisig settings -- its own transactions depend on, so the verdicts equal the reference's sequential walk
+    (src/tx/verify.rs:301-374) however the batch is cut.  Returns (local code, first failing tx as an index into the whole
+    batch, sigma partial enc, range partial enc, timings); state updates are held back until commit_pending()."""
+    lib = _lib()
+    bl = prepared or _Blobs(blobs)
+    fi = C.c_long(-1)
+    tm = (C.c_double * 7)()
+    part = C.create_string_buffer(64)
+    rc = lib.xheh_verify_batch_shard(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, lo, hi, seed, len(seed) if seed else 0, threads,
+                                     _MODE_FLAGS[fiat_shamir] | (_DETERMINISTIC if deterministic else 0), C.byref(fi), tm, part)
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
@@ -145,6 +178,16 @@ def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None
 
 def commit_pending(ctx, ledger):
     return _lib().xheh_commit_pending(ctx.p, ledger.ptr)
+
+
+def export_taken(handle):
+    """the balance updates a detached shard-mode batch holds (take_pending), as 128-byte records (account, asset, new
+    ciphertext) in update order -- what a rank sends to its peers when every replica of the state must stay complete"""
+    lib = _lib()
+    n = lib.xheh_export_taken(handle, None, 0)
+    buf = C.create_string_buffer(128 * max(n, 1))
+    lib.xheh_export_taken(handle, buf, 128 * n)
+    return buf.raw[:128 * n]
 
 
 def take_pending(ctx):
