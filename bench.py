@@ -1,14 +1,17 @@
 #!/usr/bin/env python3
 """bench.py -- verified TX/s on a 10k-transfer batch (BASELINE.json metric), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--shape a1k1] [--txs 10000]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--shape a1k1] [--txs 10000] [--secondary full|min|off]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...     # the CPU path (oracle port of the reference; the Rust crate cannot run here)
 
-A step = one verification of one batch of T synthetic transfer transactions per GPU (weak scaling: every rank verifies a
-T-transaction shard, the per-rank partial MSM points are all-gathered over NCCL and summed before the identity check).
-`value` times the device kernels with the batch resident in HBM (xhe_batch_run); `e2e` times the reference-facing call
-(host parsing + state resolution + Merlin transcripts + H2D + kernels + D2H + signature hashes) from host buffers.
+A step = one verification of one batch of T synthetic transfer transactions per GPU.  At N > 1 the batch holds N x T
+transactions; every rank holds all of it and verifies its own contiguous shard (weak scaling, the headline), and the same
+machinery verifies ONE T-transaction batch cut N ways (`strong`).  Inside the `value` event pair at N > 1: the shard's kernels,
+the rank's record (verdict word + partial sigma / range MSM encodings) built on the device, the NCCL all-gather of the
+records, and the joint decision kernel (sum of the partial encodings, identity tests, reference precedence).
+`value` times the device with the batch resident in HBM; `e2e` times the reference-facing call (host header walk + state
+resolution + H2D + kernels + D2H + state update, or host Merlin transcripts in the north_star split) from host buffers.
 """
 import argparse
 import ctypes as C
@@ -33,7 +36,10 @@ def parse_args():
     ap.add_argument("--shape", default="a1k1")
     ap.add_argument("--cpu-sample", type=int, default=0, help="transactions per host thread in the CPU baseline (default: the whole batch in the cpu_baseline leg, 2,500 per step in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the MSM points/s and ciphertext-update (HBM) side measurements")
+    ap.add_argument("--secondary", default="full", choices=["full", "min", "off"], help="BASELINE.json's other configs (N = 1 only): full = other shapes, one-sender chain, mixed batch with reject paths, 16x255, MSM sweep, ciphertext updates; min = MSM 2^20 + ciphertext updates")
+    ap.add_argument("--no-secondary", action="store_true", help="same as --secondary off")
+    ap.add_argument("--mixed-txs", type=int, default=100000, help="size of the mixed (config 5) batch")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
     ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
     ap.add_argument("--fiat-shamir", default="fast", choices=["fast", "device", "host"], help="where the Merlin transcripts run (host = north_star split; device = SURVEY 8 f.1)")
     return ap.parse_args()
@@ -42,6 +48,20 @@ def parse_args():
 def shape_ak(shape):
     a, k = shape[1:].split("k")
     return int(a), int(k)
+
+
+def canonical_lp_per_tx(a, k):
+    """algorithmic limb products of one transaction with a assets and k transfers"""
+    m = 1
+    while m < a + k:
+        m *= 2
+    lg = 6 + m.bit_length() - 1
+    return (5 + 6 * a + 9 * k + 2 * lg) * 12632 + (2 + 2 * a + 2 * k) * 12688 + ((7 * a + 8 * k) + (4 + 2 * lg + m)) * 8064 + 8 * 64 * m * 136 + 160000
+
+
+def a_msm(n):
+    """canonical work of an n-point MSM (16 windows), limb products"""
+    return 8064.0 * n + 6.04e8
 
 
 class ClockSampler(threading.Thread):
@@ -85,67 +105,178 @@ def cpu_baseline(batch, threads, sample):
             "seconds": t, "readme_figure_tx_s_per_thread": 2500}
 
 
+class Dev:
+    """ctypes plumbing shared by the measurements"""
 
-def secondary_metrics(lib, ctx, stream, hbm_peak_gbs):
-    """BASELINE.json's other single-GPU figures, measured live on the device (CUDA events on the ctx stream, L2-sized
-    inputs): MSM points/s on 2^20 resident points (config 2) and the resident ciphertext update (config 4, HBM-bound)."""
-    import ctypes as C
-    import torch
-    out = {}
-    g = torch.Generator(device="cuda"); g.manual_seed(7)
-    n = 1 << 20
+    def __init__(self, lib):
+        self.lib = lib
+        lib.xhe_batch_run.argtypes = [C.c_void_p]; lib.xhe_batch_run.restype = C.c_int32
+        lib.xhe_batch_h2d_bytes.restype = C.c_size_t; lib.xhe_batch_h2d_bytes.argtypes = [C.c_void_p]
+        lib.xhe_batch_d2h_bytes.restype = C.c_size_t; lib.xhe_batch_d2h_bytes.argtypes = [C.c_void_p]
+        lib.xhe_ctx_timing.argtypes = [C.c_void_p, C.c_int]
+        lib.xhe_ctx_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
+        lib.xhe_ctx_set_serial.argtypes = [C.c_void_p, C.c_int]
+        lib.xhe_ctx_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+        lib.xhe_msm_workspace_bytes.restype = C.c_size_t; lib.xhe_msm_workspace_bytes.argtypes = [C.c_void_p, C.c_size_t]
+        lib.xhe_msm_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        lib.xhe_ct_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        lib.xhe_ct_update_resident_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
 
-    def timed(fn, iters=5, warm=3):
+
+def timed_runs(torch, stream, fn, iters, warm, flush=None):
+    """mean ms of fn() over `iters` launches on `stream` (CUDA events on that stream, L2 flushed outside the event pairs)"""
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            assert fn() == 0
+    torch.cuda.synchronize()
+    tot = 0.0
+    for i in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
-            for _ in range(warm):
-                assert fn() == 0
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            if flush is not None:
+                flush.fill_(i & 0xFF)
             e0.record(stream)
-            for _ in range(iters):
-                assert fn() == 0
+            assert fn() == 0
             e1.record(stream)
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def measure_config(name, torch, xhe, verifier, dev, stream, flush, batch_blobs, records, multisig, party_capacity, steps, e2e_steps, rejects, host_threads, canonical_lp=None, peak=None):
+    """One BASELINE configuration end to end on one GPU: accept verdict, device-resident `value`, host-buffer `e2e` (single call),
+    and for every (label, tampered blobs, expected verdict) in `rejects` the verdict and the reject-path throughput."""
+    ctx = xhe.Ctx(torch.cuda.current_device(), party_capacity=party_capacity)
+    ctx.set_stream(stream.cuda_stream)
+    try:
+        def ledger():
+            led = verifier.Ledger(); led.import_records(records)
+            for pk, signers, th in multisig:
+                led.set_multisig(pk, signers, th)
+            return led
+        n = len(batch_blobs)
+        prepared = verifier.prepare_blobs(batch_blobs)
+        out = {"txs": n}
+        for w in range(2):
+            code, idx, tm = verifier.verify_batch(ctx, None, ledger(), seed=b"sec-warm%d" % w, threads=host_threads, prepared=prepared, fiat_shamir="fast")
+            assert (code, idx) == (0, -1), (name, code, idx)
+        out["accepted"] = True; out["path"] = "fast (device transcripts + device layout)" if tm["fast_path"] else "exact (host state walk and tables, device transcripts): multisig transactions / accounts in the batch"
+        ms = timed_runs(torch, stream, lambda: dev.lib.xhe_batch_run(ctx.p), steps, 2, flush)
+        out["value"] = {"value": n / ms * 1e3, "unit": "TX/s", "ms_per_step": ms}
+        if canonical_lp and peak:
+            out["value"]["step_frac"] = canonical_lp / (ms * 1e-3) / peak
+        t = 0.0
+        for s in range(e2e_steps):
+            led = ledger(); flush.fill_(s); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            code, idx, tm = verifier.verify_batch(ctx, None, led, seed=b"sec%d" % s, threads=host_threads, prepared=prepared, fiat_shamir="fast")
+            t += time.perf_counter() - t0
+            assert (code, idx) == (0, -1)
+        out["e2e_single_call"] = {"value": n * e2e_steps / t, "unit": "TX/s", "ms_per_step": 1e3 * t / e2e_steps, "h2d_bytes_per_step": int(dev.lib.xhe_batch_h2d_bytes(ctx.p)), "d2h_bytes_per_step": int(dev.lib.xhe_batch_d2h_bytes(ctx.p)),
+                                  "phases_ms": {k: round(v, 3) for k, v in tm.items() if k.endswith("_ms")}}
+        rj = {}
+        for label, blobs, want in rejects:
+            pb = verifier.prepare_blobs(blobs)
+            verifier.verify_batch(ctx, None, ledger(), seed=b"rj-warm", threads=host_threads, prepared=pb, fiat_shamir="fast")
+            t, reps = 0.0, 2
+            for s in range(reps):
+                led = ledger(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                code, idx, tm = verifier.verify_batch(ctx, None, led, seed=b"rj%d" % s, threads=host_threads, prepared=pb, fiat_shamir="fast")
+                t += time.perf_counter() - t0
+            assert (code, idx) == tuple(want), (name, label, code, idx, want)
+            rj[label] = {"verdict": [code, idx], "matches_expected": True, "reject_path_tx_per_s": len(blobs) * reps / t, "ms": 1e3 * t / reps, "decided_by": "fast path + exact verdict of one transaction" if tm["fast_path"] else "exact path"}
+        if rj:
+            out["rejects"] = rj
+            out["reject_over_accept_time"] = max(v["ms"] for v in rj.values()) / out["e2e_single_call"]["ms_per_step"]
+        return out
+    finally:
+        ctx.close()
+
+
+def tamper_classes(oracle, batch, seed, victim, a, k, resignable=True):
+    """(label, blobs, expected verdict) per tamper class on transaction `victim` of a minted batch; expectations follow from the
+    construction and are cross-checked against the oracle on that ONE transaction (accounts of a minted batch are independent)"""
+    SIG, DECOMP, GENERIC, RANGE, TRANSCRIPT, NONCE = 1, 2, 5, 6, 7, 9
+    blobs = list(batch.blobs)
+
+    def mut(off, bit=1):
+        t = bytearray(blobs[victim]); t[off] ^= bit; return bytes(t)
+    cases = [("bad_signature", mut(len(blobs[victim]) - 1), (SIG, victim)), ("bad_nonce", mut(56), (NONCE, victim))]
+    if resignable:
+        kp = oracle.minted_keypair(seed, victim); rng = oracle.Rng(b"bench-tamper")
+        rp0 = 64 + 324 * k
+        cases += [("bad_validity_proof_resigned", oracle.resign(mut(64 + 160 + 128), kp, rng), (GENERIC, -1)),
+                  ("bad_range_proof_resigned", oracle.resign(mut(rp0 + 128), kp, rng), (RANGE, -1)),
+                  ("identity_Y0_resigned", oracle.resign(blobs[victim][:64 + 160] + bytes(32) + blobs[victim][64 + 160 + 32:], kp, rng), (TRANSCRIPT, victim)),
+                  ("non_canonical_point_resigned", oracle.resign(blobs[victim][:64 + 64] + b"\xff" * 32 + blobs[victim][64 + 96:], kp, rng), (DECOMP, victim))]
+    out = []
+    for label, bad, want in cases:
+        one = oracle.verify_batch([bad], batch.ledger())
+        assert one == (want[0], 0 if want[1] >= 0 else -1), (label, one, want)      # the oracle agrees on the class
+        out.append((label, blobs[:victim] + [bad] + blobs[victim + 1:], want))
+    return out
+
+
+def msm_sweep(torch, lib, ctx, stream, oracle, logs, cpu_logs, peak):
+    """config 2: MSM over resident decompressed points, 2^16..2^22; the CPU Pippenger (oracle: dalek's algorithm choices, one
+    thread) is timed beside it on the same distribution at the sizes in cpu_logs"""
+    out = {}
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    for logn in logs:
+        n = 1 << logn
+        with torch.cuda.stream(stream):
+            uni = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=g)
+            enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda"); niels = torch.empty((n, 24), dtype=torch.int32, device="cuda"); ok = torch.empty((n,), dtype=torch.uint8, device="cuda")
+            sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g); sc[:, 31] &= 0x0F
+            assert lib.xhe_from_uniform_dev(ctx.p, uni.data_ptr(), n, enc.data_ptr()) == 0
+            assert lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, None, niels.data_ptr(), ok.data_ptr()) == 0
+        wsb = lib.xhe_msm_workspace_bytes(ctx.p, n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda"); res = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        ms = timed_runs(torch, stream, lambda: lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32), 5, 3)
+        c, W = ctx.msm_plan(n)
+        row = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3, "alg_TLP_s": a_msm(n) / ms / 1e9, "msm_frac": a_msm(n) / (ms * 1e-3) / peak, "c": c, "windows": W}
+        if logn in cpu_logs:
+            s_host, p_host = bytes(sc.cpu().numpy()), bytes(enc.cpu().numpy())
+            t, enc_cpu = oracle.msm_timed(s_host, p_host)
+            row["cpu_pippenger"] = {"seconds": t, "points_per_s": n / t, "threads": 1, "kind": "port (dalek's Straus / Pippenger w = 6,7,8 choices, 64-bit limbs)"}
+            row["bit_exact_vs_cpu"] = bytes(res[:32].cpu().numpy()) == enc_cpu
+            assert row["bit_exact_vs_cpu"], "MSM encoding differs from the CPU oracle at 2^%d" % logn
+        out["2^%d" % logn] = row
+        del uni, enc, niels, ok, sc, ws
+        torch.cuda.empty_cache()
+    return out
+
+
+def ct_update_metrics(torch, lib, ctx, stream, hbm_peak_gbs):
+    """config 4: batched Twisted-ElGamal balance update over 1 M accounts, resident (HBM-bound) and compressed I/O (integer-bound)"""
+    out = {}
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    n = 1 << 20
     with torch.cuda.stream(stream):
         uni = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=g)
-        enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda"); aff = torch.empty((n, 16), dtype=torch.int32, device="cuda")
-        niels = torch.empty((n, 24), dtype=torch.int32, device="cuda"); ok = torch.empty((n,), dtype=torch.uint8, device="cuda")
-        sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g); sc[:, 31] &= 0x0F      # < 2^252 < l
+        enc = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
         assert lib.xhe_from_uniform_dev(ctx.p, uni.data_ptr(), n, enc.data_ptr()) == 0
-        assert lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()) == 0
-    lib.xhe_msm_workspace_bytes.restype = C.c_size_t; lib.xhe_msm_workspace_bytes.argtypes = [C.c_void_p, C.c_size_t]
-    wsb = lib.xhe_msm_workspace_bytes(ctx.p, n)
-    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda"); res = torch.zeros(64, dtype=torch.uint8, device="cuda")
-    lib.xhe_msm_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
-    ms = timed(lambda: lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32))
-    out["msm_2p20"] = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3, "alg_TLP_s": (8064.0 * n + 6.04e8) / ms / 1e9,
-                       "note": "resident decompressed points (affine Niels, 96 MB), uniform 252-bit scalars; bit-exactness against the oracle: tests/test_gpu_msm.py"}
-    ms_dec = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr()))
-    out["decompress_2p20"] = {"ms": ms_dec, "points_per_s": n / ms_dec * 1e3, "alg_TLP_s": n * 12632.0 / ms_dec / 1e9}
-    ms_both = timed(lambda: lib.xhe_decompress_dev(ctx.p, enc.data_ptr(), n, aff.data_ptr(), niels.data_ptr(), ok.data_ptr())
-                    or lib.xhe_msm_dev(ctx.p, sc.data_ptr(), niels.data_ptr(), n, ws.data_ptr(), wsb, res.data_ptr(), res.data_ptr() + 32))
-    out["msm_2p20"]["incl_decompression"] = {"ms": ms_both, "points_per_s": n / ms_both * 1e3}
-    # config 4, compressed I/O: 64-byte ciphertexts in and out (4 decodes + 2 encodes per account: integer-bound)
     na_c = 1 << 19
     subc = torch.randint(0, 2, (na_c,), dtype=torch.uint8, device="cuda", generator=g)
     outb = torch.empty((na_c, 64), dtype=torch.uint8, device="cuda"); okb = torch.empty((na_c,), dtype=torch.uint8, device="cuda")
     bal = enc[: 2 * na_c].reshape(na_c, 64); delta = enc.flip(0)[: 2 * na_c].reshape(na_c, 64).contiguous()
-    lib.xhe_ct_update_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
-    ms_c = timed(lambda: lib.xhe_ct_update_dev(ctx.p, bal.data_ptr(), delta.data_ptr(), subc.data_ptr(), na_c, outb.data_ptr(), okb.data_ptr()))
+    ms_c = timed_runs(torch, stream, lambda: lib.xhe_ct_update_dev(ctx.p, bal.data_ptr(), delta.data_ptr(), subc.data_ptr(), na_c, outb.data_ptr(), okb.data_ptr()), 5, 3)
     out["ct_update_compressed_512k"] = {"accounts": na_c, "ms": ms_c, "accounts_per_s": na_c / ms_c * 1e3, "alg_TLP_s": na_c * 76000.0 / ms_c / 1e9}
-    del uni, aff, ws
+    del uni
     na = 1 << 20
     balr = torch.randint(0, 2**31 - 1, (4, 2 * na, 8), dtype=torch.int32, device="cuda", generator=g)
     dn = torch.randint(0, 2**31 - 1, (3, 2 * na, 8), dtype=torch.int32, device="cuda", generator=g)
     sub = torch.randint(0, 2, (na,), dtype=torch.uint8, device="cuda", generator=g)
-    lib.xhe_ct_update_resident_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
-    ms = timed(lambda: lib.xhe_ct_update_resident_dev(ctx.p, balr.data_ptr(), dn.data_ptr(), sub.data_ptr(), na), iters=10)
+    ms = timed_runs(torch, stream, lambda: lib.xhe_ct_update_resident_dev(ctx.p, balr.data_ptr(), dn.data_ptr(), sub.data_ptr(), na), 10, 3)
     bytes_per_account = 2 * (128 + 128 + 96)       # two points per account: extended balance read + write, affine-Niels delta read
     gbs = na * bytes_per_account / ms / 1e6
     out["ct_update_resident_1M"] = {"accounts": na, "ms": ms, "accounts_per_s": na / ms * 1e3,
-                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s", "frac": gbs / hbm_peak_gbs, "traffic": 688.9e6, "traffic_note": "dram__bytes_read.sum (470.8 MB = 2 M points x 224 B, exactly the operands) + dram__bytes_write.sum (218.1 MB; the rest of the 268 MB written is still in L2 when the kernel ends) of one launch, ncu, profiles/r01_ct_resident_traffic.csv: no re-reads",
+                                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s", "frac": gbs / hbm_peak_gbs, "traffic": 688.9e6,
+                                                 "traffic_note": "dram__bytes_read.sum (470.8 MB = 2 M points x 224 B, exactly the operands) + dram__bytes_write.sum (218.1 MB; the rest of the 268 MB written is still in L2 when the kernel ends) of one launch, ncu, profiles/r01_ct_resident_traffic.csv: no re-reads",
                                                  "algorithmic_bytes_per_account": bytes_per_account, "working_set_mb": na * bytes_per_account / 1e6}}
     return out
+
 
 def main():
     # exactly one JSON line may reach stdout: libraries (NCCL's version banner, torchrun) write there too, so everything else
@@ -157,11 +288,13 @@ def main():
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     args = parse_args()
+    if args.no_secondary:
+        args.secondary = "off"
     a, k = shape_ak(args.shape)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     ncpu = len(os.sched_getaffinity(0))
     workload = f"batch verify {args.txs} transfer TXs per GPU, shape {args.shape} (assets a, transfers k), 64-bit aggregated range proofs + sigma proofs + signatures"
-    config = {"workload": workload, "txs_per_gpu": args.txs, "shape": args.shape, "parallelism": f"tx-shard x{world}" if world > 1 else "single",
+    config = {"workload": workload, "txs_per_gpu": args.txs, "shape": args.shape, "parallelism": f"tx-shard x{world}: one batch of {world * args.txs} transactions, rank r verifies shard r" if world > 1 else "single",
               "l2": "L2 flushed (256 MiB write) between timed steps"}
 
     import oracle   # checker / CPU baseline / test-vector minting only (never on the product path)
@@ -197,18 +330,22 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # ---- synthetic workload: rank 0 mints with all host threads, the other ranks receive the same bytes
+    # ---- synthetic workload: every rank mints ITS OWN shard (distinct accounts), then the ranks exchange the bytes so that each
+    # holds the whole batch -- as every node of a network holds the whole block
     t_mint = time.time()
-    if rank == 0:
-        batch = oracle.mint_transfers(77, args.txs, a, k, threads=ncpu)
-        blobs = batch.blobs; records = batch.ledger().dump()
-    else:
-        batch, blobs, records = None, None, None
+    mint_threads = max(1, ncpu // max(1, min(world, 8)))
+    batch = oracle.mint_transfers(77 + rank, args.txs, a, k, threads=mint_threads)
+    my_records = batch.ledger().dump()
     if world > 1:
-        obj = [blobs, records]
-        dist.broadcast_object_list(obj, src=0)
-        blobs, records = obj
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (batch.blobs, my_records))
+        blobs = [b for part in gathered for b in part[0]]
+        records = [r for part in gathered for r in part[1]]
+        strong_blobs, strong_records = gathered[0]            # the strong-scaling batch: rank 0's T transactions, cut N ways
+    else:
+        blobs, records = batch.blobs, my_records
     t_mint = time.time() - t_mint
+    n_total = len(blobs)
     m = 1
     while m < a + k:
         m *= 2
@@ -217,6 +354,7 @@ def main():
     streams = [torch.cuda.Stream()]
     ctx.set_stream(streams[0].cuda_stream)
     lib = ctx.lib
+    dev = Dev(lib)
     ledger0 = verifier.Ledger(); ledger0.import_records(records)
     prepared = verifier.prepare_blobs(blobs)
     host_threads = max(1, ncpu // max(1, min(world, 8)))
@@ -225,29 +363,24 @@ def main():
 
     fs_mode = [args.fiat_shamir]
 
-    def e2e_step(seed):
-        led = ledger0.clone()
+    def e2e_step(seed, prep=None, led0=None):
+        led = (led0 or ledger0).clone()
         t0 = time.perf_counter()
         if dist:     # sharded batch: local partial verification + 80-byte all-gather over NCCL + joint decision on every rank
-            code, idx, tm = xd.verify_batch_distributed(ctx, None, led, rank * args.txs, seed=seed + b"r%d" % rank, threads=host_threads, prepared=prepared, commit=False, fiat_shamir=fs_mode[0])
+            code, idx, tm = xd.verify_batch_distributed(ctx, None, led, seed=seed + b"r%d" % rank, threads=host_threads, prepared=prep or prepared, commit=True, fiat_shamir=fs_mode[0])
         else:
-            code, idx, tm = verifier.verify_batch(ctx, None, led, seed=seed, threads=host_threads, prepared=prepared, fiat_shamir=fs_mode[0])
+            code, idx, tm = verifier.verify_batch(ctx, None, led, seed=seed, threads=host_threads, prepared=prep or prepared, fiat_shamir=fs_mode[0])
         return time.perf_counter() - t0, code, idx, tm
 
     # ---- correctness gate + warm-up (also leaves the batch resident in HBM for the device-only timing)
     for w in range(max(args.warmup, 3)):
         dt, code, idx, tm = e2e_step(b"warm%d" % w)
         assert (code, idx) == (0, -1), (code, idx)
-    if rank == 0 and args.txs <= 20000:
+    if args.txs <= 20000:
         sl = min(64, args.txs)
-        assert oracle.verify_batch(blobs[:sl], batch.slice(sl).ledger()) == (0, -1)      # the oracle agrees on a prefix of the workload
+        assert oracle.verify_batch(batch.blobs[:sl], batch.slice(sl).ledger()) == (0, -1)      # the oracle agrees on a prefix of this rank's shard
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    lib.xhe_batch_run.argtypes = [C.c_void_p]; lib.xhe_batch_run.restype = C.c_int32
-    lib.xhe_batch_h2d_bytes.restype = C.c_size_t; lib.xhe_batch_h2d_bytes.argtypes = [C.c_void_p]
-    lib.xhe_batch_d2h_bytes.restype = C.c_size_t; lib.xhe_batch_d2h_bytes.argtypes = [C.c_void_p]
-    lib.xhe_ctx_timing.argtypes = [C.c_void_p, C.c_int]
-    lib.xhe_ctx_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
     for _ in range(max(args.warmup, 3)):
         assert lib.xhe_batch_run(ctx.p) == 0
     torch.cuda.synchronize()
@@ -257,27 +390,36 @@ def main():
         if dist:
             dist.barrier()
 
+    rec_local = torch.zeros(80, dtype=torch.uint8, device="cuda"); rec_all = torch.zeros(80 * world, dtype=torch.uint8, device="cuda"); decision = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    ts = streams[0]
+
+    def device_steps(nsteps):
+        """nsteps timed steps of the resident shard: kernels + (N > 1) record, all-gather, joint decision -- all on the ctx stream"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        for s in range(nsteps):
+            with torch.cuda.stream(ts):
+                flush.fill_(s & 0xFF)              # evict the previous step's working set from L2 (outside the event pair)
+                ev[s][0].record(ts)
+                assert lib.xhe_batch_run(ctx.p) == 0
+                if dist:
+                    assert lib.xhe_batch_record_dev(ctx.p, rec_local.data_ptr()) == 0
+                    dist.all_gather_into_tensor(rec_all, rec_local)      # the per-batch exchange: (verdict, partial sigma / range encodings) of every rank
+                    assert lib.xhe_shard_decide_dev(ctx.p, rec_all.data_ptr(), world, decision.data_ptr()) == 0
+                ev[s][1].record(ts)
+        torch.cuda.synchronize()
+        if dist:
+            d = bytes(decision.cpu().numpy())
+            assert int.from_bytes(d[:4], "little", signed=True) == 0 and int.from_bytes(d[8:16], "little", signed=True) == -1, "joint decision of the timed steps is not Accept"
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev)
+
     # ---- timed region 1: device kernels on the resident batch (value)
     sampler = ClockSampler(local); sampler.start()
     barrier()
     launches0 = ctx.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rec_local = torch.zeros(80, dtype=torch.uint8, device="cuda"); rec_all = torch.zeros(80 * world, dtype=torch.uint8, device="cuda")
-    ts = streams[0]
-    for s in range(args.steps):
-        with torch.cuda.stream(ts):
-            flush.fill_(s & 0xFF)              # evict the previous step's working set from L2 (outside the event pair)
-            ev[s][0].record(ts)
-            assert lib.xhe_batch_run(ctx.p) == 0
-            if dist:
-                dist.all_gather_into_tensor(rec_all, rec_local)     # the per-batch exchange of (verdict, partial encodings)
-            ev[s][1].record(ts)
-    torch.cuda.synchronize()
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    launches = ctx.launches - launches0
+    dev_ms = device_steps(args.steps)
+    launches = ctx.launches - launches0                                     # ours only: NCCL's all-gather kernel is not counted
     # isolated per-kernel durations for the roofline: the same steps with the pipelines serialised on one stream and
     # CUDA events around the main kernels (timers under stream concurrency would include the overlapped neighbours)
-    lib.xhe_ctx_set_serial.argtypes = [C.c_void_p, C.c_int]
     lib.xhe_ctx_set_serial(ctx.p, 1); lib.xhe_ctx_timing(ctx.p, 1)
     with torch.cuda.stream(ts):
         for s in range(args.steps):
@@ -288,8 +430,7 @@ def main():
     nk = lib.xhe_ctx_timing_read(ctx.p, names, kms, kl, ku, 16)
     kernels = {names[i].decode(): {"ms_per_step": kms[i] / args.steps, "launches": int(kl[i]), "alg_lp_per_step": ku[i] / args.steps} for i in range(nk)}
     lib.xhe_ctx_timing(ctx.p, 0); lib.xhe_ctx_set_serial(ctx.p, 0)
-    # where each kernel sits inside one concurrent step (four stream pipelines): start/end in ms from the step start
-    lib.xhe_ctx_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+    # where each kernel sits inside one concurrent step (stream pipelines): start/end in ms from the step start
     lib.xhe_ctx_timing(ctx.p, 1)
     with torch.cuda.stream(ts):
         flush.fill_(1)
@@ -302,8 +443,8 @@ def main():
     lib.xhe_ctx_timing(ctx.p, 0)
     barrier()
     # ---- timed region 2: end to end through the host API, host buffers in, verdict out (e2e).
-    # (a) one call at a time (latency); (b) two batches in flight on two contexts of the same GPU, so the host phase of
-    # one batch overlaps the device phase of the other -- what a node verifying a stream of batches does.
+    # (a) one call at a time (latency); (b) several batches in flight on as many contexts of the same GPU, so the host phase of
+    # one batch overlaps the device phase of the others -- what a node verifying a stream of batches does.
     single_s = 0.0; phases = {}
     for s in range(args.steps):
         flush.fill_(s & 0xFF); torch.cuda.synchronize()
@@ -326,6 +467,7 @@ def main():
         streams_keep = torch.cuda.Stream(priority=-1); dec_ctx.set_stream(streams_keep.cuda_stream)      # its tiny kernels must not queue behind the batches
         decider = xd.AsyncDecider(dec_ctx, None, torch.device("cuda", local))
     wthreads = max(1, host_threads // nfl)
+    lo_w, hi_w = xd.shard_bounds(n_total, rank, world)
 
     def worker(widx, nsteps, out, ledgers=None):
         c = workers[widx]
@@ -334,8 +476,8 @@ def main():
             led = ledgers[s] if ledgers else ledger0.clone()      # fresh state per step (cloned before the clock starts)
             if dist:
                 seq = seq_base[0] + s * nfl + widx
-                code, idx, s_enc, r_enc, tmw = verifier.verify_batch_partial(c, None, led, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
-                decider.submit(seq, xd.pack_local(code, idx, rank * args.txs, s_enc, r_enc), verifier.take_pending(c), led)
+                code, idx, s_enc, r_enc, tmw = verifier.verify_batch_shard(c, None, led, lo_w, hi_w, seed=b"p%d-%d-%d" % (widx, s, rank), threads=wthreads, prepared=prepared, fiat_shamir=args.fiat_shamir)
+                decider.submit(seq, xd.pack_local(code, idx, 0, s_enc, r_enc), verifier.take_pending(c), led)
                 pipe_phases.append(tmw)
                 out.append(seq)
                 continue
@@ -403,15 +545,43 @@ def main():
     fs_mode[0] = args.fiat_shamir
     e2e_step(b"restore")      # leave the primary mode's batch resident
     barrier()
-    clocks = sampler.summary()
     h2d, d2h = lib.xhe_batch_h2d_bytes(ctx.p), lib.xhe_batch_d2h_bytes(ctx.p)
 
-    if dist:
-        t = torch.tensor([dev_ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    # ---- strong scaling: ONE batch of T transactions (rank 0's), cut N ways -- T / N transactions per GPU
+    strong = None
+    if dist and not args.no_strong:
+        sl0 = verifier.Ledger(); sl0.import_records(strong_records)
+        sprep = verifier.prepare_blobs(strong_blobs)
+        for w in range(3):
+            dt, code, idx, tm = e2e_step(b"strong-warm%d" % w, sprep, sl0)
+            assert (code, idx) == (0, -1)
+        barrier()
+        s_dev_ms = device_steps(args.steps)
+        barrier()
+        s_e2e = 0.0
+        for s in range(args.steps):
+            torch.cuda.synchronize()
+            dt, code, idx, tm = e2e_step(b"strong%d" % s, sprep, sl0)
+            assert (code, idx) == (0, -1)
+            s_e2e += dt
+        barrier()
+        t = torch.tensor([s_dev_ms, s_e2e * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms_max, e2e_ms_max = t.tolist()
+        s_dev_ms, s_e2e_ms = t.tolist()
+        strong = {"scaling": "strong", "txs_total": len(strong_blobs), "txs_per_gpu": len(strong_blobs) // world,
+                  "value": len(strong_blobs) * args.steps / (s_dev_ms * 1e-3), "ms_per_step": s_dev_ms / args.steps, "unit": "TX/s",
+                  "e2e_single_call": {"value": len(strong_blobs) * args.steps / (s_e2e_ms * 1e-3), "ms_per_step": s_e2e_ms / args.steps},
+                  "note": "one 10k batch cut N ways: kernels of the shard + record + NCCL all-gather + joint decision inside the event pair; e2e = verify_batch_distributed, one call at a time"}
+        e2e_step(b"restore2")
+        barrier()
+    clocks = sampler.summary()
+
+    if dist:
+        t = torch.tensor([dev_ms, e2e_s * 1e3, single_s * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max, e2e_ms_max, single_ms_max = t.tolist()
     else:
-        dev_ms_max, e2e_ms_max = dev_ms, e2e_s * 1e3
+        dev_ms_max, e2e_ms_max, single_ms_max = dev_ms, e2e_s * 1e3, single_s * 1e3
 
     if rank != 0:
         if dist:
@@ -420,38 +590,112 @@ def main():
     total_tx = args.txs * world * args.steps
     value = total_tx / (dev_ms_max * 1e-3)
     e2e = total_tx / (e2e_ms_max * 1e-3)
-    # ---- roofline of the dominant kernel (integer-multiply pipe; tensor cores unused by design)
+    # ---- roofline (integer-multiply pipe; tensor cores unused by design).  `kernel` = the kernel with the largest isolated time
+    # of the step; step_frac = canonical work of the whole step / step time / peak; per_kernel_isolated lists every timed kernel.
     peak_wide = ctx.int_peak(2); peak_chain = ctx.int_peak(3)
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         hbm_peak = 6553.9          # the figure MEASURED_PEAKS.json held when this was written
     leaf = {n: v for n, v in kernels.items() if not n.startswith("msm_")}      # msm_* timers wrap several kernels
-    # dominant kernel = the one carrying the largest share of the step's algorithmic work (limb products); the per-kernel
-    # table below lists every timed kernel, including the latency-bound one-thread-per-item kernels
-    dom = max(leaf, key=lambda n: leaf[n]["alg_lp_per_step"])
+    dom = max(leaf, key=lambda n: leaf[n]["ms_per_step"])
     ach = leaf[dom]["alg_lp_per_step"] / (leaf[dom]["ms_per_step"] * 1e-3)
     work = {n: {"ms": round(v["ms_per_step"], 4), "TLP_s": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12, 3), "frac": round(v["alg_lp_per_step"] / (v["ms_per_step"] * 1e-3) / peak_wide, 4)}
-            for n, v in leaf.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
-    roofline = {"bound": "int-mul", "kernel": dom, "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide, "share_of_step_work": leaf[dom]["alg_lp_per_step"] / max(1.0, sum(v["alg_lp_per_step"] for n, v in leaf.items())),
-                "peak_source": "measured live: IMAD.WIDE.U32 Rd64, Ra, Rb, RZ microkernel (two vector multiplicands, both result words live; SASS checked: IMAD.WIDE only)", "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": ach / peak_chain,
-                "traffic": 13.39e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress launch of this workload (ncu --set full, profiles/r01_ncu_full_v3.md); algorithmic bytes are 65.6 MB (32 B in, 160 B out per point): the outputs stay in the 126 MB L2",
-                "per_kernel_isolated": work, "note": "every 32x32->64 form (IMAD.WIDE, IMAD.WIDE.X carry chains, IMAD.HI) issues at 4 cycles per warp instruction per SM sub-partition on sm_100a, half the rate of the 32-bit IMAD; bench lines before r01 v5 divided by an 18.4 T/s figure that turned out to measure IADD3 pairs (DESIGN.md 4.1)"}
+            for n, v in kernels.items() if v["alg_lp_per_step"] > 0 and v["ms_per_step"] > 0}
+    step_lp = canonical_lp_per_tx(a, k) * args.txs
+    step_ms = dev_ms_max / args.steps
+    n_sigma = args.txs * (7 * a + 8 * k) + 2
+    lgm = 6 + (m.bit_length() - 1)
+    n_dyn = args.txs * (4 + 2 * lgm + m)
+    msm_in_batch = {}
+    for nm, npts, extra in (("msm_sigma", n_sigma, kernels.get("msm_sigma_sort", {}).get("ms_per_step", 0.0)), ("msm_range_dyn", n_dyn, 0.0)):
+        if nm in kernels and kernels[nm]["ms_per_step"] > 0:
+            ms_ = kernels[nm]["ms_per_step"] + extra
+            msm_in_batch[nm] = {"points": npts, "ms_isolated": round(ms_, 4), "msm_frac": round(a_msm(npts) / (ms_ * 1e-3) / peak_wide, 4)}
+    roofline = {"bound": "int-mul", "kernel": dom, "kernel_choice": "largest isolated time among the kernels of one step", "achieved": ach / 1e12, "peak": peak_wide / 1e12, "unit": "TLP/s (32x32->64 limb products)", "frac": ach / peak_wide,
+                "step_frac": step_lp / (step_ms * 1e-3) / peak_wide, "step_canonical_TLP": step_lp / 1e12, "msm_frac_in_batch": msm_in_batch,
+                "share_of_step_time_isolated": leaf[dom]["ms_per_step"] / max(1e-9, sum(v["ms_per_step"] for v in leaf.values())),
+                "peak_source": "measured live: IMAD.WIDE.U32 Rd64, Ra, Rb, RZ microkernel (two vector multiplicands, both result words live; SASS checked: IMAD.WIDE only)", "peak_carry_chain": peak_chain / 1e12,
+                "traffic": None, "traffic_note": "integer-bound kernel: operands are a 64-byte signature and one 32-byte key per thread (DRAM traffic of the HBM-bound kernel: secondary.ct_update_resident_1M.roofline)",
+                "per_kernel_isolated": work, "canonical_units": "SURVEY.md 8d: decode 12,632 LP, encode 12,688, mixed add 504, A_msm(n) = 8,064 n + 6.04e8 (16 windows whatever window the plan picks), signature 160,000",
+                "note": "every 32x32->64 form (IMAD.WIDE, IMAD.WIDE.X carry chains, IMAD.HI) issues at 4 cycles per warp instruction per SM sub-partition on sm_100a, half the rate of the 32-bit IMAD (DESIGN.md 4.1)"}
+    kf = phases.get("keccak_f", -1)
     line = {"metric": "verified TX/s (10k-transfer batch)", "value": value, "unit": "TX/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "vs_baseline_note": "reference README: ~0.40 ms/TX on one CPU thread (hardware unstated)",
-            "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic (valid TXs minted by the oracle prover; ranks share one minted batch)", "config": config,
+            "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic (valid TXs minted by the oracle prover; every rank mints its own shard, all ranks hold the whole batch)", "config": config,
             "e2e": {"value": e2e, "unit": "TX/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps, "host_threads": host_threads, "batches_in_flight": nfl,
-                    "single_call": {"value": args.txs * args.steps / single_s, "ms_per_step": 1e3 * single_s / args.steps},
-                    "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": phases.get("keccak_f", 0) / args.txs,
+                    "single_call": {"value": total_tx / (single_ms_max * 1e-3), "ms_per_step": single_ms_max / args.steps},
+                    "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": (kf / args.txs) if kf >= 0 else None,
                     "phases_ms_pipelined_mean": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None,
-                    "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir, "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
+                    "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir,
+                    "fiat_shamir_note": "fast = device transcripts + device layout (SURVEY 8 f.1 + f.2); other_mode = north_star's split (Merlin on host threads)",
+                    "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
             "value_batches_in_flight": {"value_this_rank": concurrent_value, "unit": "TX/s", "contexts": nfl, "note": "device-resident batches of all contexts in flight at once (no L2 flush); the GPU-side ceiling of the pipelined e2e"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_ms_per_step_isolated": {n: round(v["ms_per_step"], 4) for n, v in kernels.items()},
             "timeline_ms_one_step": timeline, "mint_seconds": round(t_mint, 1), "host_cores": ncpu}
     if world > 1:
-        line["collective"] = {"what": "one all_gather of 80 B per rank per batch (verdict + partial sigma / range MSM encodings) over NCCL, inside both timed regions"}
-    if world == 1 and not args.no_secondary:
-        line["secondary"] = secondary_metrics(lib, ctx, ts, hbm_peak)
+        line["collective"] = {"what": "per batch: one ncclAllGather of 80 B per rank (verdict word + partial sigma / range MSM encodings), then the joint decision kernel (sum of the partial encodings, identity tests) -- inside the value event pair and inside e2e",
+                              "cross_shard_dependencies": "followed by the host layer from the batch bytes (no extra exchange): tests/test_gpu_shards.py, tests/test_distributed_cpu.py"}
+        if strong:
+            line["strong"] = strong
+    if world == 1 and args.secondary != "off":
+        sec = {}
+        sec.update(msm_sweep(torch, lib, ctx, ts, oracle, [16, 18, 20, 22] if args.secondary == "full" else [20], [16, 18, 20] if args.secondary == "full" else [], peak_wide))
+        sec["msm_2p20"] = dict(sec["2^20"], note="resident decompressed points (affine Niels, 96 MB), uniform 252-bit scalars; bit-exactness against the oracle: tests/test_gpu_msm.py")
+        sec.update(ct_update_metrics(torch, lib, ctx, ts, hbm_peak))
+        if args.secondary == "full":
+            t_sec = time.time()
+            # config 3, other shapes: multi-destination / multi-asset transfers at 10k
+            for sa, sk_, seed in ((1, 3, 81), (2, 6, 82)):
+                sb = oracle.mint_transfers(seed, args.txs, sa, sk_, threads=ncpu)
+                sm_ = 1
+                while sm_ < sa + sk_:
+                    sm_ *= 2
+                rej = tamper_classes(oracle, sb, seed, (2 * args.txs) // 3, sa, sk_)
+                sec["a%dk%d_%d" % (sa, sk_, args.txs)] = measure_config("a%dk%d" % (sa, sk_), torch, xhe, verifier, dev, ts, flush, sb.blobs, sb.ledger().dump(), [], max(sm_, 2), 5, 3, rej, host_threads, canonical_lp_per_tx(sa, sk_) * args.txs, peak_wide)
+                del sb
+            # the headline shape's reject paths (all tamper classes)
+            sec["a1k1_rejects"] = measure_config("a1k1", torch, xhe, verifier, dev, ts, flush, batch.blobs, my_records, [], max(m, 2), 3, 2, tamper_classes(oracle, batch, 77, (2 * args.txs) // 3, a, k), host_threads)
+            # config 3, one-sender variant: the reference's own bench shape (benches/tx.rs:153-186), a length-T balance chain
+            cb = oracle.mint_chain(83, args.txs, 1, threads=ncpu)
+            cbl = list(cb.blobs)
+            i0 = max(0, min(5000, args.txs - 2))
+            swapped = cbl[:i0] + [cbl[i0 + 1], cbl[i0]] + cbl[i0 + 2:]
+            bad_sig = cbl[:-1] + [cbl[-1][:-1] + bytes([cbl[-1][-1] ^ 1])]
+            sec["one_sender_chain_%d" % args.txs] = measure_config("chain", torch, xhe, verifier, dev, ts, flush, cbl, cb.ledger().dump(), [], 2, 5, 3,
+                                                                   [("bad_signature_last", bad_sig, (1, args.txs - 1)), ("two_swapped", swapped, (5, -1))], host_threads, canonical_lp_per_tx(1, 1) * args.txs, peak_wide)
+            del cb
+            # config 5: mixed batch with multisig; one tampered run per class
+            mb = oracle.mint_mixed(84, args.mixed_txs, threads=ncpu)
+            v = (2 * args.mixed_txs) // 3
+            while mb.blobs[v][1] != 0 or mb.blobs[v][3] != 0xFF:
+                v += 1
+            kk_ = int.from_bytes(mb.blobs[v][4:8], "little")
+            rej = tamper_classes(oracle, mb, 84, v, mb.blobs[v][2], kk_)
+            sec["mixed_%d" % args.mixed_txs] = measure_config("mixed", torch, xhe, verifier, dev, ts, flush, mb.blobs, mb.ledger().dump(), mb.ledger().dump_multisig(), 8, 3, 2, rej, ncpu)
+            sec["mixed_%d" % args.mixed_txs]["mix"] = "60 % transfers (k 1..4, a 1..2), 15 % burn, 15 % contract call, 5 % multisig set-up, 5 % transfers from threshold-2 multisig accounts"
+            del mb
+            # benches/tx.rs:231-233: 16 transactions of 255 transfers each (256-party aggregated range proofs)
+            w255 = []
+            import hashlib
+            rng = oracle.Rng(b"bench-255"); led255 = oracle.Ledger(); recs255 = []
+            rcv = oracle.Keypair.derive(b"bench255-rcv"); ct = rcv.encrypt(0, rng); led255.set_balance(rcv.pk, oracle.NATIVE, ct); led255.set_nonce(rcv.pk, 0); recs255.append((rcv.pk, oracle.NATIVE, ct))
+            kps = [oracle.Keypair.derive(b"bench255-%d" % i) for i in range(16)]
+            for kp in kps:
+                ct = kp.encrypt(10**7, rng); led255.set_balance(kp.pk, oracle.NATIVE, ct); led255.set_nonce(kp.pk, 0); recs255.append((kp.pk, oracle.NATIVE, ct))
+            res255 = [None] * 16
+
+            def build255(i):
+                res255[i] = oracle.build_tx(kps[i], led255, oracle.Rng(b"bench-255-%d" % i), fee=3, transfers=[(oracle.NATIVE, rcv.pk, 1)] * 255, balances=[(oracle.NATIVE, 10**7)])
+            th255 = [threading.Thread(target=build255, args=(i,)) for i in range(16)]
+            for t_ in th255:
+                t_.start()
+            for t_ in th255:
+                t_.join()
+            sec["16x255_transfers"] = measure_config("16x255", torch, xhe, verifier, dev, ts, flush, res255, recs255, [], 256, 5, 3,
+                                                     [("bad_signature", res255[:9] + [res255[9][:-1] + bytes([res255[9][-1] ^ 1])] + res255[10:], (1, 9))], host_threads, canonical_lp_per_tx(1, 255) * 16, peak_wide)
+            sec["secondary_seconds"] = round(time.time() - t_sec, 1)
+        line["secondary"] = sec
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(batch, ncpu, args.cpu_sample or args.txs)
     emit(line)

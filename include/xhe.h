@@ -171,6 +171,29 @@ int32_t xhe_shard_decide_dev(xhe_ctx* ctx, const void* d_records, uint32_t world
  * ctx stream -- for small control messages that must not queue behind bulk transfers on the copy engines */
 int32_t xhe_copy_small(xhe_ctx* ctx, void* dst, const void* src, size_t nbytes);
 
+/* ---- device-resident ledger: a state backend for BlockchainVerificationState (src/tx/verify.rs:25-77) whose
+ * balances live on the device as decompressed points (coordinate-planar extended, 256 B per (account, asset)); the
+ * (account || asset) -> slot index stays with the host.  Balances are compressed only on export.  A ledger belongs to one ctx. */
+typedef struct xhe_ledger xhe_ledger;
+int32_t xhe_ledger_create(xhe_ctx* ctx, size_t capacity /* (account, asset) slots */, xhe_ledger** out);
+void    xhe_ledger_destroy(xhe_ledger* ledger);
+size_t  xhe_ledger_size(const xhe_ledger* ledger);
+/* insert / overwrite n balances: keys n x 64 (account || asset), cts n x 64 CompressedCiphertext (src/compressed.rs:37-41), decoded on
+ * the device.  ok[i] (optional) = 0 when ciphertext i does not decode (it is then reported as not found). */
+int32_t xhe_ledger_load(xhe_ledger* ledger, const uint8_t* keys, const uint8_t* cts, size_t n, uint8_t* ok);
+/* ElGamalCiphertext Add / Sub in place (src/elgamal.rs:322-342; apply_without_verify's algebra, src/tx/verify.rs:574,602):
+ * bal[key_i] +/- delta_i with 64-byte compressed deltas; repeated keys are applied in order.  status[i] (optional): 0 applied,
+ * 1 unknown key, 2 ill-formed delta (balance untouched). */
+int32_t xhe_ledger_update(xhe_ledger* ledger, const uint8_t* keys, const uint8_t* deltas, const uint8_t* sub, size_t n, uint8_t* status);
+/* the same for EVERY slot [0, size) in slot (= insertion) order, deltas resident on the device as planar affine Niels
+ * [y+x | y-x | 2dxy][2 size][8 words]: config 4's HBM-bound form, asynchronous on the ctx stream */
+int32_t xhe_ledger_update_dense_dev(xhe_ledger* ledger, const void* d_delta_niels_planar, const void* d_sub /* size bytes */);
+/* compressed export on demand (what get_account_balance returns): found[i] (optional) = 0 for an unknown key (64 zero bytes out) */
+int32_t xhe_ledger_export(xhe_ledger* ledger, const uint8_t* keys, size_t n, uint8_t* out_cts, uint8_t* found);
+/* the table itself for callers that launch their own kernels: 4 planes X, Y, Z, T of *plane_stride_points points x 32 bytes;
+ * slot s owns points 2s (commitment) and 2s + 1 (handle) */
+void*   xhe_ledger_device_table(const xhe_ledger* ledger, size_t* plane_stride_points);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* integer-multiply pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE.U32; returns
  * achieved instructions/s summed over the device in *rate. */

@@ -231,6 +231,13 @@ def mint_chain(seed, T, k=1, threads=1):
     return Batch(lib.xo_mint_chain(C.c_uint64(seed), C.c_size_t(T), k))
 
 
+def minted_keypair(seed, i, which="s"):
+    """Keypair of sender ("s") / receiver ("r") i of a batch minted with `seed` (mint_transfers, mint_mixed)"""
+    out = (C.c_uint8 * 32)()
+    lib.xo_mint_secret(C.c_uint64(seed), ord(which), C.c_uint64(i), out)
+    return Keypair(bytes(out))
+
+
 def mint_mixed(seed, T, threads=8):
     """config 5: transfers (k 1..4, a 1..2), burns, contract calls, multisig set-ups and transfers from threshold-2 multisig accounts"""
     return Batch(lib.xo_mint_mixed(C.c_uint64(seed), C.c_size_t(T), threads))

@@ -184,6 +184,9 @@ xo_batch *xo_mint_mixed(uint64_t seed, size_t T, int threads) {
 }
 /* the multisig settings of a batch's initial ledger as records pk[32] n[1] threshold[1] signers[n x 32] (for importing into another ledger) */
 size_t xo_ledger_dump_multisig(const xo_ledger *l, uint8_t *out, size_t cap);
+/* secret key of sender (which = 's') / receiver ('r') i of a batch minted by xo_mint_transfers / xo_mint_mixed with `seed`: lets a
+ * test re-sign a deliberately broken transaction of a big minted batch (xo_resign) */
+void xo_mint_secret(uint64_t seed, int which, uint64_t i, uint8_t sk_out[32]) { sc sk; char tag[2] = {(char)which, 0}; derive_key(seed, tag, i, &sk); sc_tobytes(sk_out, &sk); }
 void xo_batch_free(xo_batch *b) { if (!b) return; free(b->blobs); free(b->offsets); xo_ledger_free(b->ledger); free(b); }
 /* verify a whole batch against a clone of its ledger; returns verdict */
 int xo_batch_verify(const xo_batch *b, uint64_t rng_seed, long *fail_index, xo_ledger **final_state) {

@@ -1,0 +1,152 @@
+"""Device-resident ledger (include/xhe.h xhe_ledger_*): balances live decompressed in HBM, the balance
+algebra of src/elgamal.rs:322-342 runs in place, and the compressed export must equal the oracle's bytes after every step.
+Also the direct tests VERDICT r1 asked for: xhe_sig_r against the oracle, and the generator table against SURVEY appendix B."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import xelis_he_b200 as xhe
+    c = xhe.Ctx(0, party_capacity=2)
+    yield c
+    c.close()
+
+
+def _cts(seed, n):
+    """n ciphertexts = pairs of valid ristretto encodings"""
+    u = hashlib.shake_256(b"ledger-test" + seed).digest(128 * n)
+    return [oracle.from_uniform(u[128 * i:128 * i + 64]) + oracle.from_uniform(u[128 * i + 64:128 * i + 128]) for i in range(n)]
+
+
+def test_ledger_load_update_export_matches_oracle(ctx):
+    import xelis_he_b200 as xhe
+    n = 600
+    keys = [hashlib.sha256(b"acct%d" % i).digest() + (bytes(32) if i % 3 else bytes([55]) * 32) for i in range(n)]
+    bal = _cts(b"bal", n)
+    led = xhe.DeviceLedger(ctx, capacity=1024)
+    assert led.load((k[:32], k[32:], c) for k, c in zip(keys, bal)) == b"\x01" * n and len(led) == n
+    out, found = led.export(b"".join(keys))
+    assert found == b"\x01" * n and out == b"".join(bal)                      # decode -> extended -> encode round trip is the identity on bytes
+    # round 1: every account once, half add, half sub
+    delta = _cts(b"d1", n); sub = bytes(i & 1 for i in range(n))
+    assert led.update(b"".join(keys), b"".join(delta), sub) == bytes(n)
+    want, ok = oracle.ct_update(b"".join(bal), b"".join(delta), sub)
+    assert ok == b"\x01" * n
+    out, _ = led.export(b"".join(keys)); assert out == want
+    # round 2: repeated keys inside one call are applied in order; an unknown key and an ill-formed delta are reported, not applied
+    idx = [5, 9, 5, 5, 17, 9, 400]
+    d2 = _cts(b"d2", len(idx)); s2 = bytes([0, 1, 1, 0, 0, 0, 1])
+    cur = {i: want[64 * i:64 * i + 64] for i in set(idx)}
+    for j, i in enumerate(idx):
+        cur[i] = oracle.ct_update(cur[i], d2[j], bytes([s2[j]]))[0]
+    ks = [keys[i] for i in idx] + [hashlib.sha256(b"nobody").digest() + bytes(32), keys[3]]
+    ds = d2 + [d2[0], b"\xff" * 64]
+    st = led.update(b"".join(ks), b"".join(ds), s2 + bytes(2))
+    assert st == bytes(len(idx)) + bytes([1, 2])
+    out, found = led.export(b"".join(keys[i] for i in sorted(cur)) + ks[-2])
+    assert found == b"\x01" * len(cur) + b"\x00"
+    assert out[:64 * len(cur)] == b"".join(cur[i] for i in sorted(cur)) and out[64 * len(cur):] == bytes(64)
+    out3, _ = led.export(keys[3]); assert out3 == want[64 * 3:64 * 4]         # the ill-formed delta left balance 3 alone
+    # a balance that does not decode is refused at load time
+    assert led.load([(hashlib.sha256(b"bad").digest(), bytes(32), b"\xff" * 64)]) == b"\x00"
+    led.close()
+
+
+def test_ledger_dense_update_is_config4(ctx):
+    """config 4 on the table: every account +/- a resident delta (the HBM-bound kernel); export equals the oracle on a sample"""
+    import torch
+    import xelis_he_b200 as xhe
+    n = 4096
+    keys = [hashlib.sha256(b"dense%d" % i).digest() + bytes(32) for i in range(n)]
+    bal = _cts(b"dbal", n); delta = _cts(b"ddel", n)
+    led = xhe.DeviceLedger(ctx, capacity=n)
+    led.load((k[:32], k[32:], c) for k, c in zip(keys, bal))
+    lib = ctx.lib
+    d_enc = torch.frombuffer(bytearray(b"".join(delta)), dtype=torch.uint8).cuda()
+    niels = torch.empty((2 * n, 24), dtype=torch.int32, device="cuda"); ok = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    assert lib.xhe_decompress_dev(ctx.p, d_enc.data_ptr(), 2 * n, None, niels.data_ptr(), ok.data_ptr()) == 0
+    planar = niels.reshape(2 * n, 3, 8).permute(1, 0, 2).contiguous()          # [ypx | ymx | t2d][2n][8]
+    sub = torch.tensor([i % 2 for i in range(n)], dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    led.update_dense_dev(planar.data_ptr(), sub.data_ptr())
+    ctx.sync()
+    want, _ = oracle.ct_update(b"".join(bal), b"".join(delta), bytes(i % 2 for i in range(n)))
+    out, _ = led.export(b"".join(keys))
+    assert out == want
+    led.close()
+
+
+def test_sig_r_matches_oracle(ctx):
+    """xhe_sig_r (Signature::verify's group part, src/elgamal.rs:38-42): r = s*H - e*P, byte-identical to the oracle's scalar mults"""
+    H = bytes.fromhex("8c9240b456a9e6dc65c377a1048d745f94a08cdb7f44cbcd7b46f34048871134")
+    n = 33
+    rnd = hashlib.shake_256(b"sig-r").digest(64 * 3 * n)
+    s = [oracle.sc_reduce_wide(rnd[64 * i:64 * i + 64]) for i in range(n)]
+    e = [oracle.sc_reduce_wide(rnd[64 * (n + i):64 * (n + i) + 64]) for i in range(n)]
+    pk = [oracle.from_uniform(rnd[64 * (2 * n + i):64 * (2 * n + i) + 64]) for i in range(n)]
+    s[0] = bytes(32); e[1] = bytes(32); s[2] = (L - 1).to_bytes(32, "little"); pk[3] = bytes(32)      # edge scalars, identity key
+    pk[4] = b"\xff" * 32                                                                              # invalid key: flagged
+    lib = ctx.lib
+    lib.xhe_sig_r.restype = C.c_int32
+    lib.xhe_sig_r.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    r = C.create_string_buffer(32 * n); ok = C.create_string_buffer(n)
+    assert lib.xhe_sig_r(ctx.p, b"".join(s), b"".join(e), b"".join(pk), n, r, ok) == 0
+    for i in range(n):
+        if i == 4:
+            assert ok.raw[i] == 0
+            continue
+        sH = oracle.scalarmult(s[i], H); eP = oracle.scalarmult(e[i], pk[i])
+        assert ok.raw[i] == 1 and r.raw[32 * i:32 * i + 32] == oracle.point_add(sH, eP, sub=True), i
+    # a non-canonical scalar is a bad argument, not a verdict
+    assert lib.xhe_sig_r(ctx.p, L.to_bytes(32, "little"), e[0], pk[0], 1, r, ok) == -1
+
+
+def test_generator_table_matches_survey_appendix_b():
+    """BP_GENS / PC_GENS (src/proofs.rs:19-22): G, H and the first G_vec / H_vec generators as they sit in the device table,
+    against the encodings recorded in SURVEY.md appendix B, and the whole table against the oracle's derivation"""
+    import torch
+    import xelis_he_b200 as xhe
+    c = xhe.Ctx(0, party_capacity=2)
+    lib = c.lib
+    lib.xhe_ctx_generators_dev.restype = C.c_void_p; lib.xhe_ctx_generators_dev.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    n = C.c_size_t(0)
+    d = lib.xhe_ctx_generators_dev(c.p, C.byref(n))
+    assert n.value == 2 + 128 * 2
+    # affine Niels (y+x, y-x, 2dxy) -> affine x||y on the host with python integers, then compress on the device
+    raw = (C.c_uint8 * (96 * n.value))()
+    import ctypes
+    libcudart = ctypes.CDLL("libcudart.so")
+    assert libcudart.cudaMemcpy(raw, C.c_void_p(d), C.c_size_t(96 * n.value), 2) == 0
+    p = 2**255 - 19
+    xy = b""
+    for i in range(n.value):
+        ypx = int.from_bytes(bytes(raw[96 * i:96 * i + 32]), "little") % p; ymx = int.from_bytes(bytes(raw[96 * i + 32:96 * i + 64]), "little") % p
+        inv2 = pow(2, p - 2, p)
+        y = (ypx + ymx) * inv2 % p; x = (ypx - ymx) * inv2 % p
+        xy += x.to_bytes(32, "little") + y.to_bytes(32, "little")
+    enc = c.compress(xy)
+    g = lambda i: enc[32 * i:32 * i + 32].hex()
+    assert g(0) == "e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"          # G (RFC 9496)
+    assert g(1) == "8c9240b456a9e6dc65c377a1048d745f94a08cdb7f44cbcd7b46f34048871134"          # H = B_blinding
+    assert g(2) == "fc3b25801422672a6a8d3adb5d8457d4301fe92324b4fc56ae934c8713ddfe2d"          # G_vec[0][0]
+    assert g(3) == "ae817fdef62f713dd169dc8a26406f68be0bd3cd53652614636b0801567c4264"          # G_vec[0][1]
+    assert g(2 + 64) == "0eeebec183d151ded1e24320cf43c987617b36e77114788e5ae8ace41570b74b"     # G_vec[1][0]
+    assert g(2 + 128) == "ba698f6dd08c501e32b55d2ee7259f6019d629fa2ba4d7039c5de157cba4df73"    # H_vec[0][0]
+    assert g(2 + 129) == "acf2d2b95428fac99b12da3bab92edf8ea3788c2fd16769e586397eede7b5052"    # H_vec[0][1]
+    assert g(2 + 128 + 64) == "c4d0c6aa6c07db20798b35906c8a8940fa8a1e2f6bf699ee13aaf3eb1f636d24"   # H_vec[1][0]
+    # every entry: SHAKE256("GeneratorsChain" || label || party) blocks through the one-way map (oracle)
+    for which, label in ((0, b"G"), (1, b"H")):
+        for party in range(2):
+            stream = hashlib.shake_256(b"GeneratorsChain" + label + party.to_bytes(4, "little")).digest(64 * 64)
+            for i in range(64):
+                assert enc[32 * (2 + which * 128 + party * 64 + i):][:32] == oracle.from_uniform(stream[64 * i:64 * i + 64])
+    c.close()

@@ -51,6 +51,14 @@ def load_library():
         "xhe_msm_vartime": (i32, [vp, u8p, u8p, sz, vp, C.POINTER(C.c_int32)]),
         "xhe_sum_encodings": (i32, [vp, u8p, sz, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "xhe_copy_small": (i32, [vp, vp, vp, sz]),
+        "xhe_ledger_create": (i32, [vp, sz, C.POINTER(vp)]),
+        "xhe_ledger_destroy": (None, [vp]),
+        "xhe_ledger_size": (sz, [vp]),
+        "xhe_ledger_load": (i32, [vp, u8p, u8p, sz, vp]),
+        "xhe_ledger_update": (i32, [vp, u8p, u8p, u8p, sz, vp]),
+        "xhe_ledger_update_dense_dev": (i32, [vp, vp, vp]),
+        "xhe_ledger_export": (i32, [vp, u8p, sz, vp, vp]),
+        "xhe_ledger_device_table": (vp, [vp, C.POINTER(sz)]),
         "xhe_batch_record_dev": (i32, [vp, vp]),
         "xhe_shard_decide_dev": (i32, [vp, vp, C.c_uint32, vp]),
         "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -167,3 +175,45 @@ class Ctx:
         out = np.zeros_like(a)
         self._chk(self.lib.xhe_selftest_fe(self.p, op, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
         return out
+
+
+class DeviceLedger:
+    """Device-resident ledger (include/xhe.h, xhe_ledger_*): balances stay decompressed in HBM; keys are account || asset."""
+
+    def __init__(self, ctx, capacity):
+        self.ctx, self.lib = ctx, ctx.lib
+        p = C.c_void_p()
+        ctx._chk(self.lib.xhe_ledger_create(ctx.p, capacity, C.byref(p)))
+        self.p = p
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.lib.xhe_ledger_destroy(self.p); self.p = None
+
+    __del__ = close
+
+    def __len__(self):
+        return int(self.lib.xhe_ledger_size(self.p))
+
+    def load(self, records):
+        """records: iterable of (pk, asset, ct64); returns per-record ok flags"""
+        records = list(records)
+        keys = b"".join(pk + asset for pk, asset, _ in records); cts = b"".join(ct for _, _, ct in records)
+        ok = C.create_string_buffer(max(len(records), 1))
+        self.ctx._chk(self.lib.xhe_ledger_load(self.p, keys, cts, len(records), ok))
+        return ok.raw[:len(records)]
+
+    def update(self, keys: bytes, deltas: bytes, sub: bytes):
+        n = len(sub)
+        st = C.create_string_buffer(max(n, 1))
+        self.ctx._chk(self.lib.xhe_ledger_update(self.p, keys, deltas, sub, n, st))
+        return st.raw[:n]
+
+    def update_dense_dev(self, d_delta_niels_planar, d_sub):
+        self.ctx._chk(self.lib.xhe_ledger_update_dense_dev(self.p, C.c_void_p(d_delta_niels_planar), C.c_void_p(d_sub)))
+
+    def export(self, keys: bytes):
+        n = len(keys) // 64
+        out = C.create_string_buffer(64 * max(n, 1)); found = C.create_string_buffer(max(n, 1))
+        self.ctx._chk(self.lib.xhe_ledger_export(self.p, keys, n, out, found))
+        return out.raw[:64 * n], found.raw[:n]

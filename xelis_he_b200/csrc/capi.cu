@@ -5,7 +5,7 @@
 #include <algorithm>
 
 int32_t xhe_from_uniform_niels_dev(xhe_ctx* ctx, const void* d_u, size_t n, void* d_niels);
-size_t xhe_preload_msm(); size_t xhe_preload_verify(); size_t xhe_preload_fs(); size_t xhe_preload_point();
+size_t xhe_preload_msm(); size_t xhe_preload_verify(); size_t xhe_preload_fs(); size_t xhe_preload_point(); size_t xhe_preload_ledger();
 int32_t xhe_compress_xy_bytes_dev(xhe_ctx* ctx, const void* d_xy, size_t n, void* d_enc);
 int32_t xhe_affine_to_bytes_dev(xhe_ctx* ctx, const void* d_aff, size_t n, void* d_xy);
 
@@ -28,7 +28,7 @@ extern "C" int32_t xhe_ctx_create(int device, uint32_t party_capacity, xhe_ctx**
   // a larger per-thread stack than any before it (k_rp_prep: 3.5 KB against the 1 KB default).  Both happen here instead.
   { static bool loaded[64] = {false};
     if (device < 64 && !loaded[device]) {
-      size_t frame = std::max(std::max(xhe_preload_msm(), xhe_preload_verify()), std::max(xhe_preload_fs(), xhe_preload_point()));
+      size_t frame = std::max(std::max(xhe_preload_msm(), xhe_preload_verify()), std::max(xhe_preload_fs(), std::max(xhe_preload_point(), xhe_preload_ledger())));
       size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize);
       size_t want = std::max<size_t>(4096, frame + 512);       // (the pool is this many bytes x the resident threads of the device: ~1.2 GB at 4 KB)
       if (cur < want) cudaDeviceSetLimit(cudaLimitStackSize, want);

@@ -636,7 +636,7 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
   }
   const uint32_t kpg = (uint32_t)(p.Wg * p.B);
   AccumOut ao{q.part, q.pstart, q.pcount, q.heavy, kpg};
-  { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * p.W);
+  { XheTimed timed(ctx, "k_msm_accum_tiles", 504.0 * (double)n * 16.0);      // canonical units: 16 windows, whatever W the plan picked
     for (int g = 0; g < p.G; g++) {
       const uint32_t klo = (uint32_t)g * kpg, khi = (uint32_t)std::min<size_t>(m, (size_t)(g + 1) * kpg);
       switch (g_accum_variant) {

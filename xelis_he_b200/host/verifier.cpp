@@ -383,6 +383,41 @@ static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g
 
 static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm);
 
+// The (account, asset) keys an xtx1 blob touches, read straight from its framing without validating it: f(account, asset).
+// Used to find, among the EARLIER shards of a sharded batch, the few transactions whose balance chains a shard must follow.
+template <class F>
+static bool scan_keys(const uint8_t* b, size_t n, F&& f) {
+  if (n < 128) return false;
+  const uint8_t type = b[1], n_sc = b[2]; const uint32_t count = rd32(b + 4), aux = rd32(b + 8), rp_len = rd32(b + 12);
+  size_t off = 64;
+  if (type == 0) { for (uint32_t i = 0; i < count; i++) { if (off + 324 > n) return false; f(b + off + 32, b + off); uint32_t el = rd32(b + off + 320); off += 324 + (el == 0xFFFFFFFFu ? 0 : (size_t)el); } }
+  else if (type == 1) off += 40;
+  else if (type == 2) { off += 32 + 40 * (size_t)count; for (uint32_t i = 0; i < 2 * aux; i++) { if (off + 4 > n) return false; off += 4 + (size_t)rd32(b + off); } }
+  else if (type == 3) off += aux;
+  else if (type == 4) off += 32 * (size_t)count;
+  else return false;
+  off += rp_len;
+  if (off + 256 * (size_t)n_sc > n) return false;
+  for (uint32_t q = 0; q < n_sc; q++) f(b + 16, b + off + 256 * (size_t)q);
+  return true;
+}
+// indices i < lo of the transactions that touch one of `keys`, or set the multisig of one of `sources` (in batch order)
+static std::vector<size_t> foreign_hits(const uint8_t* const* blobs, const size_t* lens, size_t lo, const FlatTable<64, uint8_t>& keys, const FlatTable<32, uint8_t>& sources, int threads) {
+  std::vector<std::vector<size_t>> part(std::max(1, threads));
+  parallel_for(lo, threads, [&](size_t a, size_t b, int tid) {
+    for (size_t i = a; i < b; i++) {
+      bool hit = false;
+      scan_keys(blobs[i], lens[i], [&](const uint8_t* account, const uint8_t* asset) { if (!hit && keys.find(MockLedger::key(account, asset).data())) hit = true; });
+      if (!hit && lens[i] >= 128 && blobs[i][1] == 4 && sources.find(blobs[i] + 16)) hit = true;
+      if (hit) part[tid].push_back(i);
+    }
+  });
+  std::vector<size_t> out;
+  for (auto& p : part) out.insert(out.end(), p.begin(), p.end());
+  std::sort(out.begin(), out.end());
+  return out;
+}
+
 // the reference's verdict for ONE transaction of the batch (it is known to be the first one that fails a per-transaction
 // check): the exact path over the one-transaction shard [i, i+1) -- earlier transactions only advance its balance chains
 static int exact_verdict_of(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, size_t i) {
@@ -406,9 +441,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
   uint8_t seed[32];
   if (!make_seed(opt, seed)) return 0;
-  std::vector<TxView> txs(hi); std::vector<int> parse_rc(hi, 0);
-  parallel_for(hi, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
-  for (size_t i = lo; i < hi; i++) if (parse_rc[i]) return 0;
+  std::vector<TxView> txs(n); std::vector<int> parse_rc(n, 0);      // this shard's transactions: txs[j] = blobs[lo + j]
+  parallel_for(n, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) parse_rc[j] = txs[j].parse(blobs[lo + j], lens[lo + j]); });
+  for (size_t j = 0; j < n; j++) if (parse_rc[j]) return 0;
   double t1 = now_ms();
   FastCache& F = fast_cache_for(ctx);
   const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
@@ -443,14 +478,15 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   // rank verifies them); its ciphertext points travel in region B.
   if (lo > 0) {
     FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * n); sources.reserve(n);
-    for (size_t i = lo; i < hi; i++) {
-      const TxView& tx = txs[i]; sources.insert(tx.source);
+    for (size_t j = 0; j < n; j++) {
+      const TxView& tx = txs[j]; sources.insert(tx.source);
       for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
       for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
     }
-    for (size_t i = 0; i < lo; i++) {
-      if (parse_rc[i]) continue;
-      const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
+    TxView ftx;
+    for (size_t i : foreign_hits(blobs, lens, lo, keys, sources, threads)) {
+      if (ftx.parse(blobs[i], lens[i])) continue;
+      const TxView& tx = ftx; const uint32_t k = tx.n_transfers();
       if (tx.type == 4 && sources.find(tx.source)) return 0;                    // multisig setting for one of our senders: exact path
       for (uint32_t q = 0; q < tx.n_sc; q++) {
         const uint8_t* asset = tx.sc + 256 * q;
@@ -482,13 +518,13 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); Ct64 kk = MockLedger::key(tx.source, tx.sc + 256 * q); chains.prefetch(kk.data()); }
     for (uint32_t t = 0; t < tx.n_transfers(); t++) { const TransferView& tr = tx.transfers[t]; state.prefetch_balance(tr.dest, tr.asset); Ct64 kk = MockLedger::key(tr.dest, tr.asset); chains.prefetch(kk.data()); }
   };
-  for (size_t j = 0; j < n && j < AHEAD; j++) announce(txs[lo + j]);
+  for (size_t j = 0; j < n && j < AHEAD; j++) announce(txs[j]);
   // A transaction that fails one of the HOST-side checks ends the walk (n_run transactions go to the device): the reference
   // stops at the first failing transaction, so whatever comes after it cannot change the verdict.
   size_t n_run = n; bool host_fail = false;
   for (size_t j = 0; j < n; j++) {
-    const TxView& tx = txs[lo + j];
-    if (j + AHEAD < n) announce(txs[lo + j + AHEAD]);
+    const TxView& tx = txs[j];
+    if (j + AHEAD < n) announce(txs[j + AHEAD]);
     if (tx.type == 4 || tx.n_ms >= 0) return 0;                               // multisig: exact path
     uint64_t nonce;
     if (!state.get_account_nonce(tx.source, &nonce) || nonce != tx.nonce || !verify_commitment_assets(tx)) { n_run = j; host_fail = true; break; }
@@ -643,10 +679,11 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
 
   // ---- parse (parallel)
-  std::vector<TxView> txs(hi); std::vector<int> parse_rc(hi, 0);
-  parallel_for(hi, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) parse_rc[i] = txs[i].parse(blobs[i], lens[i]); });
+  const size_t nsh = hi - lo;
+  std::vector<TxView> txs(nsh); std::vector<int> parse_rc(nsh, 0);  // this shard's transactions: txs[i - lo] = blobs[i]
+  parallel_for(nsh, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) parse_rc[j] = txs[j].parse(blobs[lo + j], lens[lo + j]); });
   size_t n_live = hi; int parse_err = XHE_OK;
-  for (size_t i = lo; i < hi; i++) if (parse_rc[i]) { n_live = i; parse_err = parse_rc[i]; break; }
+  for (size_t i = lo; i < hi; i++) if (parse_rc[i - lo]) { n_live = i; parse_err = parse_rc[i - lo]; break; }
   double t1 = now_ms();
 
   // ---- phase A: sequential state resolution and batch layout (mirrors pre_verify's order, src/tx/verify.rs:203-485)
@@ -655,7 +692,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   Staged staged;
   {
     size_t tk = 0, ta = 0, tlg = 0;
-    for (size_t i = lo; i < n_live; i++) { tk += txs[i].n_transfers(); ta += txs[i].n_sc; tlg += (txs[i].rp_len / 32 - 9) / 2; }
+    for (size_t i = lo; i < n_live; i++) { tk += txs[i - lo].n_transfers(); ta += txs[i - lo].n_sc; tlg += (txs[i - lo].rp_len / 32 - 9) / 2; }
     size_t nl = n_live - std::min(lo, n_live), npts = 1 + nl * 5 + tk * 9 + ta * 6 + 2 * tlg + 8;
     B.points.reserve(32 * npts); B.checks.reserve(npts + 2 * nl); B.sigs.reserve(nl + 8);
     B.op_prev.reserve(2 * (ta + tk)); B.op_amount.reserve(2 * (ta + tk)); B.op_term_off.reserve(2 * (ta + tk) + 1); B.op_terms.reserve(2 * (ta + 2 * tk));
@@ -672,13 +709,16 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   if (lo > 0 && n_live > lo) {
     FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * (n_live - lo)); sources.reserve(n_live - lo);
     for (size_t i = lo; i < n_live; i++) {
-      const TxView& tx = txs[i]; sources.insert(tx.source);
+      const TxView& tx = txs[i - lo]; sources.insert(tx.source);
       for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
       for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
     }
-    for (size_t i = 0; i < lo; i++) {
-      if (parse_rc[i]) continue;
-      const TxView& tx = txs[i]; const uint32_t k = tx.n_transfers();
+    // the earlier transactions are only SCANNED for these keys (scan_keys reads the framing, nothing else); the few that touch
+    // one are parsed.  The points of a foreign transaction must outlive this loop: they are copied into the point table.
+    TxView ftx;
+    for (size_t i : foreign_hits(blobs, lens, lo, keys, sources, threads)) {
+      if (ftx.parse(blobs[i], lens[i])) continue;
+      const TxView& tx = ftx; const uint32_t k = tx.n_transfers();
       if (tx.type == 4 && sources.find(tx.source) && multisig_payload_ok(tx)) staged.set_multisig(tx.source, tx.body, tx.count, (uint8_t)tx.aux, true);
       for (uint32_t q = 0; q < tx.n_sc; q++) {
         const uint8_t* asset = tx.sc + 256 * q;
@@ -708,7 +748,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   size_t n_reached = n_live;    // txs after the first host-side hard error are never reached by the reference
   long capacity_fail = -1;
   for (size_t i = lo; i < n_live; i++) {
-    const TxView& tx = txs[i]; TxPlan& P = plan[i - lo];
+    const TxView& tx = txs[i - lo]; TxPlan& P = plan[i - lo];
     P.check_begin = (uint32_t)B.checks.size(); P.sig_begin = (uint32_t)B.sigs.size();
     auto host_fail = [&](int err) { B.checks.push_back({CK_HOST, err, 0}); };
     auto finish = [&]() { P.check_end = (uint32_t)B.checks.size(); P.sig_end = (uint32_t)B.sigs.size(); };
@@ -861,7 +901,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
     std::vector<uint8_t> bytes; uint64_t kf = 0;
     for (size_t j = ja; j < jb; j++) {
       const size_t i = lo + j;
-      const TxView& tx = txs[i]; const TxPlan& P = plan[j];
+      const TxView& tx = txs[j]; const TxPlan& P = plan[j];
       // signature message hashes: SHA3-512(pk || message || r) -- absorb everything but r now (src/elgamal.rs:53-65)
       // (device Fiat-Shamir mode: only multisig co-signatures, which need BLAKE3, are still hashed here)
       if (P.sig_end > P.sig_begin && (!dev_fs || P.sig_end - P.sig_begin > 1)) {

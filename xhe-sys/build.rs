@@ -13,7 +13,7 @@ fn main() {
             .flag("-gencode").flag("arch=compute_100a,code=sm_100a")
             .flag("-O3").flag("-lineinfo").flag("-std=c++17")
             .include(root.join("include"));
-        for f in ["capi.cu", "fiat_shamir.cu", "kernels_point.cu", "msm.cu", "verify.cu"] {
+        for f in ["capi.cu", "fiat_shamir.cu", "kernels_point.cu", "ledger.cu", "msm.cu", "verify.cu"] {
             b.file(csrc.join(f));
             println!("cargo:rerun-if-changed={}", csrc.join(f).display());
         }

@@ -34,6 +34,10 @@ pub const XHE_OP_PLUS_AMOUNT: i64 = 1 << 50;
 pub struct xhe_ctx {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct xhe_ledger {
+    _private: [u8; 0],
+}
 
 /// `xhe_batch` of include/xhe.h.  All pointers are HOST memory; point index 0 must be the identity encoding.
 #[repr(C)]
@@ -143,12 +147,15 @@ extern "C" {
     // sharded batches
     pub fn xhe_combine_partials(ctx: *mut xhe_ctx, ext: *const u8, n: usize, out_enc: *mut u8, is_identity: *mut i32) -> i32;
     pub fn xhe_sum_encodings(ctx: *mut xhe_ctx, enc: *const u8, n: usize, out_enc: *mut u8, is_identity: *mut i32, all_valid: *mut i32) -> i32;
-    // device-resident ledger
-    pub fn xhe_ledger_create(ctx: *mut xhe_ctx, capacity: usize, out: *mut *mut c_void) -> i32;
-    pub fn xhe_ledger_destroy(ledger: *mut c_void);
-    pub fn xhe_ledger_load(ledger: *mut c_void, keys: *const u8, cts: *const u8, n: usize) -> i32;
-    pub fn xhe_ledger_update(ledger: *mut c_void, keys: *const u8, deltas: *const u8, sub: *const u8, n: usize, missing: *mut u8) -> i32;
-    pub fn xhe_ledger_export(ledger: *mut c_void, keys: *const u8, n: usize, out_cts: *mut u8, found: *mut u8) -> i32;
+    // device-resident ledger: BlockchainVerificationState backend with balances decompressed on the device
+    pub fn xhe_ledger_create(ctx: *mut xhe_ctx, capacity: usize, out: *mut *mut xhe_ledger) -> i32;
+    pub fn xhe_ledger_destroy(ledger: *mut xhe_ledger);
+    pub fn xhe_ledger_size(ledger: *const xhe_ledger) -> usize;
+    pub fn xhe_ledger_load(ledger: *mut xhe_ledger, keys: *const u8, cts: *const u8, n: usize, ok: *mut u8) -> i32;
+    pub fn xhe_ledger_update(ledger: *mut xhe_ledger, keys: *const u8, deltas: *const u8, sub: *const u8, n: usize, status: *mut u8) -> i32;
+    pub fn xhe_ledger_update_dense_dev(ledger: *mut xhe_ledger, d_delta_niels_planar: *const c_void, d_sub: *const c_void) -> i32;
+    pub fn xhe_ledger_export(ledger: *mut xhe_ledger, keys: *const u8, n: usize, out_cts: *mut u8, found: *mut u8) -> i32;
+    pub fn xhe_ledger_device_table(ledger: *const xhe_ledger, plane_stride_points: *mut usize) -> *mut c_void;
 }
 
 #[cfg(test)]
