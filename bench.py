@@ -155,7 +155,7 @@ def measure_config(name, torch, xhe, verifier, dev, stream, flush, batch_blobs, 
                 led.set_multisig(pk, signers, th)
             return led
         n = len(batch_blobs)
-        prepared = verifier.prepare_blobs(batch_blobs)
+        prepared = verifier.prepare_blobs_pinned(batch_blobs)
         out = {"txs": n}
         for w in range(2):
             code, idx, tm = verifier.verify_batch(ctx, None, ledger(), seed=b"sec-warm%d" % w, threads=host_threads, prepared=prepared, fiat_shamir="fast")
@@ -356,7 +356,7 @@ def main():
     lib = ctx.lib
     dev = Dev(lib)
     ledger0 = verifier.Ledger(); ledger0.import_records(records)
-    prepared = verifier.prepare_blobs(blobs)
+    prepared = verifier.prepare_blobs_pinned(blobs)      # the batch in one page-locked buffer, device layout: uploaded in place (zero-copy input)
     host_threads = max(1, ncpu // max(1, min(world, 8)))
 
     from xelis_he_b200 import distributed as xd
@@ -551,7 +551,7 @@ def main():
     strong = None
     if dist and not args.no_strong:
         sl0 = verifier.Ledger(); sl0.import_records(strong_records)
-        sprep = verifier.prepare_blobs(strong_blobs)
+        sprep = verifier.prepare_blobs_pinned(strong_blobs)
         for w in range(3):
             dt, code, idx, tm = e2e_step(b"strong-warm%d" % w, sprep, sl0)
             assert (code, idx) == (0, -1)

@@ -93,6 +93,12 @@ int32_t xheh_commit_taken(void* pending, void* ledger);
 size_t  xheh_export_taken(void* pending, uint8_t* out, size_t cap);
 void    xheh_drop_taken(void* pending);
 
+/* zero-copy input: a page-locked buffer in which the caller lays the batch out the way the device reads it -- the
+ * xtx1 blobs back to back, each padded to a multiple of 16 bytes.  When blobs[i] point into such a buffer in that order, the fast
+ * path uploads them where they are instead of gathering them into its staging buffer first. */
+void*   xheh_blob_arena_alloc(size_t bytes);
+void    xheh_blob_arena_free(void* arena);
+
 /* ---- Transaction::apply_without_verify over a list of transactions, in order (src/tx/verify.rs:545-619) ---- */
 int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n);
 

@@ -147,3 +147,34 @@ def test_factors_differ_between_shards(ctx):
         verifier.drop_taken(verifier.take_pending(ctx))
         recs.append((code, idx, s_enc, r_enc))
     assert all(r[0] == OK and r[2] == bytes(32) and r[3] == bytes(32) for r in recs)
+
+
+def test_device_side_record_and_joint_decision(ctx):
+    """xhe_batch_record_dev + xhe_shard_decide_dev (what bench.py times at N > 1): the records of two simulated ranks gathered on
+    the device give the same decision as distributed.decide on the host-side records"""
+    import torch
+    from xelis_he_b200 import distributed as xd, verifier
+    b = oracle.mint_transfers(63, 10, 1, 1, threads=4)
+    records = b.ledger().dump()
+    lib = ctx.lib
+    for blobs, want in ((list(b.blobs), (OK, -1)), (b.blobs[:7] + [_mut(b.blobs[7], 64 + 160 + 128)] + b.blobs[8:], None)):
+        gathered = torch.zeros(160, dtype=torch.uint8, device="cuda")
+        host_recs = []
+        for r, (lo, hi) in enumerate(((0, 5), (5, 10))):
+            code, idx, s_enc, r_enc, _ = verifier.verify_batch_shard(ctx, blobs, host_ledger(records), lo, hi, seed=SEED, threads=2, fiat_shamir="fast")
+            verifier.drop_taken(verifier.take_pending(ctx))
+            host_recs.append(xd.pack_local(code, idx, 0, s_enc, r_enc))
+            if want:      # honest shard: the device can build the record itself from the resident batch
+                assert lib.xhe_batch_record_dev(ctx.p, gathered.data_ptr() + 80 * r) == 0
+                ctx.sync()
+                assert bytes(gathered[80 * r:80 * r + 80].cpu().numpy())[:76] == host_recs[-1][:76]
+            else:
+                gathered[80 * r:80 * r + 80] = torch.frombuffer(bytearray(host_recs[-1]), dtype=torch.uint8).cuda()
+        out = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        assert lib.xhe_shard_decide_dev(ctx.p, gathered.data_ptr(), 2, out.data_ptr()) == 0
+        ctx.sync()
+        raw = bytes(out.cpu().numpy())
+        got = (int.from_bytes(raw[:4], "little", signed=True), int.from_bytes(raw[8:16], "little", signed=True))
+        assert got == xd.decide(host_recs, lambda encs: xd.sum_is_identity(ctx, encs))
+        if want:
+            assert got == want

@@ -70,11 +70,13 @@ MsmPlan make_plan(size_t n) {
   p.c = bc; p.W = (254 + bc - 1) / bc; p.B = 1u << (bc - 1); p.total_buckets = (size_t)p.W * p.B;
   // window groups: the reduction + Horner segment of a group overlaps the accumulation of the next one.  Small inputs are
   // pure latency (one launch wave per group at best): no split.
-  // A group's accumulation launch must still fill the machine for a few waves (measured: four launches of 183 blocks each
-  // took 2.2x the time of one launch of 732), so a group gets at least ~5 M list entries; 4 groups from 2^20 points up.
-  static const int g_env = getenv("XHE_MSM_GROUPS") ? atoi(getenv("XHE_MSM_GROUPS")) : 0;
-  int G = g_env > 0 ? g_env : (int)std::min<size_t>(4, std::max<size_t>(1, n * (size_t)p.W / ((size_t)5 << 20)));
-  G = std::max(1, std::min(G, MSM_MAX_GROUPS));
+  // Measured on B200 (profiles/r02_msm_sweep.md): splitting never paid -- a group's launch of the accumulation is a partial
+  // wave at 150 k points (four launches of 183 blocks took 2.2x one launch of 732), and at 2^20..2^22 the reduction kernels
+  // that run beside the next group's accumulation slow it by as much as they hide (2.43 ms at G = 1, 2.50-2.55 at G = 3..4).
+  // One group is the default; XHE_MSM_GROUPS keeps the experiment reproducible.
+  static const int g_env = getenv("XHE_MSM_GROUPS") ? atoi(getenv("XHE_MSM_GROUPS")) : 1;
+  int G = std::max(1, std::min(g_env, MSM_MAX_GROUPS));
+  if (n * (size_t)p.W < ((size_t)1 << 17)) G = 1;
   p.Wg = (p.W + G - 1) / G; p.G = (p.W + p.Wg - 1) / p.Wg;
   size_t o = 0;
   p.off_counts = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);

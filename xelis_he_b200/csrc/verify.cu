@@ -521,14 +521,16 @@ __global__ void __launch_bounds__(32) k_sum_encodings(const uint8_t* __restrict_
 // ---- sharded batches: record + joint decision on the device (what bench.py times inside `value` at N > 1) ---------------
 // record of one rank, 80 bytes: int32 code, int64 first failing tx (index into the whole batch, -1 none) at offset 4, sigma
 // partial encoding at 12, range partial encoding at 44, 4 bytes padding -- the layout distributed.pack_local produces
+// (the record's fields sit at 4-byte, not natural, alignment: everything moves as 32-bit words)
 __global__ void k_make_record(const uint32_t* __restrict__ results, uint8_t* __restrict__ rec) {
   const uint32_t t = threadIdx.x;
   if (t >= 32) return;
+  uint32_t* w32 = reinterpret_cast<uint32_t*>(rec);            // 20 words
   const uint32_t flags = results[98];
   // per-transaction anomalies are the host's to name (it re-decides that transaction): code 0xFF = "this shard needs its host"
-  if (t == 0) { int32_t code = (flags & 15u) ? 0xFF : ((flags & 16u) ? XHE_ERR_RANGE_PROOF : XHE_OK); long long idx = -1; memcpy(rec, &code, 4); memcpy(rec + 4, &idx, 8); rec[76] = rec[77] = rec[78] = rec[79] = 0; }
-  if (t < 8) { uint32_t w = results[t]; memcpy(rec + 12 + 4 * t, &w, 4); }
-  else if (t < 16) { uint32_t w = results[48 + (t - 8)]; memcpy(rec + 44 + 4 * (t - 8), &w, 4); }
+  if (t == 0) { w32[0] = (flags & 15u) ? 0xFFu : ((flags & 16u) ? (uint32_t)XHE_ERR_RANGE_PROOF : (uint32_t)XHE_OK); w32[1] = 0xFFFFFFFFu; w32[2] = 0xFFFFFFFFu; w32[19] = 0; }
+  if (t < 8) w32[3 + t] = results[t];
+  else if (t < 16) w32[11 + (t - 8)] = results[48 + (t - 8)];
 }
 // joint decision over the gathered records of all ranks, in the reference's order (distributed.decide): the first failing
 // transaction of the whole batch, then the sigma check on the SUM of the partials (src/proofs.rs:49-67), then a shard's
@@ -536,18 +538,28 @@ __global__ void k_make_record(const uint32_t* __restrict__ results, uint8_t* __r
 __global__ void __launch_bounds__(32) k_shard_decide(const uint8_t* __restrict__ recs, uint32_t world, uint8_t* __restrict__ out) {
   __shared__ uint32_t pts[32 * 16]; __shared__ uint32_t okw[32];
   int32_t code_out = XHE_OK; long long idx_out = -1; bool per_tx = false, other = false, rp_struct = false;
+  const uint32_t* w32 = reinterpret_cast<const uint32_t*>(recs);
   for (uint32_t r = 0; r < world; r++) {
-    int32_t code; long long idx; memcpy(&code, recs + 80 * (size_t)r, 4); memcpy(&idx, recs + 80 * (size_t)r + 4, 8);
+    const int32_t code = (int32_t)w32[20 * r]; const long long idx = (long long)((unsigned long long)w32[20 * r + 1] | ((unsigned long long)w32[20 * r + 2] << 32));
     if (code != XHE_OK && idx >= 0) { if (!per_tx || idx < idx_out) { idx_out = idx; code_out = code; } per_tx = true; }
     else if (code == XHE_ERR_RANGE_PROOF) rp_struct = true;
     else if (code != XHE_OK && code != XHE_ERR_GENERIC_PROOF && !other && !per_tx) { other = true; code_out = code; idx_out = idx; }
   }
   bool ident[2] = {true, true};
   for (int which = 0; which < 2; which++) {
+    // honest shards each report the identity (32 zero bytes): the sum needs no arithmetic then (distributed.sum_is_identity)
+    uint32_t nz = 0;
+    for (uint32_t i = threadIdx.x; i < world; i += 32) for (int q = 0; q < 8; q++) nz |= w32[20 * i + 3 + 8 * which + q];
+    if (!__any_sync(0xffffffffu, nz != 0)) continue;
     ge acc = ge_identity(); bool all_ok = true;
     for (uint32_t base = 0; base < world; base += 32) {
       uint32_t i = base + threadIdx.x; ge_aff a; bool ok = true;
-      if (i < world) { ok = decode_words(a, recs + 80 * (size_t)i + 12 + 32 * which); for (int q = 0; q < 8; q++) { pts[16 * threadIdx.x + q] = a.x.v[q]; pts[16 * threadIdx.x + 8 + q] = a.y.v[q]; } }
+      if (i < world) {
+        uint8_t e32[32];
+        for (int q = 0; q < 8; q++) { uint32_t w = w32[20 * i + 3 + 8 * which + q]; e32[4 * q] = (uint8_t)w; e32[4 * q + 1] = (uint8_t)(w >> 8); e32[4 * q + 2] = (uint8_t)(w >> 16); e32[4 * q + 3] = (uint8_t)(w >> 24); }
+        ok = ristretto_decode(a, e32);
+        for (int q = 0; q < 8; q++) { pts[16 * threadIdx.x + q] = a.x.v[q]; pts[16 * threadIdx.x + 8 + q] = a.y.v[q]; }
+      }
       okw[threadIdx.x] = ok ? 1u : 0u;
       __syncwarp();
       if (threadIdx.x == 0) for (uint32_t k = 0; k < 32 && base + k < world; k++) {
@@ -564,7 +576,8 @@ __global__ void __launch_bounds__(32) k_shard_decide(const uint8_t* __restrict__
     if (!ident[0]) { code_out = XHE_ERR_GENERIC_PROOF; idx_out = -1; }
     else if (rp_struct || !ident[1]) { code_out = XHE_ERR_RANGE_PROOF; idx_out = -1; }
   }
-  memcpy(out, &code_out, 4); memset(out + 4, 0, 4); memcpy(out + 8, &idx_out, 8);
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+  o32[0] = (uint32_t)code_out; o32[1] = 0; o32[2] = (uint32_t)(unsigned long long)idx_out; o32[3] = (uint32_t)((unsigned long long)idx_out >> 32);
 }
 
 inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }

@@ -596,14 +596,29 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   for (size_t q = 0; q < F.prev.size(); q++) if (F.prev[q] <= -RB && F.prev[q] > -XHE_OP_PLUS_AMOUNT) F.prev[q] = -(1 + (long long)n_a_end + (-F.prev[q] - RB));
   for (size_t pos : rb_terms) F.terms[pos] = (F.terms[pos] & 0x80000000u) | (n_a_end + (F.terms[pos] & 0x7fffffffu));
   double t2 = now_ms();
-  F.blob.resize(off);
-  parallel_for(n_run, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) memcpy(&F.blob[F.off[j]], blobs[lo + j], lens[lo + j]); });
+  // Zero-copy upload: when the caller's transactions already sit back to back (16-byte aligned, the layout
+  // the device reads) in ONE page-locked buffer -- xheh_blob_arena_* builds such a buffer -- the DMA reads them where they
+  // are; otherwise they are gathered into this context's pinned staging buffer first.
+  const uint8_t* blob_base = nullptr;
+  {
+    bool contiguous = (((uintptr_t)blobs[lo]) & 15) == 0;
+    for (size_t j = 0; contiguous && j + 1 < n_run; j++) contiguous = blobs[lo + j + 1] == blobs[lo + j] + ((lens[lo + j] + 15) & ~(size_t)15);
+    if (contiguous) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, blobs[lo]) == cudaSuccess && at.type == cudaMemoryTypeHost) blob_base = blobs[lo]; else cudaGetLastError();
+    }
+  }
+  if (!blob_base) {
+    F.blob.resize(off);
+    parallel_for(n_run, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) memcpy(&F.blob[F.off[j]], blobs[lo + j], lens[lo + j]); });
+    blob_base = F.blob.data();
+  }
   double t3 = now_ms();
   xhe_batch xb; memset(&xb, 0, sizeof xb); xb.struct_size = (uint32_t)sizeof xb;
   xb.n_tx = (uint32_t)n_run; xb.n_points = n_points; xb.n_sigs = (uint32_t)n_run;
   xb.n_ops = (uint32_t)F.prev.size(); xb.op_prev = (const int64_t*)F.prev.data(); xb.op_term_off = F.term_off.data(); xb.op_terms = F.terms.data(); xb.op_amount = F.amount.data(); xb.max_chain = max_chain;
   xb.n_eq = n_eq; xb.n_val = n_val; xb.n_rp = (uint32_t)n_run; xb.rp_m = F.rp_m.data(); xb.rp_point_off = F.rp_pt_off.data(); xb.rp_chal_off = F.rp_ch_off.data();
-  xb.fs_blobs = F.blob.data(); xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32); xb.fs_index_base = lo;
+  xb.fs_blobs = blob_base; xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32); xb.fs_index_base = lo;
   xb.layout_on_device = 1; xb.n_region_b = n_rb; xb.region_b = F.region_b.data();
   PinnedVec<uint8_t>& op_out = F.op_out; op_out.n = 0; op_out.reserve(32 * (size_t)xb.n_ops + 64); op_out.n = 32 * (size_t)xb.n_ops;
   PinnedVec<uint8_t>& txf = F.tx_flags; txf.n = 0; txf.reserve(n_run + 64); txf.n = n_run;
@@ -1165,6 +1180,10 @@ int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(
 void* xheh_take_pending(xhe_ctx* ctx) { return take_pending(ctx); }
 int32_t xheh_commit_taken(void* pending, void* ledger) { if (!pending) return XHE_E_ARG; Pending* P = (Pending*)pending; int rc = apply_pending(*P, *(MockLedger*)ledger); delete P; return rc; }
 void xheh_drop_taken(void* pending) { delete (Pending*)pending; }
+// a page-locked buffer for a batch's transactions laid out the way the device reads them (back to back, each padded to 16
+// bytes): transactions that live there are uploaded without the gather into staging (zero-copy input)
+void* xheh_blob_arena_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void xheh_blob_arena_free(void* p) { if (p) cudaFreeHost(p); }
 // the balance updates a detached shard-mode batch holds, as 128-byte records (account, asset, new ciphertext) in update order
 size_t xheh_export_taken(void* pending, uint8_t* out, size_t cap) { return export_pending(pending, out, cap); }
 // apply such records to a ledger (a peer rank's updates): update_account_balance per record, in order

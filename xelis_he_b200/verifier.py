@@ -120,6 +120,37 @@ class _Blobs:
         self.n = n
 
 
+class _PinnedBlobs:
+    """the batch in ONE page-locked buffer, laid out as the device reads it (blobs back to back, padded to 16 bytes): the fast
+    path uploads it in place -- zero-copy input.  Same interface as _Blobs."""
+
+    def __init__(self, blobs):
+        lib = _lib()
+        lib.xheh_blob_arena_alloc.restype = C.c_void_p; lib.xheh_blob_arena_alloc.argtypes = [C.c_size_t]
+        lib.xheh_blob_arena_free.argtypes = [C.c_void_p]
+        n = len(blobs)
+        offs, off = [], 0
+        for b in blobs:
+            offs.append(off); off += (len(b) + 15) & ~15
+        self.lib, self.base = lib, lib.xheh_blob_arena_alloc(max(off, 16))
+        if not self.base:
+            raise XheError(-3, "page-locked allocation failed")
+        buf = (C.c_uint8 * max(off, 16)).from_address(self.base)
+        mv = memoryview(buf).cast("B")
+        for b, o in zip(blobs, offs):
+            mv[o:o + len(b)] = b
+        self.ptrs = (C.c_void_p * max(n, 1))(*[self.base + o for o in offs])
+        self.lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+        self.n = n
+
+    def __del__(self):
+        try:
+            if self.base:
+                self.lib.xheh_blob_arena_free(self.base); self.base = None
+        except Exception:
+            pass
+
+
 def verify_batch(ctx, blobs, ledger, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False):
     """Transaction::verify_batch.  Returns (code, first_failing_tx, timings dict); code 0 = Ok, >0 = verdicts (ERR_NAMES).
     fiat_shamir = "host" (Merlin transcripts on host threads, north_star's split), "device"  or "fast"
@@ -225,3 +256,4 @@ def apply_without_verify(ctx, blobs, ledger):
 
 
 prepare_blobs = _Blobs
+prepare_blobs_pinned = _PinnedBlobs
