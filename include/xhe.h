@@ -34,6 +34,7 @@ enum {
 };
 
 typedef struct xhe_ctx xhe_ctx;
+struct xhe_ledger;
 
 /* Replaces the lazy_statics H, BP_GENS = BulletproofGens::new(64, 512), PC_GENS (src/elgamal.rs:16-24,
  * src/proofs.rs:19-22): builds G/H tables and the 2*64*party_capacity generator table on `device`. */
@@ -84,6 +85,7 @@ int32_t xhe_msm_dev(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, si
  * for the dud commitments of src/tx/verify.rs:466-475).  Indices >= n_points address balance-chain outputs
  * (n_points + j = output of op j). ----------------------------------------------------------------------------------- */
 #define XHE_OP_PLUS_AMOUNT (1LL << 50)
+#define XHE_OP_FROM_LEDGER (1LL << 49)
 typedef struct xhe_batch {
   uint32_t struct_size;            /* = sizeof(xhe_batch): a caller compiled against another layout is refused with XHE_E_ARG */
   uint32_t n_tx;
@@ -95,7 +97,9 @@ typedef struct xhe_batch {
    * and prev_j < 0 encodes the initial balance point -(1+index).  One op per ciphertext half (commitment / handle).
    * prev_j = -(1+index) - XHE_OP_PLUS_AMOUNT makes the op ADD amount_j*G instead: with index 0 (the identity) and
    * unsigned terms that is one half of get_sender_output_ct (src/tx/verify.rs:107-144), the ciphertext the reference
-   * hands to BlockchainVerificationState::set_output_ciphertext (src/tx/verify.rs:339-340, 582). */
+   * hands to BlockchainVerificationState::set_output_ciphertext (src/tx/verify.rs:339-340, 582).
+   * prev_j = -(1+p) - XHE_OP_FROM_LEDGER takes the initial balance from point p of the device-resident ledger `ledger` below
+   * (p = 2 * slot for the commitment, 2 * slot + 1 for the handle): nothing is uploaded or decompressed for it. */
   uint32_t n_ops; const int64_t* op_prev; const uint32_t* op_term_off /* n_ops+1 */; const uint32_t* op_terms /* bit 31 = subtract */;
   const uint64_t* op_amount; uint32_t max_chain /* longest chain length (>= 1) */;
   /* CommitmentEqProof::pre_verify (src/proofs.rs:134-211): points P_src,Y0,D_src,C_src,Y1,C_dst,Y2; scalars z_s,z_x,z_r,c,w,bf */
@@ -124,6 +128,8 @@ typedef struct xhe_batch {
    * + first balance-op index; the per-tx point layout is documented at k_layout) and the state-derived encodings
    * (initial balance halves) region_b, placed at point indices [n_points - n_region_b, n_points). */
   uint32_t layout_on_device; uint32_t n_region_b; const uint8_t* region_b;
+  /* OPTIONAL device-resident ledger (xhe_ledger_* below): the table that XHE_OP_FROM_LEDGER ops read */
+  const struct xhe_ledger* ledger;
 } xhe_batch;
 
 typedef struct xhe_verdict {
@@ -190,6 +196,16 @@ int32_t xhe_ledger_update(xhe_ledger* ledger, const uint8_t* keys, const uint8_t
 int32_t xhe_ledger_update_dense_dev(xhe_ledger* ledger, const void* d_delta_niels_planar, const void* d_sub /* size bytes */);
 /* compressed export on demand (what get_account_balance returns): found[i] (optional) = 0 for an unknown key (64 zero bytes out) */
 int32_t xhe_ledger_export(xhe_ledger* ledger, const uint8_t* keys, size_t n, uint8_t* out_cts, uint8_t* found);
+/* After an ACCEPTED batch that is still resident on its ctx (xhe_verify_batch / xhe_batch_run): write the outputs of balance-chain
+ * ops ops[i] -- commitment op, its handle op is ops[i] + 1 -- into slots slots[i], in order, on the device (asynchronous on the
+ * ctx stream; no balance crosses the bus in either direction).  This is update_account_balance (src/tx/verify.rs:329-336,367-374)
+ * for a state whose balances live in the ledger. */
+int32_t xhe_ledger_commit_batch(xhe_ledger* ledger, xhe_ctx* ctx, const uint32_t* slots, const uint32_t* ops, size_t n);
+/* slot of a key (0xFFFFFFFF: unknown, or stored ciphertext undecodable) */
+uint32_t xhe_ledger_slot(const xhe_ledger* ledger, const uint8_t key64[64]);
+/* device-side snapshot / restore of the whole table (tests and benchmarks that re-verify the same batch) */
+int32_t xhe_ledger_snapshot(xhe_ledger* ledger);
+int32_t xhe_ledger_restore(xhe_ledger* ledger);
 /* the table itself for callers that launch their own kernels: 4 planes X, Y, Z, T of *plane_stride_points points x 32 bytes;
  * slot s owns points 2s (commitment) and 2s + 1 (handle) */
 void*   xhe_ledger_device_table(const xhe_ledger* ledger, size_t* plane_stride_points);

@@ -68,6 +68,17 @@ void    xheh_ledger_record_outputs(void* ledger, int on);
 size_t  xheh_ledger_outputs_size(void* ledger);
 size_t  xheh_ledger_export_outputs(void* ledger, uint8_t* out, size_t cap);
 
+/* ---- device-resident state: the same interface over an xhe_ledger on ctx's device.  A handle returned here is
+ * accepted wherever a `ledger` is (verify, apply, commit): the fast path then reads balances from the device table and commits the
+ * accepted updates there -- no balance crosses the bus; other paths see the compressed view (export on demand). ---- */
+void*   xheh_dledger_new(xhe_ctx* ctx, size_t capacity);
+void    xheh_dledger_free(void* dledger);
+int32_t xheh_dledger_import(void* dledger, const uint8_t* records, size_t n);        /* pk[32] asset[32] ct[64]; nonce 0 for new accounts */
+size_t  xheh_dledger_export(void* dledger, uint8_t* out, size_t cap);                /* every balance, same record layout (compressed on demand) */
+void    xheh_dledger_set_multisig(void* dledger, const uint8_t pk[32], const uint8_t* signers, size_t n, uint8_t threshold);
+int32_t xheh_dledger_snapshot(void* dledger);                                        /* device-side copy of the table ... */
+int32_t xheh_dledger_restore(void* dledger);                                         /* ... and back (re-verifying the same batch) */
+
 /* ---- Transaction::verify_batch (src/tx/verify.rs:487-517) ---------------------------------------------------------
  * flags: bit 0 device-side Fiat-Shamir; bit 1 shard mode (partial64 != NULL: no identity decision here, the
  * partial sigma / range encodings are returned and the state updates are held back); bit 2 fast path (device-side layout,

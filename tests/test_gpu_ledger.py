@@ -150,3 +150,48 @@ def test_generator_table_matches_survey_appendix_b():
             for i in range(64):
                 assert enc[32 * (2 + which * 128 + party * 64 + i):][:32] == oracle.from_uniform(stream[64 * i:64 * i + 64])
     c.close()
+
+
+def test_verify_batch_on_a_device_resident_state():
+    """BlockchainVerificationState backed by the device ledger: the fast path reads the balances from the table and commits the
+    accepted updates there.  After every scenario the exported (compressed) state equals the oracle's ledger byte for byte; a
+    rejected batch leaves the table untouched; the other paths (host transcripts, multisig) see the same state through export."""
+    import scenarios
+    import xelis_he_b200 as xhe
+    from xelis_he_b200 import verifier
+    ctx = xhe.Ctx(0, party_capacity=8)
+    try:
+        for mint in (lambda: oracle.mint_transfers(71, 40, 1, 1, threads=4), lambda: oracle.mint_transfers(72, 12, 2, 6, threads=4), lambda: oracle.mint_chain(73, 20, 1)):
+            b = mint()
+            ol = b.ledger(); assert oracle.verify_batch(b.blobs, ol) == (0, -1)
+            dl = verifier.DeviceLedgerState(ctx, 4096); dl.import_records(b.ledger().dump())
+            assert dl.dump() == sorted(b.ledger().dump())
+            # a tampered batch first: rejected like the oracle says, table untouched
+            bad = list(b.blobs); t = bytearray(bad[3]); t[-1] ^= 1; bad[3] = bytes(t)
+            assert verifier.verify_batch(ctx, bad, dl, seed=b"dl", fiat_shamir="fast")[:2] == oracle.verify_batch(bad, b.ledger())
+            assert dl.dump() == sorted(b.ledger().dump())
+            code, idx, tm = verifier.verify_batch(ctx, b.blobs, dl, seed=b"dl", fiat_shamir="fast")
+            assert (code, idx) == (0, -1) and tm["fast_path"]
+            assert dl.dump() == sorted(ol.dump())
+            # snapshot / restore (what the benchmark uses to re-verify the same batch)
+            dl2 = verifier.DeviceLedgerState(ctx, 4096); dl2.import_records(b.ledger().dump()); dl2.snapshot()
+            for _ in range(2):
+                assert verifier.verify_batch(ctx, b.blobs, dl2, seed=b"dl", fiat_shamir="fast")[:2] == (0, -1)
+                assert dl2.dump() == sorted(ol.dump())
+                dl2.restore()
+            assert dl2.dump() == sorted(b.ledger().dump())
+            # the exact path on the same state (compressed view): same verdict, same final bytes
+            dl3 = verifier.DeviceLedgerState(ctx, 4096); dl3.import_records(b.ledger().dump())
+            assert verifier.verify_batch(ctx, b.blobs, dl3, seed=b"dl", fiat_shamir="host")[:2] == (0, -1)
+            assert dl3.dump() == sorted(ol.dump())
+            for d in (dl, dl2, dl3):
+                d.close()
+        # the reference's realistic_test (dependent transactions, two assets) and a second batch on the advanced state
+        w, txs, _ = scenarios.realistic_world()
+        ol = w.ledger.clone(); assert oracle.verify_batch(txs, ol) == (0, -1)
+        dl = verifier.DeviceLedgerState(ctx, 64); dl.import_records(w.records)
+        assert verifier.verify_batch(ctx, txs, dl, seed=b"dl", fiat_shamir="fast")[:2] == (0, -1)
+        assert dl.dump() == sorted(ol.dump())
+        dl.close()
+    finally:
+        ctx.close()

@@ -83,6 +83,7 @@ extern "C" void xhe_ctx_destroy(xhe_ctx* ctx) {
   if (ctx->h_res) cudaFreeHost(ctx->h_res);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->d_commit) cudaFree(ctx->d_commit);
   for (auto& st : ctx->aux) if (st) cudaStreamDestroy(st);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);

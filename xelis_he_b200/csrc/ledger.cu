@@ -20,6 +20,7 @@ struct xhe_ledger {
   xhe_host::FlatTable<64, uint32_t> index;
   std::vector<uint8_t> slot_ok;         // 0 for a slot whose stored ciphertext did not decode
   // grow-only staging
+  uint32_t* d_snap = nullptr;           // snapshot of the table (xhe_ledger_snapshot)
   void* d_tmp = nullptr; size_t tmp_bytes = 0;
   void* h_tmp = nullptr; size_t h_bytes = 0;
 };
@@ -89,7 +90,7 @@ extern "C" int32_t xhe_ledger_create(xhe_ctx* ctx, size_t capacity, xhe_ledger**
 extern "C" void xhe_ledger_destroy(xhe_ledger* l) {
   if (!l) return;
   cudaSetDevice(l->ctx->device);
-  cudaFree(l->d_bal); if (l->d_tmp) cudaFree(l->d_tmp); if (l->h_tmp) cudaFreeHost(l->h_tmp);
+  cudaFree(l->d_bal); if (l->d_snap) cudaFree(l->d_snap); if (l->d_tmp) cudaFree(l->d_tmp); if (l->h_tmp) cudaFreeHost(l->h_tmp);
   delete l;
 }
 extern "C" size_t xhe_ledger_size(const xhe_ledger* l) { return l ? l->index.size() : 0; }
@@ -179,6 +180,25 @@ extern "C" int32_t xhe_ledger_export(xhe_ledger* l, const uint8_t* keys, size_t 
   XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
   for (size_t i = 0; i < n; i++) { if (fnd[i]) memcpy(out_cts + 64 * i, h + 64 * i, 64); else memset(out_cts + 64 * i, 0, 64); }
   if (found) memcpy(found, fnd.data(), n);
+  return XHE_OK;
+}
+
+extern "C" uint32_t xhe_ledger_slot(const xhe_ledger* l, const uint8_t key64[64]) {
+  if (!l || !key64) return 0xFFFFFFFFu;
+  const uint32_t* v = l->index.find(key64);
+  return (v && l->slot_ok[*v]) ? *v : 0xFFFFFFFFu;
+}
+extern "C" int32_t xhe_ledger_snapshot(xhe_ledger* l) {
+  if (!l) return XHE_E_ARG;
+  xhe_ctx* ctx = l->ctx; const size_t bytes = 4 * 2 * l->cap * 32;
+  if (!l->d_snap) XHE_CUDA_OK(ctx, cudaMalloc(&l->d_snap, bytes));
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(l->d_snap, l->d_bal, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return XHE_OK;
+}
+extern "C" int32_t xhe_ledger_restore(xhe_ledger* l) {
+  if (!l || !l->d_snap) return XHE_E_ARG;
+  xhe_ctx* ctx = l->ctx;
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(l->d_bal, l->d_snap, 4 * 2 * l->cap * 32, cudaMemcpyDeviceToDevice, ctx->stream));
   return XHE_OK;
 }
 

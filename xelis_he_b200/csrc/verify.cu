@@ -21,6 +21,7 @@ using namespace xhe;
 
 int32_t xhe_launch_msm_ex(xhe_ctx* ctx, const void* d_scalars, const void* d_niels, size_t n, void* d_ws, size_t ws_bytes, void* d_out_enc, void* d_is_id, void* d_out_ext, void* d_bad_flag);
 extern "C" size_t xhe_msm_workspace_bytes(const xhe_ctx*, size_t n);
+extern "C" void* xhe_ledger_device_table(const xhe_ledger* l, size_t* plane_stride_points);
 int32_t xhe_launch_fiat_shamir(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, const uint8_t* d_seed, unsigned long long index_base,
                                uint32_t* d_eq_sc, uint32_t* d_val_sc, uint32_t* d_rp_sc, uint32_t* d_rp_chal, const uint32_t* d_rp_m);
 int32_t xhe_launch_sig_hash_prefix(xhe_ctx* ctx, const uint8_t* d_blobs, const unsigned long long* d_off, const uint32_t* d_plan, uint32_t plan_stride, uint32_t n_tx, unsigned long long* d_state);
@@ -146,16 +147,27 @@ __global__ void __launch_bounds__(128) k_op_jump(const uint32_t* __restrict__ ac
   if (p >= 0) { ge b; ld_ge(b, acc_in + 32 * (size_t)p); a = ge_add(a, b); p = ptr_in[p]; }
   st_ge(acc_out + 32 * (size_t)j, a); ptr_out[j] = p;
 }
-// out_j = initial balance half + accumulated deltas; emit encoding, affine and affine-Niels (MSM operand) forms
+// out_j = initial balance half + accumulated deltas; emit encoding, affine and affine-Niels (MSM operand) forms.  The initial
+// half is a decompressed point of the batch (affine), or -- XHE_OP_FROM_LEDGER -- a point of the device-resident ledger
+// (extended, coordinate-planar: ledger.cu), in which case nothing was uploaded or decompressed for it.
 __global__ void __launch_bounds__(128) k_op_finish(const uint32_t* __restrict__ acc, const long long* __restrict__ ptr, uint32_t n_ops, uint32_t n_points,
-                                                   uint32_t* __restrict__ pt_aff, uint32_t* __restrict__ pt_niels, uint8_t* __restrict__ out_enc) {
+                                                   uint32_t* __restrict__ pt_aff, uint32_t* __restrict__ pt_niels, uint8_t* __restrict__ out_enc,
+                                                   const uint32_t* __restrict__ ledger_tab, size_t ledger_stride) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_ops) return;
-  long long p = ptr[j];          // always < 0 after enough rounds: -(1 + initial point index)
-  uint32_t init = (uint32_t)(-(p + 1));
-  ge_aff ia; ld_fe(ia.x, pt_aff + 16 * (size_t)init); ld_fe(ia.y, pt_aff + 16 * (size_t)init + 8);
+  long long p = ptr[j];          // always < 0 after enough rounds: -(1 + initial point index) [- flags]
+  const unsigned long long v = (unsigned long long)(-(p + 1));
   ge a; ld_ge(a, acc + 32 * (size_t)j);
-  ge r = ge_add(ge_from_affine(ia), a);
+  ge r;
+  if (v & (unsigned long long)XHE_OP_FROM_LEDGER) {
+    const size_t lp = (size_t)(v & 0xFFFFFFFFull);
+    ge b; ld_fe(b.X, ledger_tab + 8 * lp); ld_fe(b.Y, ledger_tab + 8 * (ledger_stride + lp)); ld_fe(b.Z, ledger_tab + 8 * (2 * ledger_stride + lp)); ld_fe(b.T, ledger_tab + 8 * (3 * ledger_stride + lp));
+    r = ge_add(b, a);
+  } else {
+    uint32_t init = (uint32_t)(v & 0xFFFFFFFFull);
+    ge_aff ia; ld_fe(ia.x, pt_aff + 16 * (size_t)init); ld_fe(ia.y, pt_aff + 16 * (size_t)init + 8);
+    r = ge_add(ge_from_affine(ia), a);
+  }
   // the encode's inverse square root also yields 1/Z (z_inv = den1*den2*T = T/(XY) = 1/Z) whenever X*Y != 0; the points
   // with X*Y == 0 (the four-element identity coset) take the explicit inversion
   ge_aff ra;
@@ -164,6 +176,17 @@ __global__ void __launch_bounds__(128) k_op_finish(const uint32_t* __restrict__ 
   size_t slot = (size_t)n_points + j;
   st_fe(pt_aff + 16 * slot, ra.x); st_fe(pt_aff + 16 * slot + 8, ra.y);
   st_niels(pt_niels + 24 * slot, niels_from_affine(ra));
+}
+// update_account_balance for a device-resident ledger: the (affine) outputs of the ops become the new resident balances
+__global__ void __launch_bounds__(128) k_ledger_commit(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ ops, uint32_t n, uint32_t n_points, const uint32_t* __restrict__ pt_aff,
+                                                       uint32_t* __restrict__ tab, size_t stride) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per point: 2 per update
+  if (t >= 2 * n) return;
+  const uint32_t i = t >> 1, half = t & 1;
+  const size_t src = (size_t)n_points + ops[i] + half, dst = 2 * (size_t)slots[i] + half;
+  ge_aff a; ld_fe(a.x, pt_aff + 16 * src); ld_fe(a.y, pt_aff + 16 * src + 8);
+  ge e = ge_from_affine(a);
+  st_fe(tab + 8 * dst, e.X); st_fe(tab + 8 * (stride + dst), e.Y); st_fe(tab + 8 * (2 * stride + dst), e.Z); st_fe(tab + 8 * (3 * stride + dst), e.T);
 }
 
 // ---- sigma proof weights ----------------------------------------------------------------------------------------------
@@ -681,6 +704,25 @@ extern "C" int32_t xhe_shard_decide_dev(xhe_ctx* ctx, const void* d_records, uin
   return XHE_OK;
 }
 
+// device-resident ledger: commit the outputs of an accepted, still resident batch (ledger.cu owns the table)
+extern "C" int32_t xhe_ledger_commit_batch(xhe_ledger* ledger, xhe_ctx* ctx, const uint32_t* slots, const uint32_t* ops, size_t n) {
+  if (!ledger || !ctx || !ctx->resident || (n && (!slots || !ops))) return XHE_E_ARG;
+  if (!n) return XHE_OK;
+  DeviceBatch& D = *(DeviceBatch*)ctx->resident;
+  for (size_t i = 0; i < n; i++) if (ops[i] + 1 >= D.h.n_ops) { ctx->err = "ledger commit: op index out of range"; return XHE_E_ARG; }
+  size_t stride = 0; uint32_t* tab = (uint32_t*)xhe_ledger_device_table(ledger, &stride);
+  // slots / ops travel through the ctx's pinned staging (grow-only)
+  const size_t bytes = 8 * n;
+  if (ctx->pinned_bytes < bytes) { if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->pinned_bytes = 0; XHE_CUDA_OK(ctx, cudaHostAlloc(&ctx->h_pinned, 2 * bytes, cudaHostAllocDefault)); ctx->pinned_bytes = 2 * bytes; }
+  if (ctx->commit_bytes < bytes) { if (ctx->d_commit) cudaFree(ctx->d_commit); ctx->d_commit = nullptr; ctx->commit_bytes = 0; XHE_CUDA_OK(ctx, cudaMalloc(&ctx->d_commit, 2 * bytes)); ctx->commit_bytes = 2 * bytes; }
+  XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, ctx->stream));       // the staging buffer may still feed the previous commit
+  memcpy(ctx->h_pinned, slots, 4 * n); memcpy((uint8_t*)ctx->h_pinned + 4 * n, ops, 4 * n);
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_commit, ctx->h_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_ledger_commit<<<nblk(2 * n, 128), 128, 0, ctx->stream>>>((const uint32_t*)ctx->d_commit, (const uint32_t*)ctx->d_commit + n, (uint32_t)n, D.h.n_points, D.d_aff, tab, stride); XHE_LAUNCHED(ctx);
+  XHE_CUDA_OK(ctx, cudaGetLastError());
+  return XHE_OK;
+}
+
 // stage 1: allocate from the ctx arena and upload the host description
 extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   if (!ctx || !b) return XHE_E_ARG;
@@ -918,7 +960,8 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
       k_op_jump<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, acc_nxt, ptr_nxt); XHE_LAUNCHED(ctx);
       std::swap(acc_cur, acc_nxt); std::swap(ptr_cur, ptr_nxt);
     }
-    k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, D.d_aff, D.d_niels, D.d_op_out); XHE_LAUNCHED(ctx);
+    { size_t lstride = 0; const uint32_t* ltab = b->ledger ? (const uint32_t*)xhe_ledger_device_table(b->ledger, &lstride) : nullptr;
+      k_op_finish<<<nblk(b->n_ops, 128), 128, 0, st>>>(acc_cur, ptr_cur, b->n_ops, b->n_points, D.d_aff, D.d_niels, D.d_op_out, ltab, lstride); XHE_LAUNCHED(ctx); }
   }
   // ---- range proofs.  Their MSM is computed as two partial sums: the proofs' own points (A, S, T1, T2, L_j, R_j, V_j --
   // scalars known after k_rp_prep) on s_dyn, beside the static-generator weights (k_rp_gens) and the small MSM over the
@@ -1062,7 +1105,7 @@ extern "C" int32_t xhe_sig_r(xhe_ctx* ctx, const uint8_t* s, const uint8_t* e, c
 // to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
 // kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
 size_t xhe_preload_verify() {      // returns the largest per-thread local-memory frame among them
-  const void* ks[] = {(const void*)k_build_tab8, (const void*)k_sig_r, (const void*)k_op_delta, (const void*)k_op_jump, (const void*)k_op_finish, (const void*)k_sigma_weights, (const void*)k_reduce_scalars, (const void*)k_rp_prep, (const void*)k_pow2_table, (const void*)k_rp_gens, (const void*)k_fb_build, (const void*)k_fb_digits, (const void*)k_fb_buckets, (const void*)k_fb_reduce, (const void*)k_gather_niels, (const void*)k_copy_words, (const void*)k_combine, (const void*)k_combine_out, (const void*)k_sum_encodings, (const void*)k_copy_bytes, (const void*)k_make_record, (const void*)k_shard_decide};
+  const void* ks[] = {(const void*)k_build_tab8, (const void*)k_sig_r, (const void*)k_op_delta, (const void*)k_op_jump, (const void*)k_op_finish, (const void*)k_sigma_weights, (const void*)k_reduce_scalars, (const void*)k_rp_prep, (const void*)k_pow2_table, (const void*)k_rp_gens, (const void*)k_fb_build, (const void*)k_fb_digits, (const void*)k_fb_buckets, (const void*)k_fb_reduce, (const void*)k_gather_niels, (const void*)k_copy_words, (const void*)k_combine, (const void*)k_combine_out, (const void*)k_sum_encodings, (const void*)k_copy_bytes, (const void*)k_make_record, (const void*)k_shard_decide, (const void*)k_ledger_commit};
   cudaFuncAttributes a; size_t mx = 0;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
   return mx;

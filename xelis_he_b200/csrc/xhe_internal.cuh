@@ -25,6 +25,7 @@ struct xhe_ctx {
   void* d_fb_tab = nullptr; void* d_fb_dig = nullptr; void* d_fb_bsum = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;       // grow-only device scratch for host-buffer entry points
   void* h_pinned = nullptr; size_t pinned_bytes = 0;         // grow-only pinned staging
+  void* d_commit = nullptr; size_t commit_bytes = 0;         // slots / ops of xhe_ledger_commit_batch
   // optional CUDA-event timing of the main kernels (bench.py roofline): accumulated since the last reset
   bool timing = false;
   bool serial = false;                                        // diagnostics: run the pipelines of xhe_batch_run back to back on one stream

@@ -137,7 +137,7 @@ inline bool apply_update(VerificationState& state, const uint8_t* account, const
   return output ? state.set_output_ciphertext(account, asset, ct) : state.update_account_balance(account, asset, ct, role);
 }
 const long long OUT_PREV_C = -1 - XHE_OP_PLUS_AMOUNT, OUT_PREV_D = -1;   // output-ciphertext ops start from the identity (point 0); the commitment half ADDS amount*G
-struct Chain { long last_c = -1, last_d = -1; uint32_t length = 0; };
+struct Chain { long last_c = -1, last_d = -1; uint32_t length = 0; uint32_t slot = 0xFFFFFFFFu; /* device-resident ledger slot of this key, if any */ };
 
 struct TxPlan {
   uint32_t check_begin = 0, check_end = 0;
@@ -460,10 +460,18 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   F.rp_pt_off[0] = 0; F.rp_ch_off[0] = 0;
   std::vector<Bytes32> signers;
   std::vector<size_t> rb_terms;                // positions in F.terms that hold a region-B slot (foreign ciphertext points)
+  // a state whose balances live on this context's device: chains start from ledger slots, nothing is uploaded
+  // or decompressed for them, and the accepted outputs go back into the slots on the device.  (Shard mode keeps the compressed
+  // route: its updates wait for the cross-rank decision while the context moves on to the next batch.)
+  xhe_ledger* dl = opt.partial_out ? nullptr : state.device_ledger();
   auto touch = [&](const uint8_t* account, const uint8_t* asset, Role role, long long* pc, long long* pd) -> Chain* {
     Ct64 kk = MockLedger::key(account, asset); bool fresh = false;
     Chain& c = *chains.insert(kk.data(), &fresh);
-    if (fresh) {
+    if (fresh && dl) {
+      uint32_t slot;
+      if (!state.device_slot(account, asset, &slot)) return nullptr;
+      c.last_c = -(1 + 2 * (long long)slot) - XHE_OP_FROM_LEDGER; c.last_d = -(1 + 2 * (long long)slot + 1) - XHE_OP_FROM_LEDGER; c.length = 0; c.slot = slot;
+    } else if (fresh) {
       uint8_t ct[64];
       if (!state.get_account_balance(account, asset, role, ct)) return nullptr;
       long long j = (long long)(F.region_b.size() / 32); F.region_b.append(ct, 64);
@@ -593,7 +601,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   }
   F.off[n_run] = off;
   const uint32_t n_a_end = pt, n_rb = (uint32_t)(F.region_b.size() / 32), n_points = n_a_end + n_rb;
-  for (size_t q = 0; q < F.prev.size(); q++) if (F.prev[q] <= -RB && F.prev[q] > -XHE_OP_PLUS_AMOUNT) F.prev[q] = -(1 + (long long)n_a_end + (-F.prev[q] - RB));
+  for (size_t q = 0; q < F.prev.size(); q++) if (F.prev[q] <= -RB && F.prev[q] > -XHE_OP_FROM_LEDGER) F.prev[q] = -(1 + (long long)n_a_end + (-F.prev[q] - RB));
   for (size_t pos : rb_terms) F.terms[pos] = (F.terms[pos] & 0x80000000u) | (n_a_end + (F.terms[pos] & 0x7fffffffu));
   double t2 = now_ms();
   // Zero-copy upload: when the caller's transactions already sit back to back (16-byte aligned, the layout
@@ -619,10 +627,10 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   xb.n_ops = (uint32_t)F.prev.size(); xb.op_prev = (const int64_t*)F.prev.data(); xb.op_term_off = F.term_off.data(); xb.op_terms = F.terms.data(); xb.op_amount = F.amount.data(); xb.max_chain = max_chain;
   xb.n_eq = n_eq; xb.n_val = n_val; xb.n_rp = (uint32_t)n_run; xb.rp_m = F.rp_m.data(); xb.rp_point_off = F.rp_pt_off.data(); xb.rp_chal_off = F.rp_ch_off.data();
   xb.fs_blobs = blob_base; xb.fs_blob_off = F.off.data(); xb.fs_plan = F.plan.data(); memcpy(xb.fs_seed, seed, 32); xb.fs_index_base = lo;
-  xb.layout_on_device = 1; xb.n_region_b = n_rb; xb.region_b = F.region_b.data();
+  xb.layout_on_device = 1; xb.n_region_b = n_rb; xb.region_b = F.region_b.data(); xb.ledger = dl;
   PinnedVec<uint8_t>& op_out = F.op_out; op_out.n = 0; op_out.reserve(32 * (size_t)xb.n_ops + 64); op_out.n = 32 * (size_t)xb.n_ops;
   PinnedVec<uint8_t>& txf = F.tx_flags; txf.n = 0; txf.reserve(n_run + 64); txf.n = n_run;
-  xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.op_out = op_out.data(); v.tx_flags = txf.data();
+  xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.op_out = (dl && !want_out) ? nullptr : op_out.data(); v.tx_flags = txf.data();      // resident ledger: no balance comes back
   int32_t rc = xhe_verify_batch(ctx, &xb, &v);
   double t4 = now_ms();
   if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->total_ms = t4 - t0; }
@@ -656,6 +664,14 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     for (const Upd& u : updates) { StateUpdate su; memcpy(su.account.data(), u.account, 32); memcpy(su.asset.data(), u.asset, 32); su.role = u.role; su.op_c = u.op_c; su.op_d = u.op_c + 1; su.output = u.output; Pn.updates.push_back(su); }
     std::lock_guard<std::mutex> g(g_pending_mu);
     g_pending[ctx] = std::move(Pn);
+  } else if (opt.apply_state && dl) {
+    // update_account_balance on the device: the LAST op of every chain is that key's new balance (src/tx/verify.rs:329-336,367-374)
+    if (staged.apply(state) != XHE_OK) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; }
+    std::vector<uint32_t> slots, ops; slots.reserve(chains.size()); ops.reserve(chains.size());
+    chains.for_each([&](const uint8_t*, const Chain& c) { if (c.slot != 0xFFFFFFFFu && c.last_c >= 0) { slots.push_back(c.slot); ops.push_back((uint32_t)c.last_c); } });
+    int32_t crc = xhe_ledger_commit_batch(dl, ctx, slots.data(), ops.data(), slots.size());
+    if (crc != XHE_OK) { *rc_out = crc; *fail_out = -1; return crc < 0 ? 0 : 2; }
+    if (want_out) for (const Upd& u : updates) if (u.output) { uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 64); if (!state.set_output_ciphertext(u.account, u.asset, ct)) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; } }
   } else if (opt.apply_state) {
     if (staged.apply(state) != XHE_OK) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; }
     for (size_t j = 0; j < updates.size(); j++) {
@@ -1120,35 +1136,44 @@ int apply_without_verify(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t
 // ------------------------------------------------------------------------------------------------------------------
 using namespace xhe_host;
 extern "C" {
-void* xheh_ledger_new() { return new MockLedger(); }
-void* xheh_ledger_clone(const void* l) { return new MockLedger(*(const MockLedger*)l); }
-void xheh_ledger_free(void* l) { delete (MockLedger*)l; }
-void xheh_ledger_set_balance(void* l, const uint8_t* pk, const uint8_t* asset, const uint8_t* ct) { ((MockLedger*)l)->set_balance(pk, asset, ct); }
-int xheh_ledger_get_balance(void* l, const uint8_t* pk, const uint8_t* asset, uint8_t* ct) { return ((MockLedger*)l)->get_account_balance(pk, asset, Sender, ct) ? 1 : 0; }
-void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { ((MockLedger*)l)->set_nonce(pk, nonce); }
-void xheh_ledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { ((MockLedger*)l)->set_multisig_for_account(pk, signers, n, threshold); }
-int xheh_ledger_has_multisig(void* l, const uint8_t* pk) { std::vector<Bytes32> s; uint8_t t; bool p; ((MockLedger*)l)->get_multisig_for_account(pk, &s, &t, &p); return p ? 1 : 0; }
-size_t xheh_ledger_size(void* l) { return ((MockLedger*)l)->balances.size(); }
+// (every ledger handle is a VerificationState*: the mock and the device-resident state are passed to the same verify entry points)
+void* xheh_ledger_new() { return static_cast<VerificationState*>(new MockLedger()); }
+// device-resident state: balances in an xhe_ledger on ctx's device
+void* xheh_dledger_new(xhe_ctx* ctx, size_t capacity) { DeviceLedgerState* d = new DeviceLedgerState(ctx, capacity); if (!d->led) { delete d; return nullptr; } return static_cast<VerificationState*>(d); }
+void xheh_dledger_free(void* l) { delete static_cast<DeviceLedgerState*>((VerificationState*)l); }
+int32_t xheh_dledger_import(void* l, const uint8_t* recs, size_t n) { return static_cast<DeviceLedgerState*>((VerificationState*)l)->import_records(recs, n) ? XHE_OK : XHE_ERR_STATE; }
+size_t xheh_dledger_export(void* l, uint8_t* out, size_t cap) { return static_cast<DeviceLedgerState*>((VerificationState*)l)->export_all(out, cap); }
+void xheh_dledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { static_cast<DeviceLedgerState*>((VerificationState*)l)->set_multisig_for_account(pk, signers, n, threshold); }
+int32_t xheh_dledger_snapshot(void* l) { return xhe_ledger_snapshot(static_cast<DeviceLedgerState*>((VerificationState*)l)->led); }
+int32_t xheh_dledger_restore(void* l) { return xhe_ledger_restore(static_cast<DeviceLedgerState*>((VerificationState*)l)->led); }
+void* xheh_ledger_clone(const void* l) { return static_cast<VerificationState*>(new MockLedger(*static_cast<const MockLedger*>((const VerificationState*)l))); }
+void xheh_ledger_free(void* l) { delete static_cast<MockLedger*>((VerificationState*)l); }
+void xheh_ledger_set_balance(void* l, const uint8_t* pk, const uint8_t* asset, const uint8_t* ct) { (static_cast<MockLedger*>((VerificationState*)l))->set_balance(pk, asset, ct); }
+int xheh_ledger_get_balance(void* l, const uint8_t* pk, const uint8_t* asset, uint8_t* ct) { return (static_cast<MockLedger*>((VerificationState*)l))->get_account_balance(pk, asset, Sender, ct) ? 1 : 0; }
+void xheh_ledger_set_nonce(void* l, const uint8_t* pk, uint64_t nonce) { (static_cast<MockLedger*>((VerificationState*)l))->set_nonce(pk, nonce); }
+void xheh_ledger_set_multisig(void* l, const uint8_t* pk, const uint8_t* signers, size_t n, uint8_t threshold) { (static_cast<MockLedger*>((VerificationState*)l))->set_multisig_for_account(pk, signers, n, threshold); }
+int xheh_ledger_has_multisig(void* l, const uint8_t* pk) { std::vector<Bytes32> s; uint8_t t; bool p; (static_cast<MockLedger*>((VerificationState*)l))->get_multisig_for_account(pk, &s, &t, &p); return p ? 1 : 0; }
+size_t xheh_ledger_size(void* l) { return (static_cast<MockLedger*>((VerificationState*)l))->balances.size(); }
 // output ciphertexts (set_output_ciphertext, src/tx/verify.rs:60-66): off by default like the reference mock, which drops them
-void xheh_ledger_record_outputs(void* l, int on) { ((MockLedger*)l)->record_outputs = on != 0; }
-size_t xheh_ledger_outputs_size(void* l) { return ((MockLedger*)l)->outputs.size(); }
-size_t xheh_ledger_export_outputs(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; L->outputs.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
+void xheh_ledger_record_outputs(void* l, int on) { (static_cast<MockLedger*>((VerificationState*)l))->record_outputs = on != 0; }
+size_t xheh_ledger_outputs_size(void* l) { return (static_cast<MockLedger*>((VerificationState*)l))->outputs.size(); }
+size_t xheh_ledger_export_outputs(void* l, uint8_t* out, size_t cap) { MockLedger* L = static_cast<MockLedger*>((VerificationState*)l); size_t i = 0; L->outputs.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
 // bulk import of records (pk[32] asset[32] ct[64]) and nonce-0 accounts
-void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; L->balances.reserve(L->balances.size() + n); L->nonces.reserve(L->nonces.size() + n);
+void xheh_ledger_import(void* l, const uint8_t* recs, size_t n) { MockLedger* L = static_cast<MockLedger*>((VerificationState*)l); L->balances.reserve(L->balances.size() + n); L->nonces.reserve(L->nonces.size() + n);
   for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; L->set_balance(r, r + 32, r + 64); bool fresh = false; uint64_t* v = L->nonces.insert(r, &fresh); if (fresh) *v = 0; } }
-size_t xheh_ledger_export(void* l, uint8_t* out, size_t cap) { MockLedger* L = (MockLedger*)l; size_t i = 0; L->balances.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
+size_t xheh_ledger_export(void* l, uint8_t* out, size_t cap) { MockLedger* L = static_cast<MockLedger*>((VerificationState*)l); size_t i = 0; L->balances.for_each([&](const uint8_t* k, const Ct64& v) { if ((i + 1) * 128 <= cap) { memcpy(out + 128 * i, k, 64); memcpy(out + 128 * i + 64, v.data(), 64); } i++; }); return i; }
 // timings: parse, resolve, transcript, device, finish, total (ms), keccak permutations
 int32_t xheh_verify_batch(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, long* fail_index, double* timings7) {
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len;
   BatchTimings tm;
-  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
   return rc;
 }
 int32_t xheh_verify_batch_partial(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, long* fail_index, double* timings7, uint8_t* partial64) {
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.partial_out = partial64;
   BatchTimings tm;
-  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = (double)tm.keccak_f; }
   return rc;
 }
@@ -1158,7 +1183,7 @@ int32_t xheh_verify_batch_ex(xhe_ctx* ctx, void* ledger, const uint8_t* const* b
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = (flags & 2u) ? partial64 : nullptr; opt.fast_path = (flags & 4u) != 0;
   opt.deterministic_seed = (flags & 8u) != 0;
   BatchTimings tm;
-  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
   return rc;
 }
@@ -1171,14 +1196,14 @@ int32_t xheh_verify_batch_shard(xhe_ctx* ctx, void* ledger, const uint8_t* const
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = partial64; opt.fast_path = (flags & 4u) != 0;
   opt.deterministic_seed = (flags & 8u) != 0; opt.shard_lo = lo; opt.shard_hi = hi;
   BatchTimings tm;
-  int rc = verify_batch(ctx, blobs, lens, n, *(MockLedger*)ledger, opt, fail_index, &tm);
+  int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
   return rc;
 }
-int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(ctx, *(MockLedger*)ledger); }
+int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(ctx, *(VerificationState*)ledger); }
 // detached form: take the held-back updates now, commit (or drop) them when the cross-rank decision is known
 void* xheh_take_pending(xhe_ctx* ctx) { return take_pending(ctx); }
-int32_t xheh_commit_taken(void* pending, void* ledger) { if (!pending) return XHE_E_ARG; Pending* P = (Pending*)pending; int rc = apply_pending(*P, *(MockLedger*)ledger); delete P; return rc; }
+int32_t xheh_commit_taken(void* pending, void* ledger) { if (!pending) return XHE_E_ARG; Pending* P = (Pending*)pending; int rc = apply_pending(*P, *(VerificationState*)ledger); delete P; return rc; }
 void xheh_drop_taken(void* pending) { delete (Pending*)pending; }
 // a page-locked buffer for a batch's transactions laid out the way the device reads them (back to back, each padded to 16
 // bytes): transactions that live there are uploaded without the gather into staging (zero-copy input)
@@ -1187,8 +1212,8 @@ void xheh_blob_arena_free(void* p) { if (p) cudaFreeHost(p); }
 // the balance updates a detached shard-mode batch holds, as 128-byte records (account, asset, new ciphertext) in update order
 size_t xheh_export_taken(void* pending, uint8_t* out, size_t cap) { return export_pending(pending, out, cap); }
 // apply such records to a ledger (a peer rank's updates): update_account_balance per record, in order
-int32_t xheh_ledger_apply_records(void* l, const uint8_t* recs, size_t n) { MockLedger* L = (MockLedger*)l; for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; if (!L->update_account_balance(r, r + 32, r + 64, Receiver)) return XHE_ERR_STATE; } return XHE_OK; }
-int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(MockLedger*)ledger); }
+int32_t xheh_ledger_apply_records(void* l, const uint8_t* recs, size_t n) { MockLedger* L = static_cast<MockLedger*>((VerificationState*)l); for (size_t i = 0; i < n; i++) { const uint8_t* r = recs + 128 * i; if (!L->update_account_balance(r, r + 32, r + 64, Receiver)) return XHE_ERR_STATE; } return XHE_OK; }
+int32_t xheh_apply_without_verify(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n) { return apply_without_verify(ctx, blobs, lens, n, *(VerificationState*)ledger); }
 // host-only helpers exposed for CPU tests of the host logic
 void xheh_merlin_test(const char* proto, const char* label, const uint8_t* msg, size_t n, const char* chal_label, uint8_t* out, size_t outlen) { Transcript t(proto); t.append(label, msg, n); t.challenge(chal_label, out, outlen); }
 void xheh_sha3_512(const uint8_t* m, size_t n, uint8_t* out) { sha3_512(m, n, out); }

@@ -44,6 +44,12 @@ struct VerificationState {               // src/tx/verify.rs:25-77; every call r
   // optional hints (not part of the reference trait): the batch front end announces the lookups it is about to make
   virtual void prefetch_account(const uint8_t[32]) const {}
   virtual void prefetch_balance(const uint8_t[32], const uint8_t[32]) const {}
+  // optional device-resident backend (not part of the reference trait): a state whose balances live in an
+  // xhe_ledger on the verifying context's device hands out the ledger and the slot of a key.  The fast path then reads the
+  // balance where it is (no upload, no decompression) and commits the update on the device (no download, no re-encoding on
+  // the host side); get_account_balance / update_account_balance stay available as the compressed view of the same data.
+  virtual xhe_ledger* device_ledger() { return nullptr; }
+  virtual bool device_slot(const uint8_t /*account*/[32], const uint8_t /*asset*/[32], uint32_t* /*slot*/) { return false; }
 };
 
 struct KeyHash { size_t operator()(const Ct64& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); uint64_t g; memcpy(&g, k.data() + 37, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull ^ g); } };
@@ -128,6 +134,54 @@ class MockLedger : public VerificationState {   // src/lib.rs:106-201
     if (*present) { *signers = it->second.first; *threshold = it->second.second; } return true; }
   void prefetch_account(const uint8_t account[32]) const override { nonces.prefetch(account); }
   void prefetch_balance(const uint8_t account[32], const uint8_t asset[32]) const override { balances.prefetch(key(account, asset).data()); }
+};
+
+// BlockchainVerificationState over a device-resident ledger (include/xhe.h, xhe_ledger_*): balances are decompressed points in
+// HBM, nonces and multisig settings stay in host tables like the mock's.
+class DeviceLedgerState : public VerificationState {
+ public:
+  xhe_ctx* ctx; xhe_ledger* led = nullptr;
+  FlatTable<32, uint64_t> nonces;
+  std::unordered_map<Bytes32, std::pair<std::vector<Bytes32>, uint8_t>, Key32Hash> multisig;
+  std::vector<Ct64> keys;                       // insertion order = slot order
+  DeviceLedgerState(xhe_ctx* c, size_t capacity) : ctx(c) { if (xhe_ledger_create(c, capacity, &led) != XHE_OK) led = nullptr; }
+  ~DeviceLedgerState() override { if (led) xhe_ledger_destroy(led); }
+  bool import_records(const uint8_t* recs, size_t n) {      // pk[32] asset[32] ct[64]; accounts get nonce 0
+    std::vector<uint8_t> k(64 * n), c(64 * n), ok(n);
+    for (size_t i = 0; i < n; i++) { memcpy(&k[64 * i], recs + 128 * i, 64); memcpy(&c[64 * i], recs + 128 * i + 64, 64); }
+    const size_t before = xhe_ledger_size(led);
+    if (xhe_ledger_load(led, k.data(), c.data(), n, ok.data()) != XHE_OK) return false;
+    for (size_t i = 0; i < n; i++) { bool fresh = false; uint64_t* v = nonces.insert(recs + 128 * i, &fresh); if (fresh) *v = 0; }
+    if (xhe_ledger_size(led) != before) { keys.clear(); }   // rebuilt lazily by export_all
+    for (size_t i = 0; i < n; i++) { Ct64 kk; memcpy(kk.data(), &k[64 * i], 64); all_keys_.insert(kk.data()); }
+    return true;
+  }
+  size_t export_all(uint8_t* out, size_t cap) {             // records pk asset ct of every balance
+    std::vector<uint8_t> k; all_keys_.for_each([&](const uint8_t* key, const uint8_t&) { k.insert(k.end(), key, key + 64); });
+    const size_t n = k.size() / 64;
+    if (out && 128 * n <= cap) { std::vector<uint8_t> c(64 * n + 64), f(n + 1); xhe_ledger_export(led, k.data(), n, c.data(), f.data()); for (size_t i = 0; i < n; i++) { memcpy(out + 128 * i, &k[64 * i], 64); memcpy(out + 128 * i + 64, &c[64 * i], 64); } }
+    return n;
+  }
+  bool get_account_balance(const uint8_t account[32], const uint8_t asset[32], Role, uint8_t out_ct[64]) override {
+    Ct64 k = MockLedger::key(account, asset); uint8_t f = 0; return xhe_ledger_export(led, k.data(), 1, out_ct, &f) == XHE_OK && f; }
+  bool update_account_balance(const uint8_t account[32], const uint8_t asset[32], const uint8_t new_ct[64], Role) override {
+    Ct64 k = MockLedger::key(account, asset); if (xhe_ledger_slot(led, k.data()) == 0xFFFFFFFFu) return false; uint8_t ok = 0; return xhe_ledger_load(led, k.data(), new_ct, 1, &ok) == XHE_OK && ok; }
+  bool get_account_nonce(const uint8_t account[32], uint64_t* nonce) override { const uint64_t* v = nonces.find(account); if (!v) return false; *nonce = *v; return true; }
+  bool update_account_nonce(const uint8_t account[32], uint64_t nonce) override { uint64_t* v = nonces.find(account); if (!v) return false; *v = nonce; return true; }
+  bool set_multisig_for_account(const uint8_t account[32], const uint8_t* signers, size_t n, uint8_t threshold) override {
+    Bytes32 k; memcpy(k.data(), account, 32);
+    if (n == 0) { multisig.erase(k); return true; }
+    std::vector<Bytes32> v(n); for (size_t i = 0; i < n; i++) memcpy(v[i].data(), signers + 32 * i, 32);
+    multisig[k] = std::make_pair(v, threshold); return true; }
+  bool get_multisig_for_account(const uint8_t account[32], std::vector<Bytes32>* signers, uint8_t* threshold, bool* present) override {
+    if (multisig.empty()) { *present = false; return true; }
+    Bytes32 k; memcpy(k.data(), account, 32); auto it = multisig.find(k); *present = it != multisig.end();
+    if (*present) { *signers = it->second.first; *threshold = it->second.second; } return true; }
+  void prefetch_account(const uint8_t account[32]) const override { nonces.prefetch(account); }
+  xhe_ledger* device_ledger() override { return led; }
+  bool device_slot(const uint8_t account[32], const uint8_t asset[32], uint32_t* slot) override { Ct64 k = MockLedger::key(account, asset); uint32_t s = xhe_ledger_slot(led, k.data()); if (s == 0xFFFFFFFFu) return false; *slot = s; return true; }
+ private:
+  FlatTable<64, uint8_t> all_keys_;
 };
 
 struct TransferView { const uint8_t *asset, *dest, *commitment, *sender_handle, *receiver_handle, *proof, *extra; uint32_t extra_len; bool has_extra; };

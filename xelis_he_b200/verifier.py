@@ -111,6 +111,55 @@ class Ledger:
             pass
 
 
+class DeviceLedgerState:
+    """BlockchainVerificationState over a device-resident ledger: pass it wherever a Ledger is accepted.  The
+    fast path reads balances from the device table and commits accepted updates there; dump() compresses on demand."""
+
+    def __init__(self, ctx, capacity):
+        self.lib = _lib()
+        lib = self.lib
+        lib.xheh_dledger_new.restype = C.c_void_p; lib.xheh_dledger_new.argtypes = [C.c_void_p, C.c_size_t]
+        lib.xheh_dledger_free.argtypes = [C.c_void_p]
+        lib.xheh_dledger_import.restype = C.c_int32; lib.xheh_dledger_import.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        lib.xheh_dledger_export.restype = C.c_size_t; lib.xheh_dledger_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.xheh_dledger_set_multisig.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_uint8]
+        lib.xheh_dledger_snapshot.restype = C.c_int32; lib.xheh_dledger_snapshot.argtypes = [C.c_void_p]
+        lib.xheh_dledger_restore.restype = C.c_int32; lib.xheh_dledger_restore.argtypes = [C.c_void_p]
+        p = lib.xheh_dledger_new(ctx.p, capacity)
+        if not p:
+            raise XheError(-3, "device ledger allocation failed")
+        self.ptr = C.c_void_p(p)
+        self.ctx = ctx
+
+    def import_records(self, records):
+        blob = b"".join(pk + asset + ct for pk, asset, ct in records)
+        rc = self.lib.xheh_dledger_import(self.ptr, blob, len(blob) // 128)
+        if rc:
+            raise XheError(rc, "device ledger import failed")
+
+    def set_multisig(self, pk, signers, threshold):
+        self.lib.xheh_dledger_set_multisig(self.ptr, pk, b"".join(signers), len(signers), threshold)
+
+    def dump(self):
+        n = self.lib.xheh_dledger_export(self.ptr, None, 0)
+        buf = C.create_string_buffer(128 * max(n, 1))
+        self.lib.xheh_dledger_export(self.ptr, buf, 128 * n)
+        raw = buf.raw[:128 * n]
+        return sorted((raw[i:i + 32], raw[i + 32:i + 64], raw[i + 64:i + 128]) for i in range(0, len(raw), 128))
+
+    def snapshot(self):
+        return self.lib.xheh_dledger_snapshot(self.ptr)
+
+    def restore(self):
+        return self.lib.xheh_dledger_restore(self.ptr)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.lib.xheh_dledger_free(self.ptr); self.ptr = None
+
+    __del__ = close
+
+
 class _Blobs:
     def __init__(self, blobs):
         n = len(blobs)

@@ -29,6 +29,7 @@ pub const XHE_E_NOMEM: i32 = -3;
 pub const XHE_E_NCCL: i32 = -4;
 pub const XHE_E_CAPACITY: i32 = -5;
 pub const XHE_OP_PLUS_AMOUNT: i64 = 1 << 50;
+pub const XHE_OP_FROM_LEDGER: i64 = 1 << 49;
 
 #[repr(C)]
 pub struct xhe_ctx {
@@ -79,6 +80,8 @@ pub struct xhe_batch {
     pub layout_on_device: u32,
     pub n_region_b: u32,
     pub region_b: *const u8,
+    // optional: device-resident ledger read by XHE_OP_FROM_LEDGER ops
+    pub ledger: *const xhe_ledger,
 }
 
 impl Default for xhe_batch {
@@ -155,6 +158,10 @@ extern "C" {
     pub fn xhe_ledger_update(ledger: *mut xhe_ledger, keys: *const u8, deltas: *const u8, sub: *const u8, n: usize, status: *mut u8) -> i32;
     pub fn xhe_ledger_update_dense_dev(ledger: *mut xhe_ledger, d_delta_niels_planar: *const c_void, d_sub: *const c_void) -> i32;
     pub fn xhe_ledger_export(ledger: *mut xhe_ledger, keys: *const u8, n: usize, out_cts: *mut u8, found: *mut u8) -> i32;
+    pub fn xhe_ledger_commit_batch(ledger: *mut xhe_ledger, ctx: *mut xhe_ctx, slots: *const u32, ops: *const u32, n: usize) -> i32;
+    pub fn xhe_ledger_slot(ledger: *const xhe_ledger, key64: *const u8) -> u32;
+    pub fn xhe_ledger_snapshot(ledger: *mut xhe_ledger) -> i32;
+    pub fn xhe_ledger_restore(ledger: *mut xhe_ledger) -> i32;
     pub fn xhe_ledger_device_table(ledger: *const xhe_ledger, plane_stride_points: *mut usize) -> *mut c_void;
 }
 
@@ -164,7 +171,7 @@ mod tests {
     // layout pins against include/xhe.h on x86-64 / aarch64 (LP64): a drift shows up here before it shows up as XHE_E_ARG
     #[test]
     fn struct_sizes_match_the_header() {
-        assert_eq!(std::mem::size_of::<xhe_batch>(), 280);
+        assert_eq!(std::mem::size_of::<xhe_batch>(), 288);
         assert_eq!(std::mem::size_of::<xhe_verdict>(), 384);
     }
 }
