@@ -45,8 +45,8 @@ def launches(path, plain_json=None):
     for i in reversed(starts):
         ends = [j for j in range(i, len(seq)) if seq[j][0].startswith("k_combine_out")]
         if ends:
-            if i > 0 and seq[i - 1][0].startswith("k_fiat_shamir"):
-                i -= 1                     # the transcript kernel is issued on its own stream just before k_layout
+            while i > 0 and seq[i - 1][0].startswith(("k_fiat_shamir", "k_sig_hash_prefix")):
+                i -= 1                     # the transcript / hash-prefix kernels are issued on their own streams just before k_layout
             step = seq[i:ends[0] + 1]
             break
     for n, v in step:

@@ -24,6 +24,7 @@
 //
 // Algorithmic work: n*W mixed adds of 7 M = 504 limb products each dominate.
 #include <stdlib.h>
+#include <stddef.h>
 #include "xhe_internal.cuh"
 #include "quad.cuh"
 #include <algorithm>
@@ -44,6 +45,7 @@ struct MsmPlan {
   uint32_t B;           // buckets per window = 2^(c-1)
   size_t total_buckets; // W * B
   int G, Wg;            // window groups (most significant first) and windows per group (the last group may be shorter)
+  int seg_log;          // log2 of the buckets one quad folds in the first reduction level (2 or 4)
   // workspace offsets (bytes)
   size_t n_tiles, max_runs;
   size_t off_counts, off_offsets, off_cursor, off_blocksums, off_list, off_tileg0, off_runs, off_runoff, off_part, off_pstart, off_pcount, off_heavy, off_nodes_a, off_nodes_b, off_hnodes, off_hacc, off_ready, off_flag, total;
@@ -78,6 +80,12 @@ MsmPlan make_plan(size_t n) {
   int G = std::max(1, std::min(g_env, MSM_MAX_GROUPS));
   if (n * (size_t)p.W < ((size_t)1 << 17)) G = 1;
   p.Wg = (p.W + G - 1) / G; p.G = (p.W + p.Wg - 1) / p.Wg;
+  // first reduction level: a quad folds 4 buckets (5 dependent point operations: small MSMs are latency-bound there) or 16 (30
+  // operations, but a quarter of the nodes reach the scan kernels, which spend 10 operations per node: large MSMs are
+  // throughput-bound there -- 2^20 points: 0.39 ms -> see profiles/r02_msm_sweep.md)
+  static const int seg_env = getenv("XHE_MSM_SEG_LOG") ? atoi(getenv("XHE_MSM_SEG_LOG")) : 0;
+  p.seg_log = seg_env == 2 || seg_env == 4 ? seg_env : (p.total_buckets > ((size_t)1 << 17) ? 4 : 2);
+  if ((1u << p.seg_log) > p.B) p.seg_log = 2;
   size_t o = 0;
   p.off_counts = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
   p.off_offsets = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
@@ -257,10 +265,28 @@ __device__ __forceinline__ void flush_run(const AccumOut& o, uint32_t slot, uint
     h[1 + atomicAdd(&h[0], 1u)] = g;
   }
 }
-template <int MINB>
+// SMEM_ACC is the A/B for north_star's "shared-memory bucket accumulation": the same kernel with the running bucket sum kept in
+// the CTA's shared memory (128 B per thread, read and written around every addition) instead of registers.  XHE_MSM_SMEM_ACC=1
+// selects it; the measured difference is in DESIGN.md 4.4.
+__device__ __forceinline__ void lds_ge(ge& g, const uint32_t* p) {      // volatile 128-bit shared-memory accesses: the compiler may not keep the sum in registers
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  uint32_t* w = &g.X.v[0];
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * i]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3]) : "r"(a + 16 * i));
+}
+__device__ __forceinline__ void sts_ge(uint32_t* p, const ge& g) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  const uint32_t* w = &g.X.v[0];
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + 16 * i), "r"(w[4 * i]), "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+}
+static_assert(sizeof(ge) == 128 && offsetof(ge, Y) == 32 && offsetof(ge, Z) == 64 && offsetof(ge, T) == 96, "ge is four contiguous 8-word field elements");
+template <int MINB, bool SMEM_ACC>
 __global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* __restrict__ niels, const uint32_t* __restrict__ list, const uint32_t* __restrict__ offsets, uint32_t m,
                                                               const uint32_t* __restrict__ tile_g0, const uint32_t* __restrict__ run_off, size_t n_tiles,
                                                               uint32_t klo, uint32_t khi, AccumOut out) {
+  __shared__ __align__(16) uint32_t sacc[SMEM_ACC ? 128 * 32 : 4];
+  uint32_t* my = sacc + (SMEM_ACC ? 32 * threadIdx.x : 0);
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
   uint32_t N = __ldg(offsets + m);
@@ -275,11 +301,13 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* _
   uint32_t e = __ldg(list + start);
   ge_niels q; ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu));
   ge acc = ge_from_niels(niels_cneg(q, (e >> 31) != 0));
+  if (SMEM_ACC) sts_ge(my, acc);
   if (cnt > 1) { e = __ldg(list + start + 1); ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu)); }
   for (uint32_t j = 1; j < cnt; j++) {
     const uint32_t pos = (uint32_t)start + j;
     ge_niels cur = niels_cneg(q, (e >> 31) != 0);
     if (j + 1 < cnt) { e = __ldg(list + start + j + 1); ld_niels(q, niels + 24 * (size_t)(e & 0x7fffffffu)); }
+    if (SMEM_ACC) lds_ge(acc, my);
     if (pos == nb) {   // bucket boundary: flush the finished run, restart from this point
       flush_run(out, slot, g, acc); slot++;
       g = next_bucket(offsets, m, pos, g); nb = __ldg(offsets + g + 1);
@@ -288,7 +316,9 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accum_tiles(const uint32_t* _
     } else {
       acc = ge_madd(acc, cur);
     }
+    if (SMEM_ACC) sts_ge(my, acc);
   }
+  if (SMEM_ACC) lds_ge(acc, my);
   flush_run(out, slot, g, acc);
 }
 
@@ -332,7 +362,8 @@ __device__ __forceinline__ void st_ge_quad(uint32_t* p, const ge& g) {       // 
   st_fe(p + 8 * ql, quad_pick(g.X, g.Y, g.Z, g.T, ql));
 }
 // level 1: one CTA per 256 consecutive bucket keys.  Phase 1: thread/bucket adds up the bucket's partial sums (at most
-// HEAVY_PARTIALS after the fold).  Phase 2: quad/4 buckets running sum -> node of width 4.
+// HEAVY_PARTIALS after the fold).  Phase 2: quad/L buckets running sum -> node of width L (L = 4: all 64 quads; L = 16: 16 quads).
+template <int L>
 __global__ void __launch_bounds__(256) k_msm_bucket_seg(const uint32_t* __restrict__ part, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pcount,
                                                         uint32_t klo, uint32_t khi, uint32_t* __restrict__ nodes) {
   __shared__ __align__(16) uint32_t sm[256 * 32];
@@ -349,13 +380,14 @@ __global__ void __launch_bounds__(256) k_msm_bucket_seg(const uint32_t* __restri
   st_ge(sm + 32 * threadIdx.x, v);
   __syncthreads();
   const uint32_t q = threadIdx.x >> 2;
+  if (q >= 256 / L) return;                      // (whole warps: 256 / L quads = 64 or 16, a multiple of 8)
   ge run, wsum, s;
-  ld_ge(run, sm + 32 * (4 * q + 3)); wsum = run;
-  ld_ge(s, sm + 32 * (4 * q + 2)); run = quad_add(run, s); wsum = quad_add(wsum, run);
-  ld_ge(s, sm + 32 * (4 * q + 1)); run = quad_add(run, s); wsum = quad_add(wsum, run);
-  ld_ge(s, sm + 32 * (4 * q + 0)); run = quad_add(run, s);
-  const uint32_t kq = klo + blockIdx.x * 256 + 4 * q;
-  if (kq < khi) { uint32_t* o = nodes + 64 * (size_t)((kq - klo) >> MSM_SEG_LOG); st_ge_quad(o, run); st_ge_quad(o + 32, wsum); }
+  ld_ge(run, sm + 32 * (L * q + L - 1)); wsum = run;
+#pragma unroll 1
+  for (int r = L - 2; r >= 1; r--) { ld_ge(s, sm + 32 * (L * q + r)); run = quad_add(run, s); wsum = quad_add(wsum, run); }
+  ld_ge(s, sm + 32 * (L * q)); run = quad_add(run, s);
+  const uint32_t kq = klo + blockIdx.x * 256 + L * q;
+  if (kq < khi) { uint32_t* o = nodes + 64 * (size_t)((kq - klo) / L); st_ge_quad(o, run); st_ge_quad(o + 32, wsum); }
 }
 
 // one CTA (32 quads) folds 32 consecutive child nodes (each of width 2^child_log buckets) of ONE window into a parent:
@@ -500,7 +532,7 @@ __global__ void k_msm_empty(uint8_t* __restrict__ out_enc, uint32_t* __restrict_
   if (out_ext) st_ge(out_ext, ge_identity());
 }
 
-int g_accum_variant = 4;   // resident 128-thread blocks per SM the hot kernel is compiled for (4 -> 128 regs, 6 -> 80, 8 -> 64)
+int g_accum_variant = getenv("XHE_MSM_SMEM_ACC") && atoi(getenv("XHE_MSM_SMEM_ACC")) ? 104 : 4;   // resident 128-thread blocks per SM the hot kernel is compiled for (4 -> 128 regs, 6 -> 80, 8 -> 64); 104 = the shared-memory A/B
 inline unsigned nblk(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -621,7 +653,7 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
   // dynamic shared-memory request that caps residency at 3 blocks per SM costs the kernel little and leaves a quarter of
   // the registers to the other streams (XHE_ACCUM_SMEM overrides; 0 = no cap).
   static const size_t accum_smem = []() { const char* e = getenv("XHE_ACCUM_SMEM"); size_t v = e ? (size_t)atol(e) : (size_t)XHE_ACCUM_SMEM_DEFAULT;
-    if (v > 48 * 1024) { cudaFuncSetAttribute(k_msm_accum_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); }
+    if (v > 48 * 1024) { cudaFuncSetAttribute(k_msm_accum_tiles<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); cudaFuncSetAttribute(k_msm_accum_tiles<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v); }
     return v; }();
   // The grouped tail: accumulation launches of the window groups back to back on the caller's stream; behind each, on a
   // high-priority side stream, the group's reduction (s_red); the Horner chain on s_hor (chain_mode 0 / 1) or in the
@@ -642,9 +674,10 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
     for (int g = 0; g < p.G; g++) {
       const uint32_t klo = (uint32_t)g * kpg, khi = (uint32_t)std::min<size_t>(m, (size_t)(g + 1) * kpg);
       switch (g_accum_variant) {
-        case 6: k_msm_accum_tiles<6><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
-        case 8: k_msm_accum_tiles<8><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
-        default: k_msm_accum_tiles<4><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+        case 6: k_msm_accum_tiles<6, false><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+        case 8: k_msm_accum_tiles<8, false><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
+        case 104: k_msm_accum_tiles<4, true><<<nblk(p.n_tiles, 128), 128, 0, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;     // A/B: sum in shared memory
+        default: k_msm_accum_tiles<4, false><<<nblk(p.n_tiles, 128), 128, accum_smem, st>>>((const uint32_t*)d_niels, q.list, q.offsets, (uint32_t)m, q.tile_g0, q.run_off, p.n_tiles, klo, khi, ao); break;
       }
       XHE_LAUNCHED(ctx);
       if (s_red != st) XHE_CUDA_OK(ctx, cudaEventRecord(ev[g], st));
@@ -656,8 +689,10 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
     if (s_red != st) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_red, ev[g], 0));
     const uint32_t* heavy_g = q.heavy + (size_t)g * kpg + 8 * g;
     k_msm_fold_heavy<<<(unsigned)std::min<size_t>((khi - klo + 3) / 4, 8 * (size_t)ctx->sm_count), FOLD_THREADS, 0, s_red>>>(q.part, q.pstart, q.pcount, heavy_g); XHE_LAUNCHED(ctx);
-    k_msm_bucket_seg<<<nblk(khi - klo, 256), 256, 0, s_red>>>(q.part, q.pstart, q.pcount, klo, khi, q.nodes_a); XHE_LAUNCHED(ctx);
-    uint32_t per_window = (uint32_t)(p.B >> MSM_SEG_LOG); int child_log = MSM_SEG_LOG;
+    if (p.seg_log == 4) k_msm_bucket_seg<16><<<nblk(khi - klo, 256), 256, 0, s_red>>>(q.part, q.pstart, q.pcount, klo, khi, q.nodes_a);
+    else k_msm_bucket_seg<4><<<nblk(khi - klo, 256), 256, 0, s_red>>>(q.part, q.pstart, q.pcount, klo, khi, q.nodes_a);
+    XHE_LAUNCHED(ctx);
+    uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;
     uint32_t *cur = q.nodes_a, *nxt = q.nodes_b;
     uint32_t* hn = q.hnodes + 64 * (size_t)(klo / p.B);
     while (per_window > 1) {
@@ -721,7 +756,7 @@ extern "C" int32_t xhe_msm_vartime(xhe_ctx* ctx, const uint8_t* scalars, const u
 // to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
 // kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
 size_t xhe_preload_msm() {      // returns the largest per-thread local-memory frame among them
-  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4>, (const void*)k_msm_accum_tiles<6>, (const void*)k_msm_accum_tiles<8>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_chain, (const void*)k_msm_empty};
+  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4, false>, (const void*)k_msm_accum_tiles<6, false>, (const void*)k_msm_accum_tiles<8, false>, (const void*)k_msm_accum_tiles<4, true>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg<4>, (const void*)k_msm_bucket_seg<16>, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_chain, (const void*)k_msm_empty};
   cudaFuncAttributes a; size_t mx = 0;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
   return mx;
