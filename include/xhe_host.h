@@ -96,6 +96,18 @@ int32_t xheh_verify_batch_partial(xhe_ctx* ctx, void* ledger, const uint8_t* con
  * (src/tx/verify.rs:301-374) however the batch is cut.  Always shard mode. */
 int32_t xheh_verify_batch_shard(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi,
                                 const uint8_t* seed, size_t seed_len, int threads, uint32_t flags, long* fail_index, double* timings7, uint8_t* partial64);
+/* key-digest index of a batch: per transaction, 64-bit digests of the (account, asset) balances it moves and of a multisig
+ * setting it makes (a few 8-byte words per transaction).  Built once, where the transactions are received and framed -- the
+ * counterpart of the reference's deserialisation into `Transaction` values, which also happens before verify_batch -- and
+ * handed to the shard-mode call, which then finds the earlier transactions its shard depends on (src/tx/verify.rs:301-374)
+ * without reading the other shards' bytes.  xheh_shard_dependencies answers that question on its own (index may be NULL:
+ * the blobs are scanned); it returns the number of such transactions, in batch order, and writes at most cap indices. */
+void*   xheh_batch_index_build(const uint8_t* const* blobs, const size_t* lens, size_t n, int threads);
+void    xheh_batch_index_free(void* index);
+size_t  xheh_batch_index_bytes(const void* index);
+long    xheh_shard_dependencies(const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi, const void* index, int threads, size_t* out, size_t cap);
+int32_t xheh_verify_batch_shard_ix(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi,
+                                   const uint8_t* seed, size_t seed_len, int threads, uint32_t flags, long* fail_index, double* timings7, uint8_t* partial64, const void* index);
 /* the state updates a shard-mode call held back: apply them (after the cross-rank decision), or detach them so the context can
  * take its next batch, then commit / export (128-byte records account, asset, ciphertext) / drop */
 int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger);

@@ -140,3 +140,26 @@ def test_host_to_bytes_matches_oracle(lib):
         out = C.create_string_buffer(4096); n = C.c_size_t(0); m = C.c_size_t(0)
         assert lib.xheh_tx_to_bytes(bad, C.c_size_t(len(bad)), out, C.c_size_t(4096), C.byref(n), C.byref(m)) == 11
         assert oracle.tx_to_bytes(bad) is None
+
+
+def test_key_digest_index_finds_the_same_dependencies_as_the_blob_scan(lib):
+    """Sharded batches: the earlier transactions a shard depends on (src/tx/verify.rs:301-374) found through the
+    batch's key-digest index must be exactly those the scan of the blobs finds -- dependent worlds and an independent batch."""
+    import scenarios
+    from xelis_he_b200 import verifier
+    ms = scenarios.multisig_world()[1]
+    cases = [list(scenarios.realistic_world()[1]), list(scenarios.shared_receiver_world(6)[1]), [ms["setup"], ms["spend"]], list(scenarios.mixed_types_world(12)[1])] + [list(oracle.mint_chain(5, 24, 1).blobs), list(oracle.mint_transfers(9, 40, 1, 2, threads=4).blobs)]
+    found_dependency = False
+    for blobs in cases:
+        n = len(blobs)
+        plain, indexed = verifier.prepare_blobs(blobs), verifier.prepare_blobs(blobs, index=True)
+        assert indexed.index and indexed.index_bytes >= 4 * (n + 1)
+        for lo in range(0, n + 1):
+            for hi in sorted({lo, min(n, lo + 1), min(n, lo + 3), n}):
+                want = verifier.shard_dependencies(plain, lo, hi)
+                assert all(i < lo for i in want) and want == sorted(want)
+                assert verifier.shard_dependencies(indexed, lo, hi, threads=3) == want, (n, lo, hi)
+                found_dependency |= bool(want)
+    assert found_dependency
+    indep = list(oracle.mint_transfers(9, 40, 1, 2, threads=4).blobs)
+    assert verifier.shard_dependencies(verifier.prepare_blobs(indep, index=True), 20, 40) == []

@@ -33,6 +33,19 @@ def source_hash():
     return h.hexdigest()
 
 
+def _includes_of(path, seen=None):
+    """the file and every local header it includes, transitively (#include "...")"""
+    import re
+    seen = seen if seen is not None else set()
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for m in re.finditer(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), re.M):
+        _includes_of(os.path.join(os.path.dirname(path), m.group(1)), seen)
+    return seen
+
+
 HASH_FILE = os.path.join(HERE, "build", "libxhe_cuda.srchash")
 
 
@@ -52,9 +65,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         objs.append(obj)
-        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(p) for p in [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] +
-                [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))] + [os.path.join(HERE, "..", "include", "xhe.h")]):
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(p) for p in _includes_of(src)):
             continue
         log = open(obj + ".log", "w")
         procs.append((src, subprocess.Popen([NVCC, *FLAGS, "-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT), log))

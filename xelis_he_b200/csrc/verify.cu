@@ -266,19 +266,31 @@ __global__ void __launch_bounds__(256) k_reduce_scalars(const uint32_t* __restri
 // ---- range proofs ----------------------------------------------------------------------------------------------------
 // per-proof derived scalars written by k_rp_prep, der_stride scalars per proof.  M = Montgomery form, P = plain form: a
 // Montgomery product of a P and an M operand is the plain product, which lets k_rp_gens emit plain weights directly.
-enum { D_ALLINV = 0 /* M */, D_YINV /* M */, D_RZ /* P rho z */, D_RA /* P rho a */, D_RB /* P rho b */, D_RZZ /* unused */, D_Z /* M */, D_USQ /* M, lg entries */ };
+//
+// No inversion.  bulletproofs' verifier inverts the folding challenges u_j and y once per proof (verification_scalars; a
+// ~265-multiplication Fermat chain mod l, two thirds of this kernel when it followed that shape).  Here a proof's whole
+// equation is multiplied by kappa = (prod u_j)^2 * y^(N-1), which is non-zero and fixed by the transcript before the proof's
+// random batch factor rho is drawn: rho * kappa is as uniform as rho, so the merged check has the reference's soundness and
+// the same verdicts.  Under that scaling every weight is a product of POSITIVE powers:
+//   s_i * kappa      = y^(N-1) * U1 * prod_{set bits of i} u_j^2          (U1 = prod u_j)
+//   u_j^-2 * kappa   = y^(N-1) * prod_{i != j} u_i^2                       (prefix / suffix products)
+//   y^-i * kappa     = U2 * y^(N-1-i)                                      (U2 = U1^2; N-1-i is the bit complement of i)
+//   sum_{i<N} y^i    = prod_j (1 + y^(2^j))                                (N is a power of two)
+// kappa == 0 needs a zero challenge (probability 2^-252 per scalar); the proof is then reported as failing (flag bit 4).
+enum { D_U1 = 0 /* M prod u_j */, D_SPARE /* unused */, D_RZ /* P rho kappa z */, D_RA /* P rho y^(N-1) a */, D_RB /* P rho b */, D_RZZ /* unused */, D_Z /* unused */, D_USQ /* M u_j^2, lg entries */ };
 #define RP_MAX_LG 16                     // lg = 6 + log2(m) <= 15 for m <= 512 = BP_GENS' party capacity (src/proofs.rs:20)
-#define D_YPW (D_USQ + RP_MAX_LG)        // M: y_inv^(2^j), lg entries
-#define D_RZZJ (D_USQ + 2 * RP_MAX_LG)   // P: rho z^2 z^j, m entries
+#define D_YPW (D_USQ + RP_MAX_LG)        // M: y^(2^j), lg entries
+#define D_RZZJ (D_USQ + 2 * RP_MAX_LG)   // P: rho U2 z^2 z^j, m entries
 #define RP_DER_FIXED (7 + 2 * RP_MAX_LG) // a proof's record is der_stride = RP_DER_FIXED + m_max(batch) scalars
 
 __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ sc_in /* 7 per proof */, const uint32_t* __restrict__ chal_off,
                                                 const uint32_t* __restrict__ chal, const uint32_t* __restrict__ dyn_off /* term offset per proof */, uint32_t n_rp, uint32_t der_stride,
-                                                uint32_t* __restrict__ der, uint32_t* __restrict__ dyn_sc, uint32_t* __restrict__ gh /* 2 per proof: G (B) and H (B_blinding) */) {
+                                                uint32_t* __restrict__ der, uint32_t* __restrict__ dyn_sc, uint32_t* __restrict__ gh /* 2 per proof: G (B) and H (B_blinding) */,
+                                                uint32_t* __restrict__ flags) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_rp) return;
   const sc RR = sc_load_const(SC_RR);
-  uint32_t m = m_arr[p]; int lgm = 31 - __clz(m); int lg = 6 + lgm; uint32_t N = 64u * m;
+  uint32_t m = m_arr[p]; int lgm = 31 - __clz(m); int lg = 6 + lgm;
   sc t_x, t_x_bl, e_bl, a, b, c, rho; const uint32_t* s7 = sc_in + 56 * (size_t)p;
   ld_sc(t_x, s7); ld_sc(t_x_bl, s7 + 8); ld_sc(e_bl, s7 + 16); ld_sc(a, s7 + 24); ld_sc(b, s7 + 32); ld_sc(c, s7 + 40); ld_sc(rho, s7 + 48);
   const uint32_t* ch = chal + 8 * (size_t)chal_off[p];
@@ -286,44 +298,45 @@ __global__ void __launch_bounds__(64) k_rp_prep(const uint32_t* __restrict__ m_a
   // to Montgomery form
   sc ym = mmul_call(y, RR), zm = mmul_call(z, RR), xm = mmul_call(x, RR), wm = mmul_call(w, RR), am = mmul_call(a, RR), bm = mmul_call(b, RR), cm = mmul_call(c, RR), rm = mmul_call(rho, RR);
   sc onem = mont_one();
-  // batch inversion of u_0..u_{lg-1}, y, (y - 1)
-  sc um[RP_MAX_LG + 2], pre[RP_MAX_LG + 2];
-  for (int j = 0; j < lg; j++) { sc u; ld_sc(u, ch + 32 + 8 * j); um[j] = mmul_call(u, RR); }
-  um[lg] = ym; um[lg + 1] = sc_sub(ym, onem);
-  bool y_is_one = sc_iszero(um[lg + 1]);
-  if (y_is_one) um[lg + 1] = onem;
-  sc accp = onem;
-  for (int j = 0; j < lg + 2; j++) { pre[j] = accp; accp = mmul_call(accp, um[j]); }
-  sc inv = minv_call(accp);
-  sc uinv[RP_MAX_LG + 2];
-  for (int j = lg + 1; j >= 0; j--) { uinv[j] = mmul_call(inv, pre[j]); inv = mmul_call(inv, um[j]); }
-  // allinv = prod u_j^-1
-  sc allinv = onem;
-  for (int j = 0; j < lg; j++) allinv = mmul_call(allinv, uinv[j]);
-  sc yinv = uinv[lg], ym1inv = uinv[lg + 1];
   uint32_t* d = der + 8 * (size_t)der_stride * p;
+  // u_j^2, U1 = prod u_j, prefix products of the squares; y^(2^j), y^(N-1) = prod_j y^(2^j), sum_{i<N} y^i = prod_j (1 + y^(2^j))
+  sc usq[RP_MAX_LG], pre[RP_MAX_LG + 1];
+  sc U1 = onem; pre[0] = onem;
+  sc yp = ym, yN1 = onem, sum_y = onem;
+  for (int j = 0; j < lg; j++) {
+    sc u; ld_sc(u, ch + 32 + 8 * j); sc um = mmul_call(u, RR);
+    U1 = mmul_call(U1, um); usq[j] = msq_call(um); pre[j + 1] = mmul_call(pre[j], usq[j]);
+    st_sc(d + 8 * (D_USQ + j), usq[j]); st_sc(d + 8 * (D_YPW + j), yp);
+    yN1 = mmul_call(yN1, yp); sum_y = mmul_call(sum_y, sc_add(onem, yp));
+    if (j + 1 < lg) yp = msq_call(yp);
+  }
+  const sc U2 = pre[lg];                                    // = U1^2
+  if (sc_iszero(U1) || sc_iszero(ym)) atomicOr(flags, 16u);    // kappa == 0: a zero challenge; the scaled equation would hold trivially
+  const sc kap = mmul_call(U2, yN1), rkm = mmul_call(rm, kap), rk_p = from_mont_call(rkm), ry_p = mmul_call(rho, yN1);      // rho kappa (M, P), rho y^(N-1) (P)
   sc zzm = mmul_call(zm, zm);
-  st_sc(d + 8 * D_ALLINV, allinv); st_sc(d + 8 * D_YINV, yinv);
-  st_sc(d + 8 * D_RZ, mmul_call(rho, zm)); st_sc(d + 8 * D_RA, mmul_call(rho, am)); st_sc(d + 8 * D_RB, mmul_call(rho, bm)); st_sc(d + 8 * D_Z, zm);
-  { sc yp = yinv; for (int j = 0; j < lg; j++) { st_sc(d + 8 * (D_USQ + j), msq_call(um[j])); st_sc(d + 8 * (D_YPW + j), yp); yp = msq_call(yp); } }
-  // dynamic scalars (plain form): A: rho ; S: rho x ; T1: rho c x ; T2: rho c x^2 ; L_j: rho u_j^2 ; R_j: rho u_j^-2 ; V_j: rho c z^2 z^j
+  st_sc(d + 8 * D_U1, U1);
+  st_sc(d + 8 * D_RZ, mmul_call(rk_p, zm)); st_sc(d + 8 * D_RA, mmul_call(ry_p, am)); st_sc(d + 8 * D_RB, mmul_call(rho, bm));
+  // dynamic scalars (plain form), all times kappa: A: rho ; S: rho x ; T1: rho c x ; T2: rho c x^2 ; L_j: rho u_j^2 ; R_j: rho u_j^-2 ; V_j: rho c z^2 z^j
   uint32_t* o = dyn_sc + 8 * (size_t)dyn_off[p];
-  sc rx = mmul_call(rm, xm), rcx = mmul_call(rx, cm), rcxx = mmul_call(rcx, xm);
-  st_sc(o, rho); st_sc(o + 8, from_mont_call(rx)); st_sc(o + 16, from_mont_call(rcx)); st_sc(o + 24, from_mont_call(rcxx));
-  for (int j = 0; j < lg; j++) { st_sc(o + 8 * (4 + j), from_mont_call(mmul_call(rm, mmul_call(um[j], um[j])))); st_sc(o + 8 * (4 + lg + j), from_mont_call(mmul_call(rm, mmul_call(uinv[j], uinv[j])))); }
-  sc rczz = mmul_call(mmul_call(rm, cm), zzm), zj = onem, sum_z = sc_zero();
-  sc rzz_p = mmul_call(rho, zzm);
-  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), from_mont_call(mmul_call(rczz, zj))); st_sc(d + 8 * (D_RZZJ + j), mmul_call(rzz_p, zj)); sum_z = sc_add(sum_z, zj); zj = mmul_call(zj, zm); }
+  sc rx = mmul_call(rk_p, xm), rcx = mmul_call(rx, cm), rcxx = mmul_call(rcx, xm);
+  st_sc(o, rk_p); st_sc(o + 8, rx); st_sc(o + 16, rcx); st_sc(o + 24, rcxx);
+  { sc suf = onem;                                          // suffix product of u_i^2 for i > j
+    for (int j = lg - 1; j >= 0; j--) {
+      st_sc(o + 8 * (4 + j), mmul_call(rk_p, usq[j]));
+      st_sc(o + 8 * (4 + lg + j), mmul_call(mmul_call(ry_p, pre[j]), suf));
+      suf = mmul_call(suf, usq[j]);
+    } }
+  sc rczz = mmul_call(mmul_call(rk_p, cm), zzm), zj = onem, sum_z = sc_zero();      // P
+  sc ru2zz = mmul_call(mmul_call(rho, U2), zzm);                                    // P
+  for (uint32_t j = 0; j < m; j++) { st_sc(o + 8 * (4 + 2 * lg + j), mmul_call(rczz, zj)); st_sc(d + 8 * (D_RZZJ + j), mmul_call(ru2zz, zj)); sum_z = sc_add(sum_z, zj); zj = mmul_call(zj, zm); }
   // delta(y,z) = (z - z^2) * sum_{i<N} y^i - z^3 * (2^64 - 1) * sum_{j<m} z^j
-  sc yN = ym; for (int j = 0; j < lg; j++) yN = mmul_call(yN, yN);
-  sc sum_y = y_is_one ? mmul_call(sc_from_u64(N), RR) : mmul_call(sc_sub(yN, onem), ym1inv);
   sc two64m1 = mmul_call(sc_from_u64(0xffffffffffffffffull), RR);
   sc delta = sc_sub(mmul_call(sc_sub(zm, zzm), sum_y), mmul_call(mmul_call(mmul_call(zzm, zm), two64m1), sum_z));
-  // B (G): rho (w (t_x - a b) + c (delta - t_x)) ; B_blinding (H): rho (-e_bl - c t_x_bl)
+  // B (G): rho kappa (w (t_x - a b) + c (delta - t_x)) ; B_blinding (H): rho kappa (-e_bl - c t_x_bl)
   sc txm = mmul_call(t_x, RR);
-  sc gB = mmul_call(rm, sc_add(mmul_call(wm, sc_sub(txm, mmul_call(am, bm))), mmul_call(cm, sc_sub(delta, txm))));
-  sc hB = mmul_call(rm, sc_neg(sc_add(mmul_call(e_bl, RR), mmul_call(cm, mmul_call(t_x_bl, RR)))));
-  st_sc(gh + 16 * (size_t)p, from_mont_call(gB)); st_sc(gh + 16 * (size_t)p + 8, from_mont_call(hB));
+  sc gB = mmul_call(rk_p, sc_add(mmul_call(wm, sc_sub(txm, mmul_call(am, bm))), mmul_call(cm, sc_sub(delta, txm))));
+  sc hB = mmul_call(rk_p, sc_neg(sc_add(mmul_call(e_bl, RR), mmul_call(cm, mmul_call(t_x_bl, RR)))));
+  st_sc(gh + 16 * (size_t)p, gB); st_sc(gh + 16 * (size_t)p + 8, hB);
 }
 
 // 2^k in Montgomery form for k < 64 (filled once per ctx)
@@ -333,10 +346,12 @@ __global__ void k_pow2_table(uint32_t* __restrict__ tab) {
   st_sc(tab + 8 * k, sc_montmul(v, sc_load_const(SC_RR)));
 }
 
-// One warp per proof (warp w takes proofs w, w + #warps, ...): accumulates rho*(-z - a s_i) and
-// rho*(z + y^-i (z^2 z^j 2^k - b s_{N-1-i})) for every generator index i = 64 j + k into the warp's private row
-// part[w][2*Nmax] (plain form).  The s-vector and the powers of y^-1 are products over the set bits of i: the low (up to
-// seven) bits by a doubling table in the warp's shared-memory slice, the remaining bits as one factor per 128-index chunk.
+// One warp per proof (warp w takes proofs w, w + #warps, ...): accumulates kappa rho*(-z - a s_i) and
+// kappa rho*(z + y^-i (z^2 z^j 2^k - b s_{N-1-i})) for every generator index i = 64 j + k into the warp's private row
+// part[w][2*Nmax] (plain form), in the inversion-free form of k_rp_prep: kappa s_i = y^(N-1) U1 prod_{set bits} u_j^2 and
+// kappa y^-i = U2 y^(N-1-i), where N-1-i is the bit complement of i (the mirrored table entry, like s_{N-1-i}).  Both are
+// products over index bits: the low (up to seven) bits by a doubling table in the warp's shared-memory slice, the remaining
+// bits as one factor per 128-index chunk.
 #define RPG_WARPS 4
 #define RPG_THREADS (32 * RPG_WARPS)
 #define RPG_CHUNK 128
@@ -352,9 +367,9 @@ __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restr
   for (uint32_t p = row; p < n_rp; p += n_rows) {
     const uint32_t m = m_arr[p]; const int lg = 6 + (31 - __clz(m)), lgc = lg < 7 ? lg : 7; const uint32_t N = 64u * m, Cn = 1u << lgc, Q = N >> lgc;
     const uint32_t* d = der + 8 * (size_t)der_stride * p;
-    sc allinv; ld_sc(allinv, d + 8 * D_ALLINV);
+    sc u1; ld_sc(u1, d + 8 * D_U1);
     __syncwarp();
-    if (lane == 0) { st_sc(t, Q == 1 ? allinv : mont_one()); st_sc(yl, mont_one()); }
+    if (lane == 0) { st_sc(t, Q == 1 ? u1 : mont_one()); st_sc(yl, mont_one()); }
     __syncwarp();
     for (int r = 0; r < lgc; r++) {
       sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - r))); ld_sc(ypw, d + 8 * (D_YPW + r));
@@ -369,18 +384,18 @@ __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restr
     for (uint32_t q = 0; q < Q; q++) {
       // factors of the chunk's high index bits (bit lgc + b of i pairs with u_{lg-1-lgc-b}): s base for q and for the
       // mirrored chunk Q-1-q, and y^-(q * 2^lgc)
-      sc sb = allinv, sbr = allinv, yb = mont_one();
+      sc sb = u1, sbr = u1, ybr = mont_one();
       if (Q > 1) {
         for (int b = 0; lgc + b < lg; b++) {
           sc usq, ypw; ld_sc(usq, d + 8 * (D_USQ + (lg - 1 - lgc - b))); ld_sc(ypw, d + 8 * (D_YPW + lgc + b));
-          if ((q >> b) & 1u) { sb = mmul(sb, usq); yb = mmul(yb, ypw); } else sbr = mmul(sbr, usq);
+          if ((q >> b) & 1u) sb = mmul(sb, usq); else { sbr = mmul(sbr, usq); ybr = mmul(ybr, ypw); }
         }
       }
       for (uint32_t il = lane; il < Cn; il += 32) {
         const uint32_t i = (q << lgc) + il, j = i >> 6, k = i & 63;
         sc si, sr, ypi, p2, rzzj;
-        ld_sc_rw(si, t + 8 * il); ld_sc_rw(sr, t + 8 * (Cn - 1 - il)); ld_sc_rw(ypi, yl + 8 * il); ld_sc(p2, pow2m + 8 * k); ld_sc(rzzj, d + 8 * (D_RZZJ + j));
-        if (Q > 1) { si = mmul(si, sb); sr = mmul(sr, sbr); ypi = mmul(ypi, yb); }
+        ld_sc_rw(si, t + 8 * il); ld_sc_rw(sr, t + 8 * (Cn - 1 - il)); ld_sc_rw(ypi, yl + 8 * (Cn - 1 - il)); ld_sc(p2, pow2m + 8 * k); ld_sc(rzzj, d + 8 * (D_RZZJ + j));
+        if (Q > 1) { si = mmul(si, sb); sr = mmul(sr, sbr); ypi = mmul(ypi, ybr); }
         sc gi = sc_neg(sc_add(rz, mmul(ra, si)));
         sc hi = sc_add(rz, mmul(ypi, sc_sub(mmul(rzzj, p2), mmul(rb, sr))));
         sc g0, h0; ld_sc_rw(g0, my + 8 * i); ld_sc_rw(h0, my + 8 * (Nmax + i));
@@ -972,8 +987,8 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     if (D.fs) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_fs, 0));
     ctx->stream = s_rp;
     { cudaStream_t st = s_rp;
-      XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);
-      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.der_stride, D.d_der, D.d_range_sc, D.d_rgh); XHE_LAUNCHED(ctx); }
+      XheTimed t(ctx, "k_rp_prep", 136.0 * 450 * b->n_rp);      // canonical units: the reference shape, inversion included
+      k_rp_prep<<<nblk(b->n_rp, 64), 64, 0, st>>>(D.d_m, D.d_rp_sc, D.d_ch_off, D.d_chal, D.d_pt_off, b->n_rp, D.der_stride, D.d_der, D.d_range_sc, D.d_rgh, D.d_results + 98); XHE_LAUNCHED(ctx); }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_prep, s_rp));
     // s_dyn
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_prep, 0));

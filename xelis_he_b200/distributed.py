@@ -152,24 +152,53 @@ class OrderedGatherer:
 class AsyncDecider:
     """Cross-rank decisions off the verification threads.  A worker submits (sequence number, its shard's record, the
     detached balance updates, the ledger they belong to) and moves on to its next batch; one thread per process all-gathers
-    the records strictly in sequence order (NCCL's ordering rule), sums the partial encodings on its own small context,
-    commits or drops the updates, and keeps the verdicts.  drain() waits for everything submitted so far."""
+    the records strictly in sequence order (NCCL's ordering rule) and sums the partial encodings on its own small context;
+    a second thread commits or drops the held-back updates in the same order, so that the exchange cadence never waits for
+    a ledger update (tens of thousands of hash-table writes per batch).  drain() waits for everything submitted so far."""
 
     def __init__(self, ctx, group=None, device=None):
+        import collections
         import threading
         self.ctx, self.group, self.device = ctx, group, device
         self.cv = threading.Condition()
-        self.pending, self.verdicts, self.next_seq, self.submitted, self.stop, self.error = {}, {}, 0, 0, False, None
-        self.stats = {"n": 0, "exchanges": 0, "exchange_ms": 0.0, "decide_ms": 0.0, "commit_ms": 0.0}      # time spent by the decision thread
+        self.pending, self.verdicts, self.next_seq, self.done_seq, self.submitted, self.stop, self.error = {}, {}, 0, 0, 0, False, None
+        self.commit_q = collections.deque()
+        self.stats = {"n": 0, "exchanges": 0, "exchange_ms": 0.0, "decide_ms": 0.0, "commit_ms": 0.0}      # time spent by the two threads
         self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        self.committer = threading.Thread(target=self._commit_loop, daemon=True)
+        self.thread.start(); self.committer.start()
 
     SLOTS = 8          # decisions per exchange at most: a backlog is cleared with one all-gather instead of one each
+
+    def _commit_loop(self):
+        import time
+        from . import verifier
+        try:
+            while True:
+                with self.cv:
+                    while not self.commit_q and not self.stop:
+                        self.cv.wait(0.05)
+                    if not self.commit_q:
+                        return
+                    seq, verdict, handle, ledger = self.commit_q.popleft()
+                t0 = time.perf_counter()
+                if handle:
+                    if verdict[0] == OK and ledger is not None:
+                        verifier.commit_taken(handle, ledger)
+                    else:
+                        verifier.drop_taken(handle)
+                with self.cv:
+                    self.stats["commit_ms"] += 1e3 * (time.perf_counter() - t0)
+                    self.done_seq = seq + 1
+                    self.cv.notify_all()
+        except Exception as e:
+            with self.cv:
+                self.error = e
+                self.cv.notify_all()
 
     def _run(self):
         import time
         import torch
-        from . import verifier
         try:
             if self.device is not None and self.device.type == "cuda":
                 torch.cuda.set_device(self.device)
@@ -193,23 +222,16 @@ class AsyncDecider:
                 t1 = time.perf_counter()
                 ready = min(struct.unpack("<I", m[:4])[0] for m in msgs)      # every rank computes the same number (>= 1)
                 for j in range(ready):
-                    t2 = time.perf_counter()
                     records = [m[4 + rec_len * j:4 + rec_len * (j + 1)] for m in msgs]
                     verdict = decide(records, lambda encs: sum_is_identity(self.ctx, encs))
-                    t3 = time.perf_counter()
                     _, handle, ledger = mine[j]
-                    if handle:
-                        if verdict[0] == OK and ledger is not None:
-                            verifier.commit_taken(handle, ledger)
-                        else:
-                            verifier.drop_taken(handle)
-                    self.stats["decide_ms"] += 1e3 * (t3 - t2); self.stats["commit_ms"] += 1e3 * (time.perf_counter() - t3)
                     with self.cv:
                         del self.pending[self.next_seq]
                         self.verdicts[self.next_seq] = verdict
+                        self.commit_q.append((self.next_seq, verdict, handle, ledger))
                         self.next_seq += 1
                         self.cv.notify_all()
-                self.stats["n"] += ready; self.stats["exchanges"] += 1; self.stats["exchange_ms"] += 1e3 * (t1 - t0)
+                self.stats["n"] += ready; self.stats["exchanges"] += 1; self.stats["exchange_ms"] += 1e3 * (t1 - t0); self.stats["decide_ms"] += 1e3 * (time.perf_counter() - t1)
         except Exception as e:          # surface the failure to drain() instead of hanging the workers
             with self.cv:
                 self.error = e
@@ -222,11 +244,11 @@ class AsyncDecider:
             self.cv.notify_all()
 
     def drain(self, upto, timeout=120.0):
-        """wait until every sequence number below `upto` is decided; returns {seq: (code, first failing tx)}"""
+        """wait until every sequence number below `upto` is decided and its updates committed or dropped; returns {seq: (code, first failing tx)}"""
         import time
         deadline = time.time() + timeout
         with self.cv:
-            while self.next_seq < upto and self.error is None:
+            while self.done_seq < upto and self.error is None:
                 if time.time() > deadline:
                     raise TimeoutError("cross-rank decisions did not complete")
                 self.cv.wait(0.05)
@@ -238,7 +260,7 @@ class AsyncDecider:
         with self.cv:
             self.stop = True
             self.cv.notify_all()
-        self.thread.join(5)
+        self.thread.join(5); self.committer.join(5)
 
 
 def shard_bounds(n, rank, world):

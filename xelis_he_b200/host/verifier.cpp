@@ -401,21 +401,100 @@ static bool scan_keys(const uint8_t* b, size_t n, F&& f) {
   for (uint32_t q = 0; q < n_sc; q++) f(b + 16, b + off + 256 * (size_t)q);
   return true;
 }
-// indices i < lo of the transactions that touch one of `keys`, or set the multisig of one of `sources` (in batch order)
-static std::vector<size_t> foreign_hits(const uint8_t* const* blobs, const size_t* lens, size_t lo, const FlatTable<64, uint8_t>& keys, const FlatTable<32, uint8_t>& sources, int threads) {
-  std::vector<std::vector<size_t>> part(std::max(1, threads));
-  parallel_for(lo, threads, [&](size_t a, size_t b, int tid) {
-    for (size_t i = a; i < b; i++) {
-      bool hit = false;
-      scan_keys(blobs[i], lens[i], [&](const uint8_t* account, const uint8_t* asset) { if (!hit && keys.find(MockLedger::key(account, asset).data())) hit = true; });
-      if (!hit && lens[i] >= 128 && blobs[i][1] == 4 && sources.find(blobs[i] + 16)) hit = true;
-      if (hit) part[tid].push_back(i);
+// ---- key-digest index (built once per batch, when its transactions are received: xheh_batch_index_build) ---------------
+// digest of an (account, asset) key, and of "account sets its multisig" -- 64-bit, collisions only cost a spurious candidate
+static inline uint64_t key_digest(const uint8_t* account, const uint8_t* asset) { Ct64 kk = MockLedger::key(account, asset); return FlatTable<64, uint8_t>::hash(kk.data()) | 1u; }
+static inline uint64_t multisig_digest(const uint8_t* source) { return (FlatTable<32, uint8_t>::hash(source) ^ 0x6d756c7469736967ull) | 1u; }
+struct BatchIndex { std::vector<uint32_t> off; std::vector<uint64_t> dig; size_t n = 0; };      // digests of transaction i: dig[off[i] .. off[i+1])
+static BatchIndex* build_index(const uint8_t* const* blobs, const size_t* lens, size_t n, int threads) {
+  BatchIndex* ix = new BatchIndex(); ix->n = n; ix->off.assign(n + 1, 0);
+  threads = std::max(1, threads);
+  std::vector<uint32_t> cnt(n, 0);
+  auto each = [&](size_t i, auto&& f) {
+    scan_keys(blobs[i], lens[i], [&](const uint8_t* account, const uint8_t* asset) { f(key_digest(account, asset)); });
+    if (lens[i] >= 128 && blobs[i][1] == 4) f(multisig_digest(blobs[i] + 16));
+  };
+  parallel_for(n, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) { uint32_t c = 0; each(i, [&](uint64_t) { c++; }); cnt[i] = c; } });
+  for (size_t i = 0; i < n; i++) ix->off[i + 1] = ix->off[i] + cnt[i];
+  ix->dig.resize(ix->off[n]);
+  parallel_for(n, threads, [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) { uint64_t* d = &ix->dig[ix->off[i]]; each(i, [&](uint64_t h) { *d++ = h; }); } });
+  return ix;
+}
+struct DigestSet {      // open addressing over non-zero 64-bit digests
+  std::vector<uint64_t> slot; size_t mask = 0;
+  void reserve(size_t n) { size_t cap = 64; while (cap < 4 * n) cap <<= 1; slot.assign(cap, 0); mask = cap - 1; }
+  void insert(uint64_t h) { for (size_t i = (size_t)(h >> 17) & mask;; i = (i + 1) & mask) { if (slot[i] == h) return; if (!slot[i]) { slot[i] = h; return; } } }
+  bool has(uint64_t h) const { for (size_t i = (size_t)(h >> 17) & mask;; i = (i + 1) & mask) { if (slot[i] == h) return true; if (!slot[i]) return false; } }
+};
+
+// The (account, asset) keys a shard moves and its senders.  Their 64-bit digests are always built (one small open-addressing
+// set, reused by the calling thread from batch to batch); the exact tables only when an earlier transaction's digest matches --
+// in a batch whose shards are independent nothing bigger than that set is allocated or touched.
+struct ShardKeys {
+  const TxView* txs; size_t n; DigestSet& dig; FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; bool exact = false;
+  static DigestSet& tl_set() { static thread_local DigestSet s; return s; }
+  ShardKeys(const TxView* t, size_t count) : txs(t), n(count), dig(tl_set()) {
+    size_t nk = 0; for (size_t j = 0; j < n; j++) nk += 1 + txs[j].n_sc + txs[j].transfers.size();
+    dig.reserve(nk);
+    for (size_t j = 0; j < n; j++) {
+      const TxView& tx = txs[j]; dig.insert(multisig_digest(tx.source));
+      for (uint32_t q = 0; q < tx.n_sc; q++) dig.insert(key_digest(tx.source, tx.sc + 256 * q));
+      for (const TransferView& tr : tx.transfers) dig.insert(key_digest(tr.dest, tr.asset));
     }
-  });
+  }
+  void build_exact() {
+    if (exact) return;
+    size_t nk = 0; for (size_t j = 0; j < n; j++) nk += txs[j].n_sc + txs[j].transfers.size();
+    keys.reserve(nk + 8); sources.reserve(n + 8);
+    for (size_t j = 0; j < n; j++) {
+      const TxView& tx = txs[j]; sources.insert(tx.source);
+      for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
+      for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
+    }
+    exact = true;
+  }
+};
+
+// indices i < lo of the transactions that move one of the shard's keys, or set the multisig of one of its senders (in batch
+// order).  With the batch's key-digest index the earlier shards' BYTES are not read at all: their digests (a few 8-byte words
+// per transaction, sequential) are looked up in the shard's digest set; without it the digests are computed from the blobs'
+// framing.  Only candidates are confirmed against the exact keys.  K.exact is set iff the result is non-empty.
+static std::vector<size_t> foreign_hits(const uint8_t* const* blobs, const size_t* lens, size_t lo, ShardKeys& K, int threads, const BatchIndex* ix = nullptr) {
+  std::vector<std::vector<size_t>> part(std::max(1, threads));
+  const DigestSet& mine = K.dig;
+  if (ix && ix->n >= lo) {
+    parallel_for(lo, threads, [&](size_t a, size_t b, int tid) {
+      const uint64_t* d = ix->dig.data();
+      for (size_t i = a; i < b; i++) {
+        bool cand = false;
+        for (uint32_t q = ix->off[i]; q < ix->off[i + 1] && !cand; q++) cand = mine.has(d[q]);
+        if (cand) part[tid].push_back(i);
+      }
+    });
+  } else {
+    parallel_for(lo, threads, [&](size_t a, size_t b, int tid) {
+      for (size_t i = a; i < b; i++) {
+        if (i + 12 < b) { const uint8_t* nb = blobs[i + 12]; __builtin_prefetch(nb); __builtin_prefetch(nb + 64); if (lens[i + 12] >= 384) { __builtin_prefetch(nb + lens[i + 12] - 64 - 256); __builtin_prefetch(nb + lens[i + 12] - 64 - 192); } }      // header, first transfer, source commitment
+        bool cand = false;
+        scan_keys(blobs[i], lens[i], [&](const uint8_t* account, const uint8_t* asset) { if (!cand && mine.has(key_digest(account, asset))) cand = true; });
+        if (!cand && lens[i] >= 128 && blobs[i][1] == 4 && mine.has(multisig_digest(blobs[i] + 16))) cand = true;
+        if (cand) part[tid].push_back(i);
+      }
+    });
+  }
   std::vector<size_t> out;
   for (auto& p : part) out.insert(out.end(), p.begin(), p.end());
-  std::sort(out.begin(), out.end());
-  return out;
+  if (out.empty()) return out;
+  K.build_exact();
+  std::vector<size_t> hits;
+  for (size_t i : out) {
+    bool hit = false;
+    scan_keys(blobs[i], lens[i], [&](const uint8_t* account, const uint8_t* asset) { if (!hit && K.keys.find(MockLedger::key(account, asset).data())) hit = true; });
+    if (!hit && lens[i] >= 128 && blobs[i][1] == 4 && K.sources.find(blobs[i] + 16)) hit = true;
+    if (hit) hits.push_back(i);
+  }
+  std::sort(hits.begin(), hits.end());
+  return hits;
 }
 
 // the reference's verdict for ONE transaction of the batch (it is known to be the first one that fails a per-transaction
@@ -485,14 +564,9 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   // on.  The group operations of a foreign transaction on a shared (account, asset) are replayed here (no proofs: its own
   // rank verifies them); its ciphertext points travel in region B.
   if (lo > 0) {
-    FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * n); sources.reserve(n);
-    for (size_t j = 0; j < n; j++) {
-      const TxView& tx = txs[j]; sources.insert(tx.source);
-      for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
-      for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
-    }
+    ShardKeys K(txs.data(), n); FlatTable<64, uint8_t>& keys = K.keys; FlatTable<32, uint8_t>& sources = K.sources;      // (the exact tables are filled iff there is a hit)
     TxView ftx;
-    for (size_t i : foreign_hits(blobs, lens, lo, keys, sources, threads)) {
+    for (size_t i : foreign_hits(blobs, lens, lo, K, threads, (opt.key_index && ((const BatchIndex*)opt.key_index)->n == n_total) ? (const BatchIndex*)opt.key_index : nullptr)) {
       if (ftx.parse(blobs[i], lens[i])) continue;
       const TxView& tx = ftx; const uint32_t k = tx.n_transfers();
       if (tx.type == 4 && sources.find(tx.source)) return 0;                    // multisig setting for one of our senders: exact path
@@ -738,16 +812,11 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   // same ciphertexts as in the reference's sequential walk (src/tx/verify.rs:301-336,354-374).  MultiSig settings of earlier
   // shards are visible through the overlay.  If a foreign transaction is invalid its own rank rejects the batch.
   if (lo > 0 && n_live > lo) {
-    FlatTable<64, uint8_t> keys; FlatTable<32, uint8_t> sources; keys.reserve(4 * (n_live - lo)); sources.reserve(n_live - lo);
-    for (size_t i = lo; i < n_live; i++) {
-      const TxView& tx = txs[i - lo]; sources.insert(tx.source);
-      for (uint32_t q = 0; q < tx.n_sc; q++) keys.insert(MockLedger::key(tx.source, tx.sc + 256 * q).data());
-      for (const TransferView& tr : tx.transfers) keys.insert(MockLedger::key(tr.dest, tr.asset).data());
-    }
+    ShardKeys K(txs.data(), n_live - lo); FlatTable<64, uint8_t>& keys = K.keys; FlatTable<32, uint8_t>& sources = K.sources;      // (the exact tables are filled iff there is a hit)
     // the earlier transactions are only SCANNED for these keys (scan_keys reads the framing, nothing else); the few that touch
     // one are parsed.  The points of a foreign transaction must outlive this loop: they are copied into the point table.
     TxView ftx;
-    for (size_t i : foreign_hits(blobs, lens, lo, keys, sources, threads)) {
+    for (size_t i : foreign_hits(blobs, lens, lo, K, threads, (opt.key_index && ((const BatchIndex*)opt.key_index)->n == n_total) ? (const BatchIndex*)opt.key_index : nullptr)) {
       if (ftx.parse(blobs[i], lens[i])) continue;
       const TxView& tx = ftx; const uint32_t k = tx.n_transfers();
       if (tx.type == 4 && sources.find(tx.source) && multisig_payload_ok(tx)) staged.set_multisig(tx.source, tx.body, tx.count, (uint8_t)tx.aux, true);
@@ -1056,6 +1125,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   if (shard) { memcpy(opt.partial_out, v.sigma_enc, 32); memcpy(opt.partial_out + 32, v.range_enc, 32); }
   if (verdict == XHE_OK && !shard && !v.sigma_is_identity) verdict = XHE_ERR_GENERIC_PROOF;            // src/tx/verify.rs:500-502
   if (verdict == XHE_OK) { for (size_t j = 0; j < n_loc; j++) if (plan[j].rp_structural_fail) verdict = XHE_ERR_RANGE_PROOF; }
+  if (verdict == XHE_OK && (v.device_flags & 16u)) verdict = XHE_ERR_RANGE_PROOF;                       // a zero folding challenge (k_rp_prep: the scaled equation would hold trivially)
   if (verdict == XHE_OK && !shard && !v.range_is_identity) verdict = XHE_ERR_RANGE_PROOF;               // src/tx/verify.rs:504-514
   if (shard) {
     Pending Pn; Pn.updates = B.updates; Pn.op_out.assign(op_out.data(), op_out.data() + op_out.size()); Pn.staged = std::move(staged);
@@ -1199,6 +1269,35 @@ int32_t xheh_verify_batch_shard(xhe_ctx* ctx, void* ledger, const uint8_t* const
   int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
   return rc;
+}
+// the same with the batch's key-digest index (xheh_batch_index_build): the earlier shards' bytes are not scanned
+int32_t xheh_verify_batch_shard_ix(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi, const uint8_t* seed, size_t seed_len, int threads, uint32_t flags,
+                                   long* fail_index, double* timings7, uint8_t* partial64, const void* index) {
+  if (!partial64 || lo > hi) return XHE_E_ARG;
+  BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = partial64; opt.fast_path = (flags & 4u) != 0;
+  opt.deterministic_seed = (flags & 8u) != 0; opt.shard_lo = lo; opt.shard_hi = hi; opt.key_index = index;
+  BatchTimings tm;
+  int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
+  if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
+  return rc;
+}
+// key-digest index of a batch: per transaction, 64-bit digests of the (account, asset) balances it moves and of a multisig
+// setting it makes.  Built once, where the transactions are received and framed (next to the blob arena); a shard-mode call
+// that gets it finds the earlier transactions its own depend on without reading the earlier shards' bytes.
+void* xheh_batch_index_build(const uint8_t* const* blobs, const size_t* lens, size_t n, int threads) { return build_index(blobs, lens, n, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency())); }
+void xheh_batch_index_free(void* index) { delete (BatchIndex*)index; }
+size_t xheh_batch_index_bytes(const void* index) { const BatchIndex* ix = (const BatchIndex*)index; return ix ? 4 * ix->off.size() + 8 * ix->dig.size() : 0; }
+// the transactions of [0, lo) that shard [lo, hi) depends on (shared balances, multisig settings of its senders), in batch
+// order; index may be NULL (the blobs are scanned).  Returns the count (out receives at most cap of them); -1: a transaction of the shard does not parse.
+long xheh_shard_dependencies(const uint8_t* const* blobs, const size_t* lens, size_t n, size_t lo, size_t hi, const void* index, int threads, size_t* out, size_t cap) {
+  lo = std::min(lo, n); hi = std::min(hi, n);
+  std::vector<TxView> txs(hi - lo);
+  for (size_t j = lo; j < hi; j++) if (txs[j - lo].parse(blobs[j], lens[j])) return -1;
+  ShardKeys K(txs.data(), txs.size());
+  const BatchIndex* ix = (const BatchIndex*)index;
+  std::vector<size_t> hits = foreign_hits(blobs, lens, lo, K, std::max(1, threads), (ix && ix->n == n) ? ix : nullptr);
+  for (size_t i = 0; i < hits.size() && i < cap; i++) out[i] = hits[i];
+  return (long)hits.size();
 }
 int32_t xheh_commit_pending(xhe_ctx* ctx, void* ledger) { return commit_pending(ctx, *(VerificationState*)ledger); }
 // detached form: take the held-back updates now, commit (or drop) them when the cross-rank decision is known

@@ -205,6 +205,7 @@ struct BatchOptions { int threads = 0;
                       /* shard mode on the WHOLE batch: this rank verifies transactions [shard_lo, min(shard_hi, n)) of blobs[0..n) and reads
                        * the earlier ones only to advance the balance chains (and multisig settings) its own transactions depend on */
                       size_t shard_lo = 0, shard_hi = (size_t)-1;
+                      const void* key_index = nullptr; /* xheh_batch_index_build of the same batch (optional): earlier shards are searched through their key digests */
                       bool device_fiat_shamir = false; /* transcripts, batch factors and main-signature hashes on the GPU */
                       bool fast_path = false; /* optimistic device-layout path first (implies device Fiat-Shamir); the exact path decides on any failure */ };
 

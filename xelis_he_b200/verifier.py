@@ -160,20 +160,44 @@ class DeviceLedgerState:
     __del__ = close
 
 
+def _attach_index(bl, lib, threads=0):
+    """key-digest index of the batch (a few 8-byte words per transaction), built where the transactions are framed: a
+    shard-mode call finds the earlier transactions its shard depends on without reading the other shards' bytes"""
+    import time
+    lib.xheh_batch_index_build.restype = C.c_void_p; lib.xheh_batch_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.xheh_batch_index_free.argtypes = [C.c_void_p]; lib.xheh_batch_index_free.restype = None
+    lib.xheh_batch_index_bytes.argtypes = [C.c_void_p]; lib.xheh_batch_index_bytes.restype = C.c_size_t
+    t0 = time.perf_counter()
+    bl.index = lib.xheh_batch_index_build(bl.ptrs, bl.lens, bl.n, threads)
+    bl.index_build_ms = 1e3 * (time.perf_counter() - t0)
+    bl.index_bytes = int(lib.xheh_batch_index_bytes(bl.index))
+
+
 class _Blobs:
-    def __init__(self, blobs):
+    def __init__(self, blobs, index=False, index_threads=0):
         n = len(blobs)
         self.keep = [C.create_string_buffer(b, len(b)) for b in blobs]
         self.ptrs = (C.c_void_p * max(n, 1))(*[C.addressof(k) for k in self.keep])
         self.lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
         self.n = n
+        self.index = None
+        if index and n:
+            self.lib = _lib()
+            _attach_index(self, self.lib, index_threads)
+
+    def __del__(self):
+        try:
+            if getattr(self, "index", None):
+                self.lib.xheh_batch_index_free(self.index); self.index = None
+        except Exception:
+            pass
 
 
 class _PinnedBlobs:
     """the batch in ONE page-locked buffer, laid out as the device reads it (blobs back to back, padded to 16 bytes): the fast
     path uploads it in place -- zero-copy input.  Same interface as _Blobs."""
 
-    def __init__(self, blobs):
+    def __init__(self, blobs, index=True, index_threads=0):
         lib = _lib()
         lib.xheh_blob_arena_alloc.restype = C.c_void_p; lib.xheh_blob_arena_alloc.argtypes = [C.c_size_t]
         lib.xheh_blob_arena_free.argtypes = [C.c_void_p]
@@ -191,9 +215,14 @@ class _PinnedBlobs:
         self.ptrs = (C.c_void_p * max(n, 1))(*[self.base + o for o in offs])
         self.lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
         self.n = n
+        self.index = None
+        if index and n:
+            _attach_index(self, lib, index_threads)
 
     def __del__(self):
         try:
+            if getattr(self, "index", None):
+                self.lib.xheh_batch_index_free(self.index); self.index = None
             if self.base:
                 self.lib.xheh_blob_arena_free(self.base); self.base = None
         except Exception:
@@ -236,19 +265,27 @@ def verify_batch_partial(ctx, blobs, ledger, seed=None, threads=0, prepared=None
     return rc, fi.value, part.raw[:32], part.raw[32:], d
 
 
-def verify_batch_shard(ctx, blobs, ledger, lo, hi, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False):
+def verify_batch_shard(ctx, blobs, ledger, lo, hi, seed=None, threads=0, prepared=None, fiat_shamir="host", deterministic=False, use_index=True):
     """One rank's share of a sharded batch.  `blobs` is the WHOLE batch (every rank holds it); this call
     verifies transactions [lo, hi) and reads the earlier ones only to follow the (account, asset) balance chains -- and the
     multisig settings -- its own transactions depend on, so the verdicts equal the reference's sequential walk
-    (src/tx/verify.rs:301-374) however the batch is cut.  Returns (local code, first failing tx as an index into the whole
+    (src/tx/verify.rs:301-374) however the batch is cut.  When `prepared` carries the batch's key-digest index
+    (prepare_blobs_pinned builds it), the earlier shards are searched through it instead of through their bytes.  Returns (local code, first failing tx as an index into the whole
     batch, sigma partial enc, range partial enc, timings); state updates are held back until commit_pending()."""
     lib = _lib()
     bl = prepared or _Blobs(blobs)
     fi = C.c_long(-1)
     tm = (C.c_double * 7)()
     part = C.create_string_buffer(64)
-    rc = lib.xheh_verify_batch_shard(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, lo, hi, seed, len(seed) if seed else 0, threads,
-                                     _MODE_FLAGS[fiat_shamir] | (_DETERMINISTIC if deterministic else 0), C.byref(fi), tm, part)
+    flags = _MODE_FLAGS[fiat_shamir] | (_DETERMINISTIC if deterministic else 0)
+    index = getattr(bl, "index", None) if use_index else None
+    if index:
+        lib.xheh_verify_batch_shard_ix.restype = C.c_int32
+        lib.xheh_verify_batch_shard_ix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
+                                                   C.POINTER(C.c_long), C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = lib.xheh_verify_batch_shard_ix(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, lo, hi, seed, len(seed) if seed else 0, threads, flags, C.byref(fi), tm, part, index)
+    else:
+        rc = lib.xheh_verify_batch_shard(ctx.p, ledger.ptr, bl.ptrs, bl.lens, bl.n, lo, hi, seed, len(seed) if seed else 0, threads, flags, C.byref(fi), tm, part)
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     keys = ("parse_ms", "resolve_ms", "transcript_ms", "device_ms", "finish_ms", "total_ms", "keccak_f")
@@ -302,6 +339,19 @@ def apply_without_verify(ctx, blobs, ledger):
     if rc < 0:
         raise XheError(rc, lib.xhe_last_error(ctx.p).decode())
     return rc
+
+
+def shard_dependencies(prepared, lo, hi, use_index=True, threads=1):
+    """the transactions of [0, lo) that shard [lo, hi) of the prepared batch depends on (host-only; no device work)"""
+    lib = _lib()
+    lib.xheh_shard_dependencies.restype = C.c_long
+    lib.xheh_shard_dependencies.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    cap = max(lo, 1)
+    out = (C.c_size_t * cap)()
+    k = lib.xheh_shard_dependencies(prepared.ptrs, prepared.lens, prepared.n, lo, hi, getattr(prepared, "index", None) if use_index else None, threads, out, cap)
+    if k < 0:
+        raise XheError(4, "a transaction of the shard does not parse")
+    return list(out[:k])
 
 
 prepare_blobs = _Blobs
