@@ -640,7 +640,9 @@ def main():
     lgm = 6 + (m.bit_length() - 1)
     n_dyn = args.txs * (4 + 2 * lgm + m)
     msm_in_batch = {}
-    for nm, npts, extra in (("msm_sigma", n_sigma, kernels.get("msm_sigma_sort", {}).get("ms_per_step", 0.0)), ("msm_range_dyn", n_dyn, 0.0)):
+    # (the default step runs ONE Pippenger instance over both term sets -- msm_joint; XHE_SPLIT_MSM=1 keeps the two apart)
+    for nm, npts, extra in (("msm_joint", n_sigma + n_dyn, kernels.get("msm_joint_sort", {}).get("ms_per_step", 0.0)),
+                            ("msm_sigma", n_sigma, kernels.get("msm_sigma_sort", {}).get("ms_per_step", 0.0)), ("msm_range_dyn", n_dyn, 0.0)):
         if nm in kernels and kernels[nm]["ms_per_step"] > 0:
             ms_ = kernels[nm]["ms_per_step"] + extra
             msm_in_batch[nm] = {"points": npts, "ms_isolated": round(ms_, 4), "msm_frac": round(a_msm(npts) / (ms_ * 1e-3) / peak_wide, 4)}

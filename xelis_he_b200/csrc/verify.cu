@@ -536,6 +536,13 @@ __global__ void k_combine_out(const uint32_t* __restrict__ ext, uint32_t n, uint
 
 // sum of up to 32 * k Ristretto encodings (one warp: lanes decode in parallel, lane 0 adds): out = 32 B encoding of the
 // sum, then a word "sum is the identity", then a word "every encoding decoded"
+// joint MSM (xhe_batch_run): range slots = identity (encoding words 48..55 zero, flag 56, extended point 64..95), word 100 = 1
+__global__ void k_joint_mark(uint32_t* __restrict__ results) {
+  const uint32_t t = threadIdx.x;
+  if (t < 8) results[48 + t] = 0;
+  if (t == 0) { results[56] = 1u; results[100] = 1u; }
+  results[64 + t] = (t == 8 || t == 16) ? 1u : 0u;      // X = 0, Y = 1, Z = 1, T = 0
+}
 __global__ void __launch_bounds__(32) k_sum_encodings(const uint8_t* __restrict__ enc, uint32_t n, uint8_t* __restrict__ out) {
   __shared__ uint32_t pts[32 * 16]; __shared__ uint32_t okw[32];
   ge acc = ge_identity(); uint32_t all_ok = 1;
@@ -566,7 +573,8 @@ __global__ void k_make_record(const uint32_t* __restrict__ results, uint8_t* __r
   uint32_t* w32 = reinterpret_cast<uint32_t*>(rec);            // 20 words
   const uint32_t flags = results[98];
   // per-transaction anomalies are the host's to name (it re-decides that transaction): code 0xFF = "this shard needs its host"
-  if (t == 0) { w32[0] = (flags & 15u) ? 0xFFu : ((flags & 16u) ? (uint32_t)XHE_ERR_RANGE_PROOF : (uint32_t)XHE_OK); w32[1] = 0xFFFFFFFFu; w32[2] = 0xFFFFFFFFu; w32[19] = 0; }
+  const bool undecided = results[100] != 0 && results[8] == 0;      // joint MSM, not the identity: which check failed is not known yet (xhe_batch_fetch re-runs them apart)
+  if (t == 0) { w32[0] = ((flags & 15u) || undecided) ? 0xFFu : ((flags & 16u) ? (uint32_t)XHE_ERR_RANGE_PROOF : (uint32_t)XHE_OK); w32[1] = 0xFFFFFFFFu; w32[2] = 0xFFFFFFFFu; w32[19] = 0; }
   if (t < 8) w32[3 + t] = results[t];
   else if (t < 16) w32[11 + (t - 8)] = results[48 + (t - 8)];
 }
@@ -701,6 +709,7 @@ struct DeviceBatch {
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
   long long *d_ptr_a, *d_ptr_b, *d_ptr_init; uint64_t* d_amount;
+  bool joint_used = false, force_split = false; size_t ws_joint = 0; uint8_t* d_wsj = nullptr;      // one Pippenger instance over the sigma and the range terms (xhe_batch_run)
   double sum_m = 0; bool fs = false, layout = false; uint32_t plan_stride = 6; uint8_t *d_blobs, *d_seed, *d_sig_ok, *d_tx_flags; unsigned long long *d_blob_off, *d_sig_state; uint32_t* d_fs_plan; size_t blob_bytes = 0;
 };
 
@@ -773,6 +782,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
     XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, rpg_smem())); gens_blocks_per_sm = nb > 0 ? nb : 1; }
   D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS), std::max<size_t>(64, ((size_t)64 << 20) / (64 * (size_t)D.Nmax))) : 0;
   D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_dyn); D.ws_static = xhe_msm_workspace_bytes(ctx, D.n_range - D.n_dyn);
+  D.ws_joint = xhe_msm_workspace_bytes(ctx, D.n_sigma + D.n_dyn);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
   D.fs = b->fs_blobs != nullptr && b->n_tx > 0; D.blob_bytes = D.fs ? (size_t)b->fs_blob_off[b->n_tx] : 0;
   D.layout = D.fs && b->layout_on_device != 0; D.plan_stride = D.layout ? 8 : 6;
@@ -785,7 +795,7 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
               + 28 * (size_t)b->n_eq + 192 * (size_t)b->n_eq + 32 * (size_t)b->n_val + 160 * (size_t)b->n_val
               + 32 * n_sigma + 96 * n_sigma + 4 * n_sigma + 64 * ((size_t)b->n_eq + b->n_val) + 64 * 64
               + (size_t)b->n_rp * (4 + 4 + 4 + 224 + 32 * (size_t)D.der_stride + 64) + 4 * n_dyn + 32 * n_chal + 32 * n_range + 96 * n_range + 4 * n_range
-              + 64 * (size_t)D.rp_grid * Nmax + D.ws_sigma + D.ws_range + D.ws_static + 8192 + 512 * 64
+              + 64 * (size_t)D.rp_grid * Nmax + std::max(D.ws_sigma + D.ws_range + 512, D.ws_joint) + D.ws_static + 8192 + 512 * 64
               + D.blob_bytes + 8 * ((size_t)b->n_tx + 1) + 32 * (size_t)b->n_tx + 64 + b->n_sigs + b->n_tx + 512 + 208 * (size_t)b->n_sigs + 256;
   if (ctx->scratch_bytes < need) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -802,11 +812,16 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   TAKE(long long, d_ptr_init, b->n_ops); TAKE(long long, d_ptr_a, b->n_ops); TAKE(long long, d_ptr_b, b->n_ops); TAKE(uint64_t, d_amount, b->n_ops); TAKE(uint32_t, d_term_off, b->n_ops + 1); TAKE(uint32_t, d_terms, n_terms);
   TAKE(uint32_t, d_acc_a, 32 * (size_t)b->n_ops); TAKE(uint32_t, d_acc_b, 32 * (size_t)b->n_ops); TAKE(uint8_t, d_op_out, 32 * (size_t)b->n_ops);
   TAKE(uint32_t, d_eq_sc, 48 * (size_t)b->n_eq); TAKE(uint32_t, d_val_sc, 40 * (size_t)b->n_val); TAKE(uint32_t, d_sig_idx, n_sigma);
-  TAKE(uint32_t, d_sigma_sc, 8 * n_sigma); TAKE(uint32_t, d_sigma_niels, 24 * n_sigma); TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
-  TAKE(uint32_t, d_results, 128); TAKE(uint8_t, d_ws1, D.ws_sigma);
+  // sigma terms and range-proof terms share ONE scalar array and ONE operand array (sigma | range dynamic | range static), so that
+  // the joint MSM of xhe_batch_run runs over a prefix of both; the workspaces of the two separate MSMs alias the joint one's
+  TAKE(uint32_t, d_sigma_sc, 8 * (n_sigma + n_range)); D.d_range_sc = D.d_sigma_sc + 8 * n_sigma;
+  TAKE(uint32_t, d_sigma_niels, 24 * (n_sigma + n_range)); D.d_range_niels = D.d_sigma_niels + 24 * n_sigma;
+  TAKE(uint8_t, d_wsj, std::max(D.ws_sigma + D.ws_range + 512, D.ws_joint)); D.d_ws1 = D.d_wsj; D.d_ws2 = D.d_wsj + ((D.ws_sigma + 255) & ~(size_t)255);
+  TAKE(uint32_t, d_gh, 16 * ((size_t)b->n_eq + b->n_val) + 16); TAKE(uint32_t, d_gh_part, 16 * 64);
+  TAKE(uint32_t, d_results, 128);
   TAKE(uint32_t, d_m, b->n_rp); TAKE(uint32_t, d_pt_off, b->n_rp + 1); TAKE(uint32_t, d_ch_off, b->n_rp + 1); TAKE(uint32_t, d_rp_sc, 56 * (size_t)b->n_rp);
   TAKE(uint32_t, d_chal, 8 * n_chal); TAKE(uint32_t, d_der, 8 * (size_t)D.der_stride * b->n_rp); TAKE(uint32_t, d_rgh, 16 * (size_t)b->n_rp + 16); TAKE(uint32_t, d_rgh_part, 16 * 64);
-  TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_range_sc, 8 * n_range); TAKE(uint32_t, d_range_niels, 24 * n_range); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws2, D.ws_range); TAKE(uint8_t, d_ws3, D.ws_static); TAKE(uint32_t, d_rparts, 64);
+  TAKE(uint32_t, d_range_idx, n_dyn); TAKE(uint32_t, d_part, 16 * (size_t)D.rp_grid * Nmax); TAKE(uint8_t, d_ws3, D.ws_static); TAKE(uint32_t, d_rparts, 64);
   TAKE(uint8_t, d_blobs, D.blob_bytes); TAKE(unsigned long long, d_blob_off, b->n_tx + 1); TAKE(uint32_t, d_fs_plan, 8 * (size_t)b->n_tx); TAKE(uint8_t, d_seed, 32); TAKE(uint8_t, d_sig_ok, b->n_sigs); TAKE(uint8_t, d_tx_flags, b->n_tx); TAKE(unsigned long long, d_sig_state, 26 * (size_t)b->n_sigs);
   if (D.fs) { UP(D.d_blobs, b->fs_blobs, D.blob_bytes); UP(D.d_blob_off, b->fs_blob_off, 8 * ((size_t)b->n_tx + 1)); UP(D.d_fs_plan, b->fs_plan, 4 * (size_t)D.plan_stride * b->n_tx); UP(D.d_seed, b->fs_seed, 32); }
   if (!D.layout) {
@@ -882,6 +897,14 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   cudaEvent_t e_start = ctx->ev[0], e_dec = ctx->ev[1], e_fs = ctx->ev[2], e_sig = ctx->ev[3], e_rp = ctx->ev[4], e_lay = ctx->ev[5], e_sgsort = ctx->ev[6], e_prep = ctx->ev[7], e_dyn = ctx->ev[8], e_acc_sigma = ctx->ev[9], e_acc_dyn = ctx->ev[10], e_pre = ctx->ev[12];
   struct StreamGuard { xhe_ctx* c; cudaStream_t saved; ~StreamGuard() { c->stream = saved; } } guard{ctx, main_st};
   const uint32_t np = b->n_eq + b->n_val;
+  // ONE Pippenger instance over the sigma terms and the range proofs' own points (they share one scalar and one operand array):
+  // every proof's equation carries its own uniform random factor, so the sum of both merged checks is the identity exactly when
+  // each is (src/proofs.rs:49-67 and src/tx/verify.rs:504-514 are two such sums) -- one sort, fewer windows, one reduction tail.
+  // A sum that is NOT the identity does not say which check failed: xhe_batch_fetch then runs the batch again with the two
+  // MSMs apart (D.force_split), so the verdict and its precedence are the reference's.  XHE_SPLIT_MSM=1 keeps them apart always.
+  static const bool split_env = getenv("XHE_SPLIT_MSM") != nullptr && atoi(getenv("XHE_SPLIT_MSM")) != 0;
+  const bool joint = !split_env && !D.force_split && np > 0 && b->n_rp > 0 && !xhe_msm_chain_enabled();
+  D.joint_used = joint;
   XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_results, 0, 512, main_st));
   // The Horner chains of both MSMs are served by ONE polling kernel that is launched now, while the machine is empty, and owns
   // an SM for the whole step (msm.cu, k_msm_chain): the sigma chain on warp 0, the range chain on warp 1.
@@ -943,9 +966,9 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     } else {
       XHE_CUDA_OK(ctx, cudaMemsetAsync(D.d_sigma_sc + 8 * n_sigma_terms, 0, 64, st));
     }
-    { XheTimed t(ctx, "msm_sigma_sort", 0);
+    if (!joint) { XheTimed t(ctx, "msm_sigma_sort", 0);
       rc = xhe_msm_sort(ctx, D.d_sigma_sc, n_sigma, D.d_ws1, D.ws_sigma, D.d_results + 96); if (rc) return rc; }
-    XHE_CUDA_OK(ctx, cudaEventRecord(e_sgsort, s_fs));
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_sgsort, s_fs));      // split: sigma sort done; joint: sigma scalars in place
   }
   // ---- main: decompress
   ctx->stream = main_st;
@@ -993,12 +1016,18 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     // s_dyn
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_prep, 0));
     ctx->stream = s_dyn;
-    { XheTimed t(ctx, "msm_range_dyn", 8064.0 * n_dyn + 6.04e8);
+    if (joint) {   // the scalar half of the joint MSM (needs the sigma weights and the range scalars, no points)
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_sgsort, 0));
+      { XheTimed t(ctx, "msm_joint_sort", 0);
+        rc = xhe_msm_sort(ctx, D.d_sigma_sc, n_sigma + n_dyn, D.d_wsj, D.ws_joint, D.d_results + 96); if (rc) return rc; }
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_dec, 0));
+      k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, s_dyn>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
+    } else { XheTimed t(ctx, "msm_range_dyn", 8064.0 * n_dyn + 6.04e8);
       rc = xhe_msm_sort(ctx, D.d_range_sc, n_dyn, D.d_ws2, D.ws_range, D.d_results + 97); if (rc) return rc;
       XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_dyn, e_dec, 0));
       k_gather_niels<<<nblk(6 * n_dyn, 256), 256, 0, s_dyn>>>(D.d_niels, D.d_range_idx, (uint32_t)n_dyn, D.d_range_niels); XHE_LAUNCHED(ctx);
       rc = xhe_msm_finish(ctx, D.d_range_niels, n_dyn, D.d_ws2, D.ws_range, nullptr, nullptr, D.d_rparts, e_acc_dyn, 1, ext_chain ? 2 : 0); if (rc) return rc; }
-    XHE_CUDA_OK(ctx, cudaEventRecord(e_dyn, s_dyn));
+    XHE_CUDA_OK(ctx, cudaEventRecord(e_dyn, s_dyn));      // split: range MSM (dynamic part) done; joint: sorted list and range operands in place
   }
   // ---- main: sigma MSM over the gathered operands (inputs and balance-chain outputs)
   ctx->stream = main_st;
@@ -1007,8 +1036,15 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_sgsort, 0));
     if (np) { k_gather_niels<<<nblk(6 * n_sigma_terms, 256), 256, 0, st>>>(D.d_niels, D.d_sig_idx, (uint32_t)n_sigma_terms, D.d_sigma_niels); XHE_LAUNCHED(ctx); }
     k_copy_words<<<1, 64, 0, st>>>((const uint32_t*)ctx->d_gens_niels, 48, D.d_sigma_niels + 24 * n_sigma_terms); XHE_LAUNCHED(ctx);   // G, H
-    XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
-    rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, e_acc_sigma, 0, ext_chain ? 2 : 0); if (rc) return rc;
+    if (joint) {
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(main_st, e_dyn, 0));
+      XheTimed t(ctx, "msm_joint", 8064.0 * (n_sigma + n_dyn) + 6.04e8);
+      rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma + n_dyn, D.d_wsj, D.ws_joint, nullptr, nullptr, D.d_rparts, e_acc_sigma, 0, 0); if (rc) return rc;
+    } else {
+      XheTimed t(ctx, "msm_sigma", 8064.0 * n_sigma + 6.04e8);
+      rc = xhe_msm_finish(ctx, D.d_sigma_niels, n_sigma, D.d_ws1, D.ws_sigma, D.d_results, D.d_results + 8, D.d_results + 16, e_acc_sigma, 0, ext_chain ? 2 : 0); if (rc) return rc;
+    }
+    if (joint) XHE_CUDA_OK(ctx, cudaEventRecord(e_acc_dyn, main_st));      // joint: "the MSM is done" (s_rp combines it with the static part)
   }
   // ---- s_rp: weights of the static generators and their fixed-base MSM.  Nothing needs the result before the final
   // combination, and k_rp_gens is a one-warp-per-proof kernel whose resident blocks take most of the register file: issued
@@ -1017,7 +1053,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
   if (b->n_rp) {
     const uint32_t* gens = (const uint32_t*)ctx->d_gens_niels;
     static const bool defer_gens = getenv("XHE_GENS_EARLY") == nullptr;
-    if (defer_gens && !serial) { XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_sigma, 0)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_dyn, 0)); }
+    if (defer_gens && !serial) { XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_sigma, 0)); if (!joint) XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_acc_dyn, 0)); }
     // s_rp
     ctx->stream = s_rp;
     { cudaStream_t st = s_rp;
@@ -1041,10 +1077,15 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
         XheTimed t(ctx, "msm_range_static", 0);
         rc = xhe_launch_msm_ex(ctx, D.d_range_sc + 8 * n_dyn, D.d_range_niels + 24 * n_dyn, n_static, D.d_ws3, D.ws_static, nullptr, nullptr, D.d_rparts + 32, D.d_results + 97); if (rc) return rc;
       }
-      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, e_dyn, 0));
+      XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, joint ? e_acc_dyn : e_dyn, 0));
       // (every producer of the chain kernel is queued by now: only here may a wait on it enter a hardware queue)
       if (ext_chain) { XHE_CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], s_chain)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_rp, ctx->ev[11], 0)); }
-      k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
+      if (joint) {   // the one sum goes into the sigma slots; the range slots report the identity; word 100 marks the joint form
+        k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)D.d_results, D.d_results + 8, D.d_results + 16); XHE_LAUNCHED(ctx);
+        k_joint_mark<<<1, 32, 0, st>>>(D.d_results); XHE_LAUNCHED(ctx);
+      } else {
+        k_combine_out<<<1, 32, 0, st>>>(D.d_rparts, 2, (uint8_t*)(D.d_results + 48), D.d_results + 56, D.d_results + 64); XHE_LAUNCHED(ctx);
+      }
     }
     XHE_CUDA_OK(ctx, cudaEventRecord(e_rp, s_rp));
   }
@@ -1072,6 +1113,14 @@ extern "C" int32_t xhe_batch_fetch(xhe_ctx* ctx, xhe_verdict* v) {
   if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, D.d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
   if (v->sig_ok && D.fs && b->n_sigs) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->sig_ok, D.d_sig_ok, b->n_sigs, cudaMemcpyDeviceToHost, st));
   XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
+  if (D.joint_used && h_res[100] == 1u && h_res[8] == 0u && !(h_res[96] | h_res[97] | h_res[99])) {
+    // the joint sum is not the identity: run the batch again with the sigma and the range MSM apart, so that the verdict names
+    // the check that failed (reject path only; everything is still resident)
+    D.force_split = true; int32_t rrc = xhe_batch_run(ctx); D.force_split = false; if (rrc) return rrc;
+    XHE_CUDA_OK(ctx, cudaMemcpyAsync(h_res, D.d_results, 512, cudaMemcpyDeviceToHost, st));
+    if (v->op_out && b->n_ops) XHE_CUDA_OK(ctx, cudaMemcpyAsync(v->op_out, D.d_op_out, 32 * (size_t)b->n_ops, cudaMemcpyDeviceToHost, st));
+    XHE_CUDA_OK(ctx, xhe_wait_stream(ctx, st));
+  }
   if (h_res[96] | h_res[97]) { ctx->err = "verify_batch: non-canonical scalar reached the MSM"; return XHE_E_ARG; }
   if (h_res[99]) { char m[160]; snprintf(m, sizeof m, "verify_batch: the Horner chain kernel timed out waiting for its inputs (chain %u, group %u, %u of %u nodes)", (h_res[99] >> 28) & 7u, (h_res[99] >> 24) & 15u, h_res[99] & 0xfffu, (h_res[99] >> 12) & 0xfffu); ctx->err = m; return XHE_E_CUDA; }
   v->device_flags = h_res[98];
@@ -1120,7 +1169,7 @@ extern "C" int32_t xhe_sig_r(xhe_ctx* ctx, const uint8_t* s, const uint8_t* e, c
 // to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
 // kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
 size_t xhe_preload_verify() {      // returns the largest per-thread local-memory frame among them
-  const void* ks[] = {(const void*)k_build_tab8, (const void*)k_sig_r, (const void*)k_op_delta, (const void*)k_op_jump, (const void*)k_op_finish, (const void*)k_sigma_weights, (const void*)k_reduce_scalars, (const void*)k_rp_prep, (const void*)k_pow2_table, (const void*)k_rp_gens, (const void*)k_fb_build, (const void*)k_fb_digits, (const void*)k_fb_buckets, (const void*)k_fb_reduce, (const void*)k_gather_niels, (const void*)k_copy_words, (const void*)k_combine, (const void*)k_combine_out, (const void*)k_sum_encodings, (const void*)k_copy_bytes, (const void*)k_make_record, (const void*)k_shard_decide, (const void*)k_ledger_commit};
+  const void* ks[] = {(const void*)k_joint_mark, (const void*)k_build_tab8, (const void*)k_sig_r, (const void*)k_op_delta, (const void*)k_op_jump, (const void*)k_op_finish, (const void*)k_sigma_weights, (const void*)k_reduce_scalars, (const void*)k_rp_prep, (const void*)k_pow2_table, (const void*)k_rp_gens, (const void*)k_fb_build, (const void*)k_fb_digits, (const void*)k_fb_buckets, (const void*)k_fb_reduce, (const void*)k_gather_niels, (const void*)k_copy_words, (const void*)k_combine, (const void*)k_combine_out, (const void*)k_sum_encodings, (const void*)k_copy_bytes, (const void*)k_make_record, (const void*)k_shard_decide, (const void*)k_ledger_commit};
   cudaFuncAttributes a; size_t mx = 0;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
   return mx;
