@@ -225,6 +225,9 @@ int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64
 int32_t xhe_ctx_timeline(xhe_ctx* ctx, const char** names, float* t0, float* t1, int cap);
 /* self-test of the arithmetic layer: runs op (tests/hostemu op codes) on n operand pairs on the device */
 int32_t xhe_selftest_fe(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
+/* self-test of the warp-cooperative arithmetic of the MSM's Horner chain (csrc/oct.cuh): op 0 mul, 1 add, 2 sub over n field
+ * elements (8 words each); op 3 doubling, 4 complete addition over n extended points (32 words each: X, Y, Z, T) */
+int32_t xhe_selftest_oct(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
 
 #ifdef __cplusplus
 }

@@ -202,3 +202,50 @@ def test_sum_encodings_parity(ctx):
     assert ctx.sum_encodings(a + pts[1] + neg_a + oracle.point_add(ident, pts[1], sub=True)) == (ident, True)
     bad = b"\xff" * 32                       # non-canonical field element: not a valid encoding
     assert ctx.sum_encodings(a + bad + neg_a)[1] is False
+
+
+def test_warp_cooperative_arithmetic_vs_bigint(ctx):
+    """csrc/oct.cuh (the Horner chain of the MSM): field elements spread over 8 lanes, points over a warp -- products, sums and
+    differences against Python integers (edge values around p, 2p and 2^256 exercise the carry look-ahead and the 2^255 = 19
+    fold), doubling and complete addition against the affine twisted-Edwards law (a = -1)."""
+    rng = random.Random(17)
+    edge = [0, 1, 2, 19, 38, P - 1, P, P + 1, 2 * P, 2 * P + 37, 2**256 - 1, 2**256 - 38, 2**255, 2**255 - 1, 2**32 - 1, (2**256 - 1) ^ (2**128), 2**256 - 2**32, (2**256 - 1) ^ 0xFFFFFFFF]
+    a = edge * len(edge) + [rng.getrandbits(256) for _ in range(4099)]
+    b = [y for y in edge for _ in edge] + [rng.getrandbits(256) for _ in range(4099)]
+    A, B = _words(a), _words(b)
+    for op, f in ((0, lambda x, y: x * y), (1, lambda x, y: x + y), (2, lambda x, y: x - y)):
+        got = _ints(ctx.selftest_oct(op, A, B))
+        for x, y, g in zip(a, b, got):
+            assert g < 2**256 and g % P == f(x, y) % P, (op, hex(x), hex(y))
+    # points: random multiples of the base point in extended coordinates with random Z, plus the identity and a 2-torsion point
+    D = (-121665 * pow(121666, P - 2, P)) % P
+
+    def aff_add(p, q):
+        (x1, y1), (x2, y2) = p, q
+        t = D * x1 * x2 * y1 * y2 % P
+        return ((x1 * y2 + y1 * x2) * pow(1 + t, P - 2, P) % P, (y1 * y2 + x1 * x2) * pow(1 - t, P - 2, P) % P)
+    by = 4 * pow(5, P - 2, P) % P
+    bx = 15112221349535400772501151409588531511454012693041857206046113283949847762202
+    pts, cur = [(0, 1), (0, P - 1)], (bx, by)
+    for _ in range(70):
+        pts.append(cur); cur = aff_add(cur, (bx, by)) if rng.random() < 0.5 else aff_add(cur, cur)
+
+    def ext(p):
+        z = rng.randrange(1, P); x, y = p
+        return [x * z % P, y * z % P, z, x * y * z % P]
+
+    def rows(ps):
+        return np.array([[(c >> (32 * i)) & 0xFFFFFFFF for c in e for i in range(8)] for e in ps], dtype=np.uint32)
+
+    def affine(row):
+        X, Y, Z, T = (sum(int(row[8 * c + i]) << (32 * i) for i in range(8)) % P for c in range(4))
+        zi = pow(Z, P - 2, P)
+        assert Z and X * Y % P == T * Z % P
+        return (X * zi % P, Y * zi % P)
+    pa = [rng.choice(pts) for _ in range(333)]; pb = [rng.choice(pts) for _ in range(333)]
+    pb[:8] = pa[:8]                                               # P + P through the addition formula
+    Ea, Eb = rows([ext(p) for p in pa]), rows([ext(p) for p in pb])
+    for row, p in zip(ctx.selftest_oct(3, Ea, Eb), pa):
+        assert affine(row) == aff_add(p, p)
+    for row, p, q in zip(ctx.selftest_oct(4, Ea, Eb), pa, pb):
+        assert affine(row) == aff_add(p, q)

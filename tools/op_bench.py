@@ -17,4 +17,11 @@ for op, name in enumerate(names):
         row[f"{tpb}x{bps}"] = (round(c[0]), round(c[1] * GHZ)) if rc == 0 else rc   # (warp-0 latency cycles, cycles per warp-op per SMSP from wall time)
     res[name] = row
     print(name, row, flush=True)
+lib.xhe_bench_oct.restype = C.c_int32
+lib.xhe_bench_oct.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+for op, name in enumerate(["oct_mul", "oct_double", "oct_add_pt", "oct_add"]):      # warp-cooperative forms (csrc/oct.cuh): one warp, dependent chain
+    c = C.c_double()
+    rc = lib.xhe_bench_oct(ctx.p, op, 2000, C.byref(c))
+    res[name] = {"32x1": round(c.value)} if rc == 0 else rc
+    print(name, res[name], flush=True)
 os.makedirs("gpurun_out", exist_ok=True); json.dump(res, open("gpurun_out/op_bench.json", "w"), indent=1)

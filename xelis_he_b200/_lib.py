@@ -64,6 +64,7 @@ def load_library():
         "xhe_msm_plan": (i32, [sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
         "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),
+        "xhe_selftest_oct": (i32, [vp, C.c_int, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -174,6 +175,17 @@ class Ctx:
         n = a.size // 8
         out = np.zeros_like(a)
         self._chk(self.lib.xhe_selftest_fe(self.p, op, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
+        return out
+
+
+    def selftest_oct(self, op, a_words, b_words):
+        """csrc/oct.cuh on the device: op 0 mul, 1 add, 2 sub (rows of 8 words); 3 point doubling, 4 point addition (rows of 32 words)"""
+        import numpy as np
+        a = np.ascontiguousarray(a_words, dtype=np.uint32)
+        b = np.ascontiguousarray(b_words, dtype=np.uint32)
+        n = a.size // (8 if op < 3 else 32)
+        out = np.zeros_like(a)
+        self._chk(self.lib.xhe_selftest_oct(self.p, op, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
         return out
 
 

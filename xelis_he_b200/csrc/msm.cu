@@ -27,6 +27,7 @@
 #include <stddef.h>
 #include "xhe_internal.cuh"
 #include "quad.cuh"
+#include "oct.cuh"
 #include <algorithm>
 #include <vector>
 #include <string.h>
@@ -466,6 +467,44 @@ __global__ void __launch_bounds__(32) k_msm_horner_g(const uint32_t* __restrict_
   if (out_enc) encode_words(out_enc, acc);
   if (is_identity) *is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }
+// The same recombination with warp-cooperative arithmetic (oct.cuh): warp w first forms S_w = run_w + wsum_w, then warp 0 runs
+// the chain acc = 2^c acc + S_w with the accumulator spread over its 32 lanes (one limb of one coordinate per lane).  The
+// default for a single window group; the quad kernel above remains for window groups / the polling-chain experiment.
+#define HORNER_OCT_THREADS 256
+__global__ void __launch_bounds__(HORNER_OCT_THREADS) k_msm_horner_oct(const uint32_t* __restrict__ nodes, int n_w, int c, uint8_t* __restrict__ out_enc, uint32_t* __restrict__ is_identity, uint32_t* __restrict__ out_ext) {
+  __shared__ uint32_t sS[32 * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = warp; w < n_w; w += HORNER_OCT_THREADS / 32) sS[32 * w + lane] = oct_add_pt(__ldg(nodes + 64 * (size_t)w + lane), __ldg(nodes + 64 * (size_t)w + 32 + lane));
+  __syncthreads();
+  if (warp != 0) return;
+  uint32_t acc = sS[lane];                                  // window 0 = most significant: no doublings before it
+  for (int w = 1; w < n_w; w++) {
+#pragma unroll 1
+    for (int k = 0; k < c; k++) acc = oct_double(acc);
+    acc = oct_add_pt(acc, sS[32 * w + lane]);
+  }
+  const ge r = oct_to_ge(acc);
+  if (lane != 0) return;
+  if (out_ext) { st_fe(out_ext, fe_freeze(r.X)); st_fe(out_ext + 8, fe_freeze(r.Y)); st_fe(out_ext + 16, fe_freeze(r.Z)); st_fe(out_ext + 24, fe_freeze(r.T)); }
+  if (out_enc) encode_words(out_enc, r);
+  if (is_identity) *is_identity = ge_ristretto_is_identity(r) ? 1u : 0u;
+}
+// self-test of oct.cuh (xhe_selftest_oct): op 0 mul, 1 add, 2 sub on field elements (8 lanes each); 3 doubling, 4 addition on points (a warp each)
+__global__ void __launch_bounds__(128) k_selftest_oct(int op, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t n, uint32_t* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op < 3) {
+    const size_t i = t >> 3; const bool live = i < n;           // every lane of the warp takes part in the shuffles
+    const uint32_t x = live ? a[t] : 0u, y = live ? b[t] : 0u;
+    const uint32_t r = op == 0 ? oct_mul(x, y) : (op == 1 ? oct_add(x, y) : oct_sub(x, y));
+    if (live) out[t] = r;
+  } else {
+    const size_t i = t >> 5; const bool live = i < n;
+    const uint32_t x = live ? a[t] : oct_identity(), y = live ? b[t] : oct_identity();
+    const uint32_t r = op == 3 ? oct_double(x) : oct_add_pt(x, y);
+    if (live) out[t] = r;
+  }
+}
+
 // The same chain as ONE kernel that is launched BEFORE its inputs exist and polls for them (experiment, XHE_MSM_CHAIN=1):
 // a latency-bound chain that shares a sub-partition with the warps of a throughput-bound kernel gets 1/(N+1) of the
 // multiplier pipe and stretches N-fold (measured: the per-group Horner kernels above gained nothing beside the
@@ -704,7 +743,9 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
     if (chain_mode == 0) {
       if (s_hor != s_red) { XHE_CUDA_OK(ctx, cudaEventRecord(ev[MSM_MAX_GROUPS + g], s_red)); XHE_CUDA_OK(ctx, cudaStreamWaitEvent(s_hor, ev[MSM_MAX_GROUPS + g], 0)); }
       const bool last = g == p.G - 1;
-      k_msm_horner_g<<<1, 32, 0, s_hor>>>(hn, (int)nw, p.c, g ? q.hacc + 32 * (size_t)(g - 1) : nullptr, q.hacc + 32 * (size_t)g, last ? 1 : 0,
+      static const bool quad_horner = getenv("XHE_MSM_QUAD_HORNER") != nullptr && atoi(getenv("XHE_MSM_QUAD_HORNER")) != 0;      // A/B: the round-1 chain
+      if (p.G == 1 && !quad_horner) { k_msm_horner_oct<<<1, HORNER_OCT_THREADS, 0, s_hor>>>(hn, (int)nw, p.c, (uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx); }
+      else k_msm_horner_g<<<1, 32, 0, s_hor>>>(hn, (int)nw, p.c, g ? q.hacc + 32 * (size_t)(g - 1) : nullptr, q.hacc + 32 * (size_t)g, last ? 1 : 0,
                                           (uint8_t*)d_out_enc, (uint32_t*)d_is_id, (uint32_t*)d_out_ext); XHE_LAUNCHED(ctx);
     }
   }
@@ -752,11 +793,61 @@ extern "C" int32_t xhe_msm_vartime(xhe_ctx* ctx, const uint8_t* scalars, const u
   return XHE_OK;
 }
 
+// self-test of the warp-cooperative arithmetic (oct.cuh) against host big integers: op 0 mul, 1 add, 2 sub over n field elements
+// (8 words each); op 3 doubling, 4 addition over n extended points (32 words each: X, Y, Z, T)
+extern "C" int32_t xhe_selftest_oct(xhe_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out) {
+  if (!ctx || !a || !b || !out || op < 0 || op > 4) return XHE_E_ARG;
+  const size_t words = (op < 3 ? 8 : 32) * n;
+  uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+  XHE_CUDA_OK(ctx, cudaMalloc(&da, 4 * words + 16)); XHE_CUDA_OK(ctx, cudaMalloc(&db, 4 * words + 16)); XHE_CUDA_OK(ctx, cudaMalloc(&dout, 4 * words + 16));
+  XHE_CUDA_OK(ctx, cudaMemcpyAsync(da, a, 4 * words, cudaMemcpyHostToDevice, ctx->stream)); XHE_CUDA_OK(ctx, cudaMemcpyAsync(db, b, 4 * words, cudaMemcpyHostToDevice, ctx->stream));
+  if (words) { k_selftest_oct<<<nblk(words, 128), 128, 0, ctx->stream>>>(op, da, db, n, dout); XHE_LAUNCHED(ctx); }
+  XHE_CUDA_OK(ctx, cudaGetLastError()); XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  XHE_CUDA_OK(ctx, cudaMemcpy(out, dout, 4 * words, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout); return XHE_OK;
+}
+
+// latency of the warp-cooperative operations (design evidence, tools/op_bench.py): one warp, `iters` dependent operations
+template <int OP>
+__global__ void __launch_bounds__(32) k_bench_oct(uint32_t* out, int iters, unsigned long long* cycles) {
+  uint32_t p = 0x9e3779b9u * (threadIdx.x + 1) + 12345u, q = p * 2654435761u + 7u;
+  if ((threadIdx.x & 7u) == 7u) { p &= 0x7fffffffu; q &= 0x7fffffffu; }
+  unsigned long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+    if (OP == 0) p = oct_mul(p, q);
+    else if (OP == 1) p = oct_double(p);
+    else if (OP == 2) p = oct_add_pt(p, q);
+    else p = oct_add(p, q);
+  }
+  unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) *cycles = t1 - t0;
+  if (p == 0x12345u) out[0] = p;
+}
+extern "C" int32_t xhe_bench_oct(xhe_ctx* ctx, int op, int iters, double* cycles_per_op) {
+  if (!ctx || !cycles_per_op || op < 0 || op > 3 || iters <= 0) return XHE_E_ARG;
+  uint32_t* d_out; unsigned long long* d_c;
+  XHE_CUDA_OK(ctx, cudaMalloc(&d_out, 64)); XHE_CUDA_OK(ctx, cudaMalloc(&d_c, 8));
+  for (int rep = 0; rep < 2; rep++) {
+    switch (op) {
+      case 0: k_bench_oct<0><<<1, 32, 0, ctx->stream>>>(d_out, iters, d_c); break;
+      case 1: k_bench_oct<1><<<1, 32, 0, ctx->stream>>>(d_out, iters, d_c); break;
+      case 2: k_bench_oct<2><<<1, 32, 0, ctx->stream>>>(d_out, iters, d_c); break;
+      default: k_bench_oct<3><<<1, 32, 0, ctx->stream>>>(d_out, iters, d_c); break;
+    }
+    XHE_LAUNCHED(ctx);
+    XHE_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  unsigned long long c; XHE_CUDA_OK(ctx, cudaMemcpy(&c, d_c, 8, cudaMemcpyDeviceToHost));
+  *cycles_per_op = (double)c / iters;
+  cudaFree(d_out); cudaFree(d_c); return XHE_OK;
+}
+
 // CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2), and loading one may need every running kernel
 // to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
 // kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
 size_t xhe_preload_msm() {      // returns the largest per-thread local-memory frame among them
-  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4, false>, (const void*)k_msm_accum_tiles<6, false>, (const void*)k_msm_accum_tiles<8, false>, (const void*)k_msm_accum_tiles<4, true>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg<4>, (const void*)k_msm_bucket_seg<16>, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_chain, (const void*)k_msm_empty};
+  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4, false>, (const void*)k_msm_accum_tiles<6, false>, (const void*)k_msm_accum_tiles<8, false>, (const void*)k_msm_accum_tiles<4, true>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg<4>, (const void*)k_msm_bucket_seg<16>, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_horner_oct, (const void*)k_selftest_oct, (const void*)k_msm_chain, (const void*)k_msm_empty};
   cudaFuncAttributes a; size_t mx = 0;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
   return mx;

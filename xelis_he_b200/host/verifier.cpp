@@ -8,6 +8,7 @@
 #include <chrono>
 #include <functional>
 #include <mutex>
+#include <condition_variable>
 #include <thread>
 #include <stdio.h>
 #include <stdlib.h>
@@ -374,9 +375,60 @@ size_t export_pending(void* pending, uint8_t* out, size_t cap) {
 // 0 when ANYTHING is unusual or failed -- the caller then runs the exact path, which reproduces the reference's verdict and
 // error precedence.  Multisig accounts / multisig transactions always take the exact path.
 // ------------------------------------------------------------------------------------------------------------------
+// Device admission.  Several batches in flight (one context and one host thread each) overlap the host phase of one batch with
+// the device phase of others -- but only if the device phases END at different times: batches whose kernels all share the GPU
+// at once also finish together, their threads then run their next host phases together while the GPU idles, and the pipeline
+// could degenerate into a convoy.  XHE_DEVICE_SLOTS = k admits at most k batches into the device phase at a time, first come
+// first served.  Measured on B200 (10 k batches, 6 in flight, 16 host threads): no limit 2.78 M TX/s, k = 3: 2.20 M, k = 2:
+// 2.41 M, k = 1: 2.11 M -- the batches do not convoy, the host phases are the limit; the knob stays off (0) by default.
+struct DeviceSlots {
+  std::mutex mu; std::condition_variable cv; int free_slots; unsigned long long next_ticket = 0, serving = 0;
+  DeviceSlots() { const char* e = getenv("XHE_DEVICE_SLOTS"); free_slots = e ? atoi(e) : 0; }
+  struct Hold { DeviceSlots* d; ~Hold() { if (d) { std::lock_guard<std::mutex> g(d->mu); d->free_slots++; d->cv.notify_all(); } } };
+  Hold acquire() {
+    if (limit_off) return Hold{nullptr};
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long long t = next_ticket++;
+    cv.wait(lk, [&] { return serving == t && free_slots > 0; });
+    serving++; free_slots--; cv.notify_all();
+    return Hold{this};
+  }
+  bool limit_off = false;
+};
+static DeviceSlots& device_slots() { static DeviceSlots* d = [] { DeviceSlots* x = new DeviceSlots(); x->limit_off = x->free_slots <= 0; return x; }(); return *d; }
+
+// (account, asset) -> tail of its balance chain inside the batch, for the fast path's walk.  The walk makes one lookup per key a
+// transaction moves, so the table is kept small enough to live in the core's cache: a slot is the key's 32-bit tag and the
+// index of a densely packed entry (8 bytes; 512 KB at 30 k keys) and the entries hold POINTERS to the key bytes inside the
+// batch (which outlive the walk) instead of copies.  (The generic FlatTable<64, Chain> this replaces was a 16 MB array of
+// 128-byte entries: a cache miss per lookup.)
+class ChainTable {
+ public:
+  struct Entry { const uint8_t *account, *asset; Chain c; };
+  void reset(size_t keys) { size_t cap = 1024; while (cap < 2 * keys + 16) cap <<= 1; if (cap != slots_.size()) slots_.assign(cap, 0); else std::fill(slots_.begin(), slots_.end(), 0); entries_.clear(); entries_.reserve(keys + 16); }
+  static uint64_t digest(const uint8_t* account, const uint8_t* asset) { uint64_t h, g; memcpy(&h, account + 5, 8); memcpy(&g, asset + 5, 8); return (h * 0x9E3779B97F4A7C15ull ^ g) * 0xD6E8FEB86659FD93ull; }
+  Chain* insert(const uint8_t* account, const uint8_t* asset, bool* fresh) {
+    if (2 * (entries_.size() + 1) > slots_.size()) grow();
+    const uint64_t h = digest(account, asset); const size_t mask = slots_.size() - 1; const uint32_t tag = (uint32_t)(h >> 32) | 1u;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      const uint64_t s = slots_[i];
+      if (!s) { slots_[i] = ((uint64_t)tag << 32) | (uint32_t)entries_.size(); entries_.push_back(Entry{account, asset, Chain()}); *fresh = true; return &entries_.back().c; }
+      if ((uint32_t)(s >> 32) == tag) { Entry& e = entries_[(uint32_t)s]; if (!memcmp(e.account, account, 32) && !memcmp(e.asset, asset, 32)) { *fresh = false; return &e.c; } }
+    }
+  }
+  void prefetch(const uint8_t* account, const uint8_t* asset) const { if (!slots_.empty()) __builtin_prefetch(&slots_[(size_t)digest(account, asset) & (slots_.size() - 1)]); }
+  size_t size() const { return entries_.size(); }
+  template <typename F> void for_each(F f) const { for (const Entry& e : entries_) f(e.c); }
+ private:
+  void grow() { std::vector<uint64_t> ns(std::max<size_t>(1024, 2 * slots_.size()), 0); const size_t mask = ns.size() - 1;
+    for (size_t q = 0; q < entries_.size(); q++) { const uint64_t h = digest(entries_[q].account, entries_[q].asset); size_t i = (size_t)h & mask; while (ns[i]) i = (i + 1) & mask; ns[i] = ((uint64_t)((uint32_t)(h >> 32) | 1u) << 32) | (uint32_t)q; }
+    slots_.swap(ns); }
+  std::vector<uint64_t> slots_; std::vector<Entry> entries_;
+};
+
 struct FastCache {
   PinnedVec<uint8_t> blob, region_b, op_out, tx_flags; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
-  FlatTable<64, Chain> chains;       // (account, asset) -> tail of its balance chain inside the batch
+  ChainTable chains;                 // (account, asset) -> tail of its balance chain inside the batch
 };
 static std::unordered_map<xhe_ctx*, FastCache*> g_fast_cache;
 static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g_cache_mu); FastCache*& c = g_fast_cache[ctx]; if (!c) c = new FastCache(); return *c; }
@@ -525,11 +577,11 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   for (size_t j = 0; j < n; j++) if (parse_rc[j]) return 0;
   double t1 = now_ms();
   FastCache& F = fast_cache_for(ctx);
-  const uint32_t party_capacity = xhe_ctx_party_capacity(ctx);
+  const uint32_t party_capacity = opt.host_dry_run ? 512u : xhe_ctx_party_capacity(ctx);
   F.off.resize(n + 1); F.plan.resize(8 * n); F.rp_m.resize(n); F.rp_pt_off.resize(n + 1); F.rp_ch_off.resize(n + 1);
   F.region_b.clear(); F.terms.clear(); F.term_off.clear(); F.prev.clear(); F.amount.clear();
   F.term_off.push_back(0);
-  FlatTable<64, Chain>& chains = F.chains; chains.clear(); chains.reserve(4 * n);
+  ChainTable& chains = F.chains; { size_t nk = 0; for (size_t j = 0; j < n; j++) nk += txs[j].n_sc + txs[j].transfers.size(); chains.reset(nk); }
   struct Upd { const uint8_t *account, *asset; Role role; uint32_t op_c; bool output; };
   std::vector<Upd> updates; updates.reserve(3 * n);
   Staged staged; staged.nonces.reserve(n);
@@ -544,8 +596,8 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   // route: its updates wait for the cross-rank decision while the context moves on to the next batch.)
   xhe_ledger* dl = opt.partial_out ? nullptr : state.device_ledger();
   auto touch = [&](const uint8_t* account, const uint8_t* asset, Role role, long long* pc, long long* pd) -> Chain* {
-    Ct64 kk = MockLedger::key(account, asset); bool fresh = false;
-    Chain& c = *chains.insert(kk.data(), &fresh);
+    bool fresh = false;
+    Chain& c = *chains.insert(account, asset, &fresh);
     if (fresh && dl) {
       uint32_t slot;
       if (!state.device_slot(account, asset, &slot)) return nullptr;
@@ -597,8 +649,8 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   const size_t AHEAD = 6;
   auto announce = [&](const TxView& tx) {
     state.prefetch_account(tx.source);
-    for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); Ct64 kk = MockLedger::key(tx.source, tx.sc + 256 * q); chains.prefetch(kk.data()); }
-    for (uint32_t t = 0; t < tx.n_transfers(); t++) { const TransferView& tr = tx.transfers[t]; state.prefetch_balance(tr.dest, tr.asset); Ct64 kk = MockLedger::key(tr.dest, tr.asset); chains.prefetch(kk.data()); }
+    for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); chains.prefetch(tx.source, tx.sc + 256 * q); }
+    for (uint32_t t = 0; t < tx.n_transfers(); t++) { const TransferView& tr = tx.transfers[t]; state.prefetch_balance(tr.dest, tr.asset); chains.prefetch(tr.dest, tr.asset); }
   };
   for (size_t j = 0; j < n && j < AHEAD; j++) announce(txs[j]);
   // A transaction that fails one of the HOST-side checks ends the walk (n_run transactions go to the device): the reference
@@ -696,6 +748,10 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     blob_base = F.blob.data();
   }
   double t3 = now_ms();
+  if (opt.host_dry_run) {   // diagnostics (host-phase profiling without a device): nothing is verified, the call reports an error code
+    if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->total_ms = t3 - t0; tm->used_fast_path = true; }
+    *rc_out = XHE_E_ARG; return 0;
+  }
   xhe_batch xb; memset(&xb, 0, sizeof xb); xb.struct_size = (uint32_t)sizeof xb;
   xb.n_tx = (uint32_t)n_run; xb.n_points = n_points; xb.n_sigs = (uint32_t)n_run;
   xb.n_ops = (uint32_t)F.prev.size(); xb.op_prev = (const int64_t*)F.prev.data(); xb.op_term_off = F.term_off.data(); xb.op_terms = F.terms.data(); xb.op_amount = F.amount.data(); xb.max_chain = max_chain;
@@ -705,7 +761,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   PinnedVec<uint8_t>& op_out = F.op_out; op_out.n = 0; op_out.reserve(32 * (size_t)xb.n_ops + 64); op_out.n = 32 * (size_t)xb.n_ops;
   PinnedVec<uint8_t>& txf = F.tx_flags; txf.n = 0; txf.reserve(n_run + 64); txf.n = n_run;
   xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.op_out = (dl && !want_out) ? nullptr : op_out.data(); v.tx_flags = txf.data();      // resident ledger: no balance comes back
-  int32_t rc = xhe_verify_batch(ctx, &xb, &v);
+  int32_t rc; { DeviceSlots::Hold slot = device_slots().acquire(); rc = xhe_verify_batch(ctx, &xb, &v); }
   double t4 = now_ms();
   if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->total_ms = t4 - t0; }
   if (rc != XHE_OK) { *rc_out = rc; return 0; }
@@ -742,7 +798,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     // update_account_balance on the device: the LAST op of every chain is that key's new balance (src/tx/verify.rs:329-336,367-374)
     if (staged.apply(state) != XHE_OK) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; }
     std::vector<uint32_t> slots, ops; slots.reserve(chains.size()); ops.reserve(chains.size());
-    chains.for_each([&](const uint8_t*, const Chain& c) { if (c.slot != 0xFFFFFFFFu && c.last_c >= 0) { slots.push_back(c.slot); ops.push_back((uint32_t)c.last_c); } });
+    chains.for_each([&](const Chain& c) { if (c.slot != 0xFFFFFFFFu && c.last_c >= 0) { slots.push_back(c.slot); ops.push_back((uint32_t)c.last_c); } });
     int32_t crc = xhe_ledger_commit_batch(dl, ctx, slots.data(), ops.data(), slots.size());
     if (crc != XHE_OK) { *rc_out = crc; *fail_out = -1; return crc < 0 ? 0 : 2; }
     if (want_out) for (const Upd& u : updates) if (u.output) { uint8_t ct[64]; memcpy(ct, &op_out[32 * (size_t)u.op_c], 64); if (!state.set_output_ciphertext(u.account, u.asset, ct)) { *rc_out = XHE_ERR_STATE; *fail_out = -1; return 2; } }
@@ -1098,7 +1154,7 @@ static int verify_batch_exact(xhe_ctx* ctx, const uint8_t* const* blobs, const s
   }
   std::vector<uint8_t> point_ok(n_points + 1), sig_r(32 * n_sigs + 1), op_out(32 * (size_t)xb.n_ops + 1), sig_ok_dev(n_sigs + 1, 0);
   xhe_verdict v; memset(&v, 0, sizeof v); v.struct_size = (uint32_t)sizeof v; v.point_ok = point_ok.data(); v.sig_r = sig_r.data(); v.op_out = op_out.data(); v.sig_ok = sig_ok_dev.data();
-  int32_t rc = xhe_verify_batch(ctx, &xb, &v);
+  int32_t rc; { DeviceSlots::Hold slot = device_slots().acquire(); rc = xhe_verify_batch(ctx, &xb, &v); }
   double t4 = now_ms();
   if (rc != XHE_OK) { if (tm) { tm->parse_ms = t1 - t0; tm->resolve_ms = t2 - t1; tm->transcript_ms = t3 - t2; tm->device_ms = t4 - t3; tm->total_ms = t4 - t0; } return rc; }
 
@@ -1251,7 +1307,7 @@ int32_t xheh_verify_batch_partial(xhe_ctx* ctx, void* ledger, const uint8_t* con
 // bit 3 = replayable batch factors (tests only: the seed is used without OS entropy)
 int32_t xheh_verify_batch_ex(xhe_ctx* ctx, void* ledger, const uint8_t* const* blobs, const size_t* lens, size_t n, const uint8_t* seed, size_t seed_len, int threads, uint32_t flags, long* fail_index, double* timings7, uint8_t* partial64) {
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = (flags & 2u) ? partial64 : nullptr; opt.fast_path = (flags & 4u) != 0;
-  opt.deterministic_seed = (flags & 8u) != 0;
+  opt.deterministic_seed = (flags & 8u) != 0; opt.host_dry_run = (flags & 16u) != 0;
   BatchTimings tm;
   int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
@@ -1264,7 +1320,7 @@ int32_t xheh_verify_batch_shard(xhe_ctx* ctx, void* ledger, const uint8_t* const
                                 long* fail_index, double* timings7, uint8_t* partial64) {
   if (!partial64 || lo > hi) return XHE_E_ARG;
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = partial64; opt.fast_path = (flags & 4u) != 0;
-  opt.deterministic_seed = (flags & 8u) != 0; opt.shard_lo = lo; opt.shard_hi = hi;
+  opt.deterministic_seed = (flags & 8u) != 0; opt.host_dry_run = (flags & 16u) != 0; opt.shard_lo = lo; opt.shard_hi = hi;
   BatchTimings tm;
   int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }
@@ -1275,7 +1331,7 @@ int32_t xheh_verify_batch_shard_ix(xhe_ctx* ctx, void* ledger, const uint8_t* co
                                    long* fail_index, double* timings7, uint8_t* partial64, const void* index) {
   if (!partial64 || lo > hi) return XHE_E_ARG;
   BatchOptions opt; opt.threads = threads; opt.rng_seed = seed; opt.rng_seed_len = seed_len; opt.device_fiat_shamir = (flags & 1u) != 0; opt.partial_out = partial64; opt.fast_path = (flags & 4u) != 0;
-  opt.deterministic_seed = (flags & 8u) != 0; opt.shard_lo = lo; opt.shard_hi = hi; opt.key_index = index;
+  opt.deterministic_seed = (flags & 8u) != 0; opt.host_dry_run = (flags & 16u) != 0; opt.shard_lo = lo; opt.shard_hi = hi; opt.key_index = index;
   BatchTimings tm;
   int rc = verify_batch(ctx, blobs, lens, n, *(VerificationState*)ledger, opt, fail_index, &tm);
   if (timings7) { timings7[0] = tm.parse_ms; timings7[1] = tm.resolve_ms; timings7[2] = tm.transcript_ms; timings7[3] = tm.device_ms; timings7[4] = tm.finish_ms; timings7[5] = tm.total_ms; timings7[6] = tm.used_fast_path ? -1.0 : (double)tm.keccak_f; }

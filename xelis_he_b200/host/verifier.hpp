@@ -207,6 +207,7 @@ struct BatchOptions { int threads = 0;
                       size_t shard_lo = 0, shard_hi = (size_t)-1;
                       const void* key_index = nullptr; /* xheh_batch_index_build of the same batch (optional): earlier shards are searched through their key digests */
                       bool device_fiat_shamir = false; /* transcripts, batch factors and main-signature hashes on the GPU */
+                      bool host_dry_run = false; /* diagnostics: run the host phases of the fast path only (no device, nothing verified; the call returns XHE_E_ARG with the timings filled) */
                       bool fast_path = false; /* optimistic device-layout path first (implies device Fiat-Shamir); the exact path decides on any failure */ };
 
 // Transaction::verify_batch.  Returns XHE_OK or the verdict code; *fail_index = first failing tx (-1 for the two
