@@ -36,11 +36,13 @@ def parse_args():
     ap.add_argument("--shape", default="a1k1")
     ap.add_argument("--cpu-sample", type=int, default=0, help="transactions per host thread in the CPU baseline (default: the whole batch in the cpu_baseline leg, 2,500 per step in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mint-cache", default=None, help="development only: a pickle (tools/r02_mint_cache.py) holding the 8 x 10k a1k1 batch minted with the same seeds; skips the minting, the oracle prefix check and the CPU baseline")
     ap.add_argument("--secondary", default="full", choices=["full", "min", "off"], help="BASELINE.json's other configs (N = 1 only): full = other shapes, one-sender chain, mixed batch with reject paths, 16x255, MSM sweep, ciphertext updates; min = MSM 2^20 + ciphertext updates")
     ap.add_argument("--no-secondary", action="store_true", help="same as --secondary off")
     ap.add_argument("--mixed-txs", type=int, default=100000, help="size of the mixed (config 5) batch")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
     ap.add_argument("--no-key-index", action="store_true", help="sharded runs: find cross-shard dependencies by scanning the earlier shards' bytes instead of the batch's key-digest index")
+    ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: leave the ranks floating over all host cores instead of binding each to its own cores on its GPU's NUMA node")
     ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
     ap.add_argument("--fiat-shamir", default="fast", choices=["fast", "device", "host"], help="where the Merlin transcripts run (host = north_star split; device = SURVEY 8 f.1)")
     return ap.parse_args()
@@ -327,6 +329,13 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dist = None
+    if world > 1 and not args.no_bind:
+        # one process per GPU: each rank keeps to its own cores on its GPU's NUMA node (before anything is allocated)
+        from xelis_he_b200.distributed import bind_rank_to_local_cores
+        bound = bind_rank_to_local_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)), verbose=True)
+        ncpu_rank = len(bound)
+    else:
+        ncpu_rank = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -335,8 +344,20 @@ def main():
     # holds the whole batch -- as every node of a network holds the whole block
     t_mint = time.time()
     mint_threads = max(1, ncpu // max(1, min(world, 8)))
-    batch = oracle.mint_transfers(77 + rank, args.txs, a, k, threads=mint_threads)
-    my_records = batch.ledger().dump()
+    cached = None
+    if args.mint_cache and os.path.exists(args.mint_cache) and args.shape == "a1k1" and args.txs == 10000 and world <= 8:
+        import pickle
+        cb, cr = pickle.load(open(args.mint_cache, "rb")); per = len(cr) // 8
+        cached = (cb[rank * args.txs:(rank + 1) * args.txs], cr[rank * per:(rank + 1) * per])
+        args.no_cpu_baseline = True; args.secondary = "off"
+
+        class _B:
+            blobs = cached[0]
+        batch = _B()
+        my_records = cached[1]
+    else:
+        batch = oracle.mint_transfers(77 + rank, args.txs, a, k, threads=mint_threads)
+        my_records = batch.ledger().dump()
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, (batch.blobs, my_records))
@@ -361,7 +382,7 @@ def main():
     # index (8-byte digests of the balances each transaction moves): both are built where the transactions are received and
     # framed, before the clock -- like the reference's deserialisation into `Transaction` values
     prepared = verifier.prepare_blobs_pinned(blobs, index=world > 1 and not args.no_key_index)
-    host_threads = max(1, ncpu // max(1, min(world, 8)))
+    host_threads = ncpu_rank or max(1, ncpu // max(1, min(world, 8)))
 
     from xelis_he_b200 import distributed as xd
 
@@ -380,7 +401,7 @@ def main():
     for w in range(max(args.warmup, 3)):
         dt, code, idx, tm = e2e_step(b"warm%d" % w)
         assert (code, idx) == (0, -1), (code, idx)
-    if args.txs <= 20000:
+    if args.txs <= 20000 and cached is None:
         sl = min(64, args.txs)
         assert oracle.verify_batch(batch.blobs[:sl], batch.slice(sl).ledger()) == (0, -1)      # the oracle agrees on a prefix of this rank's shard
 
@@ -416,6 +437,21 @@ def main():
             assert int.from_bytes(d[:4], "little", signed=True) == 0 and int.from_bytes(d[8:16], "little", signed=True) == -1, "joint decision of the timed steps is not Accept"
         return sum(e0.elapsed_time(e1) for e0, e1 in ev)
 
+    # ---- host->device rate with every rank uploading at once (what the end-to-end figure can get out of this box)
+    h2d_probe = None
+    if dist:
+        pb_h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True); pb_d = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        pb_d.copy_(pb_h, non_blocking=True); barrier()
+        p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(4):
+            pb_d.copy_(pb_h, non_blocking=True)
+        p1.record(); torch.cuda.synchronize()
+        tp = torch.tensor([4 * 64 * 2**20 / (p0.elapsed_time(p1) * 1e-3) / 1e9], device="cuda", dtype=torch.float64)
+        allp = [torch.zeros_like(tp) for _ in range(world)]; dist.all_gather(allp, tp)
+        h2d_probe = {"per_rank_GBs": [round(float(x), 2) for x in allp], "aggregate_GBs": round(sum(float(x) for x in allp), 1), "what": "256 MiB pinned -> device per rank, all ranks at once"}
+        del pb_h, pb_d
+        barrier()
     # ---- timed region 1: device kernels on the resident batch (value)
     sampler = ClockSampler(local); sampler.start()
     barrier()
@@ -481,7 +517,9 @@ def main():
         e2e_step(b"restore-host-ledger")
     barrier()
     pipelined = args.fiat_shamir != "host" and args.inflight > 1
-    nfl = args.inflight if pipelined else 1
+    # batches in flight: one host thread each, so no more than the rank's cores minus one for the decision / commit threads
+    # (8 GPUs on a 32-core box = 4 cores per rank: 3 in flight measured 9.3 M TX/s against 7.8 M with 6)
+    nfl = min(args.inflight, max(2, host_threads - 1)) if pipelined else 1
     workers = [ctx] + [xhe.Ctx(local, party_capacity=max(m, 2)) for _ in range(nfl - 1)]
     for c in workers[1:]:
         streams.append(torch.cuda.Stream()); c.set_stream(streams[-1].cuda_stream)
@@ -661,7 +699,7 @@ def main():
                     "single_call": {"value": total_tx / (single_ms_max * 1e-3), "ms_per_step": single_ms_max / args.steps},
                     "phases_ms": {kk: round(vv, 3) for kk, vv in phases.items() if kk != "keccak_f"}, "host_keccak_f_per_tx": (kf / args.txs) if kf >= 0 else None,
                     "phases_ms_pipelined_mean": {kk: round(sum(t_[kk] for t_ in pipe_phases) / len(pipe_phases), 3) for kk in pipe_phases[0] if kk.endswith("_ms")} if pipe_phases else None,
-                    "resident_state": resident_state, "phases_ms_by_rank": by_rank,
+                    "resident_state": resident_state, "phases_ms_by_rank": by_rank, "h2d_all_ranks_at_once": h2d_probe,
                     "key_index": ({"bytes": prepared.index_bytes, "build_ms": round(prepared.index_build_ms, 3), "built": "with the blob arena, before the clock (as the reference deserialises before verify_batch)"} if getattr(prepared, "index", None) else None), "decision_thread_ms_per_batch": decider_stats, "fiat_shamir": args.fiat_shamir,
                     "fiat_shamir_note": "fast = device transcripts + device layout (SURVEY 8 f.1 + f.2); other_mode = north_star's split (Merlin on host threads)",
                     "other_mode": {"fiat_shamir": other, "value_this_rank": args.txs * 3 / t_other}},

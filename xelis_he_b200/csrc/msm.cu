@@ -39,6 +39,7 @@ namespace {
 #define MSM_SEG 4     // buckets per level-1 running-sum segment (one quad)
 #define MSM_SEG_LOG 2
 #define MSM_MAX_GROUPS 8
+#define NODES_SEQ_R 8    // children per parent in the work-efficient fold levels (k_msm_nodes_seq)
 #define XHE_ACCUM_SMEM_DEFAULT 0
 
 struct MsmPlan {
@@ -85,7 +86,7 @@ MsmPlan make_plan(size_t n) {
   // operations, but a quarter of the nodes reach the scan kernels, which spend 10 operations per node: large MSMs are
   // throughput-bound there -- 2^20 points: 0.39 ms -> see profiles/r02_msm_sweep.md)
   static const int seg_env = getenv("XHE_MSM_SEG_LOG") ? atoi(getenv("XHE_MSM_SEG_LOG")) : 0;
-  p.seg_log = seg_env == 2 || seg_env == 4 ? seg_env : (p.total_buckets > ((size_t)1 << 17) ? 4 : 2);
+  p.seg_log = seg_env == 2 || seg_env == 4 ? seg_env : 2;      // with the work-efficient fold levels (k_msm_nodes_seq) the short first level wins at every size: see DESIGN.md 4.4
   if ((1u << p.seg_log) > p.B) p.seg_log = 2;
   size_t o = 0;
   p.off_counts = o; o = align_up(o + 4 * (p.total_buckets + 1), 256);
@@ -105,7 +106,7 @@ MsmPlan make_plan(size_t n) {
   p.off_heavy = o; o = align_up(o + 4 * (p.total_buckets + 8 * (MSM_MAX_GROUPS + 1)), 256);      // per group: [count, bucket ids...]
   size_t nodes1 = (p.total_buckets + MSM_SEG - 1) / MSM_SEG + 64;
   p.off_nodes_a = o; o = align_up(o + 256 * nodes1, 256);
-  p.off_nodes_b = o; o = align_up(o + 256 * ((nodes1 + 31) / 32 + (size_t)p.W + 64), 256);
+  p.off_nodes_b = o; o = align_up(o + 256 * ((nodes1 + NODES_SEQ_R - 1) / NODES_SEQ_R + (size_t)p.W + 64), 256);      // first fold level: radix 8
   p.off_hnodes = o; o = align_up(o + 256 * ((size_t)p.W + 1), 256);      // one final node per window: input of the Horner stream
   p.off_hacc = o; o = align_up(o + 128 * (MSM_MAX_GROUPS + 1), 256);
   p.off_ready = o; o = align_up(o + 64, 256);          // ready[g]: final nodes of group g written; ready[8]: chain status
@@ -435,6 +436,37 @@ __global__ void __launch_bounds__(128) k_msm_nodes32(const uint32_t* __restrict_
   }
 }
 
+// The same fold for R = 8 children per parent, WORK-efficient: a pair of quads per parent walks the children from the last to
+// the first -- quad 0 keeps run' (a running sum) and sum_{c >= 1} suffix_c (the running sum added up), quad 1 sums the
+// wsum_c -- 3 additions per child instead of the ~6 of the parallel scan above, at 2 R dependent additions.  Used for the
+// wide middle levels (thousands of nodes per window), where the scan kernel was throughput-bound (2^20 points: 174 us for the
+// first level); the last level (<= 32 nodes per window) keeps the parallel form.
+__global__ void __launch_bounds__(128) k_msm_nodes_seq(const uint32_t* __restrict__ in, uint32_t children_per_window, uint32_t parents_per_window, uint32_t n_parents, int child_log, uint32_t* __restrict__ out) {
+  const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, role = (threadIdx.x >> 2) & 1u;      // role 0: run / suffix sums, role 1: wsum
+  const bool live = pair < n_parents;                                                                    // (whole warps stay in the shuffles)
+  const uint32_t w = live ? pair / parents_per_window : 0u, pidx = live ? pair % parents_per_window : 0u;
+  ge acc1 = ge_identity(), acc2 = ge_identity();
+#pragma unroll 1
+  for (int c = NODES_SEQ_R - 1; c >= 0; c--) {
+    const uint32_t child = pidx * NODES_SEQ_R + (uint32_t)c;
+    ge x = ge_identity();
+    if (live && child < children_per_window) ld_ge(x, in + 64 * ((size_t)w * children_per_window + child) + 32 * role);
+    acc1 = quad_add(acc1, x);
+    if (c >= 1) acc2 = quad_add(acc2, acc1);
+  }
+#pragma unroll 1
+  for (int k = 0; k < child_log; k++) acc2 = quad_double(acc2);
+  // quad 0 takes the other quad's sum of the wsums
+  ge W;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    W.X.v[i] = __shfl_down_sync(0xffffffffu, acc1.X.v[i], 4); W.Y.v[i] = __shfl_down_sync(0xffffffffu, acc1.Y.v[i], 4);
+    W.Z.v[i] = __shfl_down_sync(0xffffffffu, acc1.Z.v[i], 4); W.T.v[i] = __shfl_down_sync(0xffffffffu, acc1.T.v[i], 4);
+  }
+  const ge Wt = quad_add(acc2, W);
+  if (live && role == 0u) { uint32_t* o = out + 64 * ((size_t)w * parents_per_window + pidx); st_ge_quad(o, acc1); st_ge_quad(o + 32, Wt); }
+}
+
 // Horner segment over the n_w windows of one group (most significant first): acc = 2^c * acc + S_w, S_w = wsum + run
 // (bucket b carries multiplier b+1).  acc_in = the accumulator the previous group left (NULL for the first group, whose
 // first window needs no doublings).  c * n_w sequential doublings: a pure latency chain, so one quad shares every point
@@ -464,7 +496,7 @@ __global__ void __launch_bounds__(32) k_msm_horner_g(const uint32_t* __restrict_
   if (out_ext) {   // canonical coordinates so any consumer (other ranks, the CPU oracle) can read them
     st_fe(out_ext, fe_freeze(acc.X)); st_fe(out_ext + 8, fe_freeze(acc.Y)); st_fe(out_ext + 16, fe_freeze(acc.Z)); st_fe(out_ext + 24, fe_freeze(acc.T));
   }
-  if (out_enc) encode_words(out_enc, acc);
+  if (out_enc) encode_result_words(out_enc, acc);
   if (is_identity) *is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }
 // The same recombination with warp-cooperative arithmetic (oct.cuh): warp w first forms S_w = run_w + wsum_w, then warp 0 runs
@@ -486,7 +518,7 @@ __global__ void __launch_bounds__(HORNER_OCT_THREADS) k_msm_horner_oct(const uin
   const ge r = oct_to_ge(acc);
   if (lane != 0) return;
   if (out_ext) { st_fe(out_ext, fe_freeze(r.X)); st_fe(out_ext + 8, fe_freeze(r.Y)); st_fe(out_ext + 16, fe_freeze(r.Z)); st_fe(out_ext + 24, fe_freeze(r.T)); }
-  if (out_enc) encode_words(out_enc, r);
+  if (out_enc) encode_result_words(out_enc, r);
   if (is_identity) *is_identity = ge_ristretto_is_identity(r) ? 1u : 0u;
 }
 // self-test of oct.cuh (xhe_selftest_oct): op 0 mul, 1 add, 2 sub on field elements (8 lanes each); 3 doubling, 4 addition on points (a warp each)
@@ -555,7 +587,7 @@ __device__ __forceinline__ void chain_run(const ChainJob& J, uint32_t* sS, int w
   if (lane != 0) return;
   if (!ok) { *J.status = diag; if (J.is_identity) *J.is_identity = 2u; return; }      // status: which chain, which group, expected and seen node counts
   if (J.out_ext) { st_fe(J.out_ext, fe_freeze(acc.X)); st_fe(J.out_ext + 8, fe_freeze(acc.Y)); st_fe(J.out_ext + 16, fe_freeze(acc.Z)); st_fe(J.out_ext + 24, fe_freeze(acc.T)); }
-  if (J.out_enc) encode_words(J.out_enc, acc);
+  if (J.out_enc) encode_result_words(J.out_enc, acc);
   if (J.is_identity) *J.is_identity = ge_ristretto_is_identity(acc) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(512, 1) k_msm_chain(ChainJob j0, ChainJob j1, int wait) {
@@ -734,6 +766,12 @@ int32_t xhe_msm_finish(xhe_ctx* ctx, const void* d_niels, size_t n, void* d_ws, 
     uint32_t per_window = (uint32_t)(p.B >> p.seg_log); int child_log = p.seg_log;
     uint32_t *cur = q.nodes_a, *nxt = q.nodes_b;
     uint32_t* hn = q.hnodes + 64 * (size_t)(klo / p.B);
+    static const bool nodes_scan_only = getenv("XHE_MSM_NODES_SCAN") != nullptr && atoi(getenv("XHE_MSM_NODES_SCAN")) != 0;      // A/B: parallel-scan levels only
+    while (per_window > 32 && !nodes_scan_only) {      // wide levels: work-efficient radix-8 folds
+      const uint32_t parents = (per_window + NODES_SEQ_R - 1) / NODES_SEQ_R, n_par = parents * nw;
+      k_msm_nodes_seq<<<nblk(8 * (size_t)n_par, 128), 128, 0, s_red>>>(cur, per_window, parents, n_par, child_log, nxt); XHE_LAUNCHED(ctx);
+      std::swap(cur, nxt); per_window = parents; child_log += 3;
+    }
     while (per_window > 1) {
       const uint32_t parents = (per_window + 31) / 32;
       uint32_t* dst = parents == 1 ? hn : nxt;
@@ -847,7 +885,7 @@ extern "C" int32_t xhe_bench_oct(xhe_ctx* ctx, int op, int iters, double* cycles
 // to finish first: with the polling chain kernel of msm.cu in flight, the FIRST launch of any other kernel would wait for a
 // kernel that is waiting for it.  Every kernel of this file is therefore loaded when the first context is created.
 size_t xhe_preload_msm() {      // returns the largest per-thread local-memory frame among them
-  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4, false>, (const void*)k_msm_accum_tiles<6, false>, (const void*)k_msm_accum_tiles<8, false>, (const void*)k_msm_accum_tiles<4, true>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg<4>, (const void*)k_msm_bucket_seg<16>, (const void*)k_msm_nodes32, (const void*)k_msm_horner_g, (const void*)k_msm_horner_oct, (const void*)k_selftest_oct, (const void*)k_msm_chain, (const void*)k_msm_empty};
+  const void* ks[] = {(const void*)k_msm_count, (const void*)k_msm_scatter, (const void*)k_scan_blocks, (const void*)k_scan_totals, (const void*)k_scan_add, (const void*)k_msm_tile_runs, (const void*)k_msm_accum_tiles<4, false>, (const void*)k_msm_accum_tiles<6, false>, (const void*)k_msm_accum_tiles<8, false>, (const void*)k_msm_accum_tiles<4, true>, (const void*)k_msm_zero_heads, (const void*)k_msm_fold_heavy, (const void*)k_msm_bucket_seg<4>, (const void*)k_msm_bucket_seg<16>, (const void*)k_msm_nodes32, (const void*)k_msm_nodes_seq, (const void*)k_msm_horner_g, (const void*)k_msm_horner_oct, (const void*)k_selftest_oct, (const void*)k_msm_chain, (const void*)k_msm_empty};
   cudaFuncAttributes a; size_t mx = 0;
   for (const void* k : ks) if (cudaFuncGetAttributes(&a, k) == cudaSuccess && a.localSizeBytes > mx) mx = a.localSizeBytes;
   return mx;

@@ -125,6 +125,13 @@ __device__ __forceinline__ void encode_words(uint8_t* enc32, const ge& p, ge_aff
   reinterpret_cast<uint4*>(enc32)[0] = make_uint4(w[0], w[1], w[2], w[3]);
   reinterpret_cast<uint4*>(enc32)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
+// encoding of a RESULT that is usually the identity (a verified batch's MSM): every representative of the identity coset
+// (X == 0 or Y == 0) encodes to 32 zero bytes (RFC 9496 4.3.2 is constant on cosets), so the ~265-multiplication inverse
+// square root -- a 60 us single-thread chain at the very end of a step -- runs only for results that are not the identity
+__device__ __forceinline__ void encode_result_words(uint8_t* enc32, const ge& p) {
+  if (ge_ristretto_is_identity(p)) { reinterpret_cast<uint4*>(enc32)[0] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(enc32)[1] = make_uint4(0, 0, 0, 0); }
+  else encode_words(enc32, p);
+}
 __device__ __forceinline__ void ld_niels(ge_niels& n, const uint32_t* p) { ld_fe(n.ypx, p); ld_fe(n.ymx, p + 8); ld_fe(n.t2d, p + 16); }
 __device__ __forceinline__ void st_niels(uint32_t* p, const ge_niels& n) { st_fe(p, n.ypx); st_fe(p + 8, n.ymx); st_fe(p + 16, n.t2d); }
 __device__ __forceinline__ void ld_ge(ge& g, const uint32_t* p) { ld_fe_rw(g.X, p); ld_fe_rw(g.Y, p + 8); ld_fe_rw(g.Z, p + 16); ld_fe_rw(g.T, p + 24); }

@@ -263,6 +263,48 @@ class AsyncDecider:
         self.thread.join(5); self.committer.join(5)
 
 
+def bind_rank_to_local_cores(local_rank, local_world, verbose=False):
+    """Give this rank its own share of the host cores, on the NUMA node of its GPU.  With one process per GPU and a host
+    phase per batch (parsing, the state walk, launches), ranks that float over all cores of a two-socket box walk memory on
+    the other socket, feed their GPU across the inter-socket link and pre-empt each other.  The cores local to each visible
+    GPU are read from sysfs (`local_cpulist` of its PCI device); the ranks whose GPUs share a core list split it evenly.
+    Falls back to an even split of the current affinity mask.  Call it BEFORE allocating ledgers or pinned buffers (first
+    touch decides where they live).  Returns the list of cores."""
+    cur = sorted(os.sched_getaffinity(0))
+
+    def parse(txt):
+        out = []
+        for part in txt.strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            out.extend(range(int(a), int(b or a) + 1))
+        return out
+    lists = None
+    try:
+        import torch
+        lists = []
+        for d in range(local_world):
+            pr = torch.cuda.get_device_properties(d)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            lists.append(tuple(c for c in parse(open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read()) if c in cur))
+        if not all(lists):
+            lists = None
+    except Exception:
+        lists = None
+    if lists is None:
+        lists = [tuple(cur)] * local_world
+    mine = lists[local_rank]
+    peers = [r for r in range(local_world) if lists[r] == mine]
+    i, k = peers.index(local_rank), len(peers)
+    cores = list(mine[len(mine) * i // k:len(mine) * (i + 1) // k]) or list(mine)
+    os.sched_setaffinity(0, cores)
+    if verbose:
+        import sys
+        print("rank %d: cores %s" % (local_rank, cores), file=sys.stderr, flush=True)
+    return cores
+
+
 def shard_bounds(n, rank, world):
     """contiguous shard [lo, hi) of rank `rank` in a batch of n transactions"""
     return n * rank // world, n * (rank + 1) // world

@@ -429,6 +429,7 @@ class ChainTable {
 struct FastCache {
   PinnedVec<uint8_t> blob, region_b, op_out, tx_flags; PinnedVec<uint64_t> off; PinnedVec<uint32_t> plan, terms, term_off, rp_m, rp_pt_off, rp_ch_off; PinnedVec<long long> prev; PinnedVec<uint64_t> amount;
   ChainTable chains;                 // (account, asset) -> tail of its balance chain inside the batch
+  std::vector<TxView> txs;           // parsed views of the current batch (reused)
 };
 static std::unordered_map<xhe_ctx*, FastCache*> g_fast_cache;
 static FastCache& fast_cache_for(xhe_ctx* ctx) { std::lock_guard<std::mutex> g(g_cache_mu); FastCache*& c = g_fast_cache[ctx]; if (!c) c = new FastCache(); return *c; }
@@ -572,11 +573,14 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
   uint8_t seed[32];
   if (!make_seed(opt, seed)) return 0;
-  std::vector<TxView> txs(n); std::vector<int> parse_rc(n, 0);      // this shard's transactions: txs[j] = blobs[lo + j]
+  FastCache& F = fast_cache_for(ctx);
+  // this shard's transactions: txs[j] = blobs[lo + j].  The views are kept from batch to batch (their transfer lists keep their
+  // capacity: no allocation per transaction after the first batch)
+  if (F.txs.size() < n) F.txs.resize(n);
+  std::vector<TxView>& txs = F.txs; std::vector<int> parse_rc(n, 0);
   parallel_for(n, threads, [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) parse_rc[j] = txs[j].parse(blobs[lo + j], lens[lo + j]); });
   for (size_t j = 0; j < n; j++) if (parse_rc[j]) return 0;
   double t1 = now_ms();
-  FastCache& F = fast_cache_for(ctx);
   const uint32_t party_capacity = opt.host_dry_run ? 512u : xhe_ctx_party_capacity(ctx);
   F.off.resize(n + 1); F.plan.resize(8 * n); F.rp_m.resize(n); F.rp_pt_off.resize(n + 1); F.rp_ch_off.resize(n + 1);
   F.region_b.clear(); F.terms.clear(); F.term_off.clear(); F.prev.clear(); F.amount.clear();
