@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--mint-cache", default=None, help="development only: a pickle (tools/r02_mint_cache.py) holding the 8 x 10k a1k1 batch minted with the same seeds; skips the minting, the oracle prefix check and the CPU baseline")
     ap.add_argument("--secondary", default="full", choices=["full", "min", "off"], help="BASELINE.json's other configs (N = 1 only): full = other shapes, one-sender chain, mixed batch with reject paths, 16x255, MSM sweep, ciphertext updates; min = MSM 2^20 + ciphertext updates")
     ap.add_argument("--no-secondary", action="store_true", help="same as --secondary off")
+    ap.add_argument("--time-limit", type=float, default=150.0, help="wall-clock budget of the whole run in seconds: a secondary configuration (BASELINE.json's other configs, each minted by the CPU prover first) is skipped -- and listed as skipped -- when its estimated cost no longer fits; --time-limit 900 runs them all")
     ap.add_argument("--mixed-txs", type=int, default=100000, help="size of the mixed (config 5) batch")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
     ap.add_argument("--no-key-index", action="store_true", help="sharded runs: find cross-shard dependencies by scanning the earlier shards' bytes instead of the batch's key-digest index")
@@ -163,7 +164,7 @@ def measure_config(name, torch, xhe, verifier, dev, stream, flush, batch_blobs, 
         for w in range(2):
             code, idx, tm = verifier.verify_batch(ctx, None, ledger(), seed=b"sec-warm%d" % w, threads=host_threads, prepared=prepared, fiat_shamir="fast")
             assert (code, idx) == (0, -1), (name, code, idx)
-        out["accepted"] = True; out["path"] = "fast (device transcripts + device layout)" if tm["fast_path"] else "exact (host state walk and tables, device transcripts): multisig transactions / accounts in the batch"
+        out["accepted"] = True; out["path"] = "fast (device transcripts + device layout)" if tm["fast_path"] else ("exact, Merlin transcripts on the host threads: few transactions with very long transcripts (verify_batch picks north_star's split for them)" if name == "16x255" else "exact (host state walk and tables, device transcripts): multisig transactions / accounts in the batch")
         ms = timed_runs(torch, stream, lambda: dev.lib.xhe_batch_run(ctx.p), steps, 2, flush)
         out["value"] = {"value": n / ms * 1e3, "unit": "TX/s", "ms_per_step": ms}
         if canonical_lp and peak:
@@ -290,6 +291,7 @@ def main():
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
+    t_bench0 = time.time()
     args = parse_args()
     if args.no_secondary:
         args.secondary = "off"
@@ -718,55 +720,86 @@ def main():
         sec.update(ct_update_metrics(torch, lib, ctx, ts, hbm_peak))
         if args.secondary == "full":
             t_sec = time.time()
+            skipped = {}
+
+            def fits(name, est_s):
+                """run a configuration only if its estimated cost (16 host cores: the CPU prover mints its batch) still fits the budget"""
+                if time.time() - t_bench0 + est_s <= args.time_limit:
+                    return True
+                skipped[name] = {"skipped": "time budget (--time-limit %g s; about %d s)" % (args.time_limit, est_s), "builder_run": "profiles/r02_bench_1gpu_full.json"}
+                return False
+
+            def timed(name, fn):
+                t0_ = time.time(); sec[name] = fn(); sec[name]["seconds_incl_minting"] = round(time.time() - t0_, 1)
+
+            # the headline shape's reject paths (all tamper classes)
+            if fits("a1k1_rejects", 5):
+                timed("a1k1_rejects", lambda: measure_config("a1k1", torch, xhe, verifier, dev, ts, flush, batch.blobs, my_records, [], max(m, 2), 3, 2, tamper_classes(oracle, batch, 77, (2 * args.txs) // 3, a, k), host_threads))
+
+            # config 3, one-sender variant: the reference's own bench shape (benches/tx.rs:153-186), a length-T balance chain
+            def run_chain():
+                cb = oracle.mint_chain(83, args.txs, 1, threads=ncpu)
+                cbl = list(cb.blobs)
+                i0 = max(0, min(5000, args.txs - 2))
+                swapped = cbl[:i0] + [cbl[i0 + 1], cbl[i0]] + cbl[i0 + 2:]
+                bad_sig = cbl[:-1] + [cbl[-1][:-1] + bytes([cbl[-1][-1] ^ 1])]
+                return measure_config("chain", torch, xhe, verifier, dev, ts, flush, cbl, cb.ledger().dump(), [], 2, 5, 3,
+                                      [("bad_signature_last", bad_sig, (1, args.txs - 1)), ("two_swapped", swapped, (5, -1))], host_threads, canonical_lp_per_tx(1, 1) * args.txs, peak_wide)
+            if fits("one_sender_chain_%d" % args.txs, 35):
+                timed("one_sender_chain_%d" % args.txs, run_chain)
+
+            # benches/tx.rs:231-233: 16 transactions of 255 transfers each (256-party aggregated range proofs)
+            def run_255():
+                rng = oracle.Rng(b"bench-255"); led255 = oracle.Ledger(); recs255 = []
+                rcv = oracle.Keypair.derive(b"bench255-rcv"); ct = rcv.encrypt(0, rng); led255.set_balance(rcv.pk, oracle.NATIVE, ct); led255.set_nonce(rcv.pk, 0); recs255.append((rcv.pk, oracle.NATIVE, ct))
+                kps = [oracle.Keypair.derive(b"bench255-%d" % i) for i in range(16)]
+                for kp in kps:
+                    ct = kp.encrypt(10**7, rng); led255.set_balance(kp.pk, oracle.NATIVE, ct); led255.set_nonce(kp.pk, 0); recs255.append((kp.pk, oracle.NATIVE, ct))
+                res255 = [None] * 16
+
+                def build255(i):
+                    res255[i] = oracle.build_tx(kps[i], led255, oracle.Rng(b"bench-255-%d" % i), fee=3, transfers=[(oracle.NATIVE, rcv.pk, 1)] * 255, balances=[(oracle.NATIVE, 10**7)])
+                th255 = [threading.Thread(target=build255, args=(i,)) for i in range(16)]
+                for t_ in th255:
+                    t_.start()
+                for t_ in th255:
+                    t_.join()
+                return measure_config("16x255", torch, xhe, verifier, dev, ts, flush, res255, recs255, [], 256, 5, 3,
+                                      [("bad_signature", res255[:9] + [res255[9][:-1] + bytes([res255[9][-1] ^ 1])] + res255[10:], (1, 9))], host_threads, canonical_lp_per_tx(1, 255) * 16, peak_wide)
+            if fits("16x255_transfers", 10):
+                timed("16x255_transfers", run_255)
+
             # config 3, other shapes: multi-destination / multi-asset transfers at 10k
-            for sa, sk_, seed in ((1, 3, 81), (2, 6, 82)):
+            def run_shape(sa, sk_, seed):
                 sb = oracle.mint_transfers(seed, args.txs, sa, sk_, threads=ncpu)
                 sm_ = 1
                 while sm_ < sa + sk_:
                     sm_ *= 2
                 rej = tamper_classes(oracle, sb, seed, (2 * args.txs) // 3, sa, sk_)
-                sec["a%dk%d_%d" % (sa, sk_, args.txs)] = measure_config("a%dk%d" % (sa, sk_), torch, xhe, verifier, dev, ts, flush, sb.blobs, sb.ledger().dump(), [], max(sm_, 2), 5, 3, rej, host_threads, canonical_lp_per_tx(sa, sk_) * args.txs, peak_wide)
-                del sb
-            # the headline shape's reject paths (all tamper classes)
-            sec["a1k1_rejects"] = measure_config("a1k1", torch, xhe, verifier, dev, ts, flush, batch.blobs, my_records, [], max(m, 2), 3, 2, tamper_classes(oracle, batch, 77, (2 * args.txs) // 3, a, k), host_threads)
-            # config 3, one-sender variant: the reference's own bench shape (benches/tx.rs:153-186), a length-T balance chain
-            cb = oracle.mint_chain(83, args.txs, 1, threads=ncpu)
-            cbl = list(cb.blobs)
-            i0 = max(0, min(5000, args.txs - 2))
-            swapped = cbl[:i0] + [cbl[i0 + 1], cbl[i0]] + cbl[i0 + 2:]
-            bad_sig = cbl[:-1] + [cbl[-1][:-1] + bytes([cbl[-1][-1] ^ 1])]
-            sec["one_sender_chain_%d" % args.txs] = measure_config("chain", torch, xhe, verifier, dev, ts, flush, cbl, cb.ledger().dump(), [], 2, 5, 3,
-                                                                   [("bad_signature_last", bad_sig, (1, args.txs - 1)), ("two_swapped", swapped, (5, -1))], host_threads, canonical_lp_per_tx(1, 1) * args.txs, peak_wide)
-            del cb
-            # config 5: mixed batch with multisig; one tampered run per class
-            mb = oracle.mint_mixed(84, args.mixed_txs, threads=ncpu)
-            v = (2 * args.mixed_txs) // 3
-            while mb.blobs[v][1] != 0 or mb.blobs[v][3] != 0xFF:
-                v += 1
-            kk_ = int.from_bytes(mb.blobs[v][4:8], "little")
-            rej = tamper_classes(oracle, mb, 84, v, mb.blobs[v][2], kk_)
-            sec["mixed_%d" % args.mixed_txs] = measure_config("mixed", torch, xhe, verifier, dev, ts, flush, mb.blobs, mb.ledger().dump(), mb.ledger().dump_multisig(), 8, 3, 2, rej, ncpu)
-            sec["mixed_%d" % args.mixed_txs]["mix"] = "60 % transfers (k 1..4, a 1..2), 15 % burn, 15 % contract call, 5 % multisig set-up, 5 % transfers from threshold-2 multisig accounts"
-            del mb
-            # benches/tx.rs:231-233: 16 transactions of 255 transfers each (256-party aggregated range proofs)
-            w255 = []
-            import hashlib
-            rng = oracle.Rng(b"bench-255"); led255 = oracle.Ledger(); recs255 = []
-            rcv = oracle.Keypair.derive(b"bench255-rcv"); ct = rcv.encrypt(0, rng); led255.set_balance(rcv.pk, oracle.NATIVE, ct); led255.set_nonce(rcv.pk, 0); recs255.append((rcv.pk, oracle.NATIVE, ct))
-            kps = [oracle.Keypair.derive(b"bench255-%d" % i) for i in range(16)]
-            for kp in kps:
-                ct = kp.encrypt(10**7, rng); led255.set_balance(kp.pk, oracle.NATIVE, ct); led255.set_nonce(kp.pk, 0); recs255.append((kp.pk, oracle.NATIVE, ct))
-            res255 = [None] * 16
+                return measure_config("a%dk%d" % (sa, sk_), torch, xhe, verifier, dev, ts, flush, sb.blobs, sb.ledger().dump(), [], max(sm_, 2), 5, 3, rej, host_threads, canonical_lp_per_tx(sa, sk_) * args.txs, peak_wide)
+            for sa, sk_, seed, est in ((1, 3, 81, 40), (2, 6, 82, 65)):
+                if fits("a%dk%d_%d" % (sa, sk_, args.txs), est):
+                    timed("a%dk%d_%d" % (sa, sk_, args.txs), lambda: run_shape(sa, sk_, seed))
 
-            def build255(i):
-                res255[i] = oracle.build_tx(kps[i], led255, oracle.Rng(b"bench-255-%d" % i), fee=3, transfers=[(oracle.NATIVE, rcv.pk, 1)] * 255, balances=[(oracle.NATIVE, 10**7)])
-            th255 = [threading.Thread(target=build255, args=(i,)) for i in range(16)]
-            for t_ in th255:
-                t_.start()
-            for t_ in th255:
-                t_.join()
-            sec["16x255_transfers"] = measure_config("16x255", torch, xhe, verifier, dev, ts, flush, res255, recs255, [], 256, 5, 3,
-                                                     [("bad_signature", res255[:9] + [res255[9][:-1] + bytes([res255[9][-1] ^ 1])] + res255[10:], (1, 9))], host_threads, canonical_lp_per_tx(1, 255) * 16, peak_wide)
+            # config 5: mixed batch with multisig; one tampered run per class
+            def run_mixed(n_mixed):
+                mb = oracle.mint_mixed(84, n_mixed, threads=ncpu)
+                v = (2 * n_mixed) // 3
+                while mb.blobs[v][1] != 0 or mb.blobs[v][3] != 0xFF:
+                    v += 1
+                kk_ = int.from_bytes(mb.blobs[v][4:8], "little")
+                rej = tamper_classes(oracle, mb, 84, v, mb.blobs[v][2], kk_)
+                out = measure_config("mixed", torch, xhe, verifier, dev, ts, flush, mb.blobs, mb.ledger().dump(), mb.ledger().dump_multisig(), 8, 3, 2, rej, ncpu)
+                out["mix"] = "60 % transfers (k 1..4, a 1..2), 15 % burn, 15 % contract call, 5 % multisig set-up, 5 % transfers from threshold-2 multisig accounts"
+                return out
+            if fits("mixed_%d" % args.mixed_txs, 300 * args.mixed_txs / 100000.0):
+                timed("mixed_%d" % args.mixed_txs, lambda: run_mixed(args.mixed_txs))
+            else:      # the same mix at the largest size that still fits the budget (named by its size)
+                for n_small in (50000, 20000):
+                    if n_small < args.mixed_txs and time.time() - t_bench0 + 300 * n_small / 100000.0 <= args.time_limit:
+                        timed("mixed_%d" % n_small, lambda: run_mixed(n_small))
+                        break
+            sec.update(skipped)
             sec["secondary_seconds"] = round(time.time() - t_sec, 1)
         line["secondary"] = sec
     if world == 1 and not args.no_cpu_baseline:

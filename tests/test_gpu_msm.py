@@ -57,7 +57,7 @@ def test_msm_rejects_bad_arguments(ctx):
         ctx.msm(s, p[:32 * 7] + (1).to_bytes(32, "little"))                 # invalid point encoding
 
 
-@pytest.mark.parametrize("logn", [18, 20])
+@pytest.mark.parametrize("logn", [18, 20, 22])      # 2^22 = the largest size of BASELINE config 2
 def test_msm_known_answer_full_size(ctx, logn):
     """sum s_i B_{j(i)} with B_j = b_j G (256 known multiples): expected = (sum s_i b_j(i)) G, exact at any n."""
     import oracle

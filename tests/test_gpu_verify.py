@@ -42,7 +42,8 @@ def both(ctx, world, txs, expect=None):
     code_f, idx_f, tm_f = verifier.verify_batch(ctx, txs, hl_fast, seed=SEED, threads=4, fiat_shamir="fast")
     assert (code_f, idx_f) == want, ("fast path", code_f, idx_f, want)
     assert hl_fast.dump() == hl.dump()
-    if code == OK and txs and not any(t[1] == 4 or t[3] != 0xFF for t in txs) and not world.multisig:
+    long_transcripts = any(t[1] == 0 and int.from_bytes(t[4:8], "little") >= 32 for t in txs)      # few transactions with hundreds of transfers: Merlin runs on the host
+    if code == OK and txs and not any(t[1] == 4 or t[3] != 0xFF for t in txs) and not world.multisig and not long_transcripts:
         assert tm_f["fast_path"], "an honest non-multisig batch must be decided by the fast path"
     if expect is not None:
         assert code == expect

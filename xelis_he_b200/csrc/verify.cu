@@ -357,15 +357,17 @@ __global__ void k_pow2_table(uint32_t* __restrict__ tab) {
 #define RPG_CHUNK 128
 #define XHE_RPG_SMEM_EXTRA_DEFAULT 0
 __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restrict__ m_arr, const uint32_t* __restrict__ der, uint32_t der_stride, const uint32_t* __restrict__ pow2m, uint32_t n_rp,
-                                                         uint32_t Nmax, uint32_t n_rows, uint32_t* __restrict__ part) {
+                                                         uint32_t Nmax, uint32_t n_rows, uint32_t split /* warps per proof: each takes every split-th 128-index chunk */, uint32_t* __restrict__ part) {
   extern __shared__ uint32_t sm[];           // per warp: t[128] then yl[128], 8 words each (Montgomery form)
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, row = blockIdx.x * RPG_WARPS + wib;
   if (row >= n_rows) return;
   uint32_t* t = sm + (size_t)wib * 2 * RPG_CHUNK * 8; uint32_t* yl = t + RPG_CHUNK * 8;
   uint32_t* my = part + 8 * (size_t)row * 2 * Nmax;
   for (uint32_t i = lane; i < 2 * Nmax; i += 32) st_sc(my + 8 * i, sc_zero());
-  for (uint32_t p = row; p < n_rp; p += n_rows) {
+  for (uint32_t it = row; it < n_rp * split; it += n_rows) {
+    const uint32_t p = it / split, sp = it % split;
     const uint32_t m = m_arr[p]; const int lg = 6 + (31 - __clz(m)), lgc = lg < 7 ? lg : 7; const uint32_t N = 64u * m, Cn = 1u << lgc, Q = N >> lgc;
+    if (sp >= Q) continue;                       // (warp-uniform) fewer chunks than warps for this proof
     const uint32_t* d = der + 8 * (size_t)der_stride * p;
     sc u1; ld_sc(u1, d + 8 * D_U1);
     __syncwarp();
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(RPG_THREADS) k_rp_gens(const uint32_t* __restr
       __syncwarp();
     }
     sc rz, ra, rb; ld_sc(rz, d + 8 * D_RZ); ld_sc(ra, d + 8 * D_RA); ld_sc(rb, d + 8 * D_RB);
-    for (uint32_t q = 0; q < Q; q++) {
+    for (uint32_t q = sp; q < Q; q += split) {
       // factors of the chunk's high index bits (bit lgc + b of i pairs with u_{lg-1-lgc-b}): s base for q and for the
       // mirrored chunk Q-1-q, and y^-(q * 2^lgc)
       sc sb = u1, sbr = u1, ybr = mont_one();
@@ -704,7 +706,7 @@ static size_t rpg_smem() { static const size_t v = (size_t)RPG_WARPS * 2 * RPG_C
 // device-side image of one batch: every pointer lives in the ctx arena
 struct DeviceBatch {
   xhe_batch h;                       // scalar fields (counts) copied from the host description; pointers unused
-  uint32_t Nmax = 64, rp_grid = 0, der_stride = RP_DER_FIXED + 1; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
+  uint32_t Nmax = 64, rp_grid = 0, rp_split = 1, der_stride = RP_DER_FIXED + 1; size_t n_pts_total = 0, n_sigma_terms = 0, n_sigma = 0, n_dyn = 0, n_range = 0, n_chal = 0, ws_sigma = 0, ws_range = 0, n_terms = 0;
   uint8_t *d_enc, *d_ok, *d_sig_r, *d_op_out, *d_ws1, *d_ws2, *d_ws3; uint32_t* d_rparts; size_t ws_static = 0;
   uint32_t *d_aff, *d_niels, *d_sig_s, *d_sig_e, *d_sig_pk, *d_sig_tab, *d_term_off, *d_terms, *d_acc_a, *d_acc_b, *d_eq_sc, *d_val_sc, *d_sig_idx, *d_sigma_sc, *d_sigma_niels,
       *d_gh, *d_gh_part, *d_results, *d_m, *d_pt_off, *d_ch_off, *d_rp_sc, *d_chal, *d_der, *d_rgh, *d_rgh_part, *d_range_idx, *d_range_sc, *d_range_niels, *d_part;
@@ -780,7 +782,14 @@ extern "C" int32_t xhe_batch_prepare(xhe_ctx* ctx, const xhe_batch* b) {
   static int gens_blocks_per_sm = 0;
   if (!gens_blocks_per_sm) { int nb = 0; if (rpg_smem() > 48 * 1024) XHE_CUDA_OK(ctx, cudaFuncSetAttribute(k_rp_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rpg_smem()));
     XHE_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rp_gens, RPG_THREADS, rpg_smem())); gens_blocks_per_sm = nb > 0 ? nb : 1; }
-  D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>(b->n_rp, (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS), std::max<size_t>(64, ((size_t)64 << 20) / (64 * (size_t)D.Nmax))) : 0;
+  // few proofs with many parties (the reference's 16 x 255-transfer bench, benches/tx.rs:231-233: 16 proofs of 16,384 generator
+  // indices each) would leave one warp per proof working alone: such a batch gives every proof `rp_split` warps, each taking
+  // every rp_split-th 128-index chunk into its own row of partial sums (rows are 64 B x Nmax: the cap is 256 MiB then)
+  { const size_t wave = (size_t)ctx->sm_count * gens_blocks_per_sm * RPG_WARPS, chunks = std::max<size_t>(1, (size_t)D.Nmax / RPG_CHUNK);
+    size_t split = 1;
+    if (b->n_rp && b->n_rp < wave / 2) { const size_t cap_rows = std::max<size_t>(64, ((size_t)256 << 20) / (64 * (size_t)D.Nmax)); while (split * 2 <= chunks && (size_t)b->n_rp * split * 2 <= std::min(wave, cap_rows)) split *= 2; }
+    D.rp_split = (uint32_t)split;
+    D.rp_grid = b->n_rp ? (uint32_t)std::min<size_t>(std::min<size_t>((size_t)b->n_rp * split, wave), std::max<size_t>(64, ((size_t)(split > 1 ? 256 : 64) << 20) / (64 * (size_t)D.Nmax))) : 0; }
   D.ws_sigma = xhe_msm_workspace_bytes(ctx, D.n_sigma); D.ws_range = xhe_msm_workspace_bytes(ctx, D.n_dyn); D.ws_static = xhe_msm_workspace_bytes(ctx, D.n_range - D.n_dyn);
   D.ws_joint = xhe_msm_workspace_bytes(ctx, D.n_sigma + D.n_dyn);
   D.n_terms = b->n_ops ? b->op_term_off[b->n_ops] : 0;
@@ -1062,7 +1071,7 @@ extern "C" int32_t xhe_batch_run(xhe_ctx* ctx) {
     { cudaStream_t st = s_rp;
       const size_t smem = rpg_smem();
       { XheTimed t(ctx, "k_rp_gens", 136.0 * 6 * 64.0 * D.sum_m);      // 6 mod-l products per generator index, 64*m indices per proof
-        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, D.der_stride, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.d_part); XHE_LAUNCHED(ctx); }
+        k_rp_gens<<<nblk(D.rp_grid, RPG_WARPS), RPG_THREADS, smem, st>>>(D.d_m, D.d_der, D.der_stride, T->pow2m, b->n_rp, Nmax, D.rp_grid, D.rp_split, D.d_part); XHE_LAUNCHED(ctx); }
       { const uint32_t cols = 2 * Nmax, gy = cols > 32768u ? 32768u : cols;     // cols = 128 * m_max, a power of two
         k_reduce_scalars<<<dim3(1, gy, cols / gy), 256, 0, st>>>(D.d_part, D.rp_grid, 2 * Nmax, 1, D.d_range_sc + 8 * n_dyn, 2 * Nmax); XHE_LAUNCHED(ctx); }
       k_reduce_scalars<<<dim3(32, 2), 256, 0, st>>>(D.d_rgh, b->n_rp, 2, 1, D.d_rgh_part, 2); XHE_LAUNCHED(ctx);

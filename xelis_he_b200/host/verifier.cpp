@@ -820,7 +820,32 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
   return 1;
 }
 
+// Where should the Merlin transcripts of this batch run?  On the device every transaction's transcript is ONE thread's sequential
+// chain of Keccak permutations (about 16 us each at one warp per sub-partition); on the host a permutation takes well under a
+// microsecond and transactions spread over the threads.  Thousands of ordinary transactions hide the device latency (10 k
+// a1k1: 24 permutations each, 0.4 ms); a handful of transactions with hundreds of transfers each -- the reference's
+// 16 x 255-transfer bench, benches/tx.rs:231-233: ~1,300 permutations per transaction -- do not (21 ms against < 1 ms).
+static bool transcripts_favor_host(const uint8_t* const* blobs, const size_t* lens, size_t lo, size_t hi, int threads) {
+  double max_p = 0, sum_p = 0;
+  for (size_t i = lo; i < hi; i++) {
+    if (lens[i] < 128) continue;
+    const uint8_t* b = blobs[i]; const double k = b[1] == 0 ? (double)rd32(b + 4) : 0.0, a = b[2];
+    const double p = 10.0 + 14.0 * a + 5.5 * k + 16.0;       // header, per source commitment, per transfer, range proof
+    sum_p += p; if (p > max_p) max_p = p;
+  }
+  const double device_us = 16.0 * max_p, host_us = 0.7 * sum_p / std::max(1, threads);
+  return device_us > 3000.0 && device_us > 2.0 * host_us;
+}
+
 int verify_batch(xhe_ctx* ctx, const uint8_t* const* blobs, const size_t* lens, size_t n, VerificationState& state, const BatchOptions& opt, long* fail_index, BatchTimings* tm) {
+  if (opt.fast_path && !opt.host_dry_run) {
+    const size_t lo = std::min(opt.shard_lo, n), hi = std::min(opt.shard_hi, n);
+    const int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (transcripts_favor_host(blobs, lens, lo, hi, threads)) {      // few, very long transcripts: north_star's split (host Merlin, exact path)
+      BatchOptions o = opt; o.fast_path = false; o.device_fiat_shamir = false;
+      return verify_batch_exact(ctx, blobs, lens, n, state, o, fail_index, tm);
+    }
+  }
   if (opt.fast_path) {
     int rc = XHE_OK; long fi = -1;
     int how = verify_batch_fast(ctx, blobs, lens, n, state, opt, tm, &rc, &fi);
