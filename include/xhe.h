@@ -217,6 +217,21 @@ int32_t xhe_measure_int_peak(xhe_ctx* ctx, int which, double* rate);
 /* CUDA-event timing of the main kernels of xhe_batch_run / the MSM (roofline evidence): enable, run, then read.
  * units[i] = algorithmic limb products (DESIGN.md work model) accumulated for kernel i. */
 int32_t xhe_ctx_timing(xhe_ctx* ctx, int enable);
+/* ---- decoding of decrypted amounts ---------------------------------------------------------------
+ * ECDLPInstance::decode / par_decode (src/elgamal.rs:67-92; the curve25519-dalek fork's ecdlp module) and
+ * ElGamalSecretKey::decrypt (src/elgamal.rs:140-145, M = C - s * D): find v in [0, 2^range_bits) with v * G == M by a
+ * baby-step / giant-step search on the device.  A table holds 2^l1_bits baby steps (8 bytes per slot, 2^(l1_bits + 1) slots,
+ * built on the device at creation); one decode then takes 2^(range_bits - l1_bits - 1) giant steps, spread over a warp.
+ * out_value[i] = v, or -1; status[i] = 1 found, 0 no such v in range, 2 the input does not decode.  range_bits <= 62 and
+ * at most l1_bits + 33. */
+typedef struct xhe_ecdlp xhe_ecdlp;
+int32_t xhe_ecdlp_create(xhe_ctx* ctx, uint32_t l1_bits, xhe_ecdlp** out);
+void    xhe_ecdlp_destroy(xhe_ecdlp* table);
+size_t  xhe_ecdlp_table_bytes(const xhe_ecdlp* table);
+int32_t xhe_ecdlp_decode(xhe_ecdlp* table, const uint8_t* points /* n x 32: encodings of M */, size_t n, uint32_t range_bits, int64_t* out_value, uint8_t* status);
+int32_t xhe_decrypt_decode(xhe_ecdlp* table, const uint8_t secret_key[32], const uint8_t* ciphertexts /* n x 64: commitment || handle */, size_t n, uint32_t range_bits,
+                           int64_t* out_value, uint8_t* status);
+
 /* run the independent pipelines of xhe_batch_run back to back on one stream (isolated per-kernel timing; slower) */
 int32_t xhe_ctx_set_serial(xhe_ctx* ctx, int serial);
 int32_t xhe_ctx_timing_read(xhe_ctx* ctx, const char** names, double* ms, uint64_t* launches, double* units, int cap);

@@ -4,4 +4,4 @@ The product is the C-ABI library `libxhe_cuda.so` (include/xhe.h); this package 
 tests and bench.py.  There is no CPU fallback: importing works anywhere (so the export table can be checked), but every
 compute call needs a CUDA device and raises `XheError` otherwise.  Nothing here imports `oracle/`.
 """
-from ._lib import XheError, Ctx, DeviceLedger, lib_path, load_library, ERR_NAMES  # noqa: F401
+from ._lib import XheError, Ctx, DeviceLedger, Ecdlp, lib_path, load_library, ERR_NAMES  # noqa: F401

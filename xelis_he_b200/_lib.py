@@ -65,6 +65,11 @@ def load_library():
         "xhe_measure_int_peak": (i32, [vp, C.c_int, C.POINTER(C.c_double)]),
         "xhe_selftest_fe": (i32, [vp, C.c_int, vp, vp, sz, vp]),
         "xhe_selftest_oct": (i32, [vp, C.c_int, vp, vp, sz, vp]),
+        "xhe_ecdlp_create": (i32, [vp, C.c_uint32, C.POINTER(vp)]),
+        "xhe_ecdlp_destroy": (None, [vp]),
+        "xhe_ecdlp_table_bytes": (sz, [vp]),
+        "xhe_ecdlp_decode": (i32, [vp, u8p, sz, C.c_uint32, vp, vp]),
+        "xhe_decrypt_decode": (i32, [vp, u8p, u8p, sz, C.c_uint32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -187,6 +192,41 @@ class Ctx:
         out = np.zeros_like(a)
         self._chk(self.lib.xhe_selftest_oct(self.p, op, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
         return out
+
+
+class Ecdlp:
+    """Decoding of decrypted amounts on the device (include/xhe.h, xhe_ecdlp_*; reference ECDLPInstance::decode,
+    src/elgamal.rs:67-92): a baby-step table of 2^l1_bits entries, built once."""
+
+    def __init__(self, ctx, l1_bits=22):
+        self.ctx, self.lib = ctx, ctx.lib
+        p = C.c_void_p()
+        ctx._chk(self.lib.xhe_ecdlp_create(ctx.p, l1_bits, C.byref(p)))
+        self.p, self.l1_bits = p, l1_bits
+
+    @property
+    def table_bytes(self):
+        return int(self.lib.xhe_ecdlp_table_bytes(self.p))
+
+    def decode(self, points: bytes, range_bits=32):
+        """points: n x 32-byte encodings of M = v * G -> (values: list of int, -1 where not found; status bytes: 1 found, 0 not in range, 2 invalid encoding)"""
+        n = len(points) // 32
+        vals = (C.c_int64 * max(n, 1))(); st = C.create_string_buffer(max(n, 1))
+        self.ctx._chk(self.lib.xhe_ecdlp_decode(self.p, points, n, range_bits, vals, st))
+        return list(vals[:n]), st.raw[:n]
+
+    def decrypt_decode(self, secret_key: bytes, ciphertexts: bytes, range_bits=32):
+        """ElGamalSecretKey::decrypt (M = C - s * D, src/elgamal.rs:140-145) followed by decode; ciphertexts: n x 64 bytes"""
+        n = len(ciphertexts) // 64
+        vals = (C.c_int64 * max(n, 1))(); st = C.create_string_buffer(max(n, 1))
+        self.ctx._chk(self.lib.xhe_decrypt_decode(self.p, secret_key, ciphertexts, n, range_bits, vals, st))
+        return list(vals[:n]), st.raw[:n]
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.lib.xhe_ecdlp_destroy(self.p); self.p = None
+
+    __del__ = close
 
 
 class DeviceLedger:

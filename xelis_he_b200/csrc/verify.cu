@@ -654,6 +654,9 @@ static int32_t ensure_tables(xhe_ctx* ctx) {
   return XHE_OK;
 }
 
+// the context's 8-bit fixed-base table of G (8 windows: u64 * G), for the other translation units (ecdlp.cu)
+extern "C" const uint32_t* xhe_internal_tabG(xhe_ctx* ctx) { if (!ctx || ensure_tables(ctx) != XHE_OK) return nullptr; return g_tables[ctx->device]->tabG; }
+
 extern "C" int32_t xhe_combine_partials(xhe_ctx* ctx, const uint8_t* ext, size_t n, uint8_t out_enc[32], int32_t* is_identity) {
   if (!ctx || !is_identity || (n && !ext)) return XHE_E_ARG;
   void* d = nullptr; XHE_CUDA_OK(ctx, cudaMalloc(&d, 128 * n + 64));

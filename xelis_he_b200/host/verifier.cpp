@@ -59,6 +59,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 // ------------------------------------------------------------------------------------------------------------------
 int TxView::parse(const uint8_t* b, size_t n) {
   blob = b; len = n; transfers.clear();
+  body = rp = sc = ms = sig = source = nullptr; body_len = 0; n_ms = -1; n_sc = 0; count = aux = rp_len = 0;      // (a view may be reused for another transaction)
   if (n < 128) return XHE_ERR_PARSE;
   version = b[0]; type = b[1]; n_sc = b[2]; n_ms = b[3] == 0xFF ? -1 : b[3];
   count = rd32(b + 4); aux = rd32(b + 8); rp_len = rd32(b + 12); source = b + 16; fee = rd64(b + 48); nonce = rd64(b + 56);
@@ -650,7 +651,7 @@ static int verify_batch_fast(xhe_ctx* ctx, const uint8_t* const* blobs, const si
     }
   }
   // the walk below is one dependent hash lookup after another: announce the lookups a few transactions ahead
-  const size_t AHEAD = 6;
+  const size_t AHEAD = 12;
   auto announce = [&](const TxView& tx) {
     state.prefetch_account(tx.source);
     for (uint32_t q = 0; q < tx.n_sc; q++) { state.prefetch_balance(tx.source, tx.sc + 256 * q); chains.prefetch(tx.source, tx.sc + 256 * q); }
