@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
     ap.add_argument("--no-key-index", action="store_true", help="sharded runs: find cross-shard dependencies by scanning the earlier shards' bytes instead of the batch's key-digest index")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU runs: leave the ranks floating over all host cores instead of binding each to its own cores on its GPU's NUMA node")
+    ap.add_argument("--force-inflight", action="store_true", help="use --inflight as given instead of capping it at the rank's cores minus one")
     ap.add_argument("--inflight", type=int, default=6, help="batches in flight per GPU in the end-to-end measurement (one context + host thread each)")
     ap.add_argument("--fiat-shamir", default="fast", choices=["fast", "device", "host"], help="where the Merlin transcripts run (host = north_star split; device = SURVEY 8 f.1)")
     return ap.parse_args()
@@ -530,7 +531,7 @@ def main():
     pipelined = args.fiat_shamir != "host" and args.inflight > 1
     # batches in flight: one host thread each, so no more than the rank's cores minus one for the decision / commit threads
     # (8 GPUs on a 32-core box = 4 cores per rank: 3 in flight measured 9.3 M TX/s against 7.8 M with 6)
-    nfl = min(args.inflight, max(2, host_threads - 1)) if pipelined else 1
+    nfl = (args.inflight if args.force_inflight else min(args.inflight, max(2, host_threads - 1))) if pipelined else 1
     workers = [ctx] + [xhe.Ctx(local, party_capacity=max(m, 2)) for _ in range(nfl - 1)]
     for c in workers[1:]:
         streams.append(torch.cuda.Stream()); c.set_stream(streams[-1].cuda_stream)

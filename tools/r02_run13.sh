@@ -1,0 +1,12 @@
+#!/bin/bash
+N=$1
+for V in nfl6 nfl4; do
+  case $V in nfl6) A="--inflight 6 --force-inflight";; nfl4) A="--inflight 4 --force-inflight";; esac
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29570 bench.py --gpus $N --steps 20 --warmup 3 --mint-cache _cache/emul_80k.pkl --no-strong $A > gpurun_out/r02t_${N}gpu_$V.json 2> gpurun_out/r02t_${N}gpu_$V.err; echo "$V rc=$?"
+  python - $N $V <<'PY'
+import json,sys
+d=json.loads(open('gpurun_out/r02t_%sgpu_%s.json'%(sys.argv[1],sys.argv[2])).read().strip().splitlines()[-1])
+print(" ",sys.argv[2],"value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"e2e ms",round(d["e2e"]["ms_per_step"],3),"single",round(d["e2e"]["single_call"]["ms_per_step"],2),"nfl",d["e2e"]["batches_in_flight"])
+print("    pipe rank0",d["e2e"]["phases_ms_by_rank"][0]["pipelined"]); print("    pipe rank7",d["e2e"]["phases_ms_by_rank"][-1]["pipelined"])
+PY
+done

@@ -39,6 +39,10 @@ pub struct xhe_ctx {
 pub struct xhe_ledger {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct xhe_ecdlp {
+    _private: [u8; 0],
+}
 
 /// `xhe_batch` of include/xhe.h.  All pointers are HOST memory; point index 0 must be the identity encoding.
 #[repr(C)]
@@ -150,6 +154,12 @@ extern "C" {
     // sharded batches
     pub fn xhe_combine_partials(ctx: *mut xhe_ctx, ext: *const u8, n: usize, out_enc: *mut u8, is_identity: *mut i32) -> i32;
     pub fn xhe_sum_encodings(ctx: *mut xhe_ctx, enc: *const u8, n: usize, out_enc: *mut u8, is_identity: *mut i32, all_valid: *mut i32) -> i32;
+    // decoding of decrypted amounts: ECDLPInstance::decode / ElGamalSecretKey::decrypt (src/elgamal.rs:67-92, 140-145)
+    pub fn xhe_ecdlp_create(ctx: *mut xhe_ctx, l1_bits: u32, out: *mut *mut xhe_ecdlp) -> i32;
+    pub fn xhe_ecdlp_destroy(table: *mut xhe_ecdlp);
+    pub fn xhe_ecdlp_table_bytes(table: *const xhe_ecdlp) -> usize;
+    pub fn xhe_ecdlp_decode(table: *mut xhe_ecdlp, points: *const u8, n: usize, range_bits: u32, out_value: *mut i64, status: *mut u8) -> i32;
+    pub fn xhe_decrypt_decode(table: *mut xhe_ecdlp, secret_key: *const u8, ciphertexts: *const u8, n: usize, range_bits: u32, out_value: *mut i64, status: *mut u8) -> i32;
     // device-resident ledger: BlockchainVerificationState backend with balances decompressed on the device
     pub fn xhe_ledger_create(ctx: *mut xhe_ctx, capacity: usize, out: *mut *mut xhe_ledger) -> i32;
     pub fn xhe_ledger_destroy(ledger: *mut xhe_ledger);
