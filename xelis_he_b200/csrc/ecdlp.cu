@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(64) k_decrypt(const uint8_t* __restrict__ cts,
   ge acc = ge_identity();
 #pragma unroll 1
   for (int w = 64; w >= 0; w--) {
-    if (w != 64) { acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); }
+    if (w != 64) { acc = ge_double_pz(acc); acc = ge_double_pz(acc); acc = ge_double_pz(acc); acc = ge_double(acc); }
     const int dg = dig[w];
     if (dg > 0) acc = ge_add(acc, tab[dg - 1]); else if (dg < 0) acc = ge_add(acc, ge_neg(tab[-dg - 1]));
   }

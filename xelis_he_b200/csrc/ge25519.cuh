@@ -77,6 +77,15 @@ XHE_HD ge ge_double(const ge& p) {
   fe cx = fe_sub(xpy2, s), ct = fe_sub(zz2, d);
   ge r; r.X = fe_mul(cx, ct); r.Y = fe_mul(s, d); r.Z = fe_mul(d, ct); r.T = fe_mul(cx, s); return r;
 }
+// doubling whose result feeds another doubling: T is not an input of the doubling formulas, so T3 = E * H (one multiply of
+// eight) is skipped; the returned T is stale and must not be read
+XHE_HD ge ge_double_pz(const ge& p) {
+  fe xx = fe_sq(p.X), yy = fe_sq(p.Y), zz2 = fe_dbl(fe_sq(p.Z));
+  fe xpy2 = fe_sq(fe_add(p.X, p.Y));
+  fe s = fe_add(yy, xx), d = fe_sub(yy, xx);
+  fe cx = fe_sub(xpy2, s), ct = fe_sub(zz2, d);
+  ge r; r.X = fe_mul(cx, ct); r.Y = fe_mul(s, d); r.Z = fe_mul(d, ct); r.T = p.T; return r;
+}
 // Ristretto coset identity test (reference src/proofs.rs:62: RistrettoPoint::is_identity): X == 0 || Y == 0
 XHE_HD bool ge_ristretto_is_identity(const ge& p) { return fe_iszero(p.X) || fe_iszero(p.Y); }
 

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(64) k_sig_r(const uint32_t* __restrict__ s_in,
   for (int j = 0; j < 16; j++) { st_ge(tab + 32 * j, cur); cur = ge_add(cur, P); }
   ge acc = ge_identity();
   for (int w = 63; w >= 0; w--) {
-    if (w != 63) { acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); acc = ge_double(acc); }
+    if (w != 63) { acc = ge_double_pz(acc); acc = ge_double_pz(acc); acc = ge_double_pz(acc); acc = ge_double(acc); }      // only the last of the four needs T (for the addition)
     uint32_t d = (ne.v[w >> 3] >> ((w & 7) * 4)) & 15u;
     if (d) { ge t; ld_ge(t, tab + 32 * d); acc = ge_add(acc, t); }
   }
