@@ -163,3 +163,27 @@ def test_key_digest_index_finds_the_same_dependencies_as_the_blob_scan(lib):
     assert found_dependency
     indep = list(oracle.mint_transfers(9, 40, 1, 2, threads=4).blobs)
     assert verifier.shard_dependencies(verifier.prepare_blobs(indep, index=True), 20, 40) == []
+
+
+def test_fast_path_host_phases_run_without_a_device(lib):
+    """The host half of the fast path (header pass, state walk with the cache-resident chain table, cross-shard dependency
+    lookup through the key-digest index, staging) is plain C++: the diagnostics flag of xheh_verify_batch_ex / _shard_ix runs
+    it without a device.  Nothing is verified in that mode, so the call reports an error code, never XHE_OK."""
+    import ctypes as C
+    import scenarios
+    from xelis_he_b200 import verifier
+    lib.xheh_verify_batch_shard_ix.restype = C.c_int32
+    lib.xheh_verify_batch_shard_ix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
+                                               C.POINTER(C.c_long), C.c_void_p, C.c_void_p, C.c_void_p]
+    b = oracle.mint_transfers(21, 64, 1, 2, threads=4)
+    chain = oracle.mint_chain(22, 16, 1)
+    w, txs = scenarios.shared_receiver_world(6)
+    for blobs, records in ((list(b.blobs), b.ledger().dump()), (list(chain.blobs), chain.ledger().dump()), (list(txs), w.ledger.dump())):
+        led = verifier.Ledger(); led.import_records(records)
+        bl = verifier.prepare_blobs(blobs, index=True)
+        n = len(blobs)
+        for lo, hi in ((0, n), (n // 2, n), (n - 1, n)):
+            fi = C.c_long(-1); tm = (C.c_double * 7)(); part = C.create_string_buffer(64)
+            rc = lib.xheh_verify_batch_shard_ix(C.c_void_p(4096), led.ptr, bl.ptrs, bl.lens, n, lo, hi, b"dry", 3, 2, 4 | 16, C.byref(fi), tm, part, bl.index)
+            assert rc == -1, rc                      # XHE_E_ARG: a dry run never claims a verdict
+            assert tm[5] >= tm[0] >= 0 and tm[1] >= 0
