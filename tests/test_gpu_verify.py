@@ -373,3 +373,45 @@ def test_mixed_batch_config5_flavour(ctx):
         bad = list(txs); t = bytearray(bad[victim]); t[off if off >= 0 else len(t) - 1] ^= 0x01; bad[victim] = bytes(t)
         code, idx = both(ctx, w, bad)
         assert idx == victim and code in (SIG, NONCE)
+
+
+def test_joint_msm_failures_keep_the_reference_precedence(ctx):
+    """The accepting path sums the sigma and the range check in ONE MSM; a sum that is not the identity is re-run as two MSMs.
+    A batch in which BOTH checks fail (in different transactions, in either order) must report GenericProof like the reference
+    (sigma check first, src/tx/verify.rs:500-514); a failing range proof alone RangeProof; and a batch in which a sigma error
+    and a range error are made to look alike must still not be accepted."""
+    w = scenarios.World(b"joint-msm")
+    accts = [w.account(b"acct%d" % i, [(NATIVE, 1000)]) for i in range(6)]
+    sink = w.account(b"sink", [(NATIVE, 0)])
+    txs = [oracle.build_tx(a, w.ledger, w.rng, fee=1, transfers=[(NATIVE, sink.pk, 5 + i)], balances=[(NATIVE, 1000)]) for i, a in enumerate(accts)]
+    t0, rp0 = 64, 64 + 324
+    bad_sigma = oracle.resign(_mut(txs[1], t0 + 160 + 128), accts[1], w.rng)       # validity proof z_x of tx 1
+    bad_range = oracle.resign(_mut(txs[4], rp0 + 128), accts[4], w.rng)            # range proof t_x of tx 4
+    bad_range_early = oracle.resign(_mut(txs[0], rp0 + 128), accts[0], w.rng)
+    assert both(ctx, w, txs) == (OK, -1)
+    assert both(ctx, w, txs[:1] + [bad_sigma] + txs[2:4] + [bad_range] + txs[5:]) == (GENERIC, -1)
+    assert both(ctx, w, [bad_range_early] + [bad_sigma] + txs[2:]) == (GENERIC, -1)            # the range error comes first in the batch: still sigma first
+    assert both(ctx, w, txs[:4] + [bad_range] + txs[5:]) == (RANGE, -1)
+    assert both(ctx, w, txs[:1] + [bad_sigma] + txs[2:]) == (GENERIC, -1)
+
+
+def test_full_size_batch_with_a_tampered_transaction(ctx):
+    """BASELINE's batch size (10,000 transfers): a signature flipped deep inside the batch is rejected with the code and index the
+    oracle reports for the prefix that ends there, and the honest batch is accepted with every balance equal to the oracle's."""
+    from xelis_he_b200 import verifier
+    T = 10000
+    b = oracle.mint_transfers(93, T, 1, 1, threads=16)
+    records = b.ledger().dump()
+    hl = verifier.Ledger(); hl.import_records(records)
+    code, idx, tm = verifier.verify_batch(ctx, b.blobs, hl, seed=SEED, fiat_shamir="fast")
+    assert (code, idx) == (OK, -1) and tm["fast_path"]
+    ol = b.ledger()
+    for blob in b.blobs:
+        assert oracle.apply_without_verify(blob, ol) == 0
+    assert hl.dump() == sorted(ol.dump())
+    victim = 8765
+    bad = list(b.blobs); t = bytearray(bad[victim]); t[-1] ^= 0x01; bad[victim] = bytes(t)
+    hl2 = verifier.Ledger(); hl2.import_records(records)
+    got = verifier.verify_batch(ctx, bad, hl2, seed=SEED, fiat_shamir="fast")
+    assert got[:2] == oracle.verify_batch(bad[:victim + 1], b.slice(victim + 1).ledger()) == (1, victim)
+    assert hl2.dump() == sorted(records)                      # a rejected batch leaves the state untouched
