@@ -29,9 +29,10 @@ sys.path.insert(0, ROOT)
 # Several batches in flight means dozens of CUDA streams per process (six per context) plus NCCL's; with the default of 8
 # hardware queues they alias, and a stream queued behind an all-gather that waits for a slower rank stalls with it (measured at
 # 4 GPUs, 6 batches in flight: 60-84 ms per device phase instead of 6).  Must be set before CUDA initialises.
-# (One GPU, no collectives: the default 8 measured better end to end -- 2.85-3.07 against 2.43-2.69 M TX/s -- although the
-# device-only ceiling of six contexts is 5 % higher with 32: fewer queues keep the batches' completions in order.)
-if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+# (At one and two GPUs the default 8 measured better end to end -- 2.85-3.07 against 2.43-2.69 M TX/s at one, 5.3-5.5 against
+# 4.6-4.7 M at two -- although the device-only ceiling of six contexts is 5 % higher with 32: fewer queues keep the batches'
+# completions in order.  From four ranks on, with fewer host cores per rank, the stall above is what decides.)
+if int(os.environ.get("WORLD_SIZE", "1")) >= 4:
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
