@@ -76,7 +76,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(open(log.name).read())
         if rc != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"])
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-pthread"])
     with open(HASH_FILE, "w") as f:
         f.write(want + "\n")
     return LIB
