@@ -55,49 +55,6 @@ struct VerificationState {               // src/tx/verify.rs:25-77; every call r
 struct KeyHash { size_t operator()(const Ct64& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); uint64_t g; memcpy(&g, k.data() + 37, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull ^ g); } };
 struct Key32Hash { size_t operator()(const Bytes32& k) const { uint64_t h; memcpy(&h, k.data() + 5, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
 
-// Storage of the big tables: 2 MiB-aligned and advised to use transparent huge pages before it is first touched.  A lookup in
-// a 64 MB table of 4 KiB pages misses the TLB almost every time (and a miss is a nested page walk inside a VM); with huge
-// pages the same table is 32 TLB entries.  Falls back to ordinary pages silently.  T must be trivially copyable; new storage
-// is zero-filled.
-#include <stdlib.h>
-#if defined(__linux__)
-#include <sys/mman.h>
-#endif
-template <typename T>
-class HugeBuf {
- public:
-  HugeBuf() {}
-  HugeBuf(const HugeBuf& o) { assign_from(o); }
-  HugeBuf& operator=(const HugeBuf& o) { if (this != &o) { release(); assign_from(o); } return *this; }
-  ~HugeBuf() { release(); }
-  void swap(HugeBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); }
-  size_t size() const { return n_; }
-  bool empty() const { return n_ == 0; }
-  T& operator[](size_t i) { return p_[i]; }
-  const T& operator[](size_t i) const { return p_[i]; }
-  T* begin() { return p_; } T* end() { return p_ + n_; }
-  void resize_zero(size_t n) {            // discards the contents
-    release();
-    if (!n) return;
-    const size_t bytes = n * sizeof(T), huge = (size_t)1 << 21;
-    if (bytes >= huge) {
-      const size_t rounded = (bytes + huge - 1) & ~(huge - 1);
-      void* q = aligned_alloc(huge, rounded);
-      if (q) {
-#if defined(__linux__) && defined(MADV_HUGEPAGE)
-        madvise(q, rounded, MADV_HUGEPAGE);
-#endif
-        memset(q, 0, bytes); p_ = (T*)q; n_ = n; return;
-      }
-    }
-    { const size_t al = alignof(T) > 64 ? alignof(T) : 64, rounded = (bytes + al - 1) & ~(al - 1); void* q = aligned_alloc(al, rounded); if (q) { memset(q, 0, rounded); p_ = (T*)q; n_ = n; } }
-  }
- private:
-  void release() { if (p_) free(p_); p_ = nullptr; n_ = 0; }
-  void assign_from(const HugeBuf& o) { resize_zero(o.n_); if (n_) memcpy((void*)p_, (const void*)o.p_, n_ * sizeof(T)); }
-  T* p_ = nullptr; size_t n_ = 0;
-};
-
 // Open-addressing table with inline keys (linear probing, one tag byte per slot, no erase): a lookup touches one tag
 // line and one entry, and the slot of a key can be prefetched from its hash alone -- what the batch front end needs
 // when it walks 10^4 transactions' accounts in order.
@@ -137,15 +94,15 @@ class FlatTable {
     const size_t i = (size_t)hash(k) & (tags_.size() - 1);
     __builtin_prefetch(&tags_[i]); const char* e = (const char*)&entries_[i]; __builtin_prefetch(e); if (sizeof(Entry) > 64) __builtin_prefetch(e + 64);
   }
-  void clear() { if (tags_.size()) memset(&tags_[0], 0, tags_.size()); count_ = 0; }
+  void clear() { std::fill(tags_.begin(), tags_.end(), 0); count_ = 0; }
   template <typename F> void for_each(F f) const { for (size_t i = 0; i < tags_.size(); i++) if (tags_[i]) f(entries_[i].key.data(), entries_[i].val); }
  private:
   void rehash(size_t cap) {
-    HugeBuf<uint8_t> ot; HugeBuf<Entry> oe; ot.swap(tags_); oe.swap(entries_);
-    tags_.resize_zero(cap); entries_.resize_zero(cap); count_ = 0;
+    std::vector<uint8_t> ot; std::vector<Entry> oe; ot.swap(tags_); oe.swap(entries_);
+    tags_.assign(cap, 0); entries_.resize(cap); count_ = 0;
     for (size_t i = 0; i < ot.size(); i++) if (ot[i]) *insert(oe[i].key.data()) = oe[i].val;
   }
-  HugeBuf<uint8_t> tags_; HugeBuf<Entry> entries_; size_t count_ = 0;
+  std::vector<uint8_t> tags_; std::vector<Entry> entries_; size_t count_ = 0;
 };
 
 class MockLedger : public VerificationState {   // src/lib.rs:106-201
