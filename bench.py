@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--mint-cache", default=None, help="development only: a pickle (tools/r02_mint_cache.py) holding the 8 x 10k a1k1 batch minted with the same seeds; skips the minting, the oracle prefix check and the CPU baseline")
     ap.add_argument("--secondary", default="full", choices=["full", "min", "off"], help="BASELINE.json's other configs (N = 1 only): full = other shapes, one-sender chain, mixed batch with reject paths, 16x255, MSM sweep, ciphertext updates; min = MSM 2^20 + ciphertext updates")
     ap.add_argument("--no-secondary", action="store_true", help="same as --secondary off")
-    ap.add_argument("--time-limit", type=float, default=150.0, help="wall-clock budget of the whole run in seconds: a secondary configuration (BASELINE.json's other configs, each minted by the CPU prover first) is skipped -- and listed as skipped -- when its estimated cost no longer fits; --time-limit 900 runs them all")
+    ap.add_argument("--time-limit", type=float, default=160.0, help="wall-clock budget of the whole run in seconds: a secondary configuration (BASELINE.json's other configs, each minted by the CPU prover first) is skipped -- and listed as skipped -- when its estimated cost no longer fits; --time-limit 900 runs them all")
     ap.add_argument("--mixed-txs", type=int, default=100000, help="size of the mixed (config 5) batch")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement (one T-transaction batch cut N ways) at N > 1")
     ap.add_argument("--no-key-index", action="store_true", help="sharded runs: find cross-shard dependencies by scanning the earlier shards' bytes instead of the batch's key-digest index")
@@ -788,7 +788,7 @@ def main():
                     sm_ *= 2
                 rej = tamper_classes(oracle, sb, seed, (2 * args.txs) // 3, sa, sk_)
                 return measure_config("a%dk%d" % (sa, sk_), torch, xhe, verifier, dev, ts, flush, sb.blobs, sb.ledger().dump(), [], max(sm_, 2), 5, 3, rej, host_threads, canonical_lp_per_tx(sa, sk_) * args.txs, peak_wide)
-            for sa, sk_, seed, est in ((1, 3, 81, 40), (2, 6, 82, 65)):
+            for sa, sk_, seed, est in ((1, 3, 81, 40), (2, 6, 82, 55)):
                 if fits("a%dk%d_%d" % (sa, sk_, args.txs), est):
                     timed("a%dk%d_%d" % (sa, sk_, args.txs), lambda: run_shape(sa, sk_, seed))
 
