@@ -169,3 +169,30 @@ def test_async_decider_orders_decisions_across_ranks():
     for p in ps:
         p.join(60)
     assert out[0] == out[1] == want
+
+
+def test_ranks_bind_to_disjoint_core_sets():
+    """one process per GPU keeps to its own share of the host cores (distributed.bind_rank_to_local_cores); without GPUs the
+    current affinity mask is split evenly.  Run in child processes: the call changes the caller's affinity."""
+    import multiprocessing as mp
+    import os
+
+    avail = sorted(os.sched_getaffinity(0))
+    if len(avail) < 2:
+        pytest.skip("needs two host cores")
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(2) as pool:
+        got = pool.starmap(_bind_child, [(0, 2), (1, 2)])
+    assert got[0] and got[1] and not (set(got[0]) & set(got[1]))
+    assert sorted(got[0] + got[1]) == avail[:len(got[0]) + len(got[1])] or set(got[0] + got[1]) <= set(avail)
+    assert abs(len(got[0]) - len(got[1])) <= 1
+
+
+def _bind_child(rank, world):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from xelis_he_b200.distributed import bind_rank_to_local_cores
+    cores = bind_rank_to_local_cores(rank, world)
+    assert sorted(os.sched_getaffinity(0)) == sorted(cores)
+    return cores
